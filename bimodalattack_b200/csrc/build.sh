@@ -1,0 +1,17 @@
+#!/usr/bin/env bash
+# Builds libbimodal_b200.so (sm_100a only) next to the Python package. Usage: csrc/build.sh [-v]
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+OUT="$HERE/../libbimodal_b200.so"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC)
+if [[ "${1:-}" == "-v" ]]; then FLAGS+=(-Xptxas -v); fi
+mkdir -p "$HERE/_obj"
+pids=()
+for f in pgd_step sampler scoring_ops attention engine; do
+  "$NVCC" "${FLAGS[@]}" -c "$HERE/$f.cu" -o "$HERE/_obj/$f.o" &
+  pids+=($!)
+done
+for p in "${pids[@]}"; do wait "$p"; done
+"$NVCC" -shared -o "$OUT" "$HERE"/_obj/{pgd_step,sampler,scoring_ops,attention,engine}.o
+echo "built $OUT"

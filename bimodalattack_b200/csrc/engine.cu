@@ -1,0 +1,395 @@
+// C-ABI implementation (include/bimodal_b200.h): the scorer runtime that drives one decoder pass
+// over all candidates with a shared prefix KV, plus thin wrappers for the stand-alone kernels.
+// The scorer owns its activation workspace and the per-layer prefix K/V (device memory from
+// cudaMalloc); weights are borrowed pointers (the HF model's parameters or packed copies made by
+// the Python host).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/bimodal_b200.h"
+#include "gemm_host.cuh"
+#include "kernels.h"
+
+using namespace bma;
+
+namespace {
+
+thread_local std::string g_last_error;
+unsigned long long g_launches = 0;
+
+int fail(cudaError_t e, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = std::string(buf) + ": " + cudaGetErrorString(e);
+  return static_cast<int>(e == cudaSuccess ? cudaErrorUnknown : e);
+}
+#define BMA_CHECK(expr, what)                          \
+  do {                                                 \
+    cudaError_t e__ = (expr);                          \
+    ++g_launches;                                      \
+    if (e__ != cudaSuccess) return fail(e__, "%s", what); \
+  } while (0)
+
+inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
+inline const __nv_bfloat16* bf(const void* p) { return static_cast<const __nv_bfloat16*>(p); }
+inline __nv_bfloat16* bf(void* p) { return static_cast<__nv_bfloat16*>(p); }
+
+constexpr int kCeBlockN = 256;
+
+}  // namespace
+
+struct bma_scorer {
+  bma_model_desc desc;
+  std::vector<bma_layer_weights> layers;
+  const __nv_bfloat16* norm_final = nullptr;
+  const __nv_bfloat16* lm_head = nullptr;
+  const __nv_bfloat16* embed = nullptr;
+  long long ld_embed = 0;
+  int q_dim = 0, kv_dim = 0, qkv_dim = 0;
+  int prefix_len = 0;
+  // workspace
+  __nv_bfloat16 *x = nullptr, *xn = nullptr, *qkv = nullptr, *attn = nullptr, *act = nullptr;
+  __nv_bfloat16* prefix_qkv = nullptr;   // [layers][max_prefix][qkv_dim]
+  float2* ce_part = nullptr;
+  float* tgt_logit = nullptr;
+  long long* ids_dev = nullptr;          // staging for the *_host entry
+  float* loss_dev = nullptr;
+  unsigned long long* key_dev = nullptr;
+  int* flag_dev = nullptr;
+  size_t ws_bytes = 0;
+  int ce_rows_cap = 0;
+};
+
+namespace {
+
+template <typename T>
+bool dev_alloc(T** p, size_t count, size_t* total) {
+  if (cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T)) != cudaSuccess) return false;
+  *total += count * sizeof(T);
+  return true;
+}
+
+// One decoder pass over `rows` rows laid out as sequences of `seq` rows at positions
+// pos_base + (r % seq). prefill == true: rows are the prefix itself (their q/k/v land in
+// prefix_qkv and the last layer stops after its K/V are produced).
+int run_layers(bma_scorer* s, int rows, int seq, int pos_base, bool prefill, cudaStream_t st) {
+  const bma_model_desc& D = s->desc;
+  const int d = D.d_model;
+  const int P = prefill ? 0 : s->prefix_len;
+  for (int l = 0; l < D.n_layers; ++l) {
+    const bma_layer_weights& W = s->layers[l];
+    __nv_bfloat16* qkv = prefill ? s->prefix_qkv + (size_t)l * D.max_prefix * s->qkv_dim : s->qkv;
+    const __nv_bfloat16* pre = s->prefix_qkv + (size_t)l * D.max_prefix * s->qkv_dim;
+
+    BMA_CHECK(launch_rmsnorm(s->x, d, bf(W.norm_attn), s->xn, d, rows, d, D.rms_eps, D.norm_mode,
+                             0, 0, 0, st), "rmsnorm(attn)");
+    {
+      GemmParams p{};
+      p.M = rows; p.N = s->qkv_dim; p.K = d; p.group_m = 16;
+      p.C = qkv; p.ldc = s->qkv_dim;
+      p.rope_cos = W.rope_cos; p.rope_sin = W.rope_sin;
+      p.rope_cols = s->q_dim + s->kv_dim;
+      p.rows_per_seq = seq; p.pos_base = pos_base;
+      BMA_CHECK((launch_gemm<256, EPI_ROPE>(s->xn, d, bf(W.w_qkv), d, p, st)), "gemm(qkv+rope)");
+    }
+    if (prefill && l == D.n_layers - 1) break;   // only this layer's K/V are needed
+    {
+      AttnParams a{};
+      a.q = qkv; a.ldq = s->qkv_dim;
+      a.k_tail = qkv + s->q_dim; a.ldk = s->qkv_dim;
+      a.v_tail = qkv + s->q_dim + s->kv_dim; a.ldv = s->qkv_dim;
+      a.k_pre = pre + s->q_dim; a.ldkp = s->qkv_dim;
+      a.v_pre = pre + s->q_dim + s->kv_dim; a.ldvp = s->qkv_dim;
+      a.out = s->attn; a.ldo = s->q_dim;
+      a.M = rows; a.S = seq; a.P = P;
+      a.kv_group = D.n_heads / D.n_kv_heads;
+      a.scale_log2 = D.attn_scale * 1.4426950408889634f;
+      BMA_CHECK(launch_prefix_tail_attention(a, D.n_heads, st), "attention");
+    }
+    {
+      GemmParams p{};
+      p.M = rows; p.N = d; p.K = s->q_dim; p.group_m = 16;
+      p.C = s->x; p.ldc = d; p.R = s->x; p.ldr = d;
+      BMA_CHECK((launch_gemm<256, EPI_STORE>(s->attn, s->q_dim, bf(W.w_o), s->q_dim, p, st)),
+                "gemm(o_proj)");
+    }
+    BMA_CHECK(launch_rmsnorm(s->x, d, bf(W.norm_mlp), s->xn, d, rows, d, D.rms_eps, D.norm_mode,
+                             0, 0, 0, st), "rmsnorm(mlp)");
+    {
+      GemmParams p{};
+      p.M = rows; p.N = 2 * D.d_ff; p.K = d; p.group_m = 16;
+      p.C = s->act; p.ldc = D.d_ff; p.act = D.act;
+      BMA_CHECK((launch_gemm<256, EPI_GLU>(s->xn, d, bf(W.w_gate_up), d, p, st)), "gemm(gate_up)");
+    }
+    {
+      GemmParams p{};
+      p.M = rows; p.N = d; p.K = D.d_ff; p.group_m = 16;
+      p.C = s->x; p.ldc = d; p.R = s->x; p.ldr = d;
+      BMA_CHECK((launch_gemm<256, EPI_STORE>(s->act, D.d_ff, bf(W.w_down), D.d_ff, p, st)),
+                "gemm(down)");
+    }
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bma_version(void) { return 100; }
+const char* bma_last_error(void) { return g_last_error.c_str(); }
+unsigned long long bma_launch_count(void) { return g_launches; }
+
+int bma_watchdog_code(unsigned int* code_out) {
+  unsigned int v = 0;
+  cudaError_t e = cudaMemcpyFromSymbol(&v, g_watchdog_code, sizeof(v));
+  if (e != cudaSuccess) return fail(e, "watchdog read");
+  if (code_out) *code_out = v;
+  return 0;
+}
+
+int bma_pgd_step(float* image, const float* grad, const float* orig, long long n, float step,
+                 float eps, float* norm_out, const float* mean_host, const float* std_host,
+                 int channels, long long plane, void* stream) {
+  BMA_CHECK(launch_pgd_step(image, grad, orig, norm_out, n, step, eps, mean_host, std_host,
+                            channels, plane, as_stream(stream)), "pgd_step");
+  return 0;
+}
+
+int bma_token_grad(const void* grad_embeds, long long ld_g, const void* W, long long ld_w,
+                   void* out, long long ld_out, int n_tok, int d, int V, void* stream) {
+  if (n_tok <= 0 || d <= 0 || V <= 0) return fail(cudaErrorInvalidValue, "token_grad: empty shape");
+  // W is the M operand (streamed once); the few gradient rows are the N operand. Suffixes longer
+  // than one N tile are processed in slabs of 128 positions.
+  for (int t0 = 0; t0 < n_tok; t0 += 128) {
+    const int nt = n_tok - t0 < 128 ? n_tok - t0 : 128;
+    GemmParams p{};
+    p.M = V; p.N = nt; p.K = d; p.group_m = 1 << 20;
+    p.C = bf(out) + (long long)t0 * ld_out; p.ldc = ld_out;
+    const __nv_bfloat16* g = bf(grad_embeds) + (long long)t0 * ld_g;
+    if (nt <= 32) {
+      BMA_CHECK((launch_gemm<32, EPI_STORE_T>(bf(W), ld_w, g, ld_g, p, as_stream(stream))),
+                "gemm(token_grad)");
+    } else {
+      BMA_CHECK((launch_gemm<128, EPI_STORE_T>(bf(W), ld_w, g, ld_g, p, as_stream(stream))),
+                "gemm(token_grad)");
+    }
+  }
+  return 0;
+}
+
+size_t bma_sampler_workspace_bytes(int n_tok, int V, int topk) {
+  return sampler_workspace_bytes(n_tok, V, topk);
+}
+
+int bma_sample_ids(const long long* ids, const void* grad, int grad_dtype, long long row_stride,
+                   int n_tok, int V, const uint32_t* mask_bits, int search_width, int topk,
+                   int n_replace, unsigned long long seed, unsigned long long offset,
+                   void* workspace, long long* topk_ids_out, long long* new_ids,
+                   unsigned long long* offset_advance, void* stream) {
+  cudaError_t e = launch_sample_ids(ids, grad, grad_dtype, row_stride, n_tok, V, mask_bits,
+                                    search_width, topk, n_replace, seed, offset, workspace,
+                                    topk_ids_out, new_ids, offset_advance, as_stream(stream));
+  g_launches += 3;
+  if (e != cudaSuccess) return fail(e, "sample_ids");
+  return 0;
+}
+
+bma_scorer* bma_scorer_create(const bma_model_desc* desc) {
+  if (desc == nullptr) return nullptr;
+  const bma_model_desc& D = *desc;
+  if (D.head_dim != 128) {
+    g_last_error = "scorer: head_dim must be 128";
+    return nullptr;
+  }
+  if (D.n_layers <= 0 || D.d_model % 64 != 0 || D.d_ff % 128 != 0 || D.n_heads % D.n_kv_heads != 0 ||
+      D.max_rows <= 0 || D.max_prefix < 0 || D.vocab % 8 != 0) {
+    g_last_error = "scorer: unsupported model shape";
+    return nullptr;
+  }
+  bma_scorer* s = new bma_scorer();
+  s->desc = D;
+  s->layers.resize(D.n_layers);
+  s->q_dim = D.n_heads * D.head_dim;
+  s->kv_dim = D.n_kv_heads * D.head_dim;
+  s->qkv_dim = s->q_dim + 2 * s->kv_dim;
+  const size_t R = static_cast<size_t>(D.max_rows > D.max_prefix ? D.max_rows : D.max_prefix);
+  s->ce_rows_cap = D.max_rows;   // at most one target row per tail row
+  const int n_ce_tiles = (D.vocab + kCeBlockN - 1) / kCeBlockN;
+  bool ok = true;
+  ok = ok && dev_alloc(&s->x, R * D.d_model, &s->ws_bytes);
+  ok = ok && dev_alloc(&s->xn, R * D.d_model, &s->ws_bytes);
+  ok = ok && dev_alloc(&s->qkv, R * s->qkv_dim, &s->ws_bytes);
+  ok = ok && dev_alloc(&s->attn, R * s->q_dim, &s->ws_bytes);
+  ok = ok && dev_alloc(&s->act, R * D.d_ff, &s->ws_bytes);
+  ok = ok && dev_alloc(&s->prefix_qkv,
+                       static_cast<size_t>(D.n_layers) * (D.max_prefix > 0 ? D.max_prefix : 1) * s->qkv_dim,
+                       &s->ws_bytes);
+  ok = ok && dev_alloc(&s->ce_part, static_cast<size_t>(n_ce_tiles) * s->ce_rows_cap, &s->ws_bytes);
+  ok = ok && dev_alloc(&s->tgt_logit, static_cast<size_t>(s->ce_rows_cap), &s->ws_bytes);
+  ok = ok && dev_alloc(&s->ids_dev, static_cast<size_t>(D.max_rows), &s->ws_bytes);
+  ok = ok && dev_alloc(&s->loss_dev, static_cast<size_t>(D.max_rows), &s->ws_bytes);
+  ok = ok && dev_alloc(&s->key_dev, 1, &s->ws_bytes);
+  ok = ok && dev_alloc(&s->flag_dev, 1, &s->ws_bytes);
+  if (!ok) {
+    g_last_error = std::string("scorer: cudaMalloc failed: ") + cudaGetErrorString(cudaGetLastError());
+    bma_scorer_destroy(s);
+    return nullptr;
+  }
+  return s;
+}
+
+void bma_scorer_destroy(bma_scorer* s) {
+  if (s == nullptr) return;
+  cudaFree(s->x); cudaFree(s->xn); cudaFree(s->qkv); cudaFree(s->attn); cudaFree(s->act);
+  cudaFree(s->prefix_qkv); cudaFree(s->ce_part); cudaFree(s->tgt_logit);
+  cudaFree(s->ids_dev); cudaFree(s->loss_dev); cudaFree(s->key_dev); cudaFree(s->flag_dev);
+  delete s;
+}
+
+size_t bma_scorer_workspace_bytes(const bma_scorer* s) { return s ? s->ws_bytes : 0; }
+
+int bma_scorer_set_layer(bma_scorer* s, int layer, const bma_layer_weights* w) {
+  if (s == nullptr || w == nullptr || layer < 0 || layer >= s->desc.n_layers)
+    return fail(cudaErrorInvalidValue, "set_layer: bad arguments");
+  s->layers[layer] = *w;
+  return 0;
+}
+
+int bma_scorer_set_head(bma_scorer* s, const void* norm_final, const void* lm_head,
+                        const void* embed_table, long long ld_embed) {
+  if (s == nullptr) return fail(cudaErrorInvalidValue, "set_head: null scorer");
+  s->norm_final = bf(norm_final);
+  s->lm_head = bf(lm_head);
+  s->embed = bf(embed_table);
+  s->ld_embed = ld_embed;
+  return 0;
+}
+
+int bma_scorer_prefill(bma_scorer* s, const void* prefix_embeds, int P, void* stream) {
+  if (s == nullptr) return fail(cudaErrorInvalidValue, "prefill: null scorer");
+  if (P < 0 || P > s->desc.max_prefix) return fail(cudaErrorInvalidValue, "prefill: P exceeds max_prefix");
+  s->prefix_len = P;
+  if (P == 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  BMA_CHECK(cudaMemcpyAsync(s->x, prefix_embeds, (size_t)P * s->desc.d_model * sizeof(__nv_bfloat16),
+                            cudaMemcpyDeviceToDevice, st), "prefill: copy embeds");
+  return run_layers(s, P, P, 0, true, st);
+}
+
+int bma_scorer_reset_key(bma_scorer* s, unsigned long long* key, int* all_match, void* stream) {
+  (void)s;
+  BMA_CHECK(launch_init_key(key, all_match, as_stream(stream)), "init_key");
+  return 0;
+}
+
+int bma_scorer_score(bma_scorer* s, const long long* ids, int ids_stride, int B, const int* slot,
+                     const void* fixed, int S, const long long* target_ids, int T, float* loss,
+                     unsigned long long* key, int* all_match, unsigned int idx_base, void* stream) {
+  if (s == nullptr) return fail(cudaErrorInvalidValue, "score: null scorer");
+  const bma_model_desc& D = s->desc;
+  if (B <= 0) return 0;
+  if (S <= 0 || T <= 0 || T + 1 > S) return fail(cudaErrorInvalidValue, "score: need 0 < T < S");
+  if (S > D.max_rows) return fail(cudaErrorInvalidValue, "score: S exceeds max_rows");
+  if (s->lm_head == nullptr || s->norm_final == nullptr || s->embed == nullptr)
+    return fail(cudaErrorInvalidValue, "score: head weights not set");
+  cudaStream_t st = as_stream(stream);
+  const int chunk = D.max_rows / S;
+  const int d = D.d_model;
+  const int n_ce_tiles = (D.vocab + kCeBlockN - 1) / kCeBlockN;
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int nb = B - b0 < chunk ? B - b0 : chunk;
+    const int rows = nb * S;
+    BMA_CHECK(launch_build_tail_embeds(ids + (long long)b0 * ids_stride, ids_stride, slot, bf(fixed),
+                                       s->embed, s->ld_embed, D.vocab, D.embed_scale, s->x, nb, S,
+                                       d, st), "build_tail_embeds");
+    int rc = run_layers(s, rows, S, s->prefix_len, false, st);
+    if (rc != 0) return rc;
+    // final norm on the T rows per candidate whose logits predict the target tokens
+    const int ce_rows = nb * T;
+    BMA_CHECK(launch_rmsnorm(s->x, d, s->norm_final, s->xn, d, ce_rows, d, D.rms_eps, D.norm_mode,
+                             T, S, S - T - 1, st), "rmsnorm(final, gathered)");
+    {
+      GemmParams p{};
+      p.M = ce_rows; p.N = D.vocab; p.K = d; p.group_m = 16;
+      p.target_ids = target_ids; p.T = T;
+      p.ce_part = s->ce_part; p.tgt_logit = s->tgt_logit;
+      BMA_CHECK((launch_gemm<kCeBlockN, EPI_CE>(s->xn, d, s->lm_head, d, p, st)), "gemm(lm_head+ce)");
+    }
+    BMA_CHECK(launch_ce_finalize(s->ce_part, s->tgt_logit, n_ce_tiles, nb, T, loss + b0, key,
+                                 all_match, idx_base + static_cast<unsigned int>(b0), st),
+              "ce_finalize");
+  }
+  return 0;
+}
+
+int bma_scorer_score_host(bma_scorer* s, const long long* ids_host, int ids_stride, int B,
+                          const int* slot, const void* fixed, int S, const long long* target_ids,
+                          int T, float* loss_host, unsigned long long* key_host,
+                          unsigned int idx_base, void* stream) {
+  if (s == nullptr) return fail(cudaErrorInvalidValue, "score_host: null scorer");
+  if ((long long)B * ids_stride > s->desc.max_rows)
+    return fail(cudaErrorInvalidValue, "score_host: ids exceed staging capacity");
+  cudaStream_t st = as_stream(stream);
+  BMA_CHECK(cudaMemcpyAsync(s->ids_dev, ids_host, sizeof(long long) * B * ids_stride,
+                            cudaMemcpyHostToDevice, st), "score_host: H2D ids");
+  int rc = bma_scorer_reset_key(s, s->key_dev, s->flag_dev, stream);
+  if (rc != 0) return rc;
+  rc = bma_scorer_score(s, s->ids_dev, ids_stride, B, slot, fixed, S, target_ids, T, s->loss_dev,
+                        s->key_dev, s->flag_dev, idx_base, stream);
+  if (rc != 0) return rc;
+  BMA_CHECK(cudaMemcpyAsync(loss_host, s->loss_dev, sizeof(float) * B, cudaMemcpyDeviceToHost, st),
+            "score_host: D2H loss");
+  BMA_CHECK(cudaMemcpyAsync(key_host, s->key_dev, sizeof(unsigned long long),
+                            cudaMemcpyDeviceToHost, st), "score_host: D2H key");
+  BMA_CHECK(cudaStreamSynchronize(st), "score_host: sync");
+  return 0;
+}
+
+int bma_gemm_bf16(const void* A, long long lda, const void* B, long long ldb, void* C,
+                  long long ldc, const void* residual, long long ldr, int M, int N, int K,
+                  int block_n, void* stream) {
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K; p.group_m = 16;
+  p.C = bf(C); p.ldc = ldc; p.R = bf(residual); p.ldr = ldr;
+  if (block_n == 256) {
+    BMA_CHECK((launch_gemm<256, EPI_STORE>(bf(A), lda, bf(B), ldb, p, as_stream(stream))), "gemm");
+  } else if (block_n == 128) {
+    BMA_CHECK((launch_gemm<128, EPI_STORE>(bf(A), lda, bf(B), ldb, p, as_stream(stream))), "gemm");
+  } else {
+    return fail(cudaErrorInvalidValue, "gemm: block_n must be 128 or 256");
+  }
+  return 0;
+}
+
+int bma_rmsnorm(const void* x, long long ldx, const void* w, void* y, long long ldy, int rows,
+                int d, float eps, int mode, void* stream) {
+  BMA_CHECK(launch_rmsnorm(bf(x), ldx, bf(w), bf(y), ldy, rows, d, eps, mode, 0, 0, 0,
+                           as_stream(stream)), "rmsnorm");
+  return 0;
+}
+
+int bma_attention(const void* q, long long ldq, const void* k_tail, long long ldk,
+                  const void* v_tail, long long ldv, const void* k_pre, long long ldkp,
+                  const void* v_pre, long long ldvp, void* out, long long ldo, int M, int S, int P,
+                  int n_heads, int kv_group, float scale, void* stream) {
+  AttnParams a{};
+  a.q = bf(q); a.ldq = ldq;
+  a.k_tail = bf(k_tail); a.ldk = ldk;
+  a.v_tail = bf(v_tail); a.ldv = ldv;
+  a.k_pre = bf(k_pre); a.ldkp = ldkp;
+  a.v_pre = bf(v_pre); a.ldvp = ldvp;
+  a.out = bf(out); a.ldo = ldo;
+  a.M = M; a.S = S; a.P = P; a.kv_group = kv_group;
+  a.scale_log2 = scale * 1.4426950408889634f;
+  BMA_CHECK(launch_prefix_tail_attention(a, n_heads, as_stream(stream)), "attention");
+  return 0;
+}
+
+}  // extern "C"

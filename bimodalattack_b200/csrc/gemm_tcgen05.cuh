@@ -1,0 +1,391 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a:  C[M,N] = A[M,K] * B[N,K]^T  (both K-major).
+//
+//   warp 0        TMA producer   (cp.async.bulk.tensor, SWIZZLE_128B tiles, mbarrier ring)
+//   warp 1        MMA issuer     (one elected lane issues tcgen05.mma, accumulators in TMEM)
+//   warp 2        TMEM allocator
+//   warps 4..7    epilogue       (tcgen05.ld -> registers -> fused epilogue -> global)
+//
+// Two TMEM accumulator buffers let the epilogue of tile i overlap the main loop of tile i+1.
+// The epilogue is a template parameter; the variants are the fused ops of the candidate-scoring
+// path:
+//   EPI_STORE    bf16 store, optional residual add              (O-proj, down-proj)
+//   EPI_ROPE     bf16 store with rotary embedding on Q,K heads  (fused QKV projection)
+//   EPI_GLU      act(gate) * up, gate/up rows interleaved per tile (SwiGLU / GeGLU)
+//   EPI_CE       per-row online log-sum-exp partials + target-logit pick (LM head; logits
+//                are never written to memory)
+//   EPI_STORE_T  transposed store  out[n, m]                    (token gradient, W streamed as A)
+#pragma once
+#include "common.cuh"
+
+namespace bma {
+
+enum : int { EPI_STORE = 0, EPI_ROPE = 1, EPI_GLU = 2, EPI_CE = 3, EPI_STORE_T = 4 };
+
+struct GemmParams {
+  int M, N, K;
+  int group_m;                // rasterisation: m-blocks per L2 supergroup
+  // output
+  __nv_bfloat16* C;           // EPI_STORE/ROPE/GLU/STORE_T
+  long long ldc;
+  const __nv_bfloat16* R;     // optional residual (EPI_STORE), same shape as C
+  long long ldr;
+  // rotary (EPI_ROPE): tables [pos][64] fp32 (values already rounded to the model dtype)
+  const float* rope_cos;
+  const float* rope_sin;
+  int rope_cols;              // leading output columns that are Q/K heads (multiple of 128)
+  int rows_per_seq;           // position of row r is pos_base + (r % rows_per_seq)
+  int pos_base;
+  // GLU
+  int act;                    // 0 = SiLU, 1 = GELU(tanh)
+  // cross-entropy (EPI_CE)
+  const long long* target_ids;  // [T]; row r is scored against target_ids[r % T]
+  int T;
+  float2* ce_part;            // [n_tiles][M] (running max, sum of exp)
+  float* tgt_logit;           // [M]
+};
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 256;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStageBytesA = GEMM_BM * GEMM_BK * 2;
+  static constexpr int kStageBytesB = BN * GEMM_BK * 2;
+  static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
+  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 10);
+  static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float act_silu(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float act_gelu_tanh(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  float u = k0 * (x + k1 * x * x * x);
+  return 0.5f * x * (1.0f + tanhf(u));
+}
+
+__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const uint32_t (&p)[16],
+                                              int valid_cols) {
+  // dst is 16-byte aligned; valid_cols counts the columns (of 32) inside the matrix.
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    if (v * 8 + 8 <= valid_cols) {
+      uint4 q = make_uint4(p[v * 4 + 0], p[v * 4 + 1], p[v * 4 + 2], p[v * 4 + 3]);
+      *reinterpret_cast<uint4*>(dst + v * 8) = q;
+    }
+  }
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                    const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * Cfg::kStageBytesA;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;                    // [kStages]
+  uint64_t* empty_bar = bars + kStages;         // [kStages]
+  uint64_t* tmem_full = bars + 2 * kStages;     // [2]
+  uint64_t* tmem_empty = bars + 2 * kStages + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int k_blocks = (p.K + GEMM_BK - 1) / GEMM_BK;
+  const int group_m = p.group_m > 0 ? p.group_m : 16;
+
+  auto tile_coords = [&](int tile, int& m_blk, int& n_blk) {
+    const int per_group = group_m * n_tiles;
+    const int g = tile / per_group;
+    const int first_m = g * group_m;
+    const int rows_in_group = min(group_m, m_tiles - first_m);
+    const int r = tile - g * per_group;
+    m_blk = first_m + r % rows_in_group;
+    n_blk = r / rows_in_group;
+  };
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int m_blk, n_blk;
+        tile_coords(tile, m_blk, n_blk);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1, 0x100 + stage);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_2d(smem_a + stage * Cfg::kStageBytesA, &tmap_a, &full_bar[stage],
+                      kb * GEMM_BK, m_blk * GEMM_BM);
+          tma_load_2d(smem_b + stage * Cfg::kStageBytesB, &tmap_b, &full_bar[stage],
+                      kb * GEMM_BK, n_blk * BN);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 0x200 + acc);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase, 0x300 + stage);
+          tc_fence_after();
+          const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + stage * Cfg::kStageBytesA));
+          const uint64_t db = umma_desc_k_sw128(smem_u32(smem_b + stage * Cfg::kStageBytesB));
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            // advance 16 elements (32 B) along K inside the 128-B swizzle atom: +2 in 16-B units
+            umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);       // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue
+    const int sub = warp & 3;                 // TMEM sub-partition owned by this warp
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int m_blk, n_blk;
+      tile_coords(tile, m_blk, n_blk);
+      mbar_wait(&tmem_full[acc], acc_phase, 0x400 + acc);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * BN;
+      const int row = m_blk * GEMM_BM + sub * 32 + lane;
+      const bool row_ok = row < p.M;
+      const int n0 = n_blk * BN;
+
+      if constexpr (EPI == EPI_STORE) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(t_row + c0, r);
+          tmem_ld_wait();
+          const int col = n0 + c0;
+          const int valid = min(32, p.N - col);
+          if (row_ok && valid > 0) {
+            uint32_t o[16];
+            if (p.R != nullptr) {
+              const uint4* rp = reinterpret_cast<const uint4*>(p.R + (long long)row * p.ldr + col);
+#pragma unroll
+              for (int v = 0; v < 4; ++v) {
+                uint4 q = make_uint4(0, 0, 0, 0);
+                if (v * 8 + 8 <= valid) q = rp[v];
+                const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  // the GEMM result is rounded to bf16 first (as a separate Linear would), then
+                  // added to the bf16 residual.
+                  float a0 = bf16_round(__uint_as_float(r[v * 8 + 2 * j])) + bf16_lo(qq[j]);
+                  float a1 = bf16_round(__uint_as_float(r[v * 8 + 2 * j + 1])) + bf16_hi(qq[j]);
+                  o[v * 4 + j] = pack_bf16x2(a0, a1);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                o[j] = pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+            }
+            store_bf16x32(p.C + (long long)row * p.ldc + col, o, valid);
+          }
+        }
+      } else if constexpr (EPI == EPI_ROPE) {
+        const int pos = p.pos_base + (row_ok ? (row % p.rows_per_seq) : 0);
+        const float4* cosp = reinterpret_cast<const float4*>(p.rope_cos + (long long)pos * 64);
+        const float4* sinp = reinterpret_cast<const float4*>(p.rope_sin + (long long)pos * 64);
+#pragma unroll 1
+        for (int hb = 0; hb < BN; hb += 128) {
+          const int col_h = n0 + hb;
+          if (col_h >= p.N) break;
+          if (col_h < p.rope_cols) {
+#pragma unroll 1
+            for (int c0 = 0; c0 < 64; c0 += 32) {
+              uint32_t x1[32], x2[32];
+              tmem_ld_32x32(t_row + hb + c0, x1);
+              tmem_ld_32x32(t_row + hb + 64 + c0, x2);
+              tmem_ld_wait();
+              if (row_ok) {
+                uint32_t o1[16], o2[16];
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                  const float4 c = cosp[(c0 >> 2) + j4];
+                  const float4 s = sinp[(c0 >> 2) + j4];
+                  const float cc[4] = {c.x, c.y, c.z, c.w};
+                  const float ss[4] = {s.x, s.y, s.z, s.w};
+                  float y1[4], y2[4];
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    // projection output is bf16 in the reference before the rotation is applied
+                    const float a = bf16_round(__uint_as_float(x1[j4 * 4 + j]));
+                    const float b = bf16_round(__uint_as_float(x2[j4 * 4 + j]));
+                    y1[j] = bf16_round(a * cc[j]) + bf16_round(-b * ss[j]);
+                    y2[j] = bf16_round(b * cc[j]) + bf16_round(a * ss[j]);
+                  }
+                  o1[j4 * 2 + 0] = pack_bf16x2(y1[0], y1[1]);
+                  o1[j4 * 2 + 1] = pack_bf16x2(y1[2], y1[3]);
+                  o2[j4 * 2 + 0] = pack_bf16x2(y2[0], y2[1]);
+                  o2[j4 * 2 + 1] = pack_bf16x2(y2[2], y2[3]);
+                }
+                __nv_bfloat16* dst = p.C + (long long)row * p.ldc + col_h + c0;
+                store_bf16x32(dst, o1, 32);
+                store_bf16x32(dst + 64, o2, 32);
+              }
+            }
+          } else {
+#pragma unroll 1
+            for (int c0 = 0; c0 < 128; c0 += 32) {
+              uint32_t r[32];
+              tmem_ld_32x32(t_row + hb + c0, r);
+              tmem_ld_wait();
+              if (row_ok) {
+                uint32_t o[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  o[j] = pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+                store_bf16x32(p.C + (long long)row * p.ldc + col_h + c0, o,
+                              min(32, p.N - (col_h + c0)));
+              }
+            }
+          }
+        }
+      } else if constexpr (EPI == EPI_GLU) {
+        // tile columns [0, BN/2) are gate rows j0.., columns [BN/2, BN) the matching up rows
+        constexpr int H = BN / 2;
+        const int out_n = p.N / 2;
+        const int j0 = n_blk * H;
+#pragma unroll 1
+        for (int c0 = 0; c0 < H; c0 += 32) {
+          uint32_t g[32], u[32];
+          tmem_ld_32x32(t_row + c0, g);
+          tmem_ld_32x32(t_row + H + c0, u);
+          tmem_ld_wait();
+          const int col = j0 + c0;
+          const int valid = min(32, out_n - col);
+          if (row_ok && valid > 0) {
+            uint32_t o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float y[2];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const float gv = bf16_round(__uint_as_float(g[2 * j + e]));
+                const float uv = bf16_round(__uint_as_float(u[2 * j + e]));
+                const float a = bf16_round(p.act == 0 ? act_silu(gv) : act_gelu_tanh(gv));
+                y[e] = a * uv;
+              }
+              o[j] = pack_bf16x2(y[0], y[1]);
+            }
+            store_bf16x32(p.C + (long long)row * p.ldc + col, o, valid);
+          }
+        }
+      } else if constexpr (EPI == EPI_CE) {
+        const int tcol = row_ok ? static_cast<int>(p.target_ids[row % p.T]) : -1;
+        float run_m = -INFINITY, run_s = 0.0f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(t_row + c0, r);
+          tmem_ld_wait();
+          const int col = n0 + c0;
+          const int valid = min(32, p.N - col);
+          if (valid <= 0) break;
+          float v[32];
+          float cm = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            v[j] = (j < valid) ? bf16_round(__uint_as_float(r[j])) : -INFINITY;
+            cm = fmaxf(cm, v[j]);
+          }
+          if (tcol >= col && tcol < col + valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col + j == tcol) p.tgt_logit[row] = v[j];
+          }
+          const float nm = fmaxf(run_m, cm);
+          float s = 0.0f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) s += __expf(v[j] - nm);
+          run_s = run_s * __expf(run_m - nm) + s;
+          run_m = nm;
+        }
+        if (row_ok) p.ce_part[(long long)n_blk * p.M + row] = make_float2(run_m, run_s);
+      } else if constexpr (EPI == EPI_STORE_T) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          if (n0 + c0 >= p.N) break;
+          uint32_t r[32];
+          tmem_ld_32x32(t_row + c0, r);
+          tmem_ld_wait();
+          if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int n = n0 + c0 + j;
+              if (n < p.N)
+                p.C[(long long)n * p.ldc + row] = __float2bfloat16_rn(__uint_as_float(r[j]));
+            }
+          }
+        }
+      }
+
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+}  // namespace bma

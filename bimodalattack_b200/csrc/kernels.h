@@ -1,0 +1,48 @@
+// Launch entry points shared between the kernel translation units and the C-ABI layer.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace bma {
+
+struct AttnParams {
+  const __nv_bfloat16* q;       long long ldq;     // [M, ...] query rows (head h at column h*HD)
+  const __nv_bfloat16* k_tail;  long long ldk;     // [M, ...] tail keys   (kv head g at g*HD)
+  const __nv_bfloat16* v_tail;  long long ldv;
+  const __nv_bfloat16* k_pre;   long long ldkp;    // [P, ...] prefix keys
+  const __nv_bfloat16* v_pre;   long long ldvp;
+  __nv_bfloat16* out;           long long ldo;     // [M, H*HD]
+  int M, S, P;
+  int kv_group;                 // query heads per kv head
+  float scale_log2;             // softmax scale * log2(e)
+};
+
+cudaError_t launch_prefix_tail_attention(const AttnParams& p, int n_heads, cudaStream_t stream);
+
+cudaError_t launch_pgd_step(float* x, const float* g, const float* x0, float* norm_out,
+                            long long n, float step, float eps, const float* mean,
+                            const float* std_, int channels, long long plane, cudaStream_t stream);
+
+size_t sampler_workspace_bytes(int n_tok, int V, int topk);
+cudaError_t launch_sample_ids(const long long* ids, const void* grad, int grad_dtype,
+                              long long row_stride, int n_tok, int V, const uint32_t* mask_bits,
+                              int search_width, int topk, int n_replace, unsigned long long seed,
+                              unsigned long long offset, void* workspace, long long* topk_ids_out,
+                              long long* new_ids, unsigned long long* offset_advance,
+                              cudaStream_t stream);
+
+cudaError_t launch_build_tail_embeds(const long long* ids, int ids_stride, const int* slot,
+                                     const __nv_bfloat16* fixed, const __nv_bfloat16* W,
+                                     long long ldw, int V, float scale, __nv_bfloat16* out, int B,
+                                     int S, int d, cudaStream_t stream);
+cudaError_t launch_rmsnorm(const __nv_bfloat16* x, long long ldx, const __nv_bfloat16* w,
+                           __nv_bfloat16* y, long long ldy, int rows, int d, float eps, int mode,
+                           int gather_T, int gather_S, int gather_off, cudaStream_t stream);
+cudaError_t launch_init_key(unsigned long long* key, int* flag, cudaStream_t stream);
+cudaError_t launch_ce_finalize(const float2* part, const float* tgt_logit, int n_tiles, int B,
+                               int T, float* loss, unsigned long long* key, int* all_match_flag,
+                               unsigned int idx_base, cudaStream_t stream);
+
+}  // namespace bma

@@ -1,0 +1,185 @@
+// Memory-bound helpers of the candidate-scoring path:
+//   build_tail_embeds   per-candidate tail = embedding rows of the sampled suffix ids + the fixed
+//                       (after / target / ...) rows shared by all candidates; replaces the
+//                       reference's sw-fold repeat+cat of the whole prompt (bimodal_attack.py:1217-1225)
+//   rmsnorm             RMSNorm with HF's rounding points, optional row gather (target rows only)
+//   ce_finalize         combine the LM-head GEMM's per-tile (max, sum-exp) partials into per-token
+//                       CE, mean per candidate (bimodal_attack.py:1293-1298), packed argmin key
+#include "common.cuh"
+#include "kernels.h"
+
+namespace bma {
+
+// ------------------------------------------------------------------------------------------------
+// out[b*S + s, :] = slot[s] >= 0 ? round_bf16(W[ids[b, slot[s]], :] * scale) : fixed[s, :]
+__global__ void __launch_bounds__(256)
+build_tail_embeds_kernel(const long long* __restrict__ ids, int ids_stride,
+                         const int* __restrict__ slot, const __nv_bfloat16* __restrict__ fixed,
+                         const __nv_bfloat16* __restrict__ W, long long ldw, int V, float scale,
+                         __nv_bfloat16* __restrict__ out, int B, int S, int d) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= B * S) return;
+  const int b = warp / S, s = warp - b * S;
+  const int sl = slot[s];
+  const int nvec = d >> 3;
+  uint4* dst = reinterpret_cast<uint4*>(out + (long long)warp * d);
+  if (sl < 0) {
+    const uint4* src = reinterpret_cast<const uint4*>(fixed + (long long)s * d);
+    for (int v = lane; v < nvec; v += 32) dst[v] = src[v];
+    return;
+  }
+  long long tok = ids[(long long)b * ids_stride + sl];
+  if (tok < 0 || tok >= V) tok = 0;   // never read outside the table; host validates ids
+  const uint4* src = reinterpret_cast<const uint4*>(W + tok * ldw);
+  if (scale == 1.0f) {
+    for (int v = lane; v < nvec; v += 32) dst[v] = src[v];
+  } else {
+    for (int v = lane; v < nvec; v += 32) {
+      const uint4 q = src[v];
+      const uint32_t in[4] = {q.x, q.y, q.z, q.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = pack_bf16x2(bf16_lo(in[j]) * scale, bf16_hi(in[j]) * scale);
+      dst[v] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+cudaError_t launch_build_tail_embeds(const long long* ids, int ids_stride, const int* slot,
+                                     const __nv_bfloat16* fixed, const __nv_bfloat16* W,
+                                     long long ldw, int V, float scale, __nv_bfloat16* out, int B,
+                                     int S, int d, cudaStream_t stream) {
+  if (B <= 0 || S <= 0) return cudaSuccess;
+  if ((d & 7) != 0) return cudaErrorInvalidValue;
+  const long long rows = (long long)B * S;
+  const int blocks = static_cast<int>((rows * 32 + 255) / 256);
+  build_tail_embeds_kernel<<<blocks, 256, 0, stream>>>(ids, ids_stride, slot, fixed, W, ldw, V,
+                                                       scale, out, B, S, d);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// RMSNorm, one warp per output row. mode 0 (Llama): y = bf16(w * bf16(x * rstd));
+// mode 1 (Gemma): y = bf16(x * rstd * (1 + w)). Row gather: when gather_T > 0 output row r reads
+// input row (r / gather_T) * gather_S + gather_off + (r % gather_T).
+__global__ void __launch_bounds__(256)
+rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
+               const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ y, long long ldy,
+               int rows, int d, float eps, int mode, int gather_T, int gather_S, int gather_off) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  long long src_row = r;
+  if (gather_T > 0) src_row = (long long)(r / gather_T) * gather_S + gather_off + (r % gather_T);
+  const uint4* src = reinterpret_cast<const uint4*>(x + src_row * ldx);
+  const uint4* wv = reinterpret_cast<const uint4*>(w);
+  uint4* dst = reinterpret_cast<uint4*>(y + (long long)r * ldy);
+  const int nvec = d >> 3;
+  float ss = 0.0f;
+  for (int v = lane; v < nvec; v += 32) {
+    const uint4 q = src[v];
+    const uint32_t in[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a = bf16_lo(in[j]), b = bf16_hi(in[j]);
+      ss += a * a + b * b;
+    }
+  }
+  ss = warp_sum(ss);
+  const float rstd = rsqrtf(ss / static_cast<float>(d) + eps);
+  for (int v = lane; v < nvec; v += 32) {
+    const uint4 q = src[v];
+    const uint4 ww = wv[v];
+    const uint32_t in[4] = {q.x, q.y, q.z, q.w};
+    const uint32_t wi[4] = {ww.x, ww.y, ww.z, ww.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a = bf16_lo(in[j]) * rstd, b = bf16_hi(in[j]) * rstd;
+      if (mode == 0) {
+        a = bf16_round(a) * bf16_lo(wi[j]);
+        b = bf16_round(b) * bf16_hi(wi[j]);
+      } else {
+        a = a * (1.0f + bf16_lo(wi[j]));
+        b = b * (1.0f + bf16_hi(wi[j]));
+      }
+      o[j] = pack_bf16x2(a, b);
+    }
+    dst[v] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+cudaError_t launch_rmsnorm(const __nv_bfloat16* x, long long ldx, const __nv_bfloat16* w,
+                           __nv_bfloat16* y, long long ldy, int rows, int d, float eps, int mode,
+                           int gather_T, int gather_S, int gather_off, cudaStream_t stream) {
+  if (rows <= 0) return cudaSuccess;
+  if ((d & 7) != 0 || (ldx & 7) != 0 || (ldy & 7) != 0) return cudaErrorInvalidValue;
+  const int blocks = static_cast<int>(((long long)rows * 32 + 255) / 256);
+  rmsnorm_kernel<<<blocks, 256, 0, stream>>>(x, ldx, w, y, ldy, rows, d, eps, mode, gather_T,
+                                             gather_S, gather_off);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long pack_loss_key(float loss, unsigned int idx) {
+  uint32_t u = __float_as_uint(loss);
+  uint32_t ord = (loss != loss) ? 0xFFFFFFFFu : ((u & 0x80000000u) ? ~u : (u | 0x80000000u));
+  return (static_cast<unsigned long long>(ord) << 31) | static_cast<unsigned long long>(idx & 0x7FFFFFFFu);
+}
+
+__global__ void init_key_kernel(unsigned long long* key, int* flag) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    if (key != nullptr) *key = 0x7FFFFFFFFFFFFFFFull;
+    if (flag != nullptr) *flag = 0;
+  }
+}
+
+// One thread per candidate: T rows, n_tiles partials each. part is [n_tiles][M] so the reads of
+// neighbouring candidates' rows are contiguous.
+__global__ void __launch_bounds__(128)
+ce_finalize_kernel(const float2* __restrict__ part, const float* __restrict__ tgt_logit,
+                   int n_tiles, int B, int T, float* __restrict__ loss,
+                   unsigned long long* __restrict__ key, int* __restrict__ all_match_flag,
+                   unsigned int idx_base) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const long long M = (long long)B * T;
+  float acc = 0.0f;
+  bool all_match = true;
+  for (int tt = 0; tt < T; ++tt) {
+    const long long row = (long long)b * T + tt;
+    float m = -INFINITY, s = 0.0f;
+    for (int nt = 0; nt < n_tiles; ++nt) {
+      const float2 ps = part[(long long)nt * M + row];
+      const float nm = fmaxf(m, ps.x);
+      if (nm == -INFINITY) continue;
+      s = s * __expf(m - nm) + ps.y * __expf(ps.x - nm);
+      m = nm;
+    }
+    const float tl = tgt_logit[row];
+    acc += (m + logf(s)) - tl;
+    all_match = all_match && (tl >= m);
+  }
+  const float l = acc / static_cast<float>(T);
+  loss[b] = l;
+  if (key != nullptr) atomicMin(key, pack_loss_key(l, idx_base + static_cast<unsigned int>(b)));
+  if (all_match_flag != nullptr && all_match) atomicOr(all_match_flag, 1);
+}
+
+cudaError_t launch_init_key(unsigned long long* key, int* flag, cudaStream_t stream) {
+  init_key_kernel<<<1, 32, 0, stream>>>(key, flag);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ce_finalize(const float2* part, const float* tgt_logit, int n_tiles, int B,
+                               int T, float* loss, unsigned long long* key, int* all_match_flag,
+                               unsigned int idx_base, cudaStream_t stream) {
+  if (B <= 0) return cudaSuccess;
+  const int blocks = (B + 127) / 128;
+  ce_finalize_kernel<<<blocks, 128, 0, stream>>>(part, tgt_logit, n_tiles, B, T, loss, key,
+                                                 all_match_flag, idx_base);
+  return cudaGetLastError();
+}
+
+}  // namespace bma

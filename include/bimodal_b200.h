@@ -1,0 +1,134 @@
+/* bimodal_b200 -- C ABI of the B200-native GCG+PGD step engine.
+ *
+ * Drop-in boundary for the per-step hot path of Bimo99B9/BimodalAttack (pure Python; file:line
+ * below refer to the reference's bimodalattack/bimodal_attack.py). Every entry point takes plain
+ * pointers and sizes: device pointers unless the name ends in `_host`, and a CUDA stream passed as
+ * `void*` (cudaStream_t; NULL = legacy default stream). All functions return 0 on success or a
+ * non-zero cudaError_t value; bma_last_error() gives a text for the most recent failure on the
+ * calling thread. Nothing here falls back to the CPU.
+ *
+ * The Python host (bimodalattack_b200/native.py) binds these with ctypes; INTEGRATION.md shows the
+ * stub a maintainer of the reference would add.
+ */
+#ifndef BIMODAL_B200_H
+#define BIMODAL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BMA_DTYPE_BF16 0
+#define BMA_DTYPE_F16 1
+#define BMA_DTYPE_F32 2
+
+/* ---- library ---------------------------------------------------------------------------- */
+int bma_version(void);
+const char* bma_last_error(void);
+/* Code recorded by the in-kernel pipeline watchdog (0 = none). */
+int bma_watchdog_code(unsigned int* code_out);
+
+/* ---- (4) PGD image step ------------------------------------------------------------------
+ * Replaces BimodalAttack.perform_pgd_step (:1030-1037):
+ *   image <- clamp(clamp(image - step*sign(grad), orig-eps, orig+eps), 0, 1),  step = alpha*eps.
+ * fp32, in place, bit-exact with the torch sequence. If norm_out != NULL also writes
+ * (image - mean[c]) / std[c] (torchvision Normalize, reference :526/:703/:971); mean/std are HOST
+ * arrays of `channels` floats and `plane` = H*W. */
+int bma_pgd_step(float* image, const float* grad, const float* orig, long long n, float step,
+                 float eps, float* norm_out, const float* mean_host, const float* std_host,
+                 int channels, long long plane, void* stream);
+
+/* ---- (1) GCG token gradient --------------------------------------------------------------
+ * Replaces the backward of `optim_ids_onehot @ embedding_layer.weight` (:968, :1016-1025):
+ *   out[n_tok, V] = grad_embeds[n_tok, d] * W[V, d]^T     (bf16 in, fp32 accumulate, bf16 out)
+ * W is streamed exactly once through TMA as the tcgen05 A operand. */
+int bma_token_grad(const void* grad_embeds, long long ld_g, const void* W, long long ld_w,
+                   void* out, long long ld_out, int n_tok, int d, int V, void* stream);
+
+/* ---- (2) candidate sampling --------------------------------------------------------------
+ * Replaces sample_ids_from_grad (:130-163). grad is [n_tok, V] of `grad_dtype`; mask_bits is a
+ * V-bit set (uint32 words, bit i of word w <-> token 32*w+i, 1 = not allowed) or NULL; (seed,
+ * offset) is torch's CUDA Philox state; *offset_advance (host) receives how far torch's generator
+ * must be advanced afterwards. topk_ids_out ([n_tok, topk] int64) may be NULL. */
+size_t bma_sampler_workspace_bytes(int n_tok, int V, int topk);
+int bma_sample_ids(const long long* ids, const void* grad, int grad_dtype, long long row_stride,
+                   int n_tok, int V, const uint32_t* mask_bits, int search_width, int topk,
+                   int n_replace, unsigned long long seed, unsigned long long offset,
+                   void* workspace, long long* topk_ids_out, long long* new_ids,
+                   unsigned long long* offset_advance, void* stream);
+
+/* ---- (3) candidate scoring ---------------------------------------------------------------
+ * Replaces _build_input_embeds* (:1112-1276) + _compute_candidates_loss_original (:1278-1310) +
+ * loss.min()/argmin() (:550-551, :584-585, :636-637) for a Llama/Gemma-style decoder. */
+typedef struct {
+  int n_layers, d_model, n_heads, n_kv_heads, head_dim, d_ff, vocab;
+  float rms_eps;
+  int norm_mode;      /* 0: Llama  w*bf16(x*rstd);  1: Gemma  x*rstd*(1+w) */
+  int act;            /* 0: SiLU, 1: GELU(tanh) */
+  float embed_scale;  /* multiplies embedding rows of sampled ids (Gemma: sqrt(d)), else 1 */
+  float attn_scale;   /* softmax scale, e.g. head_dim^-0.5 */
+  int max_rows;       /* capacity in tail rows (candidates per pass = max_rows / S) */
+  int max_prefix;     /* capacity in prefix rows */
+} bma_model_desc;
+
+typedef struct {
+  const void* w_qkv;      /* [(H+2*Hkv)*hd, d] rows: Q heads | K heads | V heads            */
+  const void* w_o;        /* [d, H*hd]                                                      */
+  const void* w_gate_up;  /* [2*d_ff, d]; per 256-row block: 128 gate rows then 128 up rows */
+  const void* w_down;     /* [d, d_ff]                                                      */
+  const void* norm_attn;  /* [d] */
+  const void* norm_mlp;   /* [d] */
+  const float* rope_cos;  /* [max_pos, hd/2] fp32, values already rounded to the model dtype */
+  const float* rope_sin;
+} bma_layer_weights;
+
+typedef struct bma_scorer bma_scorer;
+
+bma_scorer* bma_scorer_create(const bma_model_desc* desc);
+void bma_scorer_destroy(bma_scorer* s);
+int bma_scorer_set_layer(bma_scorer* s, int layer, const bma_layer_weights* w);
+int bma_scorer_set_head(bma_scorer* s, const void* norm_final, const void* lm_head,
+                        const void* embed_table, long long ld_embed);
+size_t bma_scorer_workspace_bytes(const bma_scorer* s);
+
+/* Run the shared prefix (image tokens + prompt) once; its K/V stay resident in the scorer. */
+int bma_scorer_prefill(bma_scorer* s, const void* prefix_embeds, int P, void* stream);
+
+/* Score B candidates. ids is [B, ids_stride] int64; tail position s takes the embedding of
+ * ids[b, slot[s]] when slot[s] >= 0, else row s of fixed ([S, d] bf16). The loss of candidate b is
+ * the mean CE of target_ids[0..T) read at tail rows S-T-1 .. S-2 (:1289-1298). Outputs: loss[B]
+ * fp32; *key = min over candidates of (orderable(loss) << 31 | idx_base + b) merged into the
+ * existing value (call bma_scorer_reset_key first); *all_match != 0 if some candidate's argmax
+ * equals the target everywhere (early_stop, :1300-1306). */
+int bma_scorer_reset_key(bma_scorer* s, unsigned long long* key, int* all_match, void* stream);
+int bma_scorer_score(bma_scorer* s, const long long* ids, int ids_stride, int B, const int* slot,
+                     const void* fixed, int S, const long long* target_ids, int T, float* loss,
+                     unsigned long long* key, int* all_match, unsigned int idx_base, void* stream);
+
+/* Same call with HOST buffers for ids / loss / key (pinned recommended): copies in, scores,
+ * copies out and synchronises the stream. This is the end-to-end entry the benchmark times. */
+int bma_scorer_score_host(bma_scorer* s, const long long* ids_host, int ids_stride, int B,
+                          const int* slot, const void* fixed, int S, const long long* target_ids,
+                          int T, float* loss_host, unsigned long long* key_host,
+                          unsigned int idx_base, void* stream);
+
+/* Launches issued by this library since load (the benchmark's gpu_launches counter). */
+unsigned long long bma_launch_count(void);
+
+/* ---- kernel-level entry points (used by the parity tests) --------------------------------- */
+int bma_gemm_bf16(const void* A, long long lda, const void* B, long long ldb, void* C,
+                  long long ldc, const void* residual, long long ldr, int M, int N, int K,
+                  int block_n, void* stream);
+int bma_rmsnorm(const void* x, long long ldx, const void* w, void* y, long long ldy, int rows,
+                int d, float eps, int mode, void* stream);
+int bma_attention(const void* q, long long ldq, const void* k_tail, long long ldk,
+                  const void* v_tail, long long ldv, const void* k_pre, long long ldkp,
+                  const void* v_pre, long long ldvp, void* out, long long ldo, int M, int S, int P,
+                  int n_heads, int kv_group, float scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BIMODAL_B200_H */
