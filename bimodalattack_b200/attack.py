@@ -1,0 +1,541 @@
+"""B200-native step loop behind the reference's API (``run`` / ``BimodalAttack``).
+
+One optimisation step (reference bimodal_attack.py:441-794):
+
+  A  gradient        HF autograd at batch 1 with a *leaf* suffix embedding; the token gradient
+                     G_embeds . W_embed^T is the hand-written tcgen05 GEMM (``native.token_grad``)
+                     instead of the backward of a one-hot matmul (:959-968, :1016-1025)
+  B  PGD             one fused kernel (``native.pgd_step_``)                       (:1030-1037)
+  D  sampling        device top-k + Philox replacement, torch-RNG exact            (:130-163)
+     scoring         shared-prefix KV + tail-only decoder pass + fused LM-head CE + argmin
+                     (``ScoringEngine``), sharded over ranks with one min all-reduce
+                     (:1112-1310, :550-551)
+
+The method seams of the reference class (compute_gradient, perform_pgd_step, candidate_sampling,
+_build_input_embeds*, _compute_candidates_loss_original) are kept so A/B tests against the oracle
+read like the reference. Everything numeric that this package owns runs in ``libbimodal_b200.so``;
+the model's own forward/backward for phase A stays on PyTorch.
+"""
+from __future__ import annotations
+
+import copy
+import logging
+import os
+import time
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import torch
+import torch.nn.functional as F
+
+from . import dist as bdist
+from . import native
+from .config import BimodalAttackConfig, BimodalAttackResult
+from .engine import ScoringEngine, unpack_key
+from .segments import TailPlan, plan_tail, segment_order
+from .utils import INIT_CHARS, AttackBuffer, find_executable_batch_size, get_nonascii_toks
+
+logger = logging.getLogger("gcg")          # same logger name and format as the reference (:26-36)
+if not logger.hasHandlers():
+    _h = logging.StreamHandler()
+    _h.setFormatter(logging.Formatter("%(asctime)s [%(filename)s:%(lineno)d] %(message)s",
+                                      datefmt="%Y-%m-%d %H:%M:%S"))
+    logger.addHandler(_h)
+    logger.setLevel(logging.INFO)
+logger.propagate = False
+
+
+def image_features(model, pixel_values: torch.Tensor, gemma_processor: bool) -> torch.Tensor:
+    """``model.get_image_features`` as the reference calls it (:528-536), normalised to a tensor
+    (transformers 5.x returns BaseModelOutputWithPooling, 4.50 a tensor)."""
+    if gemma_processor:
+        out = model.get_image_features(pixel_values=pixel_values)
+    else:
+        out = model.get_image_features(pixel_values=pixel_values, vision_feature_layer=-2,
+                                       vision_feature_select_strategy="default")
+    if isinstance(out, torch.Tensor):
+        return out
+    pooled = out.pooler_output
+    return torch.stack(list(pooled), 0) if isinstance(pooled, (list, tuple)) else pooled
+
+
+def sample_ids_from_grad(ids: torch.Tensor, grad: torch.Tensor, search_width: int, topk: int = 256,
+                         n_replace: int = 1, not_allowed_ids: Optional[torch.Tensor] = None,
+                         mask_bits: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Device sampler with the reference's signature (:130-163). Consumes torch's CUDA generator
+    exactly like the reference's two draws and leaves it at the same offset. Unlike the reference
+    it does not write +inf into ``grad``."""
+    native.require_cuda(grad, "grad")
+    dev = grad.device
+    if mask_bits is None and not_allowed_ids is not None:
+        mask_bits = native.pack_mask_bits(not_allowed_ids, grad.shape[1], dev)
+    gen = torch.cuda.default_generators[dev.index if dev.index is not None else torch.cuda.current_device()]
+    seed, offset = gen.initial_seed(), gen.get_offset()
+    new_ids, advance, _ = native.sample_ids(ids, grad, search_width, topk, n_replace, mask_bits, seed, offset)
+    gen.set_offset(offset + advance)
+    return new_ids
+
+
+def filter_ids(ids: torch.Tensor, tokenizer) -> torch.Tensor:
+    """Keep rows that survive decode -> encode (:166-186). Same result as the reference's
+    per-row loop, but one batched tokenizer call and one device round trip."""
+    host = ids.cpu()
+    texts = tokenizer.batch_decode(host)
+    again = tokenizer(texts, add_special_tokens=False)["input_ids"]
+    rows = host.tolist()
+    keep = [i for i, (a, b) in enumerate(zip(rows, again)) if a == b]
+    if not keep:
+        raise RuntimeError(
+            "No token sequences are the same after decoding and re-encoding. "
+            "Consider setting filter_ids=False or trying a different optim_str_init")
+    if len(keep) == len(rows):
+        return ids
+    return ids[torch.tensor(keep, device=ids.device)]
+
+
+@dataclass
+class CandidateBatch:
+    """What ``_build_input_embeds*`` returns here instead of a materialised (sw, L, d) tensor: the
+    segment order plus the per-candidate ids; the scorer builds only the tail rows on device."""
+    order: List[str]
+    sampled_ids: torch.Tensor
+    image: Optional[torch.Tensor]
+    search_width: Optional[int]
+
+    @property
+    def shape(self):
+        return (self.sampled_ids.shape[0],)
+
+
+class BimodalAttack:
+    def __init__(self, model, tokenizer, processor, config: BimodalAttackConfig, normalize=None):
+        self.model, self.tokenizer, self.processor = model, tokenizer, processor
+        self.config, self.normalize = config, normalize
+        self.embedding_layer = model.get_input_embeddings()
+        self.device = self.embedding_layer.weight.device
+        native.load()                                   # fail loudly when the CUDA library is missing
+        native.require_cuda(self.embedding_layer.weight, "model")
+        self.not_allowed_ids = None if config.allow_non_ascii else get_nonascii_toks(tokenizer, device=self.device)
+        self._mask_bits = native.pack_mask_bits(self.not_allowed_ids, self.embedding_layer.num_embeddings, self.device)
+        self.stop_flag = False
+        self.model_type = getattr(model.config, "model_type", "")
+        self.gemma_processor = processor.__class__.__name__ == "Gemma3Processor"
+        if not getattr(tokenizer, "chat_template", None):          # :233-249
+            tpl = ("USER: <image>\n{{ messages[0]['content'][0]['text'] }} \nASSISTANT: " if config.pgd_attack
+                   else "{% for message in messages %}{{ message['content'] }}{% endfor %}")
+            logger.warning("Tokenizer does not have a chat template. Using custom chat template.")
+            tokenizer.chat_template = tpl
+            self.processor.chat_template = tpl
+        self.engine = ScoringEngine(model)
+        self._plans: Dict[Tuple[str, ...], TailPlan] = {}
+        self._prefill_tag = None
+        self.world = bdist.world()
+        self.gather_all_losses = False    # multi-rank: also all-reduce the per-candidate loss vector
+
+    # ---------------------------------------------------------------------------------------------
+    # prompt -> segments (:271-393)
+    def _prepare(self, messages, target: str):
+        cfg, tok, dev = self.config, self.tokenizer, self.device
+        msgs = [{"role": "user", "content": messages}] if isinstance(messages, str) else copy.deepcopy(messages)
+        last = msgs[-1]
+        if isinstance(last["content"], str) and "{optim_str}" not in last["content"]:
+            last["content"] = last["content"] + " {optim_str}"
+        if cfg.pgd_attack:
+            if isinstance(last["content"], str):
+                last["content"] = [{"type": "text", "text": last["content"]}, {"type": "image"}]
+            elif isinstance(last["content"], list) and not any(c.get("type") == "image" for c in last["content"]):
+                last["content"].append({"type": "image"})
+        prompt = self.processor.apply_chat_template(msgs, add_generation_prompt=True)
+        if tok.bos_token and prompt.startswith(tok.bos_token):
+            prompt = prompt.replace(tok.bos_token, "")
+
+        def enc(text, special):
+            kw = {"padding": False} if special else {"add_special_tokens": False}
+            return tok(text, return_tensors="pt", **kw)["input_ids"].to(dev, torch.int64)
+
+        ids: Dict[str, torch.Tensor] = {}
+        if cfg.pgd_attack:
+            if self.gemma_processor:
+                before, rest = prompt.split("{optim_str}", 1)
+                if "<start_of_image>" not in rest:
+                    raise ValueError("Expected <start_of_image> token in Gemma PGD prompt.")
+                head, sep, tail = rest.partition("<start_of_image>")
+                b_img, b_suf, after = before.strip(), (head + sep).strip(), tail.strip()
+            else:
+                if "<start_of_image>" in prompt:
+                    b_img, rest = prompt.split("<start_of_image>", 1)
+                elif "<image>" in prompt:
+                    b_img, rest = prompt.split("<image>", 1)
+                else:
+                    raise ValueError("No image token found in prompt for PGD attack")
+                b_suf, after = rest.split("{optim_str}", 1)
+            ids["before_img"], ids["before_suffix"] = enc(b_img, True), enc(b_suf, True)
+            ids["after"] = enc(after, False)
+        else:
+            before, after = prompt.split("{optim_str}")
+            ids["before"], ids["after"] = enc(before, True), enc(after, False)
+        ids["target"] = enc(target, False)
+        self.segment_ids = ids
+        self.target_ids = ids["target"]
+        vocab = self.embedding_layer.num_embeddings
+        if self.target_ids.numel() == 0 or int(self.target_ids.min()) < 0 or int(self.target_ids.max()) >= vocab:
+            raise ValueError("target tokenises to ids outside the vocabulary (or to nothing)")
+        with torch.no_grad():
+            self.segment_embeds = {k: self.embedding_layer(v) for k, v in ids.items()}
+        # reference attribute names (:378-393)
+        for k, v in ids.items():
+            setattr(self, f"{k}_ids", v)
+        for k, v in self.segment_embeds.items():
+            setattr(self, f"{k}_embeds", v)
+        self._plans.clear()
+        self._prefill_tag = None
+
+    # ---------------------------------------------------------------------------------------------
+    # phase A (:953-1028)
+    def compute_gradient(self, optim_ids: torch.Tensor, image: Optional[torch.Tensor] = None):
+        cfg, model, emb = self.config, self.model, self.embedding_layer
+        W = emb.weight
+        # the reference multiplies a one-hot by W (:959-968): a row gather, and -- also for Gemma --
+        # WITHOUT the embedding scale. Here the gathered rows are the autograd leaf.
+        optim_embeds = W.detach()[optim_ids].clone()
+        if cfg.gcg_attack:
+            optim_embeds.requires_grad_()
+        e = self.segment_embeds
+        if cfg.pgd_attack:
+            feats = image_features(model, self.normalize(image), self.gemma_processor)
+            seq = [e["before_img"], feats, e["before_suffix"], optim_embeds, e["after"], e["target"]]  # :981-991
+        else:
+            seq = [e["before"], optim_embeds, e["after"], e["target"]]
+        x = torch.cat(seq, dim=1)
+        logits = model(inputs_embeds=x).logits
+        shift = x.shape[1] - self.target_ids.shape[1]
+        pred = logits[..., shift - 1:-1, :].contiguous()
+        loss = F.cross_entropy(pred.view(-1, pred.size(-1)), self.target_ids.view(-1))
+        g_embeds = g_image = None
+        if cfg.pgd_attack and cfg.gcg_attack:
+            g_embeds, g_image = torch.autograd.grad(loss, (optim_embeds, image))
+        elif cfg.pgd_attack:
+            g_image = torch.autograd.grad(loss, image)[0]
+        elif cfg.gcg_attack:
+            g_embeds = torch.autograd.grad(loss, optim_embeds)[0]
+        onehot_grad = None
+        if g_embeds is not None:
+            # (1) token gradient: G_embeds . W^T on the tcgen05 GEMM, W streamed once
+            onehot_grad = native.token_grad(g_embeds[0], W.detach()).unsqueeze(0)
+        return onehot_grad, g_image
+
+    # phase B (:1030-1037)
+    def perform_pgd_step(self, image: torch.Tensor, eps: float, alpha: float, image_grad: torch.Tensor,
+                         image_original: torch.Tensor) -> torch.Tensor:
+        new = image.detach().clone()
+        # a torchvision Normalize exposes mean/std: the kernel then also emits the normalised pixels
+        mean, std = getattr(self.normalize, "mean", None), getattr(self.normalize, "std", None)
+        self._pixel_values = native.pgd_step_(new, image_grad.contiguous(), image_original, alpha * eps, eps,
+                                              mean, std)
+        self._pixel_values_of = new
+        return new.requires_grad_()
+
+    def _normalized(self, image: torch.Tensor) -> torch.Tensor:
+        """Normalised pixels for the scoring phase; reuses the PGD kernel's fused output."""
+        if getattr(self, "_pixel_values_of", None) is image and self._pixel_values is not None:
+            return self._pixel_values
+        return self.normalize(image.detach())
+
+    # phase D sampling (:908-951)
+    def candidate_sampling(self, config, i, optim_ids, optim_ids_onehot_grad, tokenizer, sampling_times,
+                           total_sampling_time):
+        width = config.search_width
+        if config.dynamic_search:
+            width = max(config.min_search_width, int(config.search_width * (1 - i / config.num_steps)))
+        if not config.gcg_attack:
+            return optim_ids, 1, 0.0, total_sampling_time
+        t0 = time.perf_counter()
+        sampled = sample_ids_from_grad(optim_ids.squeeze(0), optim_ids_onehot_grad.squeeze(0), width,
+                                       config.topk, config.n_replace, mask_bits=self._mask_bits)
+        if config.filter_ids:
+            sampled = filter_ids(sampled, tokenizer)
+        dt = time.perf_counter() - t0
+        sampling_times.append(dt)
+        return sampled, sampled.shape[0], dt, total_sampling_time + dt
+
+    # ---------------------------------------------------------------------------------------------
+    # candidate assembly (:1112-1276): returns a descriptor, nothing is repeated sw times
+    def _build_input_embeds(self, sampled_ids, image=None, search_width=None, mode="gcg", single=False,
+                            no_joint_eval=False, no_target=False) -> CandidateBatch:
+        order = segment_order(mode, self.model_type, single, no_joint_eval, no_target)
+        return CandidateBatch(order, sampled_ids, image, search_width)
+
+    def _build_input_embeds_pgd(self, sampled_ids, image, search_width, single=False):
+        return self._build_input_embeds(sampled_ids, image=image, search_width=search_width, mode="pgd", single=single)
+
+    def _build_input_embeds_gcg(self, sampled_ids, search_width, single=False, no_joint_eval=False, no_target=False):
+        return self._build_input_embeds(sampled_ids, search_width=search_width, mode="gcg", single=single,
+                                        no_joint_eval=no_joint_eval, no_target=no_target)
+
+    def _build_input_embeds_gcg_pgd(self, sampled_ids, image, search_width=None, single=False, no_target=False):
+        return self._build_input_embeds(sampled_ids, image=image, search_width=search_width, mode="gcg_pgd",
+                                        single=single, no_target=no_target)
+
+    def materialize(self, batch: CandidateBatch) -> torch.Tensor:
+        """Dense (B, L, d) embeddings of a CandidateBatch -- only for HF ``generate`` in
+        ``debug_output`` (:745-777); never on the scoring path."""
+        parts = []
+        n = batch.sampled_ids.shape[0]
+        for name in batch.order:
+            if name == "optim":
+                t = self.embedding_layer(batch.sampled_ids)
+            elif name == "image":
+                t = batch.image
+            else:
+                t = self.segment_embeds[name]
+            parts.append(t.expand(n, -1, -1) if t.shape[0] == 1 else t)
+        return torch.cat(parts, dim=1)
+
+    def _plan(self, batch: CandidateBatch) -> TailPlan:
+        if "target" not in batch.order:
+            raise ValueError("scoring needs a target segment")
+        parts = dict(self.segment_embeds)
+        if batch.image is not None:
+            parts["image"] = batch.image
+        key = tuple(batch.order)
+        has_image = "image" in batch.order
+        plan = None if has_image else self._plans.get(key)
+        if plan is None:
+            fixed = {n: parts[n] for n in batch.order if n != "optim"}
+            plan = plan_tail(batch.order, fixed, batch.sampled_ids.shape[1])
+            if not has_image:
+                self._plans[key] = plan
+        return plan
+
+    # scoring (:1278-1310). search_batch_size is accepted for interface compatibility; the native
+    # workspace is sized up front, so no OOM-driven chunk search is needed.
+    def _compute_candidates_loss_original(self, search_batch_size: int, batch: CandidateBatch) -> torch.Tensor:
+        plan = self._plan(batch)
+        tag = (tuple(batch.order), None if batch.image is None else (batch.image.data_ptr(), batch.image._version),
+               plan.n_prefix)
+        if tag != self._prefill_tag or "image" in batch.order:
+            self.engine.prefill(plan.prefix)
+            self._prefill_tag = tag
+        ids = batch.sampled_ids
+        lo, hi = bdist.shard_bounds(ids.shape[0], self.world)
+        self.engine.reset_key()
+        loss = torch.full((ids.shape[0],), float("inf"), dtype=torch.float32, device=self.device)
+        if hi > lo:
+            loss[lo:hi] = self.engine.score(ids[lo:hi], plan, self.target_ids, idx_base=lo, reset=False)
+        bdist.reduce_winner(self.engine.key, self.engine.flag, self.world)
+        if self.world.size > 1 and self.gather_all_losses:
+            bdist.gather_losses(loss, lo, hi, self.world)
+        if self.config.early_stop and int(self.engine.flag.item()) != 0:
+            self.stop_flag = True
+        return loss
+
+    def _winner(self) -> Tuple[float, int]:
+        """(min loss, argmin) from the packed key the scorer (and the all-reduce) left on device."""
+        return unpack_key(int(self.engine.key.item()))
+
+    def _save_image(self, image, path):
+        import numpy as np
+        from PIL import Image
+        arr = image.squeeze(0).detach().cpu().numpy().transpose(1, 2, 0)
+        Image.fromarray((arr * 255).astype(np.uint8)).save(path)
+
+    # ---------------------------------------------------------------------------------------------
+    def init_buffer(self, image) -> AttackBuffer:
+        """Initial suffix and its loss (:826-906)."""
+        cfg, tok, dev = self.config, self.tokenizer, self.device
+        buf = AttackBuffer(cfg.buffer_size)
+        if isinstance(cfg.optim_str_init, str):
+            init = tok(cfg.optim_str_init, add_special_tokens=False, return_tensors="pt")["input_ids"].to(dev)
+            if cfg.buffer_size > 1:
+                pool = tok(INIT_CHARS, add_special_tokens=False, return_tensors="pt")["input_ids"].squeeze().to(dev)
+                pick = torch.randint(0, pool.shape[0], (cfg.buffer_size - 1, init.shape[1]))
+                init = torch.cat([init, pool[pick]], dim=0)
+        else:
+            if len(cfg.optim_str_init) != cfg.buffer_size:
+                logger.warning(f"Using {len(cfg.optim_str_init)} initializations but buffer size is set to {cfg.buffer_size}")
+            init = tok(cfg.optim_str_init, add_special_tokens=False, return_tensors="pt")["input_ids"].to(dev)
+        n = max(1, cfg.buffer_size)
+        with torch.no_grad():
+            if cfg.pgd_attack:
+                feats = image_features(self.model, self._normalized(image), self.gemma_processor)
+                batch = self._build_input_embeds_gcg_pgd(init, feats, search_width=n, single=True)
+            else:
+                batch = self._build_input_embeds_gcg(init, search_width=n, no_joint_eval=True)
+            losses = self._compute_candidates_loss_original(n, batch)
+        for j, value in enumerate(losses.tolist()):
+            buf.add(value, init[[j]])
+        buf.log_buffer(tok, logger)
+        return buf
+
+    # ---------------------------------------------------------------------------------------------
+    def run(self, messages: Union[str, List[dict]], goal: str, target: str,
+            image: Optional[torch.Tensor] = None) -> BimodalAttackResult:
+        cfg, model, tok = self.config, self.model, self.tokenizer
+        self.initial_prompt = goal
+        if cfg.pgd_attack and cfg.images_folder:
+            os.makedirs(cfg.images_folder, exist_ok=True)
+        if cfg.seed is not None:
+            from transformers import set_seed
+            set_seed(cfg.seed)
+            torch.use_deterministic_algorithms(True, warn_only=True)
+        if cfg.pgd_attack:
+            if image is None:
+                raise ValueError("pgd_attack=True needs an image")
+            native.require_cuda(image, "image")
+        self._prepare(messages, target)
+        buffer = self.init_buffer(image)
+        optim_ids = buffer.get_best_ids()
+
+        losses, strings, suffixes, outputs = [], [], [], []
+        g_times, s_times, l_times, p_times, totals = [], [], [], [], []
+        tot_s = 0.0
+        best_loss = float("inf")
+        self.best_optim_ids = None
+        self.best_image = None
+        current = None
+        if cfg.pgd_attack:
+            logger.warning(f"Using alpha: {cfg.alpha}, eps: {cfg.eps}")
+            image.requires_grad = True                       # the reference flags the caller's tensor (:425)
+            original = image.detach().clone()
+
+        def record(loss_value, ids, img):
+            nonlocal best_loss
+            losses.append(loss_value)
+            strings.append(tok.batch_decode(ids)[0])
+            if buffer.size == 0 or loss_value < buffer.get_highest_loss():
+                buffer.add(loss_value, ids)
+            if loss_value < best_loss:
+                best_loss = loss_value
+                self.best_optim_ids = ids.clone()
+                if img is not None:
+                    self.best_image = img.detach().clone()
+
+        lead = self.world.rank == 0         # gradient, PGD and sampling run on rank 0 only
+        n_tok = optim_ids.shape[1]
+        i = -1
+        for i in range(cfg.num_steps):
+            grad_time = pgd_time = sampling_time = 0.0
+            sampled, width = None, 0
+            if lead:
+                t0 = time.perf_counter()
+                onehot_grad, image_grad = self.compute_gradient(optim_ids, image if cfg.pgd_attack else None)
+                grad_time = time.perf_counter() - t0
+                g_times.append(grad_time)
+                if cfg.pgd_attack and not cfg.pgd_after_gcg:
+                    t0 = time.perf_counter()
+                    image = self.perform_pgd_step(image, cfg.eps, cfg.alpha, image_grad, original)
+                    pgd_time = time.perf_counter() - t0
+                    p_times.append(pgd_time)
+                    if cfg.gcg_attack and not cfg.joint_eval:        # phase C (:481-491)
+                        t0 = time.perf_counter()
+                        onehot_grad, image_grad = self.compute_gradient(optim_ids, image)
+                        grad_time = time.perf_counter() - t0
+                        g_times.append(grad_time)
+                sampled, width, sampling_time, tot_s = self.candidate_sampling(cfg, i, optim_ids, onehot_grad, tok,
+                                                                              s_times, tot_s)
+            if self.world.size > 1:
+                sampled = bdist.broadcast_candidates(sampled, n_tok, self.device, self.world)
+                width = sampled.shape[0]
+                if cfg.pgd_attack and not cfg.pgd_after_gcg:
+                    shared = bdist.broadcast_tensor(image.detach(), self.world)   # same storage on rank 0
+                    image = image if lead else shared
+
+            with torch.no_grad():
+                t0 = time.perf_counter()
+                chunk = width if cfg.batch_size is None else cfg.batch_size
+                if cfg.pgd_attack:
+                    feats = image_features(model, self._normalized(image), self.gemma_processor)
+                    best_idx = 0
+                    scored_with_image = False
+                    if cfg.joint_eval:
+                        build = self._build_input_embeds_gcg_pgd if cfg.pgd_after_gcg else self._build_input_embeds_pgd
+                        batch = build(sampled, feats, search_width=width, single=True)
+                        find_executable_batch_size(self._compute_candidates_loss_original, chunk)(batch)
+                        cand_min, best_idx = self._winner()
+                        scored_with_image = True
+                    elif cfg.gcg_attack:
+                        batch = self._build_input_embeds_gcg(sampled, search_width=width, single=True)
+                        find_executable_batch_size(self._compute_candidates_loss_original, chunk)(batch)
+                        cand_min, best_idx = self._winner()
+                    chosen = sampled[best_idx].unsqueeze(0)
+                    if not cfg.pgd_after_gcg:
+                        if scored_with_image:
+                            # the reference re-scores the winner alone (:605-612); the same sequence was
+                            # just scored inside the batch, so its fp32 loss is reused
+                            current = cand_min
+                        else:
+                            full = self._build_input_embeds_gcg_pgd(chosen, feats)
+                            self._compute_candidates_loss_original(1, full)
+                            current, _ = self._winner()
+                        optim_ids = chosen
+                        record(current, optim_ids, image)
+                else:
+                    batch = self._build_input_embeds_gcg(sampled, search_width=width, no_joint_eval=True)
+                    find_executable_batch_size(self._compute_candidates_loss_original, chunk)(batch)
+                    current, best_idx = self._winner()
+                    optim_ids = sampled[best_idx].unsqueeze(0)
+                    record(current, optim_ids, None)
+                loss_time = time.perf_counter() - t0
+                l_times.append(loss_time)
+
+            if cfg.pgd_after_gcg and cfg.pgd_attack:             # phases E, F (:668-740)
+                if lead:
+                    t0 = time.perf_counter()
+                    _, image_grad = self.compute_gradient(optim_ids, image)   # still the previous suffix (:673)
+                    grad_time = time.perf_counter() - t0
+                    g_times.append(grad_time)
+                    t0 = time.perf_counter()
+                    image = self.perform_pgd_step(image, cfg.eps, cfg.alpha, image_grad, original)
+                    pgd_time = time.perf_counter() - t0
+                    p_times.append(pgd_time)
+                shared = bdist.broadcast_tensor(image.detach(), self.world)
+                image = image if lead else shared
+                with torch.no_grad():
+                    t0 = time.perf_counter()
+                    feats = image_features(model, self._normalized(image), self.gemma_processor)
+                    full = self._build_input_embeds_gcg_pgd(chosen, feats)
+                    self._compute_candidates_loss_original(1, full)
+                    current, _ = self._winner()
+                    optim_ids = chosen
+                    l_times.append(time.perf_counter() - t0)
+                    record(current, optim_ids, image)
+
+            if cfg.pgd_attack and cfg.images_folder:
+                self._save_image(image, os.path.join(cfg.images_folder, f"{i}.png"))
+            gen_output = ""
+            if cfg.debug_output and i % 10 == 0:
+                with torch.no_grad():
+                    if cfg.pgd_attack:
+                        feats = image_features(model, self._normalized(image), self.gemma_processor)
+                        dbg = self._build_input_embeds_gcg_pgd(sampled, feats, search_width=width, no_target=True)
+                    else:
+                        dbg = self._build_input_embeds_gcg(sampled, search_width=width, no_target=True)
+                    gen = model.generate(inputs_embeds=self.materialize(dbg), max_new_tokens=120)
+                    gen_output = tok.decode(gen[0], skip_special_tokens=True)
+            outputs.append(gen_output)
+            suffixes.append(tok.batch_decode(optim_ids)[0])
+            buffer.log_buffer(tok, logger)
+            if self.stop_flag:
+                logger.info("Early stopping due to finding a perfect match.")
+                break
+            totals.append(grad_time + sampling_time + pgd_time + loss_time)
+            logger.info(f"[Iteration {i}] loss {current:.4f} | grad {grad_time:.4f}s sample {sampling_time:.4f}s "
+                        f"pgd {pgd_time:.4f}s loss {loss_time:.4f}s")
+
+        self.final_image = image
+        self.final_optim_ids = optim_ids
+        best = losses.index(min(losses))
+        return BimodalAttackResult(best_loss=losses[best], best_string=strings[best], losses=losses,
+                                   strings=strings, adversarial_suffixes=suffixes, model_outputs=outputs,
+                                   gradient_times=g_times, sampling_times=s_times, loss_times=l_times,
+                                   pgd_times=p_times, total_times=totals)
+
+
+def run(model, tokenizer, processor, messages: Union[str, List[dict]], goal: str, target: str,
+        image: Optional[torch.Tensor] = None, config: Optional[BimodalAttackConfig] = None,
+        normalize=None) -> BimodalAttackResult:
+    """Drop-in for the reference's ``bimodalattack.run`` (:1323-1338)."""
+    if config is None:
+        config = BimodalAttackConfig()
+    logger.setLevel(getattr(logging, config.verbosity))
+    return BimodalAttack(model, tokenizer, processor, config, normalize).run(messages, goal, target, image)

@@ -1,0 +1,78 @@
+"""Candidate sharding across the GPUs of one box.
+
+Candidates are independent given (weights, prefix KV, target): rank r scores the contiguous slice
+``shard_bounds(n, world)`` against a replicated model and the winner is picked by ONE all-reduce
+(MIN) over a packed 64-bit key ``orderable(loss) << 31 | global_index`` -- ties resolve to the
+lowest index exactly like ``torch.argmin``. Gradient, PGD and sampling run on rank 0 and their
+(small) results are broadcast. Works with the nccl backend on GPUs and with gloo in the CPU tests.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as td
+
+
+@dataclass(frozen=True)
+class World:
+    rank: int = 0
+    size: int = 1
+
+
+def world() -> World:
+    if td.is_available() and td.is_initialized():
+        return World(td.get_rank(), td.get_world_size())
+    return World()
+
+
+def shard_bounds(n: int, w: World) -> Tuple[int, int]:
+    """Contiguous, balanced slice of ``range(n)`` owned by ``w.rank`` (first ranks get the extras)."""
+    base, extra = divmod(n, w.size)
+    lo = w.rank * base + min(w.rank, extra)
+    return lo, lo + base + (1 if w.rank < extra else 0)
+
+
+def pack_key(loss: float, index: int) -> int:
+    """Host mirror of the device packing (csrc/scoring_ops.cu:pack_loss_key)."""
+    import struct
+    bits = struct.unpack("<I", struct.pack("<f", loss))[0]
+    if loss != loss:
+        order = 0xFFFFFFFF
+    else:
+        order = (~bits) & 0xFFFFFFFF if bits & 0x80000000 else bits | 0x80000000
+    return (order << 31) | (index & 0x7FFFFFFF)
+
+
+def reduce_winner(key: torch.Tensor, flag: Optional[torch.Tensor], w: World) -> None:
+    """In-place MIN all-reduce of the int64 key (and MAX of the early-stop flag)."""
+    if w.size == 1:
+        return
+    td.all_reduce(key, op=td.ReduceOp.MIN)
+    if flag is not None:
+        td.all_reduce(flag, op=td.ReduceOp.MAX)
+
+
+def broadcast_candidates(sampled: Optional[torch.Tensor], n_tok: int, device, w: World) -> torch.Tensor:
+    """Rank 0's candidate ids (their count varies per step after filter_ids) to every rank."""
+    if w.size == 1:
+        return sampled
+    count = torch.tensor([sampled.shape[0] if w.rank == 0 else 0], dtype=torch.int64, device=device)
+    td.broadcast(count, src=0)
+    if w.rank != 0:
+        sampled = torch.empty((int(count.item()), n_tok), dtype=torch.int64, device=device)
+    td.broadcast(sampled, src=0)
+    return sampled
+
+
+def broadcast_tensor(t: torch.Tensor, w: World) -> torch.Tensor:
+    if w.size > 1:
+        td.broadcast(t, src=0)
+    return t
+
+
+def gather_losses(loss: torch.Tensor, lo: int, hi: int, w: World) -> None:
+    """Optional: fill the non-local entries of ``loss`` (MIN over ranks; unscored slots are +inf)."""
+    if w.size > 1:
+        td.all_reduce(loss, op=td.ReduceOp.MIN)

@@ -1,0 +1,223 @@
+"""Python side of the native candidate scorer (C ABI: ``bma_scorer_*`` in include/bimodal_b200.h).
+
+``ScoringEngine`` takes a Hugging Face LLaVA-style model object, packs the decoder weights into the
+layouts the tcgen05 GEMM epilogues expect (fused QKV rows; gate/up rows interleaved per 128 so the
+SwiGLU epilogue sees matching columns in one tile), builds the rotary tables with the model's own
+rotary module, and drives the scorer. All arithmetic happens in the shared library; there is no
+torch fallback for any of it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Tuple
+
+import torch
+
+from . import native
+from .segments import TailPlan
+
+KEY_IDX_BITS = 31
+KEY_INIT = (1 << 63) - 1
+
+
+def unpack_key(key: int) -> Tuple[float, int]:
+    """Inverse of the device-side packing: (loss, global candidate index)."""
+    idx = key & ((1 << KEY_IDX_BITS) - 1)
+    order = (key >> KEY_IDX_BITS) & 0xFFFFFFFF
+    bits = order & 0x7FFFFFFF if order & 0x80000000 else (~order) & 0xFFFFFFFF
+    import struct
+    return struct.unpack("<f", struct.pack("<I", bits))[0], idx
+
+
+def find_decoder(model):
+    """(decoder stack, lm_head, text_config) for transformers 4.50 and 5.x module layouts."""
+    inner = getattr(model, "model", None)
+    lm = getattr(inner, "language_model", None) if inner is not None else None
+    if lm is None:                       # 4.50: model.language_model is a *ForCausalLM
+        causal = getattr(model, "language_model", None)
+        if causal is None:
+            raise RuntimeError("bimodal_b200: cannot locate the language model inside the HF object")
+        lm = getattr(causal, "model", causal)
+    head = model.get_output_embeddings()
+    cfg = getattr(model.config, "text_config", model.config)
+    return lm, head, cfg
+
+
+class ScoringEngine:
+    def __init__(self, model, max_rows: int = 0, max_prefix: int = 0, max_positions: int = 0):
+        self.lib = native.load()
+        self.model = model
+        lm, head, cfg = find_decoder(model)
+        self.lm, self.head, self.cfg = lm, head, cfg
+        self.device = next(lm.parameters()).device
+        native.require_cuda(next(lm.parameters()), "model")
+        self.dtype = next(lm.parameters()).dtype
+        if self.dtype != torch.bfloat16:
+            raise RuntimeError(f"bimodal_b200 scorer computes in bf16; model is {self.dtype}")
+        mt = getattr(cfg, "model_type", "")
+        if mt != "llama":
+            raise RuntimeError(f"bimodal_b200 scorer: decoder type '{mt}' is not supported yet (llama only)")
+        self.d = cfg.hidden_size
+        self.n_layers = cfg.num_hidden_layers
+        self.n_heads = cfg.num_attention_heads
+        self.n_kv = getattr(cfg, "num_key_value_heads", self.n_heads) or self.n_heads
+        self.head_dim = getattr(cfg, "head_dim", None) or self.d // self.n_heads
+        self.d_ff = cfg.intermediate_size
+        self.vocab = head.weight.shape[0]
+        if getattr(cfg, "attention_bias", False) or getattr(cfg, "mlp_bias", False):
+            raise RuntimeError("bimodal_b200 scorer: projection biases are not supported")
+        act = getattr(cfg, "hidden_act", "silu")
+        if act not in ("silu", "gelu_pytorch_tanh"):
+            raise RuntimeError(f"bimodal_b200 scorer: activation '{act}' is not supported")
+        self.act = 0 if act == "silu" else 1
+        self.embed = model.get_input_embeddings()
+        self._pack_weights()
+        self._scorer = None
+        self._cap_rows = 0
+        self._cap_prefix = 0
+        self._want_rows = max_rows
+        self._want_prefix = max_prefix
+        self._max_positions = max_positions or 4096
+        self._build_rope(self._max_positions)
+        self.key = torch.empty(1, dtype=torch.int64, device=self.device)
+        self.flag = torch.empty(1, dtype=torch.int32, device=self.device)
+        self.prefix_len = 0
+        self._last_prefix: Optional[torch.Tensor] = None
+        self._prefix_stale = False
+
+    # -------------------------------------------------------------------------------------------
+    def _pack_weights(self):
+        self.w_qkv, self.w_gate_up = [], []
+        with torch.no_grad():
+            for layer in self.lm.layers:
+                a, m = layer.self_attn, layer.mlp
+                self.w_qkv.append(torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], 0).contiguous())
+                g, u = m.gate_proj.weight, m.up_proj.weight
+                if self.d_ff % 128 != 0:
+                    raise RuntimeError("bimodal_b200 scorer: intermediate_size must be a multiple of 128")
+                gu = torch.stack([g.view(self.d_ff // 128, 128, self.d), u.view(self.d_ff // 128, 128, self.d)], 1)
+                self.w_gate_up.append(gu.reshape(2 * self.d_ff, self.d).contiguous())
+
+    def _build_rope(self, max_pos: int):
+        with torch.no_grad():
+            pos = torch.arange(max_pos, device=self.device).unsqueeze(0)
+            dummy = torch.zeros(1, dtype=self.dtype, device=self.device)
+            cos, sin = self.lm.rotary_emb(dummy, pos)          # [1, max_pos, head_dim] in model dtype
+            half = self.head_dim // 2
+            self.rope_cos = cos[0, :, :half].float().contiguous()
+            self.rope_sin = sin[0, :, :half].float().contiguous()
+
+    def _ensure(self, rows: int, prefix: int):
+        if self._scorer is not None and rows <= self._cap_rows and prefix <= self._cap_prefix:
+            return
+        if self._scorer is not None:
+            self.lib.bma_scorer_destroy(self._scorer)
+            self._scorer = None
+        cap_rows = max(rows, self._want_rows, 128)
+        cap_prefix = max(prefix, self._want_prefix, 1)
+        desc = native.ModelDesc(
+            n_layers=self.n_layers, d_model=self.d, n_heads=self.n_heads, n_kv_heads=self.n_kv,
+            head_dim=self.head_dim, d_ff=self.d_ff, vocab=self.vocab,
+            rms_eps=float(getattr(self.cfg, "rms_norm_eps", 1e-6)), norm_mode=0, act=self.act,
+            embed_scale=1.0, attn_scale=float(self.head_dim) ** -0.5,
+            max_rows=cap_rows, max_prefix=cap_prefix)
+        with torch.cuda.device(self.device):
+            handle = self.lib.bma_scorer_create(C.byref(desc))
+        if not handle:
+            raise RuntimeError("bimodal_b200: scorer_create failed: " +
+                               self.lib.bma_last_error().decode("utf-8", "replace"))
+        self._scorer = handle
+        self._cap_rows, self._cap_prefix = cap_rows, cap_prefix
+        self._prefix_stale = True        # a new scorer has no prefix K/V yet
+        for i, layer in enumerate(self.lm.layers):
+            w = native.LayerWeights(
+                w_qkv=self.w_qkv[i].data_ptr(), w_o=layer.self_attn.o_proj.weight.data_ptr(),
+                w_gate_up=self.w_gate_up[i].data_ptr(), w_down=layer.mlp.down_proj.weight.data_ptr(),
+                norm_attn=layer.input_layernorm.weight.data_ptr(),
+                norm_mlp=layer.post_attention_layernorm.weight.data_ptr(),
+                rope_cos=self.rope_cos.data_ptr(), rope_sin=self.rope_sin.data_ptr())
+            if not (layer.self_attn.o_proj.weight.is_contiguous() and layer.mlp.down_proj.weight.is_contiguous()):
+                raise RuntimeError("bimodal_b200 scorer: non-contiguous projection weight")
+            native.check(self.lib.bma_scorer_set_layer(handle, i, C.byref(w)), "scorer_set_layer")
+        ew = self.embed.weight
+        native.check(self.lib.bma_scorer_set_head(handle, self.lm.norm.weight.data_ptr(),
+                                                  self.head.weight.data_ptr(), ew.data_ptr(), ew.stride(0)),
+                     "scorer_set_head")
+
+    def close(self):
+        if self._scorer is not None:
+            self.lib.bma_scorer_destroy(self._scorer)
+            self._scorer = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def workspace_bytes(self) -> int:
+        return 0 if self._scorer is None else int(self.lib.bma_scorer_workspace_bytes(self._scorer))
+
+    # -------------------------------------------------------------------------------------------
+    def reserve(self, rows: int, prefix: int):
+        self._ensure(rows, prefix)
+
+    def prefill(self, prefix_embeds: Optional[torch.Tensor]):
+        """Compute and keep the K/V of the shared prefix ([P, d] bf16; None/empty = no prefix)."""
+        P = 0 if prefix_embeds is None else prefix_embeds.shape[0]
+        self._ensure(max(self._cap_rows, P, 1), P)
+        if P > 0:
+            if P + 1 > self._max_positions:
+                raise RuntimeError("bimodal_b200 scorer: sequence longer than the rotary table")
+            pe = prefix_embeds.to(self.dtype).contiguous()
+        with torch.cuda.device(self.device):
+            native.check(self.lib.bma_scorer_prefill(self._scorer, None if P == 0 else pe.data_ptr(), P,
+                                                     native.stream_ptr(self.device)), "scorer_prefill")
+        self.prefix_len = P
+        self._last_prefix = None if P == 0 else pe
+        self._prefix_stale = False
+
+    def reset_key(self):
+        with torch.cuda.device(self.device):
+            native.check(self.lib.bma_scorer_reset_key(self._scorer, self.key.data_ptr(), self.flag.data_ptr(),
+                                                       native.stream_ptr(self.device)), "scorer_reset_key")
+
+    def score(self, ids: torch.Tensor, plan: TailPlan, target_ids: torch.Tensor, idx_base: int = 0,
+              reset: bool = True) -> torch.Tensor:
+        """Per-candidate mean CE (fp32, [B]). ``self.key`` receives the packed (loss, index) minimum
+        and ``self.flag`` the early-stop indicator."""
+        native.require_cuda(ids, "ids")
+        B = ids.shape[0]
+        S = plan.n_tail
+        T = target_ids.numel()
+        if self.prefix_len + S > self._max_positions:
+            raise RuntimeError("bimodal_b200 scorer: sequence longer than the rotary table")
+        self._ensure(max(self._cap_rows, min(B, 4096) * S), self._cap_prefix)
+        if self._prefix_stale:           # the workspace was re-created after the last prefill
+            self.prefill(self._last_prefix)
+        ids = ids.to(torch.int64).contiguous()
+        tgt = target_ids.reshape(-1).to(torch.int64).contiguous()   # validated by the caller
+        loss = torch.empty(B, dtype=torch.float32, device=self.device)
+        if reset:
+            self.reset_key()
+        with torch.cuda.device(self.device):
+            native.check(self.lib.bma_scorer_score(
+                self._scorer, ids.data_ptr(), ids.stride(0), B, plan.slot.data_ptr(), plan.fixed.data_ptr(),
+                S, tgt.data_ptr(), T, loss.data_ptr(), self.key.data_ptr(), self.flag.data_ptr(),
+                idx_base, native.stream_ptr(self.device)), "scorer_score")
+        return loss
+
+    def score_host(self, ids_host: torch.Tensor, plan: TailPlan, target_ids: torch.Tensor,
+                   loss_host: torch.Tensor, key_host: torch.Tensor, idx_base: int = 0):
+        """End-to-end entry: pinned host ids in, pinned host losses + key out (synchronises)."""
+        B, S, T = ids_host.shape[0], plan.n_tail, target_ids.numel()
+        self._ensure(max(self._cap_rows, min(B, 4096) * S, B * ids_host.shape[1]), self._cap_prefix)
+        if self._prefix_stale:
+            self.prefill(self._last_prefix)
+        with torch.cuda.device(self.device):
+            native.check(self.lib.bma_scorer_score_host(
+                self._scorer, ids_host.data_ptr(), ids_host.stride(0), B, plan.slot.data_ptr(),
+                plan.fixed.data_ptr(), S, target_ids.data_ptr(), T, loss_host.data_ptr(), key_host.data_ptr(),
+                idx_base, native.stream_ptr(self.device)), "scorer_score_host")

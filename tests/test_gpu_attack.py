@@ -1,0 +1,166 @@
+"""End-to-end parity of the B200 path against the oracle (the reference's dataflow restated in
+torch) on the GPU: gradient, candidate scoring in every segment order, winner selection, and the
+public ``run()``. Model: random-init LLaVA-architecture decoder with head_dim 128 in bf16.
+
+Tolerances (stated per assert): the reference computes the per-candidate loss in bf16 (ulp 2^-5 =
+0.031 at loss ~4-8, 2^-4 above 8); the B200 path keeps the same bf16 rounding points inside the
+decoder but accumulates the CE in fp32. Both are compared with an fp32 run of the oracle on the
+same (bf16-valued) weights.
+"""
+import copy
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+PROMPT = "w10 w11 w12 w13 w14 w15"
+TARGET = "w20 w21 w22 w23 w24"
+INIT = "x x x x x x x x x x"
+
+
+def _setup(device, size="tiny128", image_px=28, **cfg_kw):
+    import torchvision.transforms as T
+    from bimodalattack_b200 import BimodalAttackConfig, synthetic as syn
+    tok = syn.make_tokenizer(1024 if size == "tiny128" else 4096)
+    proc = syn.make_llava_processor(tok, image_px)
+    model = syn.make_llava(size, dtype=torch.bfloat16, device=device, head_gain=20.0, attn_implementation="sdpa")
+    norm = T.Normalize(syn.CLIP_MEAN, syn.CLIP_STD)
+    g = torch.Generator().manual_seed(5)
+    image = torch.rand((1, 3, image_px, image_px), generator=g).to(device)
+    kw = dict(num_steps=3, search_width=48, topk=32, seed=1, allow_non_ascii=True, alpha=4 / 255, eps=64 / 255,
+              optim_str_init=INIT, verbosity="ERROR", images_folder=None, filter_ids=True)
+    kw.update(cfg_kw)
+    return model, tok, proc, norm, image, BimodalAttackConfig(**kw)
+
+
+def _fp32_twin(model):
+    twin = copy.deepcopy(model).float()
+    return twin
+
+
+MODES = {
+    "joint": dict(pgd_attack=True, gcg_attack=True, joint_eval=True),
+    "gcg_only": dict(pgd_attack=False, gcg_attack=True),
+    "pgd_gcg_nojoint": dict(pgd_attack=True, gcg_attack=True, joint_eval=False),
+}
+
+
+@pytest.mark.parametrize("mode", list(MODES))
+def test_candidate_losses_match_oracle(cuda_device, mode):
+    from bimodalattack_b200 import BimodalAttack
+    from bimodalattack_b200.attack import image_features
+    from oracle import hotpath
+    model, tok, proc, norm, image, cfg = _setup(cuda_device, **MODES[mode])
+    atk = BimodalAttack(model, tok, proc, cfg, normalize=norm)
+    atk._prepare([{"role": "user", "content": PROMPT}], TARGET)
+    ora = hotpath.OracleAttack(model, tok, proc, cfg, normalize=norm)
+    ora32 = hotpath.OracleAttack(_fp32_twin(model), tok, proc, cfg, normalize=norm)
+    g = torch.Generator().manual_seed(17)
+    n_tok = len(tok(INIT, add_special_tokens=False)["input_ids"])
+    sampled = torch.randint(8, 1000, (48, n_tok), generator=g).to(cuda_device)
+    with torch.no_grad():
+        feats = image_features(model, norm(image), False) if cfg.pgd_attack else None
+        orders = []
+        if mode == "joint":
+            orders.append(("pgd", dict(single=True), True))
+        elif mode == "gcg_only":
+            orders.append(("gcg", dict(no_joint_eval=True), False))
+        else:
+            orders.append(("gcg", dict(single=True), False))
+            orders.append(("gcg_pgd", dict(single=True), True))
+        for omode, flags, with_img in orders:
+            batch = atk._build_input_embeds(sampled, image=feats if with_img else None, search_width=48,
+                                            mode=omode, **flags)
+            got = atk._compute_candidates_loss_original(48, batch)
+            key_loss, key_idx = atk._winner()
+            for o, dtype_tol in ((ora, None), (ora32, None)):
+                o.seg_ids = atk.segment_ids
+                o.target_ids = atk.target_ids
+                o.seg_embeds = {k: o.emb(v) for k, v in atk.segment_ids.items()}
+            order = hotpath.segment_order(omode, "llava", **flags)
+            assert order == batch.order
+            f16 = feats
+            want_bf16, _ = hotpath.candidates_loss(model, hotpath.assemble(ora._parts(sampled, f16 if with_img else None), order, 48),
+                                                   atk.target_ids, 16)
+            f32 = feats.float() if feats is not None else None
+            want_fp32, _ = hotpath.candidates_loss(ora32.model, hotpath.assemble(ora32._parts(sampled, f32 if with_img else None), order, 48),
+                                                   atk.target_ids, 16)
+            want_bf16, want_fp32 = want_bf16.float(), want_fp32.float()
+            # (1) against the reference's own bf16 value: 2 bf16 ulps at the loss magnitude
+            ulp = 2.0 ** (torch.floor(torch.log2(want_bf16.abs().clamp_min(1e-3))) - 7)
+            assert bool(((got - want_bf16).abs() <= 2 * ulp + 1e-3).all()), (got - want_bf16).abs().max()
+            # (2) against the fp32 recomputation: bf16 activation noise through the decoder
+            assert bool(((got - want_fp32).abs() <= 2e-2 * want_fp32.abs() + 1e-3).all()), (got - want_fp32).abs().max()
+            # (3) winner: packed key == fp32 argmin of the returned losses, and tie-aware vs the oracle
+            assert key_idx == int(got.argmin()) and abs(key_loss - float(got.min())) == 0.0
+            assert float(want_fp32[key_idx]) <= float(want_fp32.min()) + 2e-2 * abs(float(want_fp32.min())) + 1e-3
+            # the scores must really differ between candidates, or argmin parity would be vacuous
+            assert float(want_fp32.max() - want_fp32.min()) > 0.1
+
+
+@pytest.mark.parametrize("mode", ["joint", "gcg_only"])
+def test_gradient_matches_oracle(cuda_device, mode):
+    from bimodalattack_b200 import BimodalAttack
+    from oracle import hotpath
+    model, tok, proc, norm, image, cfg = _setup(cuda_device, **MODES[mode])
+    atk = BimodalAttack(model, tok, proc, cfg, normalize=norm)
+    atk._prepare([{"role": "user", "content": PROMPT}], TARGET)
+    ora = hotpath.OracleAttack(model, tok, proc, cfg, normalize=norm)
+    ora.seg_ids, ora.target_ids = atk.segment_ids, atk.target_ids
+    ora.seg_embeds = {k: ora.emb(v) for k, v in atk.segment_ids.items()}
+    optim_ids = tok(INIT, add_special_tokens=False, return_tensors="pt")["input_ids"].to(cuda_device)
+    img_a = image.clone().requires_grad_() if cfg.pgd_attack else None
+    img_b = image.clone().requires_grad_() if cfg.pgd_attack else None
+    g_tok, g_img = atk.compute_gradient(optim_ids, img_a)
+    w_tok, w_img = ora.gradient(optim_ids, img_b)
+    assert g_tok.shape == w_tok.shape and g_tok.dtype == w_tok.dtype == torch.bfloat16
+    # same bf16 backward up to the embedding gradient; the final contraction differs only in
+    # accumulation order -> 1 bf16 ulp relative to the row scale
+    scale = w_tok.float().abs().max()
+    assert float((g_tok.float() - w_tok.float()).abs().max()) <= 2 ** -7 * float(scale)
+    if cfg.pgd_attack:
+        assert torch.allclose(g_img, w_img, rtol=0, atol=1e-6 * float(w_img.abs().max()) + 1e-12) or \
+            float((g_img - w_img).abs().max()) <= 2e-2 * float(w_img.abs().max())
+        assert torch.equal(torch.sign(g_img), torch.sign(w_img)) or \
+            float((torch.sign(g_img) != torch.sign(w_img)).float().mean()) < 0.02
+
+
+@pytest.mark.parametrize("mode", ["joint", "gcg_only", "pgd_gcg_nojoint", "pgd_only"])
+def test_run_end_to_end(cuda_device, mode, tmp_path):
+    import bimodalattack_b200 as bma
+    flags = dict(MODES.get(mode, dict(pgd_attack=True, gcg_attack=False)))
+    model, tok, proc, norm, image, cfg = _setup(cuda_device, **flags)
+    cfg.images_folder = str(tmp_path / "img") if cfg.pgd_attack else None
+    cfg.num_steps = 4
+    res = bma.run(model, tok, proc, [{"role": "user", "content": PROMPT}], "goal", TARGET,
+                  image.clone() if cfg.pgd_attack else None, cfg, normalize=norm)
+    assert len(res.losses) == 4 and len(res.strings) == 4 and len(res.adversarial_suffixes) == 4
+    assert all(l == l and l > 0 for l in res.losses)
+    assert res.best_loss == min(res.losses)
+    assert res.losses[-1] < res.losses[0] + 0.05       # the attack makes progress (or at least holds)
+    if cfg.pgd_attack:
+        assert (tmp_path / "img" / "3.png").exists()
+
+
+def test_first_step_matches_oracle_trajectory(cuda_device):
+    """Same seed, same inputs: step 0 of run() picks a candidate whose oracle loss is (tie-aware)
+    the oracle's minimum, and the PGD image equals the oracle's image bit for bit when the image
+    gradients have the same sign pattern."""
+    import bimodalattack_b200 as bma
+    from oracle import hotpath
+    model, tok, proc, norm, image, cfg = _setup(cuda_device, **MODES["joint"])
+    cfg.num_steps = 1
+    atk = bma.BimodalAttack(model, tok, proc, cfg, normalize=norm)
+    res = atk.run([{"role": "user", "content": PROMPT}], "goal", TARGET, image.clone())
+    ora = hotpath.OracleAttack(model, tok, proc, cfg, normalize=norm)
+    log = ora.run([{"role": "user", "content": PROMPT}], TARGET, image.clone())
+    same_pixels = float((atk.final_image.detach() == ora.final_image.detach()).float().mean())
+    assert same_pixels > 0.98
+    cand = log.candidate_losses[0]
+    sampled = log.sampled[0]
+    mine = atk.final_optim_ids.squeeze(0).cpu()
+    hits = (sampled == mine).all(dim=1).nonzero()
+    if hits.numel() > 0:        # identical gradients -> identical candidate set
+        assert float(cand[int(hits[0])]) <= float(cand.min()) + 0.0625 * 2
+    assert abs(res.losses[0] - log.losses[0]) <= 0.0625 * 2 + 2e-2 * abs(log.losses[0])

@@ -59,6 +59,7 @@ def test_pgd_step_fused_normalize(lib, cuda_device):
 # ------------------------------------------------------------------------------------------------
 def test_torch_cuda_philox_contract(cuda_device):
     """The RNG contract the sampler relies on: offset advances by 4 per small draw."""
+    torch.zeros(1, device=cuda_device)   # default_generators is filled lazily on CUDA init
     torch.manual_seed(1234)
     gen = torch.cuda.default_generators[cuda_device.index]
     o0 = gen.get_offset()
