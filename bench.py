@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""Headline benchmark: GCG+PGD candidates scored/sec (and steps/sec), LLaVA-1.5-7B architecture,
+search_width 512, joint_eval (BASELINE.json config 2). Prints ONE JSON line on rank 0.
+
+  python bench.py --gpus 1 --steps 10 --warmup 3            # this repo's B200 path
+  torchrun ... bench.py --gpus N ...                         # candidates sharded over N ranks
+  python bench.py --impl reference --steps 2 --warmup 1      # the reference's dataflow on host cores
+
+What a "step" is: the scoring phase of one attack step -- from "candidate
+ids and the perturbed image are ready" to "the winner index is known on the host": vision tower +
+projector on the new image, shared-prefix KV build, tail-only decoder pass over every candidate,
+fused LM-head cross-entropy, argmin, and (N > 1) the min all-reduce.
+  value  candidates/s with ids and image already resident in HBM
+  e2e    same through the host-buffer C-ABI call: pinned ids + image copied in, losses + key out
+Also reported: full attack steps/s (gradient + PGD + sampling + scoring through ``run()``), the
+roofline of the dominant kernel class (tcgen05 GEMMs, CUDA events inside the timed steps), and the
+oracle (reference dataflow) timed on the host CPU for a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "gcg_pgd_candidates_scored_per_sec"
+UNIT = "candidates/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--model", default="7b", choices=["7b", "small128", "tiny128"])
+    ap.add_argument("--search-width", type=int, default=512)
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: search_width candidates in total; weak: search_width per GPU")
+    ap.add_argument("--full-steps", type=int, default=3, help="full attack steps timed for steps/s (0 = skip)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=1, help="candidates per CPU-baseline step")
+    return ap.parse_args()
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"bf16_burst": p["bf16_tflops"], "bf16_sustained": p["bf16_tflops_sustained"],
+                "hbm_gbs": p["hbm_gbs"], "source": "measured"}
+    return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.proc = gpu_index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [c for c in sm if c > 0]
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def algorithmic_flops(d, d_ff, n_layers, heads, head_dim, vocab, P, S, T, n_cand):
+    """linear layers 2*params*rows, attention 4*rows*(keys)*d, LM head on
+    the T target rows; prefix counted once (its last layer stops after the K/V projection)."""
+    q = heads * head_dim
+    per_row = 2 * (d * 3 * q + q * d + 3 * d * d_ff)
+    tail = n_cand * (S * per_row * n_layers + 4 * S * (P + S / 2) * q * n_layers + 2 * T * d * vocab)
+    prefix = P * per_row * n_layers + 4 * P * (P / 2) * q * n_layers
+    return tail + prefix, tail / max(n_cand, 1)
+
+
+def run_reference(args):
+    """--impl reference: the reference's dataflow (oracle/hotpath.py, pinned to the reference by
+    tests/golden) on the host cores. Each step scores ``cpu_sample`` candidates the reference's
+    way: full 638-token sequence, full-vocabulary logits, CE in model dtype."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from bimodalattack_b200 import BimodalAttackConfig, synthetic as syn
+    from oracle import hotpath
+    torch.manual_seed(0)
+    vocab = {"7b": 32000, "small128": 4000, "tiny128": 1000}[args.model]
+    px = {"7b": 336, "small128": 56, "tiny128": 28}[args.model]
+    tok, proc, norm, image, messages, target, init = syn.headline_case(vocab, px)
+    t0 = time.perf_counter()
+    model = syn.make_llava(args.model, dtype=torch.float32, device=None, head_gain=20.0,
+                           fast_init=(args.model == "7b"))
+    build_s = time.perf_counter() - t0
+    cfg = BimodalAttackConfig(num_steps=1, search_width=args.search_width, pgd_attack=True, gcg_attack=True,
+                              joint_eval=True, allow_non_ascii=True, optim_str_init=init, seed=1,
+                              alpha=4 / 255, eps=64 / 255, verbosity="ERROR", images_folder=None)
+    ora = hotpath.OracleAttack(model, tok, proc, cfg, normalize=norm)
+    msgs = hotpath.build_messages(messages, True)
+    prompt = proc.apply_chat_template(msgs, add_generation_prompt=True)
+    seg = hotpath.split_prompt(prompt, tok, True, False, "cpu")
+    ora.target_ids = tok(target, add_special_tokens=False, return_tensors="pt")["input_ids"]
+    seg["target"] = ora.target_ids
+    ora.seg_embeds = {k: ora.emb(v) for k, v in seg.items()}
+    n = args.cpu_sample
+    g = torch.Generator().manual_seed(3)
+    n_tok = len(tok(init, add_special_tokens=False)["input_ids"])
+    order = hotpath.segment_order("pgd", "llava", single=True)
+
+    def step():
+        sampled = torch.randint(8, vocab, (n, n_tok), generator=g)
+        with torch.no_grad():
+            feats = hotpath.image_features(model, norm(image), False)
+            emb = hotpath.assemble(ora._parts(sampled, feats), order, n)
+            loss, _ = hotpath.candidates_loss(model, emb, ora.target_ids, n)
+        return emb.shape[1], int(loss.argmin())
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        seq_len, _ = step()
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    cores = torch.get_num_threads()
+    sample = (f"{n} candidate(s) per step through the reference dataflow (full {seq_len}-token sequence, "
+              f"full-vocab logits, fp32), model {args.model}; search_width-{args.search_width} step extrapolates linearly")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args, seq_len - n_tok - 22, n_tok + 22),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "host_cpus": os.cpu_count(), "model_build_s": build_s},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def workload_config(args, P, S):
+    sw = args.search_width * (args.gpus if args.scaling == "weak" else 1)
+    return {"workload": f"LLaVA-1.5-{args.model} arch random-init, joint GCG+PGD scoring phase, "
+                        f"search_width {sw} ({args.scaling} scaling), 336x336 synthetic image, topk 256, n_replace 1",
+            "search_width": sw, "prefix_rows": P, "tail_rows": S,
+            "parallelism": f"candidate-sharded dp{args.gpus}, replicated model",
+            "l2": "no flush needed: every step streams ~23 GB of weights (>> 126 MB L2)"}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as td
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        td.init_process_group("nccl", device_id=dev)
+
+    from bimodalattack_b200 import BimodalAttack, BimodalAttackConfig, native, synthetic as syn
+    from bimodalattack_b200.attack import image_features
+    from bimodalattack_b200 import dist as bdist
+    lib = native.load()
+    peaks = load_peaks()
+
+    vocab = {"7b": 32000, "small128": 4000, "tiny128": 1000}[args.model]
+    px = {"7b": 336, "small128": 56, "tiny128": 28}[args.model]
+    tok, proc, norm, image_cpu, messages, target, init = syn.headline_case(vocab, px)
+    model = syn.make_llava(args.model, dtype=torch.bfloat16, device=dev, seed=0, head_gain=20.0,
+                           attn_implementation="sdpa")
+    sw = args.search_width * (world if args.scaling == "weak" else 1)
+    cfg = BimodalAttackConfig(num_steps=1, search_width=sw, topk=256, n_replace=1, pgd_attack=True,
+                              gcg_attack=True, joint_eval=True, allow_non_ascii=True, filter_ids=False,
+                              optim_str_init=init, seed=1, alpha=4 / 255, eps=64 / 255, verbosity="ERROR",
+                              images_folder=None)
+    atk = BimodalAttack(model, tok, proc, cfg, normalize=norm)
+    atk._prepare(messages, target)
+    w = atk.world
+    image = image_cpu.to(dev)
+    original = image.clone()
+
+    # one real gradient + PGD + sampling on rank 0 gives this step's inputs
+    torch.manual_seed(1)
+    optim_ids = tok(init, add_special_tokens=False, return_tensors="pt")["input_ids"].to(dev)
+    n_tok = optim_ids.shape[1]
+    sampled = None
+    if rank == 0:
+        img = image.clone().requires_grad_()
+        g_tok, g_img = atk.compute_gradient(optim_ids, img)
+        image = atk.perform_pgd_step(img, cfg.eps, cfg.alpha, g_img, original).detach()
+        sampled, _, _, _ = atk.candidate_sampling(cfg, 0, optim_ids, g_tok, tok, [], 0.0)
+    sampled = bdist.broadcast_candidates(sampled, n_tok, dev, w)
+    image = bdist.broadcast_tensor(image.contiguous(), w)
+    lo, hi = bdist.shard_bounds(sw, w)
+
+    def scoring_step():
+        with torch.no_grad():
+            feats = image_features(model, norm(image), False)
+            batch = atk._build_input_embeds_pgd(sampled, feats, search_width=sw, single=True)
+            atk._compute_candidates_loss_original(sw, batch)
+        return atk._winner()                     # one 8-byte D2H: the step's result
+
+    def barrier():
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: device-resident inputs -------------------------------------------------------
+    for _ in range(args.warmup):
+        scoring_step()
+    P = atk.engine.prefix_len
+    plan = atk._plan(atk._build_input_embeds_pgd(sampled, image_features(model, norm(image), False), sw, single=True))
+    S, T = plan.n_tail, atk.target_ids.numel()
+    atk.engine.profile(True)
+    clocks = ClockSampler(local)
+    barrier()
+    launches0 = lib.bma_launch_count()
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        win_loss, win_idx = scoring_step()
+    e1.record()
+    barrier()
+    clock_info = clocks.stop()
+    launches = lib.bma_launch_count() - launches0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        td.all_reduce(ms, op=td.ReduceOp.MAX)
+    ms_per_step = float(ms.item()) / args.steps
+    value = sw / (ms_per_step * 1e-3)
+    prof = atk.engine.profile_read()
+    atk.engine.profile(False)
+
+    # ---- e2e: host buffers through the C ABI ---------------------------------------------------
+    ids_host = sampled.cpu().pin_memory()
+    img_host = image.cpu().pin_memory()
+    loss_host = torch.empty(sw, dtype=torch.float32).pin_memory()
+    key_host = torch.empty(1, dtype=torch.int64).pin_memory()
+    img_dev = torch.empty_like(image)
+    key_dev = torch.empty(1, dtype=torch.int64, device=dev)
+
+    def e2e_step():
+        with torch.no_grad():
+            img_dev.copy_(img_host, non_blocking=True)
+            feats = image_features(model, norm(img_dev), False)
+            batch = atk._build_input_embeds_pgd(sampled, feats, search_width=sw, single=True)
+            pl = atk._plan(batch)
+            atk.engine.prefill(pl.prefix)
+            atk.engine.score_host(ids_host[lo:hi], pl, atk.target_ids, loss_host[lo:hi], key_host, idx_base=lo)
+            if world > 1:
+                key_dev.copy_(key_host, non_blocking=True)
+                td.all_reduce(key_dev, op=td.ReduceOp.MIN)
+                return int(key_dev.item())
+        return int(key_host.item())
+
+    for _ in range(max(1, args.warmup // 2)):
+        e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_key = e2e_step()
+    e1.record()
+    barrier()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        td.all_reduce(ms2, op=td.ReduceOp.MAX)
+    e2e_value = sw / (float(ms2.item()) / args.steps * 1e-3)
+    h2d = ids_host[lo:hi].numel() * 8 + img_host.numel() * 4
+    d2h = (hi - lo) * 4 + 8
+
+    # ---- full attack steps through run() ---------------------------------------------------------
+    full = None
+    if args.full_steps > 0:
+        import dataclasses
+        cfg2 = dataclasses.replace(cfg, num_steps=args.full_steps + 2)
+        atk2 = BimodalAttack(model, tok, proc, cfg2, normalize=norm, engine=atk.engine)
+        marks = []
+
+        def hook(i):
+            torch.cuda.synchronize()
+            marks.append(time.perf_counter())
+        atk2.step_hook = hook
+        res = atk2.run(messages, "goal", target, image_cpu.to(dev))
+        if len(marks) >= 3:
+            dt = torch.tensor([(marks[-1] - marks[1]) / (len(marks) - 2)], device=dev)
+            if world > 1:
+                td.all_reduce(dt, op=td.ReduceOp.MAX)
+            full = {"steps_per_sec": 1.0 / float(dt.item()), "ms_per_step": 1e3 * float(dt.item()),
+                    "timed_steps": len(marks) - 2, "losses": res.losses,
+                    "phase_s_last": {"gradient": res.gradient_times[-1] if res.gradient_times else None,
+                                     "pgd": res.pgd_times[-1] if res.pgd_times else None,
+                                     "sampling": res.sampling_times[-1] if res.sampling_times else None,
+                                     "scoring": res.loss_times[-1]}}
+
+    if rank != 0:
+        if world > 1:
+            td.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel class (tcgen05 GEMMs), from in-run CUDA events ----------
+    tc = model.config.text_config
+    gemm_classes = [k for k in prof if k.startswith("gemm")]
+    g_ms = sum(prof[k]["ms"] for k in gemm_classes)
+    g_fl = sum(prof[k]["flops"] for k in gemm_classes)
+    total_prof_ms = sum(v["ms"] for v in prof.values())
+    achieved = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+    total_flops, per_cand = algorithmic_flops(tc.hidden_size, tc.intermediate_size, tc.num_hidden_layers,
+                                              tc.num_attention_heads, 128, model.get_output_embeddings().weight.shape[0],
+                                              P, S, T, hi - lo)
+    roofline = {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel<*> (tcgen05, all epilogues)",
+                "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["bf16_sustained"], "frac_of_burst_peak": achieved / peaks["bf16_burst"],
+                "peak_source": peaks["source"] + " (sustained cuBLAS bf16; kernel timed inside a long step)",
+                "traffic": None, "share_of_scoring_kernels": g_ms / total_prof_ms if total_prof_ms else None,
+                "per_class": {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
+                                  "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 and v["flops"] > 0 else None}
+                              for k, v in prof.items()},
+                "step_tflops_algorithmic": total_flops / (ms_per_step * 1e-3) / 1e12,
+                "gflop_per_candidate": per_cand / 1e9}
+
+    # ---- CPU baseline: the oracle (reference dataflow) on the host cores, bounded sample ------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        import copy
+        from oracle import hotpath
+        t0 = time.perf_counter()
+        twin = copy.deepcopy(model).to("cpu").float()
+        ora = hotpath.OracleAttack(twin, tok, proc, cfg, normalize=norm)
+        ora.target_ids = atk.target_ids.cpu()
+        ora.seg_embeds = {k: ora.emb(v.cpu()) for k, v in atk.segment_ids.items()}
+        n = args.cpu_sample
+        cand = sampled[:n].cpu()
+        order = hotpath.segment_order("pgd", "llava", single=True)
+        img_c = image.cpu()
+        t1 = time.perf_counter()
+        with torch.no_grad():
+            feats = hotpath.image_features(twin, norm(img_c), False)
+            emb = hotpath.assemble(ora._parts(cand, feats), order, n)
+            cl, _ = hotpath.candidates_loss(twin, emb, ora.target_ids, n)
+        dt = time.perf_counter() - t1
+        cpu = {"value": n / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "host_cpus": os.cpu_count(),
+               "sample": f"{n} of {sw} candidates through the reference dataflow (full {emb.shape[1]}-token "
+                         f"sequence, full-vocab logits, fp32) in {dt:.1f}s; linear extrapolation to a full step",
+               "loss_vs_gpu_abs_diff": float((cl - loss_host[:n]).abs().max()) if lo == 0 else None,
+               "setup_s": t1 - t0}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": workload_config(args, P, S),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu,
+        "full_step": full, "winner": {"loss": win_loss, "index": win_idx, "e2e_key": e2e_key},
+        "a100_reference_published": {"cand_per_s": 10.7, "s_per_iter": 49.965,
+                                     "note": "BASELINE.md: LLaVA-1.5-7B joint_eval sw 512, A100-80GB, fp16"},
+    }
+    print(json.dumps(out))
+    if world > 1:
+        td.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

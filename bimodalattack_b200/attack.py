@@ -108,7 +108,8 @@ class CandidateBatch:
 
 
 class BimodalAttack:
-    def __init__(self, model, tokenizer, processor, config: BimodalAttackConfig, normalize=None):
+    def __init__(self, model, tokenizer, processor, config: BimodalAttackConfig, normalize=None,
+                 engine: Optional[ScoringEngine] = None):
         self.model, self.tokenizer, self.processor = model, tokenizer, processor
         self.config, self.normalize = config, normalize
         self.embedding_layer = model.get_input_embeddings()
@@ -126,11 +127,14 @@ class BimodalAttack:
             logger.warning("Tokenizer does not have a chat template. Using custom chat template.")
             tokenizer.chat_template = tpl
             self.processor.chat_template = tpl
-        self.engine = ScoringEngine(model)
+        # the engine holds the packed decoder weights and the scorer workspace; it can be shared
+        # between attacks on the same model (one per (goal, target) pair in the reference's driver)
+        self.engine = engine if engine is not None else ScoringEngine(model)
         self._plans: Dict[Tuple[str, ...], TailPlan] = {}
         self._prefill_tag = None
         self.world = bdist.world()
         self.gather_all_losses = False    # multi-rank: also all-reduce the per-candidate loss vector
+        self.step_hook = None             # optional callable(step_index) run at the end of every step
 
     # ---------------------------------------------------------------------------------------------
     # prompt -> segments (:271-393)
@@ -518,6 +522,8 @@ class BimodalAttack:
             if self.stop_flag:
                 logger.info("Early stopping due to finding a perfect match.")
                 break
+            if self.step_hook is not None:
+                self.step_hook(i)
             totals.append(grad_time + sampling_time + pgd_time + loss_time)
             logger.info(f"[Iteration {i}] loss {current:.4f} | grad {grad_time:.4f}s sample {sampling_time:.4f}s "
                         f"pgd {pgd_time:.4f}s loss {loss_time:.4f}s")

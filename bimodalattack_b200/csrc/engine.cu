@@ -29,12 +29,22 @@ int fail(cudaError_t e, const char* fmt, ...) {
   g_last_error = std::string(buf) + ": " + cudaGetErrorString(e);
   return static_cast<int>(e == cudaSuccess ? cudaErrorUnknown : e);
 }
-#define BMA_CHECK(expr, what)                          \
-  do {                                                 \
-    cudaError_t e__ = (expr);                          \
-    ++g_launches;                                      \
+// BMA_CHECK: any CUDA call; BMA_LAUNCH: a kernel launch of this library (counted).
+#define BMA_CHECK(expr, what)                             \
+  do {                                                    \
+    cudaError_t e__ = (expr);                             \
     if (e__ != cudaSuccess) return fail(e__, "%s", what); \
   } while (0)
+#define BMA_LAUNCH(expr, what)                            \
+  do {                                                    \
+    cudaError_t e__ = (expr);                             \
+    ++g_launches;                                         \
+    if (e__ != cudaSuccess) return fail(e__, "%s", what); \
+  } while (0)
+
+// Kernel classes of the scoring pass, for the optional per-class CUDA-event profile.
+enum : int { PC_EMBED = 0, PC_NORM, PC_GEMM_QKV, PC_ATTN, PC_GEMM_O, PC_GEMM_GLU, PC_GEMM_DOWN,
+             PC_GEMM_CE, PC_FINAL, PC_COUNT };
 
 inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
 inline const __nv_bfloat16* bf(const void* p) { return static_cast<const __nv_bfloat16*>(p); }
@@ -64,7 +74,29 @@ struct bma_scorer {
   int* flag_dev = nullptr;
   size_t ws_bytes = 0;
   int ce_rows_cap = 0;
+  // optional profile: event pairs around every launch, summed per class on read
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_start, ev_stop;
+  std::vector<int> ev_class;
+  std::vector<double> ev_flops;
+  size_t ev_used = 0;
 };
+
+namespace {
+struct ProfScope {
+  bma_scorer* s; cudaStream_t st; size_t slot; bool on;
+  ProfScope(bma_scorer* s_, int cls, double flops, cudaStream_t st_) : s(s_), st(st_), slot(0), on(false) {
+    if (!s->profiling || s->ev_used >= s->ev_start.size()) return;
+    on = true;
+    slot = s->ev_used++;
+    s->ev_class[slot] = cls;
+    s->ev_flops[slot] = flops;
+    cudaEventRecord(s->ev_start[slot], st);
+  }
+  ~ProfScope() { if (on) cudaEventRecord(s->ev_stop[slot], st); }
+};
+inline double gemm_flops(const GemmParams& p) { return 2.0 * p.M * static_cast<double>(p.N) * p.K; }
+}  // namespace
 
 namespace {
 
@@ -87,8 +119,11 @@ int run_layers(bma_scorer* s, int rows, int seq, int pos_base, bool prefill, cud
     __nv_bfloat16* qkv = prefill ? s->prefix_qkv + (size_t)l * D.max_prefix * s->qkv_dim : s->qkv;
     const __nv_bfloat16* pre = s->prefix_qkv + (size_t)l * D.max_prefix * s->qkv_dim;
 
-    BMA_CHECK(launch_rmsnorm(s->x, d, bf(W.norm_attn), s->xn, d, rows, d, D.rms_eps, D.norm_mode,
-                             0, 0, 0, st), "rmsnorm(attn)");
+    {
+      ProfScope ps(s, PC_NORM, 0, st);
+      BMA_LAUNCH(launch_rmsnorm(s->x, d, bf(W.norm_attn), s->xn, d, rows, d, D.rms_eps, D.norm_mode,
+                                0, 0, 0, st), "rmsnorm(attn)");
+    }
     {
       GemmParams p{};
       p.M = rows; p.N = s->qkv_dim; p.K = d; p.group_m = 16;
@@ -96,7 +131,8 @@ int run_layers(bma_scorer* s, int rows, int seq, int pos_base, bool prefill, cud
       p.rope_cos = W.rope_cos; p.rope_sin = W.rope_sin;
       p.rope_cols = s->q_dim + s->kv_dim;
       p.rows_per_seq = seq; p.pos_base = pos_base;
-      BMA_CHECK((launch_gemm<256, EPI_ROPE>(s->xn, d, bf(W.w_qkv), d, p, st)), "gemm(qkv+rope)");
+      ProfScope ps(s, PC_GEMM_QKV, gemm_flops(p), st);
+      BMA_LAUNCH((launch_gemm<256, EPI_ROPE>(s->xn, d, bf(W.w_qkv), d, p, st)), "gemm(qkv+rope)");
     }
     if (prefill && l == D.n_layers - 1) break;   // only this layer's K/V are needed
     {
@@ -110,29 +146,37 @@ int run_layers(bma_scorer* s, int rows, int seq, int pos_base, bool prefill, cud
       a.M = rows; a.S = seq; a.P = P;
       a.kv_group = D.n_heads / D.n_kv_heads;
       a.scale_log2 = D.attn_scale * 1.4426950408889634f;
-      BMA_CHECK(launch_prefix_tail_attention(a, D.n_heads, st), "attention");
+      // QK^T and PV over the visible keys: ~4 * rows * (P + seq/2) * q_dim
+      ProfScope ps(s, PC_ATTN, 4.0 * rows * (P + 0.5 * seq) * s->q_dim, st);
+      BMA_LAUNCH(launch_prefix_tail_attention(a, D.n_heads, st), "attention");
     }
     {
       GemmParams p{};
       p.M = rows; p.N = d; p.K = s->q_dim; p.group_m = 16;
       p.C = s->x; p.ldc = d; p.R = s->x; p.ldr = d;
-      BMA_CHECK((launch_gemm<256, EPI_STORE>(s->attn, s->q_dim, bf(W.w_o), s->q_dim, p, st)),
-                "gemm(o_proj)");
+      ProfScope ps(s, PC_GEMM_O, gemm_flops(p), st);
+      BMA_LAUNCH((launch_gemm<256, EPI_STORE>(s->attn, s->q_dim, bf(W.w_o), s->q_dim, p, st)),
+                 "gemm(o_proj)");
     }
-    BMA_CHECK(launch_rmsnorm(s->x, d, bf(W.norm_mlp), s->xn, d, rows, d, D.rms_eps, D.norm_mode,
-                             0, 0, 0, st), "rmsnorm(mlp)");
+    {
+      ProfScope ps(s, PC_NORM, 0, st);
+      BMA_LAUNCH(launch_rmsnorm(s->x, d, bf(W.norm_mlp), s->xn, d, rows, d, D.rms_eps, D.norm_mode,
+                                0, 0, 0, st), "rmsnorm(mlp)");
+    }
     {
       GemmParams p{};
       p.M = rows; p.N = 2 * D.d_ff; p.K = d; p.group_m = 16;
       p.C = s->act; p.ldc = D.d_ff; p.act = D.act;
-      BMA_CHECK((launch_gemm<256, EPI_GLU>(s->xn, d, bf(W.w_gate_up), d, p, st)), "gemm(gate_up)");
+      ProfScope ps(s, PC_GEMM_GLU, gemm_flops(p), st);
+      BMA_LAUNCH((launch_gemm<256, EPI_GLU>(s->xn, d, bf(W.w_gate_up), d, p, st)), "gemm(gate_up)");
     }
     {
       GemmParams p{};
       p.M = rows; p.N = d; p.K = D.d_ff; p.group_m = 16;
       p.C = s->x; p.ldc = d; p.R = s->x; p.ldr = d;
-      BMA_CHECK((launch_gemm<256, EPI_STORE>(s->act, D.d_ff, bf(W.w_down), D.d_ff, p, st)),
-                "gemm(down)");
+      ProfScope ps(s, PC_GEMM_DOWN, gemm_flops(p), st);
+      BMA_LAUNCH((launch_gemm<256, EPI_STORE>(s->act, D.d_ff, bf(W.w_down), D.d_ff, p, st)),
+                 "gemm(down)");
     }
   }
   return 0;
@@ -157,8 +201,8 @@ int bma_watchdog_code(unsigned int* code_out) {
 int bma_pgd_step(float* image, const float* grad, const float* orig, long long n, float step,
                  float eps, float* norm_out, const float* mean_host, const float* std_host,
                  int channels, long long plane, void* stream) {
-  BMA_CHECK(launch_pgd_step(image, grad, orig, norm_out, n, step, eps, mean_host, std_host,
-                            channels, plane, as_stream(stream)), "pgd_step");
+  BMA_LAUNCH(launch_pgd_step(image, grad, orig, norm_out, n, step, eps, mean_host, std_host,
+                             channels, plane, as_stream(stream)), "pgd_step");
   return 0;
 }
 
@@ -174,11 +218,11 @@ int bma_token_grad(const void* grad_embeds, long long ld_g, const void* W, long 
     p.C = bf(out) + (long long)t0 * ld_out; p.ldc = ld_out;
     const __nv_bfloat16* g = bf(grad_embeds) + (long long)t0 * ld_g;
     if (nt <= 32) {
-      BMA_CHECK((launch_gemm<32, EPI_STORE_T>(bf(W), ld_w, g, ld_g, p, as_stream(stream))),
-                "gemm(token_grad)");
+      BMA_LAUNCH((launch_gemm<32, EPI_STORE_T>(bf(W), ld_w, g, ld_g, p, as_stream(stream))),
+                 "gemm(token_grad)");
     } else {
-      BMA_CHECK((launch_gemm<128, EPI_STORE_T>(bf(W), ld_w, g, ld_g, p, as_stream(stream))),
-                "gemm(token_grad)");
+      BMA_LAUNCH((launch_gemm<128, EPI_STORE_T>(bf(W), ld_w, g, ld_g, p, as_stream(stream))),
+                 "gemm(token_grad)");
     }
   }
   return 0;
@@ -250,10 +294,43 @@ void bma_scorer_destroy(bma_scorer* s) {
   cudaFree(s->x); cudaFree(s->xn); cudaFree(s->qkv); cudaFree(s->attn); cudaFree(s->act);
   cudaFree(s->prefix_qkv); cudaFree(s->ce_part); cudaFree(s->tgt_logit);
   cudaFree(s->ids_dev); cudaFree(s->loss_dev); cudaFree(s->key_dev); cudaFree(s->flag_dev);
+  for (cudaEvent_t e : s->ev_start) cudaEventDestroy(e);
+  for (cudaEvent_t e : s->ev_stop) cudaEventDestroy(e);
   delete s;
 }
 
 size_t bma_scorer_workspace_bytes(const bma_scorer* s) { return s ? s->ws_bytes : 0; }
+
+int bma_scorer_profile(bma_scorer* s, int enable, int max_events) {
+  if (s == nullptr) return fail(cudaErrorInvalidValue, "profile: null scorer");
+  s->profiling = enable != 0;
+  s->ev_used = 0;
+  if (enable && static_cast<int>(s->ev_start.size()) < max_events) {
+    const size_t old = s->ev_start.size();
+    s->ev_start.resize(max_events); s->ev_stop.resize(max_events);
+    s->ev_class.resize(max_events); s->ev_flops.resize(max_events);
+    for (size_t i = old; i < static_cast<size_t>(max_events); ++i) {
+      BMA_CHECK(cudaEventCreate(&s->ev_start[i]), "profile: event create");
+      BMA_CHECK(cudaEventCreate(&s->ev_stop[i]), "profile: event create");
+    }
+  }
+  return 0;
+}
+
+int bma_scorer_profile_read(bma_scorer* s, double* ms, double* flops, long long* launches, int n_classes) {
+  if (s == nullptr || n_classes < PC_COUNT) return fail(cudaErrorInvalidValue, "profile_read: bad arguments");
+  for (int c = 0; c < n_classes; ++c) { ms[c] = 0; flops[c] = 0; launches[c] = 0; }
+  for (size_t i = 0; i < s->ev_used; ++i) {
+    BMA_CHECK(cudaEventSynchronize(s->ev_stop[i]), "profile_read: sync");
+    float t = 0;
+    BMA_CHECK(cudaEventElapsedTime(&t, s->ev_start[i], s->ev_stop[i]), "profile_read: elapsed");
+    ms[s->ev_class[i]] += t;
+    flops[s->ev_class[i]] += s->ev_flops[i];
+    launches[s->ev_class[i]] += 1;
+  }
+  s->ev_used = 0;
+  return 0;
+}
 
 int bma_scorer_set_layer(bma_scorer* s, int layer, const bma_layer_weights* w) {
   if (s == nullptr || w == nullptr || layer < 0 || layer >= s->desc.n_layers)
@@ -285,7 +362,7 @@ int bma_scorer_prefill(bma_scorer* s, const void* prefix_embeds, int P, void* st
 
 int bma_scorer_reset_key(bma_scorer* s, unsigned long long* key, int* all_match, void* stream) {
   (void)s;
-  BMA_CHECK(launch_init_key(key, all_match, as_stream(stream)), "init_key");
+  BMA_LAUNCH(launch_init_key(key, all_match, as_stream(stream)), "init_key");
   return 0;
 }
 
@@ -306,25 +383,35 @@ int bma_scorer_score(bma_scorer* s, const long long* ids, int ids_stride, int B,
   for (int b0 = 0; b0 < B; b0 += chunk) {
     const int nb = B - b0 < chunk ? B - b0 : chunk;
     const int rows = nb * S;
-    BMA_CHECK(launch_build_tail_embeds(ids + (long long)b0 * ids_stride, ids_stride, slot, bf(fixed),
-                                       s->embed, s->ld_embed, D.vocab, D.embed_scale, s->x, nb, S,
-                                       d, st), "build_tail_embeds");
+    {
+      ProfScope ps(s, PC_EMBED, 0, st);
+      BMA_LAUNCH(launch_build_tail_embeds(ids + (long long)b0 * ids_stride, ids_stride, slot, bf(fixed),
+                                          s->embed, s->ld_embed, D.vocab, D.embed_scale, s->x, nb, S,
+                                          d, st), "build_tail_embeds");
+    }
     int rc = run_layers(s, rows, S, s->prefix_len, false, st);
     if (rc != 0) return rc;
     // final norm on the T rows per candidate whose logits predict the target tokens
     const int ce_rows = nb * T;
-    BMA_CHECK(launch_rmsnorm(s->x, d, s->norm_final, s->xn, d, ce_rows, d, D.rms_eps, D.norm_mode,
-                             T, S, S - T - 1, st), "rmsnorm(final, gathered)");
+    {
+      ProfScope ps(s, PC_NORM, 0, st);
+      BMA_LAUNCH(launch_rmsnorm(s->x, d, s->norm_final, s->xn, d, ce_rows, d, D.rms_eps, D.norm_mode,
+                                T, S, S - T - 1, st), "rmsnorm(final, gathered)");
+    }
     {
       GemmParams p{};
       p.M = ce_rows; p.N = D.vocab; p.K = d; p.group_m = 16;
       p.target_ids = target_ids; p.T = T;
       p.ce_part = s->ce_part; p.tgt_logit = s->tgt_logit;
-      BMA_CHECK((launch_gemm<kCeBlockN, EPI_CE>(s->xn, d, s->lm_head, d, p, st)), "gemm(lm_head+ce)");
+      ProfScope ps(s, PC_GEMM_CE, gemm_flops(p), st);
+      BMA_LAUNCH((launch_gemm<kCeBlockN, EPI_CE>(s->xn, d, s->lm_head, d, p, st)), "gemm(lm_head+ce)");
     }
-    BMA_CHECK(launch_ce_finalize(s->ce_part, s->tgt_logit, n_ce_tiles, nb, T, loss + b0, key,
-                                 all_match, idx_base + static_cast<unsigned int>(b0), st),
-              "ce_finalize");
+    {
+      ProfScope ps(s, PC_FINAL, 0, st);
+      BMA_LAUNCH(launch_ce_finalize(s->ce_part, s->tgt_logit, n_ce_tiles, nb, T, loss + b0, key,
+                                    all_match, idx_base + static_cast<unsigned int>(b0), st),
+                 "ce_finalize");
+    }
   }
   return 0;
 }
@@ -359,9 +446,9 @@ int bma_gemm_bf16(const void* A, long long lda, const void* B, long long ldb, vo
   p.M = M; p.N = N; p.K = K; p.group_m = 16;
   p.C = bf(C); p.ldc = ldc; p.R = bf(residual); p.ldr = ldr;
   if (block_n == 256) {
-    BMA_CHECK((launch_gemm<256, EPI_STORE>(bf(A), lda, bf(B), ldb, p, as_stream(stream))), "gemm");
+    BMA_LAUNCH((launch_gemm<256, EPI_STORE>(bf(A), lda, bf(B), ldb, p, as_stream(stream))), "gemm");
   } else if (block_n == 128) {
-    BMA_CHECK((launch_gemm<128, EPI_STORE>(bf(A), lda, bf(B), ldb, p, as_stream(stream))), "gemm");
+    BMA_LAUNCH((launch_gemm<128, EPI_STORE>(bf(A), lda, bf(B), ldb, p, as_stream(stream))), "gemm");
   } else {
     return fail(cudaErrorInvalidValue, "gemm: block_n must be 128 or 256");
   }
@@ -370,8 +457,8 @@ int bma_gemm_bf16(const void* A, long long lda, const void* B, long long ldb, vo
 
 int bma_rmsnorm(const void* x, long long ldx, const void* w, void* y, long long ldy, int rows,
                 int d, float eps, int mode, void* stream) {
-  BMA_CHECK(launch_rmsnorm(bf(x), ldx, bf(w), bf(y), ldy, rows, d, eps, mode, 0, 0, 0,
-                           as_stream(stream)), "rmsnorm");
+  BMA_LAUNCH(launch_rmsnorm(bf(x), ldx, bf(w), bf(y), ldy, rows, d, eps, mode, 0, 0, 0,
+                            as_stream(stream)), "rmsnorm");
   return 0;
 }
 
@@ -388,7 +475,7 @@ int bma_attention(const void* q, long long ldq, const void* k_tail, long long ld
   a.out = bf(out); a.ldo = ldo;
   a.M = M; a.S = S; a.P = P; a.kv_group = kv_group;
   a.scale_log2 = scale * 1.4426950408889634f;
-  BMA_CHECK(launch_prefix_tail_attention(a, n_heads, as_stream(stream)), "attention");
+  BMA_LAUNCH(launch_prefix_tail_attention(a, n_heads, as_stream(stream)), "attention");
   return 0;
 }
 

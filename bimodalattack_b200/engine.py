@@ -156,6 +156,21 @@ class ScoringEngine:
         except Exception:
             pass
 
+    PROFILE_CLASSES = ("tail_embed", "rmsnorm", "gemm_qkv_rope", "attention", "gemm_o_proj",
+                       "gemm_gate_up_glu", "gemm_down", "gemm_lm_head_ce", "ce_finalize")
+
+    def profile(self, enable: bool, max_events: int = 8192):
+        """Per-kernel-class CUDA-event timing inside the scoring pass (used by bench.py's roofline)."""
+        self._ensure(max(self._cap_rows, 1), self._cap_prefix)
+        native.check(self.lib.bma_scorer_profile(self._scorer, int(enable), max_events), "scorer_profile")
+
+    def profile_read(self) -> dict:
+        n = len(self.PROFILE_CLASSES)
+        ms, fl, cnt = (C.c_double * n)(), (C.c_double * n)(), (C.c_longlong * n)()
+        native.check(self.lib.bma_scorer_profile_read(self._scorer, ms, fl, cnt, n), "scorer_profile_read")
+        return {name: {"ms": ms[i], "flops": fl[i], "launches": int(cnt[i])}
+                for i, name in enumerate(self.PROFILE_CLASSES)}
+
     @property
     def workspace_bytes(self) -> int:
         return 0 if self._scorer is None else int(self.lib.bma_scorer_workspace_bytes(self._scorer))

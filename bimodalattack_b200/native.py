@@ -54,6 +54,8 @@ SIGNATURES = {
     "bma_scorer_set_layer": (_I, [_P, _I, C.POINTER(LayerWeights)]),
     "bma_scorer_set_head": (_I, [_P, _P, _P, _P, _LL]),
     "bma_scorer_workspace_bytes": (C.c_size_t, [_P]),
+    "bma_scorer_profile": (_I, [_P, _I, _I]),
+    "bma_scorer_profile_read": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_LL), _I]),
     "bma_scorer_prefill": (_I, [_P, _P, _I, _P]),
     "bma_scorer_reset_key": (_I, [_P, _P, _P, _P]),
     "bma_scorer_score": (_I, [_P, _P, _I, _I, _P, _P, _I, _P, _I, _P, _P, _P, _U32, _P]),

@@ -103,8 +103,25 @@ def _finish(model, dtype, device, head_gain: float, seed: int):
     return model.eval().requires_grad_(False)
 
 
+def _tiled_init(model, seed: int):
+    """Fast CPU initialisation for timing-only models: every matrix is tiled from one N(0, 0.02)
+    block of 2^20 values, norm weights are 1, biases 0 (HF's per-parameter normal_ takes minutes
+    for 7B parameters on a few cores)."""
+    g = torch.Generator().manual_seed(seed)
+    block = torch.randn(1 << 20, generator=g) * 0.02
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if p.dim() < 2:
+                p.fill_(1.0) if ("norm" in name and name.endswith("weight")) else p.zero_()
+                continue
+            flat = p.view(-1)
+            reps = (flat.numel() + block.numel() - 1) // block.numel()
+            flat.copy_(block.repeat(reps)[: flat.numel()].to(p.dtype))
+
+
 def make_llava(size: str = "tiny", dtype=torch.float32, device=None, seed: int = 0,
-               head_gain: float = 20.0, attn_implementation: Optional[str] = None):
+               head_gain: float = 20.0, attn_implementation: Optional[str] = None,
+               fast_init: bool = False):
     """size: 'tiny' (CPU config of BASELINE.json: 2 layers, d=256, 4-token image),
     'tiny128' (same but head_dim 128 so the CUDA scorer accepts it), '7b' (LLaVA-1.5-7B arch)."""
     from transformers import LlavaForConditionalGeneration
@@ -122,7 +139,12 @@ def make_llava(size: str = "tiny", dtype=torch.float32, device=None, seed: int =
     if attn_implementation is not None:
         cfg._attn_implementation = attn_implementation
     torch.manual_seed(seed)
-    if device is not None and torch.device(device).type == "cuda":
+    if fast_init:
+        from transformers.initialization import no_init_weights
+        with no_init_weights():
+            model = LlavaForConditionalGeneration(cfg)
+        _tiled_init(model, seed)
+    elif device is not None and torch.device(device).type == "cuda":
         prev = torch.get_default_dtype()
         torch.set_default_dtype(dtype)
         try:
@@ -204,3 +226,25 @@ def make_gemma3(size: str = "tiny", dtype=torch.float32, device=None, seed: int 
 
 def synthetic_words(n: int, start: int = 10) -> str:
     return " ".join(f"w{start + i}" for i in range(n))
+
+
+def headline_case(vocab: int = 32000, image_px: int = 336, n_optim: int = 20, n_target: int = 16,
+                  seed: int = 1234):
+    """Synthetic inputs of BASELINE.json config 2: segment lengths
+    before_img 4 | image (px/14)^2 | before_suffix 16 | optim 20 | after 6 | target 16, i.e. a
+    596-row shared prefix and a 42-row tail at 336 px. Returns (tokenizer, processor, normalize,
+    image [cpu fp32], messages, target, optim_str_init)."""
+    import torchvision.transforms as T
+
+    tok = make_tokenizer(vocab)
+    proc = make_llava_processor(tok, image_px)
+    template = ("w1 w2 w3 <image> {{ messages[0]['content'][0]['text'] }} "
+                + synthetic_words(6, start=100))
+    tok.chat_template = template
+    proc.chat_template = template
+    g = torch.Generator().manual_seed(seed)
+    image = torch.rand((1, 3, image_px, image_px), generator=g)
+    messages = [{"role": "user", "content": synthetic_words(15, start=200)}]
+    target = synthetic_words(n_target, start=400)
+    init = " ".join(["x"] * n_optim)
+    return tok, proc, T.Normalize(CLIP_MEAN, CLIP_STD), image, messages, target, init

@@ -114,7 +114,15 @@ int bma_scorer_score_host(bma_scorer* s, const long long* ids_host, int ids_stri
                           int T, float* loss_host, unsigned long long* key_host,
                           unsigned int idx_base, void* stream);
 
-/* Launches issued by this library since load (the benchmark's gpu_launches counter). */
+/* Optional per-class CUDA-event profile of the scoring pass (events on the launching stream).
+ * Classes: 0 tail-embed, 1 rmsnorm, 2 gemm qkv+rope, 3 attention, 4 gemm o_proj, 5 gemm gate/up+GLU,
+ * 6 gemm down, 7 gemm lm_head+CE, 8 CE finalise. profile_read sums the elapsed ms, the algorithmic
+ * FLOPs and the launch count per class since the last read (arrays of >= 9 entries). */
+#define BMA_PROFILE_CLASSES 9
+int bma_scorer_profile(bma_scorer* s, int enable, int max_events);
+int bma_scorer_profile_read(bma_scorer* s, double* ms, double* flops, long long* launches, int n_classes);
+
+/* Kernel launches issued by this library since load (the benchmark's gpu_launches counter). */
 unsigned long long bma_launch_count(void);
 
 /* ---- kernel-level entry points (used by the parity tests) --------------------------------- */
