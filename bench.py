@@ -31,6 +31,9 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# LM-head scale of the random-init models: logit std ~ 0.02 * gain * sqrt(d), chosen so per-candidate
+# losses are spread over a few nats instead of all being ln(V) (SURVEY.md section 7 "Ties")
+HEAD_GAIN = {"7b": 2.0, "small128": 10.0, "tiny128": 20.0}
 METRIC = "gcg_pgd_candidates_scored_per_sec"
 UNIT = "candidates/s"
 
@@ -129,7 +132,7 @@ def run_reference(args):
     px = {"7b": 336, "small128": 56, "tiny128": 28}[args.model]
     tok, proc, norm, image, messages, target, init = syn.headline_case(vocab, px)
     t0 = time.perf_counter()
-    model = syn.make_llava(args.model, dtype=torch.float32, device=None, head_gain=20.0,
+    model = syn.make_llava(args.model, dtype=torch.float32, device=None, head_gain=HEAD_GAIN[args.model],
                            fast_init=(args.model == "7b"))
     build_s = time.perf_counter() - t0
     cfg = BimodalAttackConfig(num_steps=1, search_width=args.search_width, pgd_attack=True, gcg_attack=True,
@@ -179,8 +182,9 @@ def run_reference(args):
 
 def workload_config(args, P, S):
     sw = args.search_width * (args.gpus if args.scaling == "weak" else 1)
+    px = {"7b": 336, "small128": 56, "tiny128": 28}[args.model]
     return {"workload": f"LLaVA-1.5-{args.model} arch random-init, joint GCG+PGD scoring phase, "
-                        f"search_width {sw} ({args.scaling} scaling), 336x336 synthetic image, topk 256, n_replace 1",
+                        f"search_width {sw} ({args.scaling} scaling), {px}x{px} synthetic image, topk 256, n_replace 1",
             "search_width": sw, "prefix_rows": P, "tail_rows": S,
             "parallelism": f"candidate-sharded dp{args.gpus}, replicated model",
             "l2": "no flush needed: every step streams ~23 GB of weights (>> 126 MB L2)"}
@@ -209,7 +213,7 @@ def main():
     vocab = {"7b": 32000, "small128": 4000, "tiny128": 1000}[args.model]
     px = {"7b": 336, "small128": 56, "tiny128": 28}[args.model]
     tok, proc, norm, image_cpu, messages, target, init = syn.headline_case(vocab, px)
-    model = syn.make_llava(args.model, dtype=torch.bfloat16, device=dev, seed=0, head_gain=20.0,
+    model = syn.make_llava(args.model, dtype=torch.bfloat16, device=dev, seed=0, head_gain=HEAD_GAIN[args.model],
                            attn_implementation="sdpa")
     sw = args.search_width * (world if args.scaling == "weak" else 1)
     cfg = BimodalAttackConfig(num_steps=1, search_width=sw, topk=256, n_replace=1, pgd_attack=True,
@@ -261,8 +265,10 @@ def main():
     clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    torch.cuda.nvtx.range_push("bench_timed")        # lets ncu restrict itself to the timed steps
     for _ in range(args.steps):
         win_loss, win_idx = scoring_step()
+    torch.cuda.nvtx.range_pop()
     e1.record()
     barrier()
     clock_info = clocks.stop()
