@@ -1,0 +1,390 @@
+// Shared-prefix + causal-tail attention on tcgen05, persistent and warp-specialised.
+//
+// All search_width candidates share one prefix (image tokens + prompt) whose K/V were computed
+// once; each candidate owns a short tail of S rows. Query rows of all candidates are flattened to
+// [B*S] and tiled 128 rows per work item (one head), so one item covers several candidates:
+//   * prefix keys [0, P): visible to every query row;
+//   * tail keys: row rk is visible to query row rq iff both belong to the same candidate and
+//     rk <= rq (block-diagonal causal mask over the flattened rows).
+// With P = 0 and S = P_len the same kernel computes the prefix itself (plain causal attention).
+//
+//   warp 0      TMA producer: Q tile per item, then (K block, V^T block) pairs into a 2-stage ring
+//   warp 1      MMA issuer:   S_j = Q K_j^T  and  O_j = P_j V_j   (tcgen05.mma, operands in smem,
+//                             accumulators in TMEM: 2 x S[128x128] + 2 x O[128x128] = 512 columns)
+//   warp 2      TMEM allocator
+//   warps 4..7  softmax: one thread per query row reads S_j from TMEM, applies mask + online
+//               softmax, writes P_j (bf16) to smem in the UMMA K-major 128B-swizzled layout, and
+//               accumulates O_j from TMEM into fp32 registers with the usual rescale.
+// Both MMAs are K-major x K-major because the QKV projection writes V transposed ([dim][row]).
+// Key blocks have 128 keys except the last prefix / tail block, which is rounded up to 16 (the
+// UMMA N granularity), so the masked-out work stays small.
+#include <cstdlib>
+
+#include "common.cuh"
+#include "gemm_host.cuh"
+#include "kernels.h"
+
+namespace bma {
+
+constexpr int ATC_BM = 128;        // query rows per work item
+constexpr int ATC_BN = 128;        // keys per block (max)
+constexpr int ATC_HD = 128;        // head dim
+constexpr int ATC_THREADS = 256;
+constexpr int ATC_PANEL = 128 * 128;          // bytes of one [128 rows][64 cols] bf16 panel
+constexpr int ATC_TILE = 2 * ATC_PANEL;       // 128 x 128 bf16
+constexpr int ATC_SMEM = ATC_TILE /*Q*/ + 2 * 2 * ATC_TILE /*K,V^T x 2 stages*/ + 2 * ATC_TILE /*P*/ +
+                         1024 /*align*/ + 256 /*barriers*/;
+
+struct AtcParams {
+  __nv_bfloat16* out; long long ldo;
+  int M, S, P;
+  int n_heads, kv_group;
+  int q_col0, k_col0;        // column of head 0 inside the Q / K tensor maps
+  float scale_log2;
+  int debug;                 // bring-up switches (env BMA_ATC_DEBUG): 1 no QK mma, 2 no PV mma,
+                             // 4 no S tmem loads, 8 no P stores, 16 no O tmem loads
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+struct BlockInfo { int pre; int key0; int nvalid; int n_mma; };
+
+// First tail key row any query row of the tile starting at r0 can see (start of that row's
+// candidate), rounded DOWN to a multiple of 8 rows: the V^T tiles are fetched with the key index
+// as the innermost TMA coordinate, whose byte address has to stay 16-byte aligned (an unaligned
+// coordinate faults with "illegal instruction"). The up-to-7 extra keys are masked like any other
+// key that belongs to an earlier candidate.
+__device__ __forceinline__ int tail_key_start(int r0, int S) { return ((r0 / S) * S) & ~7; }
+
+__device__ __forceinline__ BlockInfo block_info(int j, int n_pre, int P, int kt0, int r1) {
+  BlockInfo b;
+  b.pre = j < n_pre;
+  b.key0 = b.pre ? j * ATC_BN : kt0 + (j - n_pre) * ATC_BN;
+  const int limit = b.pre ? P : r1;
+  b.nvalid = min(ATC_BN, limit - b.key0);
+  b.n_mma = (b.nvalid + 15) & ~15;
+  return b;
+}
+
+__global__ void __launch_bounds__(ATC_THREADS, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kt,
+                    const __grid_constant__ CUtensorMap tm_kp, const __grid_constant__ CUtensorMap tm_vt,
+                    const __grid_constant__ CUtensorMap tm_vp, const AtcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + ATC_TILE;                 // [2 stages][tile]
+  uint8_t* sV = sK + 2 * ATC_TILE;             // [2 stages][tile]  (V^T: [128 dims][keys])
+  uint8_t* sP = sV + 2 * ATC_TILE;             // [2][tile]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * ATC_TILE);
+  uint64_t* q_full = bars;            // [1]
+  uint64_t* q_empty = bars + 1;       // [1]
+  uint64_t* kv_full = bars + 2;       // [2]
+  uint64_t* kv_empty = bars + 4;      // [2]
+  uint64_t* s_full = bars + 6;        // [2]
+  uint64_t* s_empty = bars + 8;       // [2]
+  uint64_t* p_full = bars + 10;       // [2]
+  uint64_t* p_empty = bars + 12;      // [2]
+  uint64_t* o_full = bars + 14;       // [2]
+  uint64_t* o_empty = bars + 16;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (p.M + ATC_BM - 1) / ATC_BM;
+  const int n_items = m_tiles * p.n_heads;
+  const int n_pre = (p.P + ATC_BN - 1) / ATC_BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_kt); tma_prefetch_desc(&tm_kp);
+    tma_prefetch_desc(&tm_vt); tma_prefetch_desc(&tm_vp);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1); mbar_init(q_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
+      mbar_init(&s_full[i], 1);  mbar_init(&s_empty[i], 4);
+      mbar_init(&p_full[i], 4);  mbar_init(&p_empty[i], 1);
+      mbar_init(&o_full[i], 1);  mbar_init(&o_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_s = tmem_base;            // S_0 at +0, S_1 at +128
+  const uint32_t tmem_o = tmem_base + 256;      // O_0 at +256, O_1 at +384
+
+  // Every role walks the same sequence of (item, block); `it` counts blocks globally so that ring
+  // stage = it & 1 and barrier parity = (it >> 1) & 1 stay in step across work items.
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0, item_n = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
+        const int head = item / m_tiles, tile = item - head * m_tiles;
+        const int kvh = head / p.kv_group;
+        const int r0 = tile * ATC_BM, r1 = min(p.M, r0 + ATC_BM);
+        const int kt0 = tail_key_start(r0, p.S);
+        const int nb = n_pre + (r1 - kt0 + ATC_BN - 1) / ATC_BN;
+        mbar_wait(q_empty, (item_n & 1) ^ 1, 0x500);
+        mbar_arrive_expect_tx(q_full, ATC_TILE);
+        tma_load_2d(sQ, &tm_q, q_full, p.q_col0 + head * ATC_HD, r0);
+        tma_load_2d(sQ + ATC_PANEL, &tm_q, q_full, p.q_col0 + head * ATC_HD + 64, r0);
+        for (int j = 0; j < nb; ++j, ++it) {
+          const BlockInfo b = block_info(j, n_pre, p.P, kt0, r1);
+          const int st = it & 1;
+          mbar_wait(&kv_empty[st], ((it >> 1) & 1) ^ 1, 0x510 + st);
+          mbar_arrive_expect_tx(&kv_full[st], 2 * ATC_TILE);
+          const CUtensorMap* mk = b.pre ? &tm_kp : &tm_kt;
+          const CUtensorMap* mv = b.pre ? &tm_vp : &tm_vt;
+          uint8_t* dk = sK + st * ATC_TILE;
+          uint8_t* dv = sV + st * ATC_TILE;
+          tma_load_2d(dk, mk, &kv_full[st], p.k_col0 + kvh * ATC_HD, b.key0);
+          tma_load_2d(dk + ATC_PANEL, mk, &kv_full[st], p.k_col0 + kvh * ATC_HD + 64, b.key0);
+          tma_load_2d(dv, mv, &kv_full[st], b.key0, kvh * ATC_HD);
+          tma_load_2d(dv + ATC_PANEL, mv, &kv_full[st], b.key0 + 64, kvh * ATC_HD);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t it = 0, item_n = 0;
+      // O_i += P_i V_i for the block with global index `g`
+      auto issue_pv = [&](uint32_t g, int n_mma) {
+        const int st = g & 1;
+        const uint32_t par = (g >> 1) & 1;
+        mbar_wait(&p_full[st], par, 0x620 + st);
+        mbar_wait(&o_empty[st], par ^ 1, 0x630 + st);
+        tc_fence_after();
+        const uint32_t idesc = umma_idesc_bf16(ATC_BM, ATC_HD);
+        const uint32_t pa = smem_u32(sP + st * ATC_TILE), vb = smem_u32(sV + st * ATC_TILE);
+        for (int kk = 0; kk < n_mma / 16 && !(p.debug & 2); ++kk) {
+          const uint32_t off = (kk >> 2) * ATC_PANEL + (kk & 3) * 32;
+          umma_bf16_ss(tmem_o + st * 128, umma_desc_k_sw128(pa + off), umma_desc_k_sw128(vb + off), idesc,
+                       kk != 0);
+        }
+        umma_commit(&kv_empty[st]);
+        umma_commit(&p_empty[st]);
+        umma_commit(&o_full[st]);
+      };
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
+        const int head = item / m_tiles, tile = item - head * m_tiles;
+        const int r0 = tile * ATC_BM, r1 = min(p.M, r0 + ATC_BM);
+        const int kt0 = tail_key_start(r0, p.S);
+        const int nb = n_pre + (r1 - kt0 + ATC_BN - 1) / ATC_BN;
+        mbar_wait(q_full, item_n & 1, 0x600);
+        int prev_n = 0;
+        for (int j = 0; j < nb; ++j, ++it) {
+          const BlockInfo b = block_info(j, n_pre, p.P, kt0, r1);
+          const int st = it & 1;
+          const uint32_t par = (it >> 1) & 1;
+          mbar_wait(&kv_full[st], par, 0x640 + st);
+          mbar_wait(&s_empty[st], par ^ 1, 0x650 + st);
+          tc_fence_after();
+          const uint32_t idesc = umma_idesc_bf16(ATC_BM, b.n_mma);
+          const uint32_t qa = smem_u32(sQ), kb = smem_u32(sK + st * ATC_TILE);
+#pragma unroll
+          for (int ks = 0; ks < ATC_HD / 16 && !(p.debug & 1); ++ks) {
+            const uint32_t off = (ks >> 2) * ATC_PANEL + (ks & 3) * 32;
+            umma_bf16_ss(tmem_s + st * 128, umma_desc_k_sw128(qa + off), umma_desc_k_sw128(kb + off), idesc,
+                         ks != 0);
+          }
+          umma_commit(&s_full[st]);
+          if (j == nb - 1) umma_commit(q_empty);        // Q tile no longer needed after this MMA
+          if (j > 0) issue_pv(it - 1, prev_n);
+          prev_n = b.n_mma;
+        }
+        issue_pv(it - 1, prev_n);
+      }
+    }
+  } else if (warp >= 4) {
+    const int sub = warp & 3;
+    const int row_in_tile = sub * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(sub * 32) << 16;
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int head = item / m_tiles, tile = item - head * m_tiles;
+      const int r0 = tile * ATC_BM, r1 = min(p.M, r0 + ATC_BM);
+      const int kt0 = tail_key_start(r0, p.S);
+      const int nb = n_pre + (r1 - kt0 + ATC_BN - 1) / ATC_BN;
+      const int rq = r0 + row_in_tile;
+      const int cs = (rq / p.S) * p.S;
+
+      float o_reg[ATC_HD];
+#pragma unroll
+      for (int i = 0; i < ATC_HD; ++i) o_reg[i] = 0.0f;
+      float m_run = -INFINITY, l_run = 0.0f, corr_prev = 0.0f;
+
+      auto accumulate = [&](uint32_t g, float corr) {
+        const int st = g & 1;
+        mbar_wait(&o_full[st], (g >> 1) & 1, 0x700 + st);
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < ATC_HD; c0 += 32) {
+          uint32_t r[32];
+          if (p.debug & 16) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = 0;
+          } else {
+            tmem_ld_32x32(tmem_o + lane_off + st * 128 + c0, r);
+            tmem_ld_wait();
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o_reg[c0 + i] = fmaf(o_reg[c0 + i], corr, __uint_as_float(r[i]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&o_empty[st]);
+      };
+
+      for (int j = 0; j < nb; ++j, ++it) {
+        const BlockInfo b = block_info(j, n_pre, p.P, kt0, r1);
+        const int st = it & 1;
+        const uint32_t par = (it >> 1) & 1;
+        const uint32_t ts = tmem_s + lane_off + st * 128;
+        const bool need_mask = !b.pre || (b.nvalid < ATC_BN);
+        mbar_wait(&s_full[st], par, 0x710 + st);
+        tc_fence_after();
+        // pass 1: masked row maximum (in units of log2)
+        float bm = -INFINITY;
+        for (int c0 = 0; c0 < b.n_mma; c0 += 32) {
+          uint32_t r[32];
+          if (p.debug & 4) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = 0;
+          } else {
+            tmem_ld_32x32(ts + c0, r);
+            tmem_ld_wait();
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int key = b.key0 + c0 + i;
+            bool vis = true;
+            if (need_mask) vis = b.pre ? (key < p.P) : (key >= cs && key <= rq && key < r1);
+            const float v = vis ? __uint_as_float(r[i]) * p.scale_log2 : -INFINITY;
+            bm = fmaxf(bm, v);
+          }
+        }
+        const float m_new = fmaxf(m_run, bm);
+        const float m_use = (m_new == -INFINITY) ? 0.0f : m_new;
+        const float corr = ex2(m_run - m_use);            // m_run = -inf -> 0
+        // pass 2: P = exp2(s - m) as bf16 into the swizzled K-major P tile; row sum
+        mbar_wait(&p_empty[st], par ^ 1, 0x720 + st);
+        uint8_t* prow = sP + st * ATC_TILE + row_in_tile * 128;
+        float rs = 0.0f;
+        for (int c0 = 0; c0 < b.n_mma; c0 += 32) {
+          uint32_t r[32];
+          if (p.debug & 4) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = 0;
+          } else {
+            tmem_ld_32x32(ts + c0, r);
+            tmem_ld_wait();
+          }
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float pv[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int key = b.key0 + c0 + i + e;
+              bool vis = true;
+              if (need_mask) vis = b.pre ? (key < p.P) : (key >= cs && key <= rq && key < r1);
+              pv[e] = vis ? ex2(fmaf(__uint_as_float(r[i + e]), p.scale_log2, -m_use)) : 0.0f;
+            }
+            rs += pv[0] + pv[1];
+            pk[i >> 1] = pack_bf16x2(pv[0], pv[1]);
+          }
+          uint8_t* panel = prow + (c0 >> 6) * ATC_PANEL;
+          const int q0 = (c0 & 63) >> 3;                  // first 16-byte chunk of this 32-key group
+#pragma unroll
+          for (int q = 0; q < 4 && !(p.debug & 8); ++q) {
+            const int phys = (q0 + q) ^ (row_in_tile & 7);
+            *reinterpret_cast<uint4*>(panel + phys * 16) =
+                make_uint4(pk[q * 4 + 0], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+          }
+        }
+        tc_fence_before();
+        fence_proxy_async_smem();                         // P visible to the tensor-core (async) proxy
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&s_empty[st]);
+          mbar_arrive(&p_full[st]);
+        }
+        l_run = l_run * corr + rs;
+        m_run = m_new;
+        if (j > 0) accumulate(it - 1, corr_prev);         // O_{j-1}, overlapping PV_{j-1} with this softmax
+        corr_prev = corr;
+      }
+      accumulate(it - 1, corr_prev);
+
+      if (rq < p.M) {
+        const float inv = l_run > 0.0f ? 1.0f / l_run : 0.0f;
+        uint4* dst = reinterpret_cast<uint4*>(p.out + (long long)rq * p.ldo + head * ATC_HD);
+#pragma unroll
+        for (int v = 0; v < ATC_HD / 8; ++v) {
+          dst[v] = make_uint4(pack_bf16x2(o_reg[v * 8 + 0] * inv, o_reg[v * 8 + 1] * inv),
+                              pack_bf16x2(o_reg[v * 8 + 2] * inv, o_reg[v * 8 + 3] * inv),
+                              pack_bf16x2(o_reg[v * 8 + 4] * inv, o_reg[v * 8 + 5] * inv),
+                              pack_bf16x2(o_reg[v * 8 + 6] * inv, o_reg[v * 8 + 7] * inv));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+cudaError_t launch_prefix_tail_attention(const AttnParams& a, int n_heads, cudaStream_t stream) {
+  if (a.M <= 0) return cudaSuccess;
+  if (a.S <= 0 || a.P < 0 || a.kv_group <= 0) return cudaErrorInvalidValue;
+  const int kv_heads = n_heads / a.kv_group;
+  CUtensorMap tq, tkt, tkp, tvt, tvp;
+  if (!make_tmap_bf16(&tq, a.q, a.M, (long long)n_heads * ATC_HD, a.ldq, 128)) return cudaErrorInvalidValue;
+  if (!make_tmap_bf16(&tkt, a.k_tail, a.M, (long long)kv_heads * ATC_HD, a.ldk, 128)) return cudaErrorInvalidValue;
+  if (!make_tmap_bf16(&tvt, a.vt_tail, (long long)kv_heads * ATC_HD, a.M, a.ldvt, 128)) return cudaErrorInvalidValue;
+  if (a.P > 0) {
+    if (!make_tmap_bf16(&tkp, a.k_pre, a.P, (long long)kv_heads * ATC_HD, a.ldkp, 128)) return cudaErrorInvalidValue;
+    if (!make_tmap_bf16(&tvp, a.vt_pre, (long long)kv_heads * ATC_HD, a.P, a.ldvtp, 128)) return cudaErrorInvalidValue;
+  } else {
+    tkp = tkt;
+    tvp = tvt;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         ATC_SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  AtcParams p{};
+  p.out = a.out; p.ldo = a.ldo;
+  p.M = a.M; p.S = a.S; p.P = a.P;
+  p.n_heads = n_heads; p.kv_group = a.kv_group;
+  p.q_col0 = 0; p.k_col0 = 0;
+  p.scale_log2 = a.scale_log2;
+  const char* dbg = getenv("BMA_ATC_DEBUG");
+  p.debug = dbg != nullptr ? atoi(dbg) : 0;
+  watchdog_attach();
+  const int m_tiles = (a.M + ATC_BM - 1) / ATC_BM;
+  int grid = m_tiles * n_heads;
+  if (grid > num_sms()) grid = num_sms();
+  attention_tc_kernel<<<grid, ATC_THREADS, ATC_SMEM, stream>>>(tq, tkt, tkp, tvt, tvp, p);
+  return cudaGetLastError();
+}
+
+}  // namespace bma

@@ -10,9 +10,22 @@
 namespace bma {
 
 // ---------------------------------------------------------------- error flag
-// Device-side watchdog: a barrier wait that spins for more than ~2^28 polls records a code
-// here and traps, so a pipeline bug surfaces as a CUDA error instead of a hung GPU.
+// Device-side watchdog: a barrier wait that spins for more than ~2^28 polls records a code in
+// host-mapped memory (readable after the context has died) and traps, so a pipeline bug surfaces
+// as a CUDA error with a location instead of a hung GPU. Each translation unit that waits on
+// mbarriers attaches the shared host word once (watchdog_attach).
 static __device__ unsigned int g_watchdog_code = 0;
+static __device__ volatile unsigned int* g_watchdog_host = nullptr;
+
+inline unsigned int* watchdog_host_word() {
+  static unsigned int* word = nullptr;
+  if (word == nullptr) {
+    if (cudaHostAlloc(reinterpret_cast<void**>(&word), sizeof(unsigned int), cudaHostAllocMapped) != cudaSuccess)
+      return nullptr;
+    *word = 0;
+  }
+  return word;
+}
 
 // ---------------------------------------------------------------- small utils
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -89,6 +102,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 28)) {
       atomicExch(&g_watchdog_code, code);
+      if (g_watchdog_host != nullptr) {
+        *g_watchdog_host = code | (blockIdx.x << 16);
+        __threadfence_system();
+      }
       __trap();
     }
   }

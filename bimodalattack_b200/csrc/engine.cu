@@ -62,10 +62,13 @@ struct bma_scorer {
   const __nv_bfloat16* embed = nullptr;
   long long ld_embed = 0;
   int q_dim = 0, kv_dim = 0, qkv_dim = 0;
+  int qk_dim = 0;                        // row stride of the Q|K buffers (V is stored transposed)
+  long long ld_vt = 0, ld_vtp = 0;       // row strides (in keys) of the transposed V buffers
   int prefix_len = 0;
   // workspace
-  __nv_bfloat16 *x = nullptr, *xn = nullptr, *qkv = nullptr, *attn = nullptr, *act = nullptr;
-  __nv_bfloat16* prefix_qkv = nullptr;   // [layers][max_prefix][qkv_dim]
+  __nv_bfloat16 *x = nullptr, *xn = nullptr, *qk = nullptr, *vt = nullptr, *attn = nullptr, *act = nullptr;
+  __nv_bfloat16* prefix_qk = nullptr;    // [layers][max_prefix][qk_dim]   Q|K rows of the prefix
+  __nv_bfloat16* prefix_vt = nullptr;    // [layers][kv_dim][ld_vtp]       V^T of the prefix
   float2* ce_part = nullptr;
   float* tgt_logit = nullptr;
   long long* ids_dev = nullptr;          // staging for the *_host entry
@@ -116,8 +119,11 @@ int run_layers(bma_scorer* s, int rows, int seq, int pos_base, bool prefill, cud
   const int P = prefill ? 0 : s->prefix_len;
   for (int l = 0; l < D.n_layers; ++l) {
     const bma_layer_weights& W = s->layers[l];
-    __nv_bfloat16* qkv = prefill ? s->prefix_qkv + (size_t)l * D.max_prefix * s->qkv_dim : s->qkv;
-    const __nv_bfloat16* pre = s->prefix_qkv + (size_t)l * D.max_prefix * s->qkv_dim;
+    __nv_bfloat16* pre_qk = s->prefix_qk + (size_t)l * D.max_prefix * s->qk_dim;
+    __nv_bfloat16* pre_vt = s->prefix_vt + (size_t)l * s->kv_dim * s->ld_vtp;
+    __nv_bfloat16* qk = prefill ? pre_qk : s->qk;
+    __nv_bfloat16* vt = prefill ? pre_vt : s->vt;
+    const long long ldvt = prefill ? s->ld_vtp : s->ld_vt;
 
     {
       ProfScope ps(s, PC_NORM, 0, st);
@@ -127,9 +133,10 @@ int run_layers(bma_scorer* s, int rows, int seq, int pos_base, bool prefill, cud
     {
       GemmParams p{};
       p.M = rows; p.N = s->qkv_dim; p.K = d; p.group_m = 16;
-      p.C = qkv; p.ldc = s->qkv_dim;
+      p.C = qk; p.ldc = s->qk_dim;
+      p.Vt = vt; p.ldvt = ldvt;
       p.rope_cos = W.rope_cos; p.rope_sin = W.rope_sin;
-      p.rope_cols = s->q_dim + s->kv_dim;
+      p.rope_cols = s->qk_dim;
       p.rows_per_seq = seq; p.pos_base = pos_base;
       ProfScope ps(s, PC_GEMM_QKV, gemm_flops(p), st);
       BMA_LAUNCH((launch_gemm<256, EPI_ROPE>(s->xn, d, bf(W.w_qkv), d, p, st)), "gemm(qkv+rope)");
@@ -137,11 +144,11 @@ int run_layers(bma_scorer* s, int rows, int seq, int pos_base, bool prefill, cud
     if (prefill && l == D.n_layers - 1) break;   // only this layer's K/V are needed
     {
       AttnParams a{};
-      a.q = qkv; a.ldq = s->qkv_dim;
-      a.k_tail = qkv + s->q_dim; a.ldk = s->qkv_dim;
-      a.v_tail = qkv + s->q_dim + s->kv_dim; a.ldv = s->qkv_dim;
-      a.k_pre = pre + s->q_dim; a.ldkp = s->qkv_dim;
-      a.v_pre = pre + s->q_dim + s->kv_dim; a.ldvp = s->qkv_dim;
+      a.q = qk; a.ldq = s->qk_dim;
+      a.k_tail = qk + s->q_dim; a.ldk = s->qk_dim;
+      a.vt_tail = vt; a.ldvt = ldvt;
+      a.k_pre = pre_qk + s->q_dim; a.ldkp = s->qk_dim;
+      a.vt_pre = pre_vt; a.ldvtp = s->ld_vtp;
       a.out = s->attn; a.ldo = s->q_dim;
       a.M = rows; a.S = seq; a.P = P;
       a.kv_group = D.n_heads / D.n_kv_heads;
@@ -191,10 +198,9 @@ const char* bma_last_error(void) { return g_last_error.c_str(); }
 unsigned long long bma_launch_count(void) { return g_launches; }
 
 int bma_watchdog_code(unsigned int* code_out) {
-  unsigned int v = 0;
-  cudaError_t e = cudaMemcpyFromSymbol(&v, g_watchdog_code, sizeof(v));
-  if (e != cudaSuccess) return fail(e, "watchdog read");
-  if (code_out) *code_out = v;
+  // host-mapped word: stays readable after a device trap has killed the context
+  unsigned int* w = watchdog_host_word();
+  if (code_out) *code_out = (w != nullptr) ? *w : 0u;
   return 0;
 }
 
@@ -263,18 +269,23 @@ bma_scorer* bma_scorer_create(const bma_model_desc* desc) {
   s->q_dim = D.n_heads * D.head_dim;
   s->kv_dim = D.n_kv_heads * D.head_dim;
   s->qkv_dim = s->q_dim + 2 * s->kv_dim;
+  s->qk_dim = s->q_dim + s->kv_dim;
   const size_t R = static_cast<size_t>(D.max_rows > D.max_prefix ? D.max_rows : D.max_prefix);
   s->ce_rows_cap = D.max_rows;   // at most one target row per tail row
   const int n_ce_tiles = (D.vocab + kCeBlockN - 1) / kCeBlockN;
   bool ok = true;
   ok = ok && dev_alloc(&s->x, R * D.d_model, &s->ws_bytes);
   ok = ok && dev_alloc(&s->xn, R * D.d_model, &s->ws_bytes);
-  ok = ok && dev_alloc(&s->qkv, R * s->qkv_dim, &s->ws_bytes);
+  s->ld_vt = static_cast<long long>((R + 7) / 8 * 8);
+  s->ld_vtp = static_cast<long long>(((D.max_prefix > 0 ? D.max_prefix : 1) + 7) / 8 * 8);
+  ok = ok && dev_alloc(&s->qk, R * s->qk_dim, &s->ws_bytes);
+  ok = ok && dev_alloc(&s->vt, static_cast<size_t>(s->kv_dim) * s->ld_vt, &s->ws_bytes);
   ok = ok && dev_alloc(&s->attn, R * s->q_dim, &s->ws_bytes);
   ok = ok && dev_alloc(&s->act, R * D.d_ff, &s->ws_bytes);
-  ok = ok && dev_alloc(&s->prefix_qkv,
-                       static_cast<size_t>(D.n_layers) * (D.max_prefix > 0 ? D.max_prefix : 1) * s->qkv_dim,
+  ok = ok && dev_alloc(&s->prefix_qk,
+                       static_cast<size_t>(D.n_layers) * (D.max_prefix > 0 ? D.max_prefix : 1) * s->qk_dim,
                        &s->ws_bytes);
+  ok = ok && dev_alloc(&s->prefix_vt, static_cast<size_t>(D.n_layers) * s->kv_dim * s->ld_vtp, &s->ws_bytes);
   ok = ok && dev_alloc(&s->ce_part, static_cast<size_t>(n_ce_tiles) * s->ce_rows_cap, &s->ws_bytes);
   ok = ok && dev_alloc(&s->tgt_logit, static_cast<size_t>(s->ce_rows_cap), &s->ws_bytes);
   ok = ok && dev_alloc(&s->ids_dev, static_cast<size_t>(D.max_rows), &s->ws_bytes);
@@ -291,8 +302,8 @@ bma_scorer* bma_scorer_create(const bma_model_desc* desc) {
 
 void bma_scorer_destroy(bma_scorer* s) {
   if (s == nullptr) return;
-  cudaFree(s->x); cudaFree(s->xn); cudaFree(s->qkv); cudaFree(s->attn); cudaFree(s->act);
-  cudaFree(s->prefix_qkv); cudaFree(s->ce_part); cudaFree(s->tgt_logit);
+  cudaFree(s->x); cudaFree(s->xn); cudaFree(s->qk); cudaFree(s->vt); cudaFree(s->attn); cudaFree(s->act);
+  cudaFree(s->prefix_qk); cudaFree(s->prefix_vt); cudaFree(s->ce_part); cudaFree(s->tgt_logit);
   cudaFree(s->ids_dev); cudaFree(s->loss_dev); cudaFree(s->key_dev); cudaFree(s->flag_dev);
   for (cudaEvent_t e : s->ev_start) cudaEventDestroy(e);
   for (cudaEvent_t e : s->ev_stop) cudaEventDestroy(e);
@@ -367,12 +378,14 @@ int bma_scorer_reset_key(bma_scorer* s, unsigned long long* key, int* all_match,
 }
 
 int bma_scorer_score(bma_scorer* s, const long long* ids, int ids_stride, int B, const int* slot,
-                     const void* fixed, int S, const long long* target_ids, int T, float* loss,
-                     unsigned long long* key, int* all_match, unsigned int idx_base, void* stream) {
+                     const void* fixed, int S, const long long* target_ids, int T, int ce_row0,
+                     float* loss, unsigned long long* key, int* all_match, unsigned int idx_base,
+                     void* stream) {
   if (s == nullptr) return fail(cudaErrorInvalidValue, "score: null scorer");
   const bma_model_desc& D = s->desc;
   if (B <= 0) return 0;
-  if (S <= 0 || T <= 0 || T + 1 > S) return fail(cudaErrorInvalidValue, "score: need 0 < T < S");
+  if (S <= 0 || T <= 0 || ce_row0 < 0 || ce_row0 + T > S)
+    return fail(cudaErrorInvalidValue, "score: target rows [ce_row0, ce_row0+T) must lie inside the tail");
   if (S > D.max_rows) return fail(cudaErrorInvalidValue, "score: S exceeds max_rows");
   if (s->lm_head == nullptr || s->norm_final == nullptr || s->embed == nullptr)
     return fail(cudaErrorInvalidValue, "score: head weights not set");
@@ -396,7 +409,7 @@ int bma_scorer_score(bma_scorer* s, const long long* ids, int ids_stride, int B,
     {
       ProfScope ps(s, PC_NORM, 0, st);
       BMA_LAUNCH(launch_rmsnorm(s->x, d, s->norm_final, s->xn, d, ce_rows, d, D.rms_eps, D.norm_mode,
-                                T, S, S - T - 1, st), "rmsnorm(final, gathered)");
+                                T, S, ce_row0, st), "rmsnorm(final, gathered)");
     }
     {
       GemmParams p{};
@@ -418,7 +431,7 @@ int bma_scorer_score(bma_scorer* s, const long long* ids, int ids_stride, int B,
 
 int bma_scorer_score_host(bma_scorer* s, const long long* ids_host, int ids_stride, int B,
                           const int* slot, const void* fixed, int S, const long long* target_ids,
-                          int T, float* loss_host, unsigned long long* key_host,
+                          int T, int ce_row0, float* loss_host, unsigned long long* key_host,
                           unsigned int idx_base, void* stream) {
   if (s == nullptr) return fail(cudaErrorInvalidValue, "score_host: null scorer");
   if ((long long)B * ids_stride > s->desc.max_rows)
@@ -428,8 +441,8 @@ int bma_scorer_score_host(bma_scorer* s, const long long* ids_host, int ids_stri
                             cudaMemcpyHostToDevice, st), "score_host: H2D ids");
   int rc = bma_scorer_reset_key(s, s->key_dev, s->flag_dev, stream);
   if (rc != 0) return rc;
-  rc = bma_scorer_score(s, s->ids_dev, ids_stride, B, slot, fixed, S, target_ids, T, s->loss_dev,
-                        s->key_dev, s->flag_dev, idx_base, stream);
+  rc = bma_scorer_score(s, s->ids_dev, ids_stride, B, slot, fixed, S, target_ids, T, ce_row0,
+                        s->loss_dev, s->key_dev, s->flag_dev, idx_base, stream);
   if (rc != 0) return rc;
   BMA_CHECK(cudaMemcpyAsync(loss_host, s->loss_dev, sizeof(float) * B, cudaMemcpyDeviceToHost, st),
             "score_host: D2H loss");
@@ -463,15 +476,15 @@ int bma_rmsnorm(const void* x, long long ldx, const void* w, void* y, long long 
 }
 
 int bma_attention(const void* q, long long ldq, const void* k_tail, long long ldk,
-                  const void* v_tail, long long ldv, const void* k_pre, long long ldkp,
-                  const void* v_pre, long long ldvp, void* out, long long ldo, int M, int S, int P,
+                  const void* vt_tail, long long ldvt, const void* k_pre, long long ldkp,
+                  const void* vt_pre, long long ldvtp, void* out, long long ldo, int M, int S, int P,
                   int n_heads, int kv_group, float scale, void* stream) {
   AttnParams a{};
   a.q = bf(q); a.ldq = ldq;
   a.k_tail = bf(k_tail); a.ldk = ldk;
-  a.v_tail = bf(v_tail); a.ldv = ldv;
+  a.vt_tail = bf(vt_tail); a.ldvt = ldvt;
   a.k_pre = bf(k_pre); a.ldkp = ldkp;
-  a.v_pre = bf(v_pre); a.ldvp = ldvp;
+  a.vt_pre = bf(vt_pre); a.ldvtp = ldvtp;
   a.out = bf(out); a.ldo = ldo;
   a.M = M; a.S = S; a.P = P; a.kv_group = kv_group;
   a.scale_log2 = scale * 1.4426950408889634f;

@@ -23,6 +23,17 @@ inline int num_sms() {
   return g_num_sms;
 }
 
+// Points this translation unit's device-side watchdog at the process-wide host-mapped word.
+static inline void watchdog_attach() {
+  static bool done = false;
+  if (done) return;
+  unsigned int* host = watchdog_host_word();
+  unsigned int* dev = nullptr;
+  if (host != nullptr && cudaHostGetDevicePointer(reinterpret_cast<void**>(&dev), host, 0) == cudaSuccess)
+    cudaMemcpyToSymbol(g_watchdog_host, &dev, sizeof(dev));
+  done = true;
+}
+
 inline PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   if (fn == nullptr) {
@@ -103,6 +114,7 @@ inline cudaError_t launch_gemm(const __nv_bfloat16* A, long long lda, const __nv
                                int max_ctas = 0) {
   using Cfg = GemmCfg<BN>;
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) return cudaSuccess;
+  watchdog_attach();
   CUtensorMap ta, tb;
   if (!make_tmap_bf16(&ta, A, p.M, p.K, lda, GEMM_BM)) return cudaErrorInvalidValue;
   if (!make_tmap_bf16(&tb, B, p.N, p.K, ldb, BN)) return cudaErrorInvalidValue;

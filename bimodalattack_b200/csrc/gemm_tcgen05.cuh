@@ -35,6 +35,8 @@ struct GemmParams {
   int rope_cols;              // leading output columns that are Q/K heads (multiple of 128)
   int rows_per_seq;           // position of row r is pos_base + (r % rows_per_seq)
   int pos_base;
+  __nv_bfloat16* Vt;          // EPI_ROPE: columns >= rope_cols (the V heads) go here TRANSPOSED,
+  long long ldvt;             //   Vt[(col - rope_cols) * ldvt + row], for the K-major PV operand
   // GLU
   int act;                    // 0 = SiLU, 1 = GELU(tanh)
   // cross-entropy (EPI_CE)
@@ -284,12 +286,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
               tmem_ld_32x32(t_row + hb + c0, r);
               tmem_ld_wait();
               if (row_ok) {
-                uint32_t o[16];
+                // V head: transposed store; the 32 lanes of a warp hold 32 consecutive rows, so each
+                // store instruction writes one 64-byte segment of a Vt row
+                __nv_bfloat16* dst = p.Vt + (long long)(col_h + c0 - p.rope_cols) * p.ldvt + row;
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                  o[j] = pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
-                store_bf16x32(p.C + (long long)row * p.ldc + col_h + c0, o,
-                              min(32, p.N - (col_h + c0)));
+                for (int j = 0; j < 32; ++j) {
+                  if (col_h + c0 + j < p.N) dst[(long long)j * p.ldvt] = __float2bfloat16_rn(__uint_as_float(r[j]));
+                }
               }
             }
           }

@@ -10,9 +10,9 @@ namespace bma {
 struct AttnParams {
   const __nv_bfloat16* q;       long long ldq;     // [M, ...] query rows (head h at column h*HD)
   const __nv_bfloat16* k_tail;  long long ldk;     // [M, ...] tail keys   (kv head g at g*HD)
-  const __nv_bfloat16* v_tail;  long long ldv;
+  const __nv_bfloat16* vt_tail; long long ldvt;    // [Hkv*HD, M] tail values, TRANSPOSED (row = dim)
   const __nv_bfloat16* k_pre;   long long ldkp;    // [P, ...] prefix keys
-  const __nv_bfloat16* v_pre;   long long ldvp;
+  const __nv_bfloat16* vt_pre;  long long ldvtp;   // [Hkv*HD, P] prefix values, transposed
   __nv_bfloat16* out;           long long ldo;     // [M, H*HD]
   int M, S, P;
   int kv_group;                 // query heads per kv head

@@ -205,8 +205,8 @@ class ScoringEngine:
         and ``self.flag`` the early-stop indicator."""
         native.require_cuda(ids, "ids")
         B = ids.shape[0]
-        S = plan.n_tail
         T = target_ids.numel()
+        S, row0 = self._tail_rows(plan, T)
         if self.prefix_len + S > self._max_positions:
             raise RuntimeError("bimodal_b200 scorer: sequence longer than the rotary table")
         self._ensure(max(self._cap_rows, min(B, 4096) * S), self._cap_prefix)
@@ -220,19 +220,29 @@ class ScoringEngine:
         with torch.cuda.device(self.device):
             native.check(self.lib.bma_scorer_score(
                 self._scorer, ids.data_ptr(), ids.stride(0), B, plan.slot.data_ptr(), plan.fixed.data_ptr(),
-                S, tgt.data_ptr(), T, loss.data_ptr(), self.key.data_ptr(), self.flag.data_ptr(),
+                S, tgt.data_ptr(), T, row0, loss.data_ptr(), self.key.data_ptr(), self.flag.data_ptr(),
                 idx_base, native.stream_ptr(self.device)), "scorer_score")
         return loss
+
+    @staticmethod
+    def _tail_rows(plan: TailPlan, T: int):
+        """(rows to compute, first CE row). The tail ends with the T target tokens; the last one's
+        row predicts nothing that is scored and is attended to by no other row, so it is dropped."""
+        if plan.n_tail < T + 1:
+            raise RuntimeError("bimodal_b200 scorer: the tail must hold the target plus one preceding token")
+        S = plan.n_tail - 1
+        return S, S - T
 
     def score_host(self, ids_host: torch.Tensor, plan: TailPlan, target_ids: torch.Tensor,
                    loss_host: torch.Tensor, key_host: torch.Tensor, idx_base: int = 0):
         """End-to-end entry: pinned host ids in, pinned host losses + key out (synchronises)."""
-        B, S, T = ids_host.shape[0], plan.n_tail, target_ids.numel()
+        B, T = ids_host.shape[0], target_ids.numel()
+        S, row0 = self._tail_rows(plan, T)
         self._ensure(max(self._cap_rows, min(B, 4096) * S, B * ids_host.shape[1]), self._cap_prefix)
         if self._prefix_stale:
             self.prefill(self._last_prefix)
         with torch.cuda.device(self.device):
             native.check(self.lib.bma_scorer_score_host(
                 self._scorer, ids_host.data_ptr(), ids_host.stride(0), B, plan.slot.data_ptr(),
-                plan.fixed.data_ptr(), S, target_ids.data_ptr(), T, loss_host.data_ptr(), key_host.data_ptr(),
-                idx_base, native.stream_ptr(self.device)), "scorer_score_host")
+                plan.fixed.data_ptr(), S, target_ids.data_ptr(), T, row0, loss_host.data_ptr(),
+                key_host.data_ptr(), idx_base, native.stream_ptr(self.device)), "scorer_score_host")

@@ -98,20 +98,24 @@ int bma_scorer_prefill(bma_scorer* s, const void* prefix_embeds, int P, void* st
 
 /* Score B candidates. ids is [B, ids_stride] int64; tail position s takes the embedding of
  * ids[b, slot[s]] when slot[s] >= 0, else row s of fixed ([S, d] bf16). The loss of candidate b is
- * the mean CE of target_ids[0..T) read at tail rows S-T-1 .. S-2 (:1289-1298). Outputs: loss[B]
+ * the mean CE of target_ids[0..T) against the logits of tail rows ce_row0 .. ce_row0+T-1 (the
+ * reference's `logits[..., L-T-1:-1, :]`, :1289-1298). The row of the LAST target token predicts
+ * nothing that is scored and no other row attends to it, so callers pass S = (tail length - 1)
+ * and ce_row0 = S - T. Outputs: loss[B]
  * fp32; *key = min over candidates of (orderable(loss) << 31 | idx_base + b) merged into the
  * existing value (call bma_scorer_reset_key first); *all_match != 0 if some candidate's argmax
  * equals the target everywhere (early_stop, :1300-1306). */
 int bma_scorer_reset_key(bma_scorer* s, unsigned long long* key, int* all_match, void* stream);
 int bma_scorer_score(bma_scorer* s, const long long* ids, int ids_stride, int B, const int* slot,
-                     const void* fixed, int S, const long long* target_ids, int T, float* loss,
-                     unsigned long long* key, int* all_match, unsigned int idx_base, void* stream);
+                     const void* fixed, int S, const long long* target_ids, int T, int ce_row0,
+                     float* loss, unsigned long long* key, int* all_match, unsigned int idx_base,
+                     void* stream);
 
 /* Same call with HOST buffers for ids / loss / key (pinned recommended): copies in, scores,
  * copies out and synchronises the stream. This is the end-to-end entry the benchmark times. */
 int bma_scorer_score_host(bma_scorer* s, const long long* ids_host, int ids_stride, int B,
                           const int* slot, const void* fixed, int S, const long long* target_ids,
-                          int T, float* loss_host, unsigned long long* key_host,
+                          int T, int ce_row0, float* loss_host, unsigned long long* key_host,
                           unsigned int idx_base, void* stream);
 
 /* Optional per-class CUDA-event profile of the scoring pass (events on the launching stream).
@@ -131,9 +135,11 @@ int bma_gemm_bf16(const void* A, long long lda, const void* B, long long ldb, vo
                   int block_n, void* stream);
 int bma_rmsnorm(const void* x, long long ldx, const void* w, void* y, long long ldy, int rows,
                 int d, float eps, int mode, void* stream);
+/* Shared-prefix + causal-tail attention. q/k_* are row-major [rows, heads*128]; the value
+ * operands are TRANSPOSED: vt_tail is [kv_heads*128, M] (row stride ldvt), vt_pre [kv_heads*128, P]. */
 int bma_attention(const void* q, long long ldq, const void* k_tail, long long ldk,
-                  const void* v_tail, long long ldv, const void* k_pre, long long ldkp,
-                  const void* v_pre, long long ldvp, void* out, long long ldo, int M, int S, int P,
+                  const void* vt_tail, long long ldvt, const void* k_pre, long long ldkp,
+                  const void* vt_pre, long long ldvtp, void* out, long long ldo, int M, int S, int P,
                   int n_heads, int kv_group, float scale, void* stream);
 
 #ifdef __cplusplus

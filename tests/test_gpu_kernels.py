@@ -218,23 +218,39 @@ def _attn_reference(q, kt, vt, kp, vp, S, scale):
     return out
 
 
-@pytest.mark.parametrize("B,S,P,H", [(7, 42, 596, 4), (3, 42, 0, 2), (1, 596, 0, 2), (5, 130, 70, 2), (64, 42, 24, 2)])
-def test_prefix_tail_attention(lib, cuda_device, B, S, P, H):
+@pytest.mark.parametrize("B,S,P,H,G", [(7, 42, 596, 4, 1), (3, 42, 0, 2, 1), (1, 596, 0, 2, 1), (5, 130, 70, 2, 1),
+                                       (64, 42, 24, 2, 1), (512, 41, 596, 1, 1), (6, 41, 300, 4, 2), (2, 300, 17, 2, 1)])
+def test_prefix_tail_attention(lib, cuda_device, B, S, P, H, G):
+    """H query heads, H // G kv heads (G = GQA group). Values are handed over transposed
+    ([kv_heads*128, rows]) the way the fused QKV epilogue writes them."""
     from bimodalattack_b200 import native
     D = 128
+    Hkv = H // G
     g = torch.Generator(device="cpu").manual_seed(B * S + P)
     M = B * S
-    qkv = torch.randn((M, 3, H, D), generator=g).to(cuda_device).to(torch.bfloat16)
-    pre = torch.randn((max(P, 1), 2, H, D), generator=g).to(cuda_device).to(torch.bfloat16)
+    q = torch.randn((M, H, D), generator=g).to(cuda_device).to(torch.bfloat16)
+    kt = torch.randn((M, Hkv, D), generator=g).to(cuda_device).to(torch.bfloat16)
+    vt = torch.randn((M, Hkv, D), generator=g).to(cuda_device).to(torch.bfloat16)
+    kp = torch.randn((max(P, 1), Hkv, D), generator=g).to(cuda_device).to(torch.bfloat16)[:P]
+    vp = torch.randn((max(P, 1), Hkv, D), generator=g).to(cuda_device).to(torch.bfloat16)[:P]
+    ld_t = (M + 7) // 8 * 8 + 8
+    ld_p = (max(P, 1) + 7) // 8 * 8
+    vt_T = torch.full((Hkv * D, ld_t), float("nan"), dtype=torch.bfloat16, device=cuda_device)   # padding must not leak
+    vt_T[:, :M] = vt.reshape(M, Hkv * D).T
+    vp_T = torch.zeros((Hkv * D, ld_p), dtype=torch.bfloat16, device=cuda_device)
+    vp_T[:, :P] = vp.reshape(P, Hkv * D).T
+    kp_buf = torch.zeros((max(P, 1), Hkv * D), dtype=torch.bfloat16, device=cuda_device)
+    kp_buf[:P] = kp.reshape(P, Hkv * D)
     out = torch.zeros((M, H * D), dtype=torch.bfloat16, device=cuda_device)
-    q, kt, vt = qkv[:, 0], qkv[:, 1], qkv[:, 2]
-    kp, vp = pre[:P, 0], pre[:P, 1]
     scale = D ** -0.5
-    ld = qkv.stride(0)
-    native.check(lib.bma_attention(q.data_ptr(), ld, kt.data_ptr(), ld, vt.data_ptr(), ld,
-                                   pre[:, 0].data_ptr(), pre.stride(0), pre[:, 1].data_ptr(), pre.stride(0),
-                                   out.data_ptr(), out.stride(0), M, S, P, H, 1, scale, _stream()), "attention")
+    q2, k2 = q.reshape(M, H * D), kt.reshape(M, Hkv * D)
+    native.check(lib.bma_attention(q2.data_ptr(), q2.stride(0), k2.data_ptr(), k2.stride(0),
+                                   vt_T.data_ptr(), vt_T.stride(0), kp_buf.data_ptr(), kp_buf.stride(0),
+                                   vp_T.data_ptr(), vp_T.stride(0), out.data_ptr(), out.stride(0),
+                                   M, S, P, H, G, scale, _stream()), "attention")
     torch.cuda.synchronize()
-    want = _attn_reference(q, kt, vt, kp, vp, S, scale).reshape(M, H * D)
+    rep = lambda t: t.repeat_interleave(G, dim=1)
+    want = _attn_reference(q, rep(kt), rep(vt), rep(kp), rep(vp), S, scale).reshape(M, H * D)
+    assert not bool(torch.isnan(out.float()).any())
     # bf16 P and bf16 output: 2^-7 relative to the output scale (|out| <~ 1 for unit-variance V)
     assert (out.float() - want).abs().max().item() <= 2.5e-2
