@@ -9,12 +9,15 @@
 // With P = 0 and S = P_len the same kernel computes the prefix itself (plain causal attention).
 //
 //   warp 0      TMA producer: Q tile per item, then (K block, V^T block) pairs into a 2-stage ring
-//   warp 1      MMA issuer:   S_j = Q K_j^T  and  O_j = P_j V_j   (tcgen05.mma, operands in smem,
-//                             accumulators in TMEM: 2 x S[128x128] + 2 x O[128x128] = 512 columns)
+//   warp 1      MMA issuer:   S_j = Q K_j^T  and  O += P_j V_j   (tcgen05.mma, operands in smem,
+//                             accumulators in TMEM: 2 x S[128x128] + O[128x128])
 //   warp 2      TMEM allocator
-//   warps 4..7  softmax: one thread per query row reads S_j from TMEM, applies mask + online
-//               softmax, writes P_j (bf16) to smem in the UMMA K-major 128B-swizzled layout, and
-//               accumulates O_j from TMEM into fp32 registers with the usual rescale.
+//   warps 4..7  softmax: one thread per query row pulls its S_j row from TMEM into registers in
+//               one pass, applies mask + online softmax and writes P_j (bf16) to smem in the UMMA
+//               K-major 128B-swizzled layout. O stays in TMEM across all key blocks; the running
+//               maximum is only raised when a block exceeds it by more than 2^8 (so P <= 256), and
+//               only then is the O row rescaled in TMEM (tcgen05.ld / .st) -- rare after the first
+//               block. O is read once per work item, normalised and stored.
 // Both MMAs are K-major x K-major because the QKV projection writes V transposed ([dim][row]).
 // Key blocks have 128 keys except the last prefix / tail block, which is rounded up to 16 (the
 // UMMA N granularity), so the masked-out work stays small.
@@ -42,7 +45,7 @@ struct AtcParams {
   int q_col0, k_col0;        // column of head 0 inside the Q / K tensor maps
   float scale_log2;
   int debug;                 // bring-up switches (env BMA_ATC_DEBUG): 1 no QK mma, 2 no PV mma,
-                             // 4 no S tmem loads, 8 no P stores, 16 no O tmem loads
+                             // 4 no S tmem loads, 8 no P stores, 16 no final O tmem loads
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -90,9 +93,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   uint64_t* s_empty = bars + 8;       // [2]
   uint64_t* p_full = bars + 10;       // [2]
   uint64_t* p_empty = bars + 12;      // [2]
-  uint64_t* o_full = bars + 14;       // [2]
-  uint64_t* o_empty = bars + 16;      // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* o_empty = bars + 14;      // [1]  softmax has read the finished O of the item
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (p.M + ATC_BM - 1) / ATC_BM;
@@ -104,12 +106,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     tma_prefetch_desc(&tm_vt); tma_prefetch_desc(&tm_vp);
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(q_full, 1); mbar_init(q_empty, 1);
+    mbar_init(q_full, 1); mbar_init(q_empty, 1); mbar_init(o_empty, 4);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
       mbar_init(&s_full[i], 1);  mbar_init(&s_empty[i], 4);
       mbar_init(&p_full[i], 4);  mbar_init(&p_empty[i], 1);
-      mbar_init(&o_full[i], 1);  mbar_init(&o_empty[i], 4);
     }
     fence_barrier_init();
   }
@@ -122,7 +123,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_s = tmem_base;            // S_0 at +0, S_1 at +128
-  const uint32_t tmem_o = tmem_base + 256;      // O_0 at +256, O_1 at +384
+  const uint32_t tmem_o = tmem_base + 256;      // O at +256 .. +383
 
   // Every role walks the same sequence of (item, block); `it` counts blocks globally so that ring
   // stage = it & 1 and barrier parity = (it >> 1) & 1 stay in step across work items.
@@ -158,23 +159,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   } else if (warp == 1) {
     if (lane == 0) {
       uint32_t it = 0, item_n = 0;
-      // O_i += P_i V_i for the block with global index `g`
-      auto issue_pv = [&](uint32_t g, int n_mma) {
+      // O (+)= P_g V_g for the block with global index `g`; the first block of an item overwrites O
+      auto issue_pv = [&](uint32_t g, int n_mma, bool first, uint32_t item_par) {
         const int st = g & 1;
-        const uint32_t par = (g >> 1) & 1;
-        mbar_wait(&p_full[st], par, 0x620 + st);
-        mbar_wait(&o_empty[st], par ^ 1, 0x630 + st);
+        mbar_wait(&p_full[st], (g >> 1) & 1, 0x620 + st);
+        if (first) mbar_wait(o_empty, item_par ^ 1, 0x630);     // previous item's O has been read out
         tc_fence_after();
         const uint32_t idesc = umma_idesc_bf16(ATC_BM, ATC_HD);
         const uint32_t pa = smem_u32(sP + st * ATC_TILE), vb = smem_u32(sV + st * ATC_TILE);
         for (int kk = 0; kk < n_mma / 16 && !(p.debug & 2); ++kk) {
           const uint32_t off = (kk >> 2) * ATC_PANEL + (kk & 3) * 32;
-          umma_bf16_ss(tmem_o + st * 128, umma_desc_k_sw128(pa + off), umma_desc_k_sw128(vb + off), idesc,
-                       kk != 0);
+          umma_bf16_ss(tmem_o, umma_desc_k_sw128(pa + off), umma_desc_k_sw128(vb + off), idesc,
+                       !(first && kk == 0));
         }
         umma_commit(&kv_empty[st]);
         umma_commit(&p_empty[st]);
-        umma_commit(&o_full[st]);
       };
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
         const int head = item / m_tiles, tile = item - head * m_tiles;
@@ -200,34 +199,127 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           }
           umma_commit(&s_full[st]);
           if (j == nb - 1) umma_commit(q_empty);        // Q tile no longer needed after this MMA
-          if (j > 0) issue_pv(it - 1, prev_n);
+          if (j > 0) issue_pv(it - 1, prev_n, j == 1, item_n & 1);
           prev_n = b.n_mma;
         }
-        issue_pv(it - 1, prev_n);
+        issue_pv(it - 1, prev_n, nb == 1, item_n & 1);
       }
     }
   } else if (warp >= 4) {
     const int sub = warp & 3;
     const int row_in_tile = sub * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(sub * 32) << 16;
-    uint32_t it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const uint32_t to = tmem_o + lane_off;
+    constexpr float kRaise = 8.0f;         // raise the reference max only beyond 2^8: P stays <= 256
+    uint32_t it = 0, item_n = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
       const int head = item / m_tiles, tile = item - head * m_tiles;
       const int r0 = tile * ATC_BM, r1 = min(p.M, r0 + ATC_BM);
       const int kt0 = tail_key_start(r0, p.S);
       const int nb = n_pre + (r1 - kt0 + ATC_BN - 1) / ATC_BN;
       const int rq = r0 + row_in_tile;
       const int cs = (rq / p.S) * p.S;
+      float m_ref = -INFINITY, l_run = 0.0f;
 
-      float o_reg[ATC_HD];
-#pragma unroll
-      for (int i = 0; i < ATC_HD; ++i) o_reg[i] = 0.0f;
-      float m_run = -INFINITY, l_run = 0.0f, corr_prev = 0.0f;
-
-      auto accumulate = [&](uint32_t g, float corr) {
-        const int st = g & 1;
-        mbar_wait(&o_full[st], (g >> 1) & 1, 0x700 + st);
+      for (int j = 0; j < nb; ++j, ++it) {
+        const BlockInfo b = block_info(j, n_pre, p.P, kt0, r1);
+        const int st = it & 1;
+        const uint32_t par = (it >> 1) & 1;
+        const uint32_t ts = tmem_s + lane_off + st * 128;
+        mbar_wait(&s_full[st], par, 0x710 + st);
         tc_fence_after();
+        // ---- the whole S row into registers (columns >= n_mma were not computed: forced to -inf)
+        float sv[ATC_BN];
+#pragma unroll
+        for (int c0 = 0; c0 < ATC_BN; c0 += 32) {
+          uint32_t r[32];
+          if (c0 < b.n_mma && !(p.debug & 4)) {
+            tmem_ld_32x32(ts + c0, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sv[c0 + i] = __uint_as_float(r[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sv[c0 + i] = -INFINITY;
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[st]);          // S_j is in registers: the buffer is free
+        if (!b.pre || b.nvalid < ATC_BN) {                 // masked blocks: last prefix block and the tail
+#pragma unroll
+          for (int i = 0; i < ATC_BN; ++i) {
+            const int key = b.key0 + i;
+            const bool vis = b.pre ? (key < p.P) : (key >= cs && key <= rq && key < r1);
+            if (!vis) sv[i] = -INFINITY;
+          }
+        }
+        float raw = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < ATC_BN; ++i) raw = fmaxf(raw, sv[i]);
+        const float bm = raw * p.scale_log2;               // scale > 0; -inf stays -inf
+        const bool raise = bm > m_ref + kRaise;            // also true for the first finite block
+        const float m_new = raise ? bm : m_ref;
+        const float m_use = (m_new == -INFINITY) ? 0.0f : m_new;
+        const float factor = raise ? ex2(m_ref - m_use) : 1.0f;     // m_ref = -inf -> 0
+        // ---- rare: rescale this row of O in TMEM (all 32 lanes take part; others scale by 1)
+        const bool fix = raise && (m_ref != -INFINITY) && (j > 0);
+        if (__any_sync(0xffffffffu, fix)) {
+          const uint32_t g = it - 1;                       // PV_{j-1} must have retired
+          mbar_wait(&p_empty[g & 1], (g >> 1) & 1, 0x730);
+          tc_fence_after();
+          const float f = fix ? factor : 1.0f;
+#pragma unroll
+          for (int c0 = 0; c0 < ATC_HD; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32(to + c0, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
+            tmem_st_32x32(to + c0, r);
+          }
+          tmem_st_wait();
+          tc_fence_before();
+        }
+        // ---- P = exp2(s - m) as bf16 into the swizzled K-major P tile; row sum
+        mbar_wait(&p_empty[st], par ^ 1, 0x720 + st);
+        uint8_t* prow = sP + st * ATC_TILE + row_in_tile * 128;
+        float rs = 0.0f;
+#pragma unroll
+        for (int c0 = 0; c0 < ATC_BN; c0 += 32) {
+          if (c0 < b.n_mma) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float p0 = ex2(fmaf(sv[c0 + i], p.scale_log2, -m_use));       // -inf -> 0
+              const float p1 = ex2(fmaf(sv[c0 + i + 1], p.scale_log2, -m_use));
+              rs += p0 + p1;
+              pk[i >> 1] = pack_bf16x2(p0, p1);
+            }
+            uint8_t* panel = prow + (c0 >> 6) * ATC_PANEL;
+            const int q0 = (c0 & 63) >> 3;                // first 16-byte chunk of this 32-key group
+#pragma unroll
+            for (int q = 0; q < 4 && !(p.debug & 8); ++q) {
+              const int phys = (q0 + q) ^ (row_in_tile & 7);
+              *reinterpret_cast<uint4*>(panel + phys * 16) =
+                  make_uint4(pk[q * 4 + 0], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+            }
+          }
+        }
+        fence_proxy_async_smem();                         // P visible to the tensor-core (async) proxy
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[st]);
+        l_run = l_run * factor + rs;
+        m_ref = m_new;
+      }
+
+      // ---- finished item: wait for the last PV, read O once, normalise, store
+      {
+        const uint32_t g = it - 1;
+        mbar_wait(&p_empty[g & 1], (g >> 1) & 1, 0x740);
+        tc_fence_after();
+        const float inv = l_run > 0.0f ? 1.0f / l_run : 0.0f;
+        __nv_bfloat16* dst = p.out + (long long)rq * p.ldo + head * ATC_HD;
 #pragma unroll
         for (int c0 = 0; c0 < ATC_HD; c0 += 32) {
           uint32_t r[32];
@@ -235,108 +327,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 #pragma unroll
             for (int i = 0; i < 32; ++i) r[i] = 0;
           } else {
-            tmem_ld_32x32(tmem_o + lane_off + st * 128 + c0, r);
+            tmem_ld_32x32(to + c0, r);
             tmem_ld_wait();
           }
+          if (rq < p.M) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o_reg[c0 + i] = fmaf(o_reg[c0 + i], corr, __uint_as_float(r[i]));
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&o_empty[st]);
-      };
-
-      for (int j = 0; j < nb; ++j, ++it) {
-        const BlockInfo b = block_info(j, n_pre, p.P, kt0, r1);
-        const int st = it & 1;
-        const uint32_t par = (it >> 1) & 1;
-        const uint32_t ts = tmem_s + lane_off + st * 128;
-        const bool need_mask = !b.pre || (b.nvalid < ATC_BN);
-        mbar_wait(&s_full[st], par, 0x710 + st);
-        tc_fence_after();
-        // pass 1: masked row maximum (in units of log2)
-        float bm = -INFINITY;
-        for (int c0 = 0; c0 < b.n_mma; c0 += 32) {
-          uint32_t r[32];
-          if (p.debug & 4) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) r[i] = 0;
-          } else {
-            tmem_ld_32x32(ts + c0, r);
-            tmem_ld_wait();
-          }
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int key = b.key0 + c0 + i;
-            bool vis = true;
-            if (need_mask) vis = b.pre ? (key < p.P) : (key >= cs && key <= rq && key < r1);
-            const float v = vis ? __uint_as_float(r[i]) * p.scale_log2 : -INFINITY;
-            bm = fmaxf(bm, v);
-          }
-        }
-        const float m_new = fmaxf(m_run, bm);
-        const float m_use = (m_new == -INFINITY) ? 0.0f : m_new;
-        const float corr = ex2(m_run - m_use);            // m_run = -inf -> 0
-        // pass 2: P = exp2(s - m) as bf16 into the swizzled K-major P tile; row sum
-        mbar_wait(&p_empty[st], par ^ 1, 0x720 + st);
-        uint8_t* prow = sP + st * ATC_TILE + row_in_tile * 128;
-        float rs = 0.0f;
-        for (int c0 = 0; c0 < b.n_mma; c0 += 32) {
-          uint32_t r[32];
-          if (p.debug & 4) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) r[i] = 0;
-          } else {
-            tmem_ld_32x32(ts + c0, r);
-            tmem_ld_wait();
-          }
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float pv[2];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int key = b.key0 + c0 + i + e;
-              bool vis = true;
-              if (need_mask) vis = b.pre ? (key < p.P) : (key >= cs && key <= rq && key < r1);
-              pv[e] = vis ? ex2(fmaf(__uint_as_float(r[i + e]), p.scale_log2, -m_use)) : 0.0f;
+            for (int v = 0; v < 4; ++v) {
+              reinterpret_cast<uint4*>(dst + c0)[v] = make_uint4(
+                  pack_bf16x2(__uint_as_float(r[v * 8 + 0]) * inv, __uint_as_float(r[v * 8 + 1]) * inv),
+                  pack_bf16x2(__uint_as_float(r[v * 8 + 2]) * inv, __uint_as_float(r[v * 8 + 3]) * inv),
+                  pack_bf16x2(__uint_as_float(r[v * 8 + 4]) * inv, __uint_as_float(r[v * 8 + 5]) * inv),
+                  pack_bf16x2(__uint_as_float(r[v * 8 + 6]) * inv, __uint_as_float(r[v * 8 + 7]) * inv));
             }
-            rs += pv[0] + pv[1];
-            pk[i >> 1] = pack_bf16x2(pv[0], pv[1]);
-          }
-          uint8_t* panel = prow + (c0 >> 6) * ATC_PANEL;
-          const int q0 = (c0 & 63) >> 3;                  // first 16-byte chunk of this 32-key group
-#pragma unroll
-          for (int q = 0; q < 4 && !(p.debug & 8); ++q) {
-            const int phys = (q0 + q) ^ (row_in_tile & 7);
-            *reinterpret_cast<uint4*>(panel + phys * 16) =
-                make_uint4(pk[q * 4 + 0], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
           }
         }
         tc_fence_before();
-        fence_proxy_async_smem();                         // P visible to the tensor-core (async) proxy
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&s_empty[st]);
-          mbar_arrive(&p_full[st]);
-        }
-        l_run = l_run * corr + rs;
-        m_run = m_new;
-        if (j > 0) accumulate(it - 1, corr_prev);         // O_{j-1}, overlapping PV_{j-1} with this softmax
-        corr_prev = corr;
-      }
-      accumulate(it - 1, corr_prev);
-
-      if (rq < p.M) {
-        const float inv = l_run > 0.0f ? 1.0f / l_run : 0.0f;
-        uint4* dst = reinterpret_cast<uint4*>(p.out + (long long)rq * p.ldo + head * ATC_HD);
-#pragma unroll
-        for (int v = 0; v < ATC_HD / 8; ++v) {
-          dst[v] = make_uint4(pack_bf16x2(o_reg[v * 8 + 0] * inv, o_reg[v * 8 + 1] * inv),
-                              pack_bf16x2(o_reg[v * 8 + 2] * inv, o_reg[v * 8 + 3] * inv),
-                              pack_bf16x2(o_reg[v * 8 + 4] * inv, o_reg[v * 8 + 5] * inv),
-                              pack_bf16x2(o_reg[v * 8 + 6] * inv, o_reg[v * 8 + 7] * inv));
-        }
+        if (lane == 0) mbar_arrive(o_empty);
       }
     }
   }

@@ -164,3 +164,53 @@ def test_first_step_matches_oracle_trajectory(cuda_device):
     if hits.numel() > 0:        # identical gradients -> identical candidate set
         assert float(cand[int(hits[0])]) <= float(cand.min()) + 0.0625 * 2
     assert abs(res.losses[0] - log.losses[0]) <= 0.0625 * 2 + 2e-2 * abs(log.losses[0])
+
+
+def test_llava_rc_pgd_only(cuda_device, tmp_path):
+    """BASELINE config 3: LLaVA with a swapped-in robust CLIP tower at its own image size,
+    PGD-only (eps 64/255, alpha 4/255): vision-tower gradient -> fused PGD kernel -> batch-1
+    scoring. Every step must stay inside the eps-ball and [0,1], and match the oracle's first step."""
+    import bimodalattack_b200 as bma
+    from bimodalattack_b200 import synthetic as syn
+    from oracle import hotpath
+    model, tok, proc, norm, _, cfg = _setup(cuda_device, pgd_attack=True, gcg_attack=False, search_width=0)
+    syn.swap_in_robust_clip(model, image_size=42)            # 3x3 patches = 9 image tokens
+    image = torch.rand((1, 3, 42, 42), generator=torch.Generator().manual_seed(6)).to(cuda_device)
+    cfg.num_steps = 3
+    atk = bma.BimodalAttack(model, tok, proc, cfg, normalize=norm)
+    res = atk.run([{"role": "user", "content": PROMPT}], "goal", TARGET, image.clone())
+    final = atk.final_image.detach()
+    assert float((final - image).abs().max()) <= cfg.eps + 1e-6
+    assert float(final.min()) >= 0.0 and float(final.max()) <= 1.0
+    assert len(res.losses) == 3 and res.losses[-1] <= res.losses[0] + 0.05
+    cfg1 = bma.BimodalAttackConfig(**{**cfg.__dict__, "num_steps": 1})
+    log = hotpath.OracleAttack(model, tok, proc, cfg1, normalize=norm).run(
+        [{"role": "user", "content": PROMPT}], TARGET, image.clone())
+    assert abs(res.losses[0] - log.losses[0]) <= 0.0625 * 2 + 2e-2 * abs(log.losses[0])
+
+
+def test_small_model_joint_scoring_scale(cuda_device):
+    """A deeper/wider decoder (3 layers, d=512, 4 heads, 16 image tokens, sw=200 -> several
+    128-row tiles, ragged last tile): losses vs the fp32 oracle and the winner."""
+    from bimodalattack_b200 import BimodalAttack
+    from bimodalattack_b200.attack import image_features
+    from oracle import hotpath
+    model, tok, proc, norm, image, cfg = _setup(cuda_device, size="small128", image_px=56, search_width=200,
+                                                **MODES["joint"])
+    atk = BimodalAttack(model, tok, proc, cfg, normalize=norm)
+    atk._prepare([{"role": "user", "content": PROMPT}], TARGET)
+    ora32 = hotpath.OracleAttack(_fp32_twin(model), tok, proc, cfg, normalize=norm)
+    ora32.seg_embeds = {k: ora32.emb(v) for k, v in atk.segment_ids.items()}
+    n_tok = len(tok(INIT, add_special_tokens=False)["input_ids"])
+    sampled = torch.randint(8, 4000, (200, n_tok), generator=torch.Generator().manual_seed(3)).to(cuda_device)
+    with torch.no_grad():
+        feats = image_features(model, norm(image), False)
+        batch = atk._build_input_embeds_pgd(sampled, feats, search_width=200, single=True)
+        got = atk._compute_candidates_loss_original(200, batch)
+        _, idx = atk._winner()
+        order = hotpath.segment_order("pgd", "llava", single=True)
+        want, _ = hotpath.candidates_loss(ora32.model, hotpath.assemble(ora32._parts(sampled, feats.float()), order, 200),
+                                          atk.target_ids, 50)
+    assert bool(((got - want).abs() <= 2e-2 * want.abs() + 1e-3).all()), (got - want).abs().max()
+    assert idx == int(got.argmin())
+    assert float(want[idx]) <= float(want.min()) + 2e-2 * abs(float(want.min())) + 1e-3
