@@ -30,13 +30,27 @@
 namespace bma {
 
 constexpr int ATC_BM = 128;        // query rows per work item
-constexpr int ATC_BN = 128;        // keys per block (max)
-constexpr int ATC_HD = 128;        // head dim
 constexpr int ATC_THREADS = 256;
-constexpr int ATC_PANEL = 128 * 128;          // bytes of one [128 rows][64 cols] bf16 panel
-constexpr int ATC_TILE = 2 * ATC_PANEL;       // 128 x 128 bf16
-constexpr int ATC_SMEM = ATC_TILE /*Q*/ + 2 * 2 * ATC_TILE /*K,V^T x 2 stages*/ + 2 * ATC_TILE /*P*/ +
-                         1024 /*align*/ + 256 /*barriers*/;
+
+// Tile geometry for head dim HD and (at most) BN keys per block. Every operand is stored as
+// panels of [rows][64 bf16] with the 128-byte swizzle; a tile is a run of such panels.
+//   HD 128: BN 128 (LLaVA / Llama);  HD 256: BN 64 (Gemma-3), which fits the same 227 KB of smem
+template <int HD, int BN>
+struct AtcCfg {
+  static constexpr int kQPanel = ATC_BM * 128;          // [128 rows][64 dims]
+  static constexpr int kKPanel = BN * 128;              // [BN keys][64 dims]
+  static constexpr int kVPanel = HD * 128;              // [HD dims][64 keys]   (V^T)
+  static constexpr int kPPanel = ATC_BM * 128;          // [128 rows][64 keys]
+  static constexpr int kQTile = (HD / 64) * kQPanel;
+  static constexpr int kKTile = (HD / 64) * kKPanel;
+  static constexpr int kVTile = (BN / 64) * kVPanel;
+  static constexpr int kPTile = (BN / 64) * kPPanel;
+  static constexpr int kSmem = kQTile + 2 * (kKTile + kVTile) + 2 * kPTile + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kTmemS = 0;                      // S_0 at +0, S_1 at +BN
+  static constexpr int kTmemO = 2 * BN;                 // O: HD columns
+  static_assert(2 * BN + HD <= 512, "TMEM budget");
+  static_assert(HD % 64 == 0 && BN % 64 == 0 && HD <= 256, "panel geometry / UMMA N limit");
+};
 
 struct AtcParams {
   __nv_bfloat16* out; long long ldo;
@@ -56,6 +70,7 @@ __device__ __forceinline__ float ex2(float x) {
 
 struct BlockInfo { int pre; int key0; int nvalid; int n_mma; };
 
+
 // First tail key row any query row of the tile starting at r0 can see (start of that row's
 // candidate), rounded DOWN to a multiple of 8 rows: the V^T tiles are fetched with the key index
 // as the innermost TMA coordinate, whose byte address has to stay 16-byte aligned (an unaligned
@@ -63,16 +78,18 @@ struct BlockInfo { int pre; int key0; int nvalid; int n_mma; };
 // key that belongs to an earlier candidate.
 __device__ __forceinline__ int tail_key_start(int r0, int S) { return ((r0 / S) * S) & ~7; }
 
+template <int BN>
 __device__ __forceinline__ BlockInfo block_info(int j, int n_pre, int P, int kt0, int r1) {
   BlockInfo b;
   b.pre = j < n_pre;
-  b.key0 = b.pre ? j * ATC_BN : kt0 + (j - n_pre) * ATC_BN;
+  b.key0 = b.pre ? j * BN : kt0 + (j - n_pre) * BN;
   const int limit = b.pre ? P : r1;
-  b.nvalid = min(ATC_BN, limit - b.key0);
+  b.nvalid = min(BN, limit - b.key0);
   b.n_mma = (b.nvalid + 15) & ~15;
   return b;
 }
 
+template <int HD, int BN>
 __global__ void __launch_bounds__(ATC_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kt,
                     const __grid_constant__ CUtensorMap tm_kp, const __grid_constant__ CUtensorMap tm_vt,
@@ -80,11 +97,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
+  using Cfg = AtcCfg<HD, BN>;
   uint8_t* sQ = smem;
-  uint8_t* sK = sQ + ATC_TILE;                 // [2 stages][tile]
-  uint8_t* sV = sK + 2 * ATC_TILE;             // [2 stages][tile]  (V^T: [128 dims][keys])
-  uint8_t* sP = sV + 2 * ATC_TILE;             // [2][tile]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * ATC_TILE);
+  uint8_t* sK = sQ + Cfg::kQTile;              // [2 stages][tile]
+  uint8_t* sV = sK + 2 * Cfg::kKTile;          // [2 stages][tile]  (V^T: [HD dims][keys])
+  uint8_t* sP = sV + 2 * Cfg::kVTile;          // [2][tile]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * Cfg::kPTile);
   uint64_t* q_full = bars;            // [1]
   uint64_t* q_empty = bars + 1;       // [1]
   uint64_t* kv_full = bars + 2;       // [2]
@@ -99,7 +117,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (p.M + ATC_BM - 1) / ATC_BM;
   const int n_items = m_tiles * p.n_heads;
-  const int n_pre = (p.P + ATC_BN - 1) / ATC_BN;
+  const int n_pre = (p.P + BN - 1) / BN;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_q); tma_prefetch_desc(&tm_kt); tma_prefetch_desc(&tm_kp);
@@ -122,8 +140,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_s = tmem_base;            // S_0 at +0, S_1 at +128
-  const uint32_t tmem_o = tmem_base + 256;      // O at +256 .. +383
+  const uint32_t tmem_s = tmem_base + Cfg::kTmemS;   // S_0 at +0, S_1 at +BN
+  const uint32_t tmem_o = tmem_base + Cfg::kTmemO;   // O: HD columns
 
   // Every role walks the same sequence of (item, block); `it` counts blocks globally so that ring
   // stage = it & 1 and barrier parity = (it >> 1) & 1 stay in step across work items.
@@ -135,24 +153,27 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         const int kvh = head / p.kv_group;
         const int r0 = tile * ATC_BM, r1 = min(p.M, r0 + ATC_BM);
         const int kt0 = tail_key_start(r0, p.S);
-        const int nb = n_pre + (r1 - kt0 + ATC_BN - 1) / ATC_BN;
+        const int nb = n_pre + (r1 - kt0 + BN - 1) / BN;
         mbar_wait(q_empty, (item_n & 1) ^ 1, 0x500);
-        mbar_arrive_expect_tx(q_full, ATC_TILE);
-        tma_load_2d(sQ, &tm_q, q_full, p.q_col0 + head * ATC_HD, r0);
-        tma_load_2d(sQ + ATC_PANEL, &tm_q, q_full, p.q_col0 + head * ATC_HD + 64, r0);
+        mbar_arrive_expect_tx(q_full, Cfg::kQTile);
+#pragma unroll
+        for (int c = 0; c < HD / 64; ++c)
+          tma_load_2d(sQ + c * Cfg::kQPanel, &tm_q, q_full, p.q_col0 + head * HD + c * 64, r0);
         for (int j = 0; j < nb; ++j, ++it) {
-          const BlockInfo b = block_info(j, n_pre, p.P, kt0, r1);
+          const BlockInfo b = block_info<BN>(j, n_pre, p.P, kt0, r1);
           const int st = it & 1;
           mbar_wait(&kv_empty[st], ((it >> 1) & 1) ^ 1, 0x510 + st);
-          mbar_arrive_expect_tx(&kv_full[st], 2 * ATC_TILE);
+          mbar_arrive_expect_tx(&kv_full[st], Cfg::kKTile + Cfg::kVTile);
           const CUtensorMap* mk = b.pre ? &tm_kp : &tm_kt;
           const CUtensorMap* mv = b.pre ? &tm_vp : &tm_vt;
-          uint8_t* dk = sK + st * ATC_TILE;
-          uint8_t* dv = sV + st * ATC_TILE;
-          tma_load_2d(dk, mk, &kv_full[st], p.k_col0 + kvh * ATC_HD, b.key0);
-          tma_load_2d(dk + ATC_PANEL, mk, &kv_full[st], p.k_col0 + kvh * ATC_HD + 64, b.key0);
-          tma_load_2d(dv, mv, &kv_full[st], b.key0, kvh * ATC_HD);
-          tma_load_2d(dv + ATC_PANEL, mv, &kv_full[st], b.key0 + 64, kvh * ATC_HD);
+          uint8_t* dk = sK + st * Cfg::kKTile;
+          uint8_t* dv = sV + st * Cfg::kVTile;
+#pragma unroll
+          for (int c = 0; c < HD / 64; ++c)
+            tma_load_2d(dk + c * Cfg::kKPanel, mk, &kv_full[st], p.k_col0 + kvh * HD + c * 64, b.key0);
+#pragma unroll
+          for (int c = 0; c < BN / 64; ++c)
+            tma_load_2d(dv + c * Cfg::kVPanel, mv, &kv_full[st], b.key0 + c * 64, kvh * HD);
         }
       }
     }
@@ -165,11 +186,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         mbar_wait(&p_full[st], (g >> 1) & 1, 0x620 + st);
         if (first) mbar_wait(o_empty, item_par ^ 1, 0x630);     // previous item's O has been read out
         tc_fence_after();
-        const uint32_t idesc = umma_idesc_bf16(ATC_BM, ATC_HD);
-        const uint32_t pa = smem_u32(sP + st * ATC_TILE), vb = smem_u32(sV + st * ATC_TILE);
+        const uint32_t idesc = umma_idesc_bf16(ATC_BM, HD);
+        const uint32_t pa = smem_u32(sP + st * Cfg::kPTile), vb = smem_u32(sV + st * Cfg::kVTile);
         for (int kk = 0; kk < n_mma / 16 && !(p.debug & 2); ++kk) {
-          const uint32_t off = (kk >> 2) * ATC_PANEL + (kk & 3) * 32;
-          umma_bf16_ss(tmem_o, umma_desc_k_sw128(pa + off), umma_desc_k_sw128(vb + off), idesc,
+          const uint32_t off_p = (kk >> 2) * Cfg::kPPanel + (kk & 3) * 32;
+          const uint32_t off_v = (kk >> 2) * Cfg::kVPanel + (kk & 3) * 32;
+          umma_bf16_ss(tmem_o, umma_desc_k_sw128(pa + off_p), umma_desc_k_sw128(vb + off_v), idesc,
                        !(first && kk == 0));
         }
         umma_commit(&kv_empty[st]);
@@ -179,22 +201,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         const int head = item / m_tiles, tile = item - head * m_tiles;
         const int r0 = tile * ATC_BM, r1 = min(p.M, r0 + ATC_BM);
         const int kt0 = tail_key_start(r0, p.S);
-        const int nb = n_pre + (r1 - kt0 + ATC_BN - 1) / ATC_BN;
+        const int nb = n_pre + (r1 - kt0 + BN - 1) / BN;
         mbar_wait(q_full, item_n & 1, 0x600);
         int prev_n = 0;
         for (int j = 0; j < nb; ++j, ++it) {
-          const BlockInfo b = block_info(j, n_pre, p.P, kt0, r1);
+          const BlockInfo b = block_info<BN>(j, n_pre, p.P, kt0, r1);
           const int st = it & 1;
           const uint32_t par = (it >> 1) & 1;
           mbar_wait(&kv_full[st], par, 0x640 + st);
           mbar_wait(&s_empty[st], par ^ 1, 0x650 + st);
           tc_fence_after();
           const uint32_t idesc = umma_idesc_bf16(ATC_BM, b.n_mma);
-          const uint32_t qa = smem_u32(sQ), kb = smem_u32(sK + st * ATC_TILE);
+          const uint32_t qa = smem_u32(sQ), kb = smem_u32(sK + st * Cfg::kKTile);
 #pragma unroll
-          for (int ks = 0; ks < ATC_HD / 16 && !(p.debug & 1); ++ks) {
-            const uint32_t off = (ks >> 2) * ATC_PANEL + (ks & 3) * 32;
-            umma_bf16_ss(tmem_s + st * 128, umma_desc_k_sw128(qa + off), umma_desc_k_sw128(kb + off), idesc,
+          for (int ks = 0; ks < HD / 16 && !(p.debug & 1); ++ks) {
+            const uint32_t off_q = (ks >> 2) * Cfg::kQPanel + (ks & 3) * 32;
+            const uint32_t off_k = (ks >> 2) * Cfg::kKPanel + (ks & 3) * 32;
+            umma_bf16_ss(tmem_s + st * BN, umma_desc_k_sw128(qa + off_q), umma_desc_k_sw128(kb + off_k), idesc,
                          ks != 0);
           }
           umma_commit(&s_full[st]);
@@ -216,22 +239,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       const int head = item / m_tiles, tile = item - head * m_tiles;
       const int r0 = tile * ATC_BM, r1 = min(p.M, r0 + ATC_BM);
       const int kt0 = tail_key_start(r0, p.S);
-      const int nb = n_pre + (r1 - kt0 + ATC_BN - 1) / ATC_BN;
+      const int nb = n_pre + (r1 - kt0 + BN - 1) / BN;
       const int rq = r0 + row_in_tile;
       const int cs = (rq / p.S) * p.S;
       float m_ref = -INFINITY, l_run = 0.0f;
 
       for (int j = 0; j < nb; ++j, ++it) {
-        const BlockInfo b = block_info(j, n_pre, p.P, kt0, r1);
+        const BlockInfo b = block_info<BN>(j, n_pre, p.P, kt0, r1);
         const int st = it & 1;
         const uint32_t par = (it >> 1) & 1;
-        const uint32_t ts = tmem_s + lane_off + st * 128;
+        const uint32_t ts = tmem_s + lane_off + st * BN;
         mbar_wait(&s_full[st], par, 0x710 + st);
         tc_fence_after();
         // ---- the whole S row into registers (columns >= n_mma were not computed: forced to -inf)
-        float sv[ATC_BN];
+        float sv[BN];
 #pragma unroll
-        for (int c0 = 0; c0 < ATC_BN; c0 += 32) {
+        for (int c0 = 0; c0 < BN; c0 += 32) {
           uint32_t r[32];
           if (c0 < b.n_mma && !(p.debug & 4)) {
             tmem_ld_32x32(ts + c0, r);
@@ -246,9 +269,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[st]);          // S_j is in registers: the buffer is free
-        if (!b.pre || b.nvalid < ATC_BN) {                 // masked blocks: last prefix block and the tail
+        if (!b.pre || b.nvalid < BN) {                 // masked blocks: last prefix block and the tail
 #pragma unroll
-          for (int i = 0; i < ATC_BN; ++i) {
+          for (int i = 0; i < BN; ++i) {
             const int key = b.key0 + i;
             const bool vis = b.pre ? (key < p.P) : (key >= cs && key <= rq && key < r1);
             if (!vis) sv[i] = -INFINITY;
@@ -256,7 +279,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         }
         float raw = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < ATC_BN; ++i) raw = fmaxf(raw, sv[i]);
+        for (int i = 0; i < BN; ++i) raw = fmaxf(raw, sv[i]);
         const float bm = raw * p.scale_log2;               // scale > 0; -inf stays -inf
         const bool raise = bm > m_ref + kRaise;            // also true for the first finite block
         const float m_new = raise ? bm : m_ref;
@@ -270,7 +293,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           tc_fence_after();
           const float f = fix ? factor : 1.0f;
 #pragma unroll
-          for (int c0 = 0; c0 < ATC_HD; c0 += 32) {
+          for (int c0 = 0; c0 < HD; c0 += 32) {
             uint32_t r[32];
             tmem_ld_32x32(to + c0, r);
             tmem_ld_wait();
@@ -283,10 +306,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         }
         // ---- P = exp2(s - m) as bf16 into the swizzled K-major P tile; row sum
         mbar_wait(&p_empty[st], par ^ 1, 0x720 + st);
-        uint8_t* prow = sP + st * ATC_TILE + row_in_tile * 128;
+        uint8_t* prow = sP + st * Cfg::kPTile + row_in_tile * 128;
         float rs = 0.0f;
 #pragma unroll
-        for (int c0 = 0; c0 < ATC_BN; c0 += 32) {
+        for (int c0 = 0; c0 < BN; c0 += 32) {
           if (c0 < b.n_mma) {
             uint32_t pk[16];
 #pragma unroll
@@ -296,7 +319,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
               rs += p0 + p1;
               pk[i >> 1] = pack_bf16x2(p0, p1);
             }
-            uint8_t* panel = prow + (c0 >> 6) * ATC_PANEL;
+            uint8_t* panel = prow + (c0 >> 6) * Cfg::kPPanel;
             const int q0 = (c0 & 63) >> 3;                // first 16-byte chunk of this 32-key group
 #pragma unroll
             for (int q = 0; q < 4 && !(p.debug & 8); ++q) {
@@ -319,9 +342,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         mbar_wait(&p_empty[g & 1], (g >> 1) & 1, 0x740);
         tc_fence_after();
         const float inv = l_run > 0.0f ? 1.0f / l_run : 0.0f;
-        __nv_bfloat16* dst = p.out + (long long)rq * p.ldo + head * ATC_HD;
+        __nv_bfloat16* dst = p.out + (long long)rq * p.ldo + head * HD;
 #pragma unroll
-        for (int c0 = 0; c0 < ATC_HD; c0 += 32) {
+        for (int c0 = 0; c0 < HD; c0 += 32) {
           uint32_t r[32];
           if (p.debug & 16) {
 #pragma unroll
@@ -356,25 +379,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   }
 }
 
-cudaError_t launch_prefix_tail_attention(const AttnParams& a, int n_heads, cudaStream_t stream) {
-  if (a.M <= 0) return cudaSuccess;
-  if (a.S <= 0 || a.P < 0 || a.kv_group <= 0) return cudaErrorInvalidValue;
+template <int HD, int BN>
+static cudaError_t launch_atc(const AttnParams& a, int n_heads, cudaStream_t stream) {
+  using Cfg = AtcCfg<HD, BN>;
   const int kv_heads = n_heads / a.kv_group;
   CUtensorMap tq, tkt, tkp, tvt, tvp;
-  if (!make_tmap_bf16(&tq, a.q, a.M, (long long)n_heads * ATC_HD, a.ldq, 128)) return cudaErrorInvalidValue;
-  if (!make_tmap_bf16(&tkt, a.k_tail, a.M, (long long)kv_heads * ATC_HD, a.ldk, 128)) return cudaErrorInvalidValue;
-  if (!make_tmap_bf16(&tvt, a.vt_tail, (long long)kv_heads * ATC_HD, a.M, a.ldvt, 128)) return cudaErrorInvalidValue;
+  if (!make_tmap_bf16(&tq, a.q, a.M, (long long)n_heads * HD, a.ldq, ATC_BM)) return cudaErrorInvalidValue;
+  if (!make_tmap_bf16(&tkt, a.k_tail, a.M, (long long)kv_heads * HD, a.ldk, BN)) return cudaErrorInvalidValue;
+  if (!make_tmap_bf16(&tvt, a.vt_tail, (long long)kv_heads * HD, a.M, a.ldvt, HD)) return cudaErrorInvalidValue;
   if (a.P > 0) {
-    if (!make_tmap_bf16(&tkp, a.k_pre, a.P, (long long)kv_heads * ATC_HD, a.ldkp, 128)) return cudaErrorInvalidValue;
-    if (!make_tmap_bf16(&tvp, a.vt_pre, (long long)kv_heads * ATC_HD, a.P, a.ldvtp, 128)) return cudaErrorInvalidValue;
+    if (!make_tmap_bf16(&tkp, a.k_pre, a.P, (long long)kv_heads * HD, a.ldkp, BN)) return cudaErrorInvalidValue;
+    if (!make_tmap_bf16(&tvp, a.vt_pre, (long long)kv_heads * HD, a.P, a.ldvtp, HD)) return cudaErrorInvalidValue;
   } else {
     tkp = tkt;
     tvp = tvt;
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         ATC_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<HD, BN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -390,8 +413,16 @@ cudaError_t launch_prefix_tail_attention(const AttnParams& a, int n_heads, cudaS
   const int m_tiles = (a.M + ATC_BM - 1) / ATC_BM;
   int grid = m_tiles * n_heads;
   if (grid > num_sms()) grid = num_sms();
-  attention_tc_kernel<<<grid, ATC_THREADS, ATC_SMEM, stream>>>(tq, tkt, tkp, tvt, tvp, p);
+  attention_tc_kernel<HD, BN><<<grid, ATC_THREADS, Cfg::kSmem, stream>>>(tq, tkt, tkp, tvt, tvp, p);
   return cudaGetLastError();
+}
+
+cudaError_t launch_prefix_tail_attention(const AttnParams& a, int n_heads, cudaStream_t stream) {
+  if (a.M <= 0) return cudaSuccess;
+  if (a.S <= 0 || a.P < 0 || a.kv_group <= 0) return cudaErrorInvalidValue;
+  if (a.head_dim == 128) return launch_atc<128, 128>(a, n_heads, stream);
+  if (a.head_dim == 256) return launch_atc<256, 64>(a, n_heads, stream);
+  return cudaErrorInvalidValue;
 }
 
 }  // namespace bma

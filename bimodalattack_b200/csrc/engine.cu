@@ -113,10 +113,15 @@ bool dev_alloc(T** p, size_t count, size_t* total) {
 // One decoder pass over `rows` rows laid out as sequences of `seq` rows at positions
 // pos_base + (r % seq). prefill == true: rows are the prefix itself (their q/k/v land in
 // prefix_qkv and the last layer stops after its K/V are produced).
+//   Llama layer:  x += o(attn(norm_attn x));                x += down(glu(norm_mlp x))
+//   Gemma layer:  x += norm_post_attn(o(attn(norm_attn x))); x += norm_post_mlp(down(glu(norm_mlp x)))
+// In the Gemma form the residual adds cannot ride in the GEMM epilogue (a row norm sits in
+// between), so each (post-norm + add + next pre-norm) triple is one fused row kernel.
 int run_layers(bma_scorer* s, int rows, int seq, int pos_base, bool prefill, cudaStream_t st) {
   const bma_model_desc& D = s->desc;
   const int d = D.d_model;
   const int P = prefill ? 0 : s->prefix_len;
+  const bool sandwich = D.sandwich_norm != 0;
   for (int l = 0; l < D.n_layers; ++l) {
     const bma_layer_weights& W = s->layers[l];
     __nv_bfloat16* pre_qk = s->prefix_qk + (size_t)l * D.max_prefix * s->qk_dim;
@@ -125,7 +130,7 @@ int run_layers(bma_scorer* s, int rows, int seq, int pos_base, bool prefill, cud
     __nv_bfloat16* vt = prefill ? pre_vt : s->vt;
     const long long ldvt = prefill ? s->ld_vtp : s->ld_vt;
 
-    {
+    if (!sandwich || l == 0) {     // sandwich layers > 0 got xn from the previous layer's add_norm
       ProfScope ps(s, PC_NORM, 0, st);
       BMA_LAUNCH(launch_rmsnorm(s->x, d, bf(W.norm_attn), s->xn, d, rows, d, D.rms_eps, D.norm_mode,
                                 0, 0, 0, st), "rmsnorm(attn)");
@@ -138,8 +143,16 @@ int run_layers(bma_scorer* s, int rows, int seq, int pos_base, bool prefill, cud
       p.rope_cos = W.rope_cos; p.rope_sin = W.rope_sin;
       p.rope_cols = s->qk_dim;
       p.rows_per_seq = seq; p.pos_base = pos_base;
+      if (D.qk_norm) {
+        p.q_norm_w = bf(W.q_norm); p.k_norm_w = bf(W.k_norm);
+        p.q_cols = s->q_dim; p.qk_norm_eps = D.rms_eps;
+      }
       ProfScope ps(s, PC_GEMM_QKV, gemm_flops(p), st);
-      BMA_LAUNCH((launch_gemm<256, EPI_ROPE>(s->xn, d, bf(W.w_qkv), d, p, st)), "gemm(qkv+rope)");
+      if (D.head_dim == 128) {
+        BMA_LAUNCH((launch_gemm<256, EPI_ROPE, 128>(s->xn, d, bf(W.w_qkv), d, p, st)), "gemm(qkv+rope)");
+      } else {
+        BMA_LAUNCH((launch_gemm<256, EPI_ROPE, 256>(s->xn, d, bf(W.w_qkv), d, p, st)), "gemm(qkv+rope)");
+      }
     }
     if (prefill && l == D.n_layers - 1) break;   // only this layer's K/V are needed
     {
@@ -152,6 +165,7 @@ int run_layers(bma_scorer* s, int rows, int seq, int pos_base, bool prefill, cud
       a.out = s->attn; a.ldo = s->q_dim;
       a.M = rows; a.S = seq; a.P = P;
       a.kv_group = D.n_heads / D.n_kv_heads;
+      a.head_dim = D.head_dim;
       a.scale_log2 = D.attn_scale * 1.4426950408889634f;
       // QK^T and PV over the visible keys: ~4 * rows * (P + seq/2) * q_dim
       ProfScope ps(s, PC_ATTN, 4.0 * rows * (P + 0.5 * seq) * s->q_dim, st);
@@ -160,15 +174,21 @@ int run_layers(bma_scorer* s, int rows, int seq, int pos_base, bool prefill, cud
     {
       GemmParams p{};
       p.M = rows; p.N = d; p.K = s->q_dim; p.group_m = 16;
-      p.C = s->x; p.ldc = d; p.R = s->x; p.ldr = d;
+      if (sandwich) { p.C = s->xn; p.ldc = d; }                       // y: normed before the add
+      else { p.C = s->x; p.ldc = d; p.R = s->x; p.ldr = d; }
       ProfScope ps(s, PC_GEMM_O, gemm_flops(p), st);
       BMA_LAUNCH((launch_gemm<256, EPI_STORE>(s->attn, s->q_dim, bf(W.w_o), s->q_dim, p, st)),
                  "gemm(o_proj)");
     }
     {
       ProfScope ps(s, PC_NORM, 0, st);
-      BMA_LAUNCH(launch_rmsnorm(s->x, d, bf(W.norm_mlp), s->xn, d, rows, d, D.rms_eps, D.norm_mode,
-                                0, 0, 0, st), "rmsnorm(mlp)");
+      if (sandwich) {
+        BMA_LAUNCH(launch_add_norm(s->xn, d, bf(W.norm_post_attn), s->x, d, bf(W.norm_mlp), s->xn, d,
+                                   rows, d, D.rms_eps, D.norm_mode, st), "add_norm(post_attn, pre_mlp)");
+      } else {
+        BMA_LAUNCH(launch_rmsnorm(s->x, d, bf(W.norm_mlp), s->xn, d, rows, d, D.rms_eps, D.norm_mode,
+                                  0, 0, 0, st), "rmsnorm(mlp)");
+      }
     }
     {
       GemmParams p{};
@@ -180,10 +200,17 @@ int run_layers(bma_scorer* s, int rows, int seq, int pos_base, bool prefill, cud
     {
       GemmParams p{};
       p.M = rows; p.N = d; p.K = D.d_ff; p.group_m = 16;
-      p.C = s->x; p.ldc = d; p.R = s->x; p.ldr = d;
+      if (sandwich) { p.C = s->xn; p.ldc = d; }
+      else { p.C = s->x; p.ldc = d; p.R = s->x; p.ldr = d; }
       ProfScope ps(s, PC_GEMM_DOWN, gemm_flops(p), st);
       BMA_LAUNCH((launch_gemm<256, EPI_STORE>(s->act, D.d_ff, bf(W.w_down), D.d_ff, p, st)),
                  "gemm(down)");
+    }
+    if (sandwich) {
+      const __nv_bfloat16* next = (l + 1 < D.n_layers) ? bf(s->layers[l + 1].norm_attn) : nullptr;
+      ProfScope ps(s, PC_NORM, 0, st);
+      BMA_LAUNCH(launch_add_norm(s->xn, d, bf(W.norm_post_mlp), s->x, d, next, s->xn, d, rows, d,
+                                 D.rms_eps, D.norm_mode, st), "add_norm(post_mlp, next input)");
     }
   }
   return 0;
@@ -254,8 +281,8 @@ int bma_sample_ids(const long long* ids, const void* grad, int grad_dtype, long 
 bma_scorer* bma_scorer_create(const bma_model_desc* desc) {
   if (desc == nullptr) return nullptr;
   const bma_model_desc& D = *desc;
-  if (D.head_dim != 128) {
-    g_last_error = "scorer: head_dim must be 128";
+  if (D.head_dim != 128 && D.head_dim != 256) {
+    g_last_error = "scorer: head_dim must be 128 or 256";
     return nullptr;
   }
   if (D.n_layers <= 0 || D.d_model % 64 != 0 || D.d_ff % 128 != 0 || D.n_heads % D.n_kv_heads != 0 ||
@@ -346,6 +373,10 @@ int bma_scorer_profile_read(bma_scorer* s, double* ms, double* flops, long long*
 int bma_scorer_set_layer(bma_scorer* s, int layer, const bma_layer_weights* w) {
   if (s == nullptr || w == nullptr || layer < 0 || layer >= s->desc.n_layers)
     return fail(cudaErrorInvalidValue, "set_layer: bad arguments");
+  if (s->desc.qk_norm && (w->q_norm == nullptr || w->k_norm == nullptr))
+    return fail(cudaErrorInvalidValue, "set_layer: qk_norm needs q_norm and k_norm weights");
+  if (s->desc.sandwich_norm && (w->norm_post_attn == nullptr || w->norm_post_mlp == nullptr))
+    return fail(cudaErrorInvalidValue, "set_layer: sandwich_norm needs the two post-norm weights");
   s->layers[layer] = *w;
   return 0;
 }
@@ -475,11 +506,20 @@ int bma_rmsnorm(const void* x, long long ldx, const void* w, void* y, long long 
   return 0;
 }
 
+int bma_add_norm(const void* y, long long ldy, const void* w_post, void* x, long long ldx,
+                 const void* w_next, void* xn, long long ldxn, int rows, int d, float eps, int mode,
+                 void* stream) {
+  BMA_LAUNCH(launch_add_norm(bf(y), ldy, bf(w_post), bf(x), ldx, bf(w_next), bf(xn), ldxn, rows, d, eps,
+                             mode, as_stream(stream)), "add_norm");
+  return 0;
+}
+
 int bma_attention(const void* q, long long ldq, const void* k_tail, long long ldk,
                   const void* vt_tail, long long ldvt, const void* k_pre, long long ldkp,
                   const void* vt_pre, long long ldvtp, void* out, long long ldo, int M, int S, int P,
-                  int n_heads, int kv_group, float scale, void* stream) {
+                  int n_heads, int kv_group, int head_dim, float scale, void* stream) {
   AttnParams a{};
+  a.head_dim = head_dim;
   a.q = bf(q); a.ldq = ldq;
   a.k_tail = bf(k_tail); a.ldk = ldk;
   a.vt_tail = bf(vt_tail); a.ldvt = ldvt;

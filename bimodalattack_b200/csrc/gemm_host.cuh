@@ -108,7 +108,7 @@ inline bool make_tmap_bf16(CUtensorMap* out, const void* ptr, long long rows, lo
   return true;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int HD = 128>
 inline cudaError_t launch_gemm(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B,
                                long long ldb, GemmParams p, cudaStream_t stream,
                                int max_ctas = 0) {
@@ -120,7 +120,7 @@ inline cudaError_t launch_gemm(const __nv_bfloat16* A, long long lda, const __nv
   if (!make_tmap_bf16(&tb, B, p.N, p.K, ldb, BN)) return cudaErrorInvalidValue;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, EPI>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, EPI, HD>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
@@ -131,7 +131,7 @@ inline cudaError_t launch_gemm(const __nv_bfloat16* A, long long lda, const __nv
   int grid = m_tiles * n_tiles;
   const int cap = max_ctas > 0 ? max_ctas : num_sms();
   if (grid > cap) grid = cap;
-  gemm_bf16_tn_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  gemm_bf16_tn_kernel<BN, EPI, HD><<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, p);
   return cudaGetLastError();
 }
 

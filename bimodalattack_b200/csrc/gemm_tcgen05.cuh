@@ -37,6 +37,12 @@ struct GemmParams {
   int pos_base;
   __nv_bfloat16* Vt;          // EPI_ROPE: columns >= rope_cols (the V heads) go here TRANSPOSED,
   long long ldvt;             //   Vt[(col - rope_cols) * ldvt + row], for the K-major PV operand
+  // optional per-head RMSNorm on Q and K before the rotation (Gemma-3 q_norm / k_norm):
+  // y = bf16(x * rstd * (1 + w)), w is [head_dim]; columns < q_cols are Q heads
+  const __nv_bfloat16* q_norm_w;
+  const __nv_bfloat16* k_norm_w;
+  int q_cols;
+  float qk_norm_eps;
   // GLU
   int act;                    // 0 = SiLU, 1 = GELU(tanh)
   // cross-entropy (EPI_CE)
@@ -79,7 +85,7 @@ __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const uint32_t
   }
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int HD = 128>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
@@ -238,19 +244,40 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
           }
         }
       } else if constexpr (EPI == EPI_ROPE) {
+        static_assert(BN % HD == 0 && HD % 64 == 0, "a tile holds whole heads");
+        constexpr int HALF = HD / 2;
         const int pos = p.pos_base + (row_ok ? (row % p.rows_per_seq) : 0);
-        const float4* cosp = reinterpret_cast<const float4*>(p.rope_cos + (long long)pos * 64);
-        const float4* sinp = reinterpret_cast<const float4*>(p.rope_sin + (long long)pos * 64);
+        const float4* cosp = reinterpret_cast<const float4*>(p.rope_cos + (long long)pos * HALF);
+        const float4* sinp = reinterpret_cast<const float4*>(p.rope_sin + (long long)pos * HALF);
 #pragma unroll 1
-        for (int hb = 0; hb < BN; hb += 128) {
+        for (int hb = 0; hb < BN; hb += HD) {
           const int col_h = n0 + hb;
           if (col_h >= p.N) break;
           if (col_h < p.rope_cols) {
+            // optional q_norm / k_norm: RMS over the head's HD columns of the bf16 projection
+            const __nv_bfloat16* nw = nullptr;
+            float rstd = 1.0f;
+            if (p.q_norm_w != nullptr) {
+              nw = col_h < p.q_cols ? p.q_norm_w : p.k_norm_w;
+              float ss = 0.0f;
 #pragma unroll 1
-            for (int c0 = 0; c0 < 64; c0 += 32) {
+              for (int c0 = 0; c0 < HD; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32(t_row + hb + c0, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  const float a = bf16_round(__uint_as_float(r[j]));
+                  ss = fmaf(a, a, ss);
+                }
+              }
+              rstd = rsqrtf(ss * (1.0f / HD) + p.qk_norm_eps);
+            }
+#pragma unroll 1
+            for (int c0 = 0; c0 < HALF; c0 += 32) {
               uint32_t x1[32], x2[32];
               tmem_ld_32x32(t_row + hb + c0, x1);
-              tmem_ld_32x32(t_row + hb + 64 + c0, x2);
+              tmem_ld_32x32(t_row + hb + HALF + c0, x2);
               tmem_ld_wait();
               if (row_ok) {
                 uint32_t o1[16], o2[16];
@@ -264,8 +291,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
                   for (int j = 0; j < 4; ++j) {
                     // projection output is bf16 in the reference before the rotation is applied
-                    const float a = bf16_round(__uint_as_float(x1[j4 * 4 + j]));
-                    const float b = bf16_round(__uint_as_float(x2[j4 * 4 + j]));
+                    float a = bf16_round(__uint_as_float(x1[j4 * 4 + j]));
+                    float b = bf16_round(__uint_as_float(x2[j4 * 4 + j]));
+                    if (nw != nullptr) {
+                      const int cn = c0 + j4 * 4 + j;
+                      a = bf16_round((a * rstd) * (1.0f + __bfloat162float(nw[cn])));
+                      b = bf16_round((b * rstd) * (1.0f + __bfloat162float(nw[HALF + cn])));
+                    }
                     y1[j] = bf16_round(a * cc[j]) + bf16_round(-b * ss[j]);
                     y2[j] = bf16_round(b * cc[j]) + bf16_round(a * ss[j]);
                   }
@@ -276,12 +308,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 }
                 __nv_bfloat16* dst = p.C + (long long)row * p.ldc + col_h + c0;
                 store_bf16x32(dst, o1, 32);
-                store_bf16x32(dst + 64, o2, 32);
+                store_bf16x32(dst + HALF, o2, 32);
               }
             }
           } else {
 #pragma unroll 1
-            for (int c0 = 0; c0 < 128; c0 += 32) {
+            for (int c0 = 0; c0 < HD; c0 += 32) {
               uint32_t r[32];
               tmem_ld_32x32(t_row + hb + c0, r);
               tmem_ld_wait();

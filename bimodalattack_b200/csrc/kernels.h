@@ -8,14 +8,15 @@
 namespace bma {
 
 struct AttnParams {
-  const __nv_bfloat16* q;       long long ldq;     // [M, ...] query rows (head h at column h*HD)
-  const __nv_bfloat16* k_tail;  long long ldk;     // [M, ...] tail keys   (kv head g at g*HD)
+  const __nv_bfloat16* q;       long long ldq;     // [M, ...] query rows (head h at column h*head_dim)
+  const __nv_bfloat16* k_tail;  long long ldk;     // [M, ...] tail keys   (kv head g at g*head_dim)
   const __nv_bfloat16* vt_tail; long long ldvt;    // [Hkv*HD, M] tail values, TRANSPOSED (row = dim)
   const __nv_bfloat16* k_pre;   long long ldkp;    // [P, ...] prefix keys
   const __nv_bfloat16* vt_pre;  long long ldvtp;   // [Hkv*HD, P] prefix values, transposed
   __nv_bfloat16* out;           long long ldo;     // [M, H*HD]
   int M, S, P;
   int kv_group;                 // query heads per kv head
+  int head_dim;                 // 128 or 256
   float scale_log2;             // softmax scale * log2(e)
 };
 
@@ -40,6 +41,10 @@ cudaError_t launch_build_tail_embeds(const long long* ids, int ids_stride, const
 cudaError_t launch_rmsnorm(const __nv_bfloat16* x, long long ldx, const __nv_bfloat16* w,
                            __nv_bfloat16* y, long long ldy, int rows, int d, float eps, int mode,
                            int gather_T, int gather_S, int gather_off, cudaStream_t stream);
+cudaError_t launch_add_norm(const __nv_bfloat16* y, long long ldy, const __nv_bfloat16* w_post,
+                            __nv_bfloat16* x, long long ldx, const __nv_bfloat16* w_next,
+                            __nv_bfloat16* xn, long long ldxn, int rows, int d, float eps, int mode,
+                            cudaStream_t stream);
 cudaError_t launch_init_key(unsigned long long* key, int* flag, cudaStream_t stream);
 cudaError_t launch_ce_finalize(const float2* part, const float* tgt_logit, int n_tiles, int B,
                                int T, float* loss, unsigned long long* key, int* all_match_flag,

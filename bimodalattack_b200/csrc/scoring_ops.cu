@@ -122,6 +122,86 @@ cudaError_t launch_rmsnorm(const __nv_bfloat16* x, long long ldx, const __nv_bfl
 }
 
 // ------------------------------------------------------------------------------------------------
+// Sandwich-norm step of a Gemma-style layer, one warp per row:
+//   x  <- bf16(x + norm(y; w_post))            (post_attention / post_feedforward norm + residual)
+//   xn <- norm(x; w_next)   if w_next != null  (the next pre-norm: pre_feedforward / input norm)
+// y and xn may alias (each lane rewrites only elements it has already consumed).
+__device__ __forceinline__ float norm_apply(float v, float rstd, float w, int mode) {
+  return mode == 0 ? bf16_round(v * rstd) * w : (v * rstd) * (1.0f + w);
+}
+
+__global__ void __launch_bounds__(256)
+add_norm_kernel(const __nv_bfloat16* y, long long ldy, const __nv_bfloat16* __restrict__ w_post,
+                __nv_bfloat16* x, long long ldx, const __nv_bfloat16* __restrict__ w_next,
+                __nv_bfloat16* xn, long long ldxn, int rows, int d, float eps, int mode) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const uint4* yv = reinterpret_cast<const uint4*>(y + (long long)r * ldy);
+  uint4* xv = reinterpret_cast<uint4*>(x + (long long)r * ldx);
+  const int nvec = d >> 3;
+  float ss = 0.0f;
+  for (int v = lane; v < nvec; v += 32) {
+    const uint4 q = yv[v];
+    const uint32_t in[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a = bf16_lo(in[j]), b = bf16_hi(in[j]);
+      ss += a * a + b * b;
+    }
+  }
+  ss = warp_sum(ss);
+  const float rstd_y = rsqrtf(ss / static_cast<float>(d) + eps);
+  const uint4* wp = reinterpret_cast<const uint4*>(w_post);
+  float sx = 0.0f;
+  for (int v = lane; v < nvec; v += 32) {
+    const uint4 q = yv[v];
+    const uint4 xx = xv[v];
+    const uint4 ww = wp[v];
+    const uint32_t in[4] = {q.x, q.y, q.z, q.w};
+    const uint32_t xi[4] = {xx.x, xx.y, xx.z, xx.w};
+    const uint32_t wi[4] = {ww.x, ww.y, ww.z, ww.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a = bf16_round(bf16_lo(xi[j]) + bf16_round(norm_apply(bf16_lo(in[j]), rstd_y, bf16_lo(wi[j]), mode)));
+      const float b = bf16_round(bf16_hi(xi[j]) + bf16_round(norm_apply(bf16_hi(in[j]), rstd_y, bf16_hi(wi[j]), mode)));
+      sx += a * a + b * b;
+      o[j] = pack_bf16x2(a, b);
+    }
+    xv[v] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+  if (w_next == nullptr) return;
+  sx = warp_sum(sx);
+  const float rstd_x = rsqrtf(sx / static_cast<float>(d) + eps);
+  const uint4* wn = reinterpret_cast<const uint4*>(w_next);
+  uint4* dst = reinterpret_cast<uint4*>(xn + (long long)r * ldxn);
+  for (int v = lane; v < nvec; v += 32) {
+    const uint4 xx = xv[v];                     // this lane's own stores above
+    const uint4 ww = wn[v];
+    const uint32_t xi[4] = {xx.x, xx.y, xx.z, xx.w};
+    const uint32_t wi[4] = {ww.x, ww.y, ww.z, ww.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      o[j] = pack_bf16x2(norm_apply(bf16_lo(xi[j]), rstd_x, bf16_lo(wi[j]), mode),
+                         norm_apply(bf16_hi(xi[j]), rstd_x, bf16_hi(wi[j]), mode));
+    dst[v] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+cudaError_t launch_add_norm(const __nv_bfloat16* y, long long ldy, const __nv_bfloat16* w_post,
+                            __nv_bfloat16* x, long long ldx, const __nv_bfloat16* w_next,
+                            __nv_bfloat16* xn, long long ldxn, int rows, int d, float eps, int mode,
+                            cudaStream_t stream) {
+  if (rows <= 0) return cudaSuccess;
+  if ((d & 7) != 0 || (ldx & 7) != 0 || (ldy & 7) != 0 || (ldxn & 7) != 0) return cudaErrorInvalidValue;
+  const int blocks = static_cast<int>(((long long)rows * 32 + 255) / 256);
+  add_norm_kernel<<<blocks, 256, 0, stream>>>(y, ldy, w_post, x, ldx, w_next, xn, ldxn, rows, d, eps, mode);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long pack_loss_key(float loss, unsigned int idx) {
   uint32_t u = __float_as_uint(loss);
   uint32_t ord = (loss != loss) ? 0xFFFFFFFFu : ((u & 0x80000000u) ? ~u : (u | 0x80000000u));

@@ -56,8 +56,9 @@ class ScoringEngine:
         if self.dtype != torch.bfloat16:
             raise RuntimeError(f"bimodal_b200 scorer computes in bf16; model is {self.dtype}")
         mt = getattr(cfg, "model_type", "")
-        if mt != "llama":
-            raise RuntimeError(f"bimodal_b200 scorer: decoder type '{mt}' is not supported yet (llama only)")
+        if mt not in ("llama", "gemma3_text"):
+            raise RuntimeError(f"bimodal_b200 scorer: decoder type '{mt}' is not supported (llama, gemma3_text)")
+        self.gemma = mt == "gemma3_text"
         self.d = cfg.hidden_size
         self.n_layers = cfg.num_hidden_layers
         self.n_heads = cfg.num_attention_heads
@@ -67,11 +68,29 @@ class ScoringEngine:
         self.vocab = head.weight.shape[0]
         if getattr(cfg, "attention_bias", False) or getattr(cfg, "mlp_bias", False):
             raise RuntimeError("bimodal_b200 scorer: projection biases are not supported")
-        act = getattr(cfg, "hidden_act", "silu")
+        act = getattr(cfg, "hidden_activation", None) or getattr(cfg, "hidden_act", "silu")
         if act not in ("silu", "gelu_pytorch_tanh"):
             raise RuntimeError(f"bimodal_b200 scorer: activation '{act}' is not supported")
         self.act = 0 if act == "silu" else 1
         self.embed = model.get_input_embeddings()
+        self.embed_scale, self.attn_scale = 1.0, float(self.head_dim) ** -0.5
+        self.max_seq = 1 << 30
+        if self.gemma:
+            # Gemma-3 decoder (HF modeling_gemma3.py): (1+w) RMSNorm, q/k-norm, 4 norms per layer, GeGLU,
+            # scaled embeddings, softmax scale query_pre_attn_scalar^-0.5, local/global rotary tables.
+            if getattr(cfg, "attn_logit_softcapping", None) is not None:
+                raise RuntimeError("bimodal_b200 scorer: attn_logit_softcapping is not supported")
+            if getattr(cfg, "use_bidirectional_attention", False):
+                raise RuntimeError("bimodal_b200 scorer: bidirectional attention is not supported")
+            if type(model).__name__.endswith("ForCausalLM") and getattr(cfg, "final_logit_softcapping", None) is not None:
+                raise RuntimeError("bimodal_b200 scorer: final_logit_softcapping is not supported")
+            scale = getattr(self.embed, "embed_scale", None)
+            if scale is not None:        # HF multiplies by the scale cast to the weight dtype
+                self.embed_scale = float(torch.as_tensor(scale).to(self.dtype).float())
+            self.attn_scale = float(cfg.query_pre_attn_scalar) ** -0.5
+            if "sliding_attention" in getattr(cfg, "layer_types", []):
+                # the local layers' window never binds while the whole sequence fits inside it
+                self.max_seq = int(cfg.sliding_window)
         self._pack_weights()
         self._scorer = None
         self._cap_rows = 0
@@ -100,13 +119,20 @@ class ScoringEngine:
                 self.w_gate_up.append(gu.reshape(2 * self.d_ff, self.d).contiguous())
 
     def _build_rope(self, max_pos: int):
+        """Rotary tables from the model's own rotary module, one (cos, sin) pair per layer type."""
         with torch.no_grad():
             pos = torch.arange(max_pos, device=self.device).unsqueeze(0)
             dummy = torch.zeros(1, dtype=self.dtype, device=self.device)
-            cos, sin = self.lm.rotary_emb(dummy, pos)          # [1, max_pos, head_dim] in model dtype
             half = self.head_dim // 2
-            self.rope_cos = cos[0, :, :half].float().contiguous()
-            self.rope_sin = sin[0, :, :half].float().contiguous()
+            self.rope = {}
+            kinds = sorted(set(self.cfg.layer_types)) if self.gemma else [None]
+            for kind in kinds:
+                cos, sin = (self.lm.rotary_emb(dummy, pos) if kind is None
+                            else self.lm.rotary_emb(dummy, pos, layer_type=kind))   # [1, max_pos, head_dim]
+                self.rope[kind] = (cos[0, :, :half].float().contiguous(), sin[0, :, :half].float().contiguous())
+
+    def _layer_rope(self, i: int):
+        return self.rope[self.cfg.layer_types[i] if self.gemma else None]
 
     def _ensure(self, rows: int, prefix: int):
         if self._scorer is not None and rows <= self._cap_rows and prefix <= self._cap_prefix:
@@ -119,9 +145,9 @@ class ScoringEngine:
         desc = native.ModelDesc(
             n_layers=self.n_layers, d_model=self.d, n_heads=self.n_heads, n_kv_heads=self.n_kv,
             head_dim=self.head_dim, d_ff=self.d_ff, vocab=self.vocab,
-            rms_eps=float(getattr(self.cfg, "rms_norm_eps", 1e-6)), norm_mode=0, act=self.act,
-            embed_scale=1.0, attn_scale=float(self.head_dim) ** -0.5,
-            max_rows=cap_rows, max_prefix=cap_prefix)
+            rms_eps=float(getattr(self.cfg, "rms_norm_eps", 1e-6)), norm_mode=int(self.gemma), act=self.act,
+            embed_scale=self.embed_scale, attn_scale=self.attn_scale,
+            max_rows=cap_rows, max_prefix=cap_prefix, qk_norm=int(self.gemma), sandwich_norm=int(self.gemma))
         with torch.cuda.device(self.device):
             handle = self.lib.bma_scorer_create(C.byref(desc))
         if not handle:
@@ -131,12 +157,20 @@ class ScoringEngine:
         self._cap_rows, self._cap_prefix = cap_rows, cap_prefix
         self._prefix_stale = True        # a new scorer has no prefix K/V yet
         for i, layer in enumerate(self.lm.layers):
+            cos, sin = self._layer_rope(i)
             w = native.LayerWeights(
                 w_qkv=self.w_qkv[i].data_ptr(), w_o=layer.self_attn.o_proj.weight.data_ptr(),
                 w_gate_up=self.w_gate_up[i].data_ptr(), w_down=layer.mlp.down_proj.weight.data_ptr(),
                 norm_attn=layer.input_layernorm.weight.data_ptr(),
-                norm_mlp=layer.post_attention_layernorm.weight.data_ptr(),
-                rope_cos=self.rope_cos.data_ptr(), rope_sin=self.rope_sin.data_ptr())
+                rope_cos=cos.data_ptr(), rope_sin=sin.data_ptr())
+            if self.gemma:       # HF names: post_attention_layernorm is the POST-attention norm here
+                w.norm_mlp = layer.pre_feedforward_layernorm.weight.data_ptr()
+                w.norm_post_attn = layer.post_attention_layernorm.weight.data_ptr()
+                w.norm_post_mlp = layer.post_feedforward_layernorm.weight.data_ptr()
+                w.q_norm = layer.self_attn.q_norm.weight.data_ptr()
+                w.k_norm = layer.self_attn.k_norm.weight.data_ptr()
+            else:                # Llama: post_attention_layernorm is the pre-MLP norm
+                w.norm_mlp = layer.post_attention_layernorm.weight.data_ptr()
             if not (layer.self_attn.o_proj.weight.is_contiguous() and layer.mlp.down_proj.weight.is_contiguous()):
                 raise RuntimeError("bimodal_b200 scorer: non-contiguous projection weight")
             native.check(self.lib.bma_scorer_set_layer(handle, i, C.byref(w)), "scorer_set_layer")
@@ -207,8 +241,7 @@ class ScoringEngine:
         B = ids.shape[0]
         T = target_ids.numel()
         S, row0 = self._tail_rows(plan, T)
-        if self.prefix_len + S > self._max_positions:
-            raise RuntimeError("bimodal_b200 scorer: sequence longer than the rotary table")
+        self._check_length(S)
         self._ensure(max(self._cap_rows, min(B, 4096) * S), self._cap_prefix)
         if self._prefix_stale:           # the workspace was re-created after the last prefill
             self.prefill(self._last_prefix)
@@ -224,6 +257,12 @@ class ScoringEngine:
                 idx_base, native.stream_ptr(self.device)), "scorer_score")
         return loss
 
+    def _check_length(self, S: int):
+        if self.prefix_len + S > self._max_positions:
+            raise RuntimeError("bimodal_b200 scorer: sequence longer than the rotary table")
+        if self.prefix_len + S + 1 > self.max_seq:
+            raise RuntimeError("bimodal_b200 scorer: sequence longer than the sliding window of the local layers")
+
     @staticmethod
     def _tail_rows(plan: TailPlan, T: int):
         """(rows to compute, first CE row). The tail ends with the T target tokens; the last one's
@@ -238,6 +277,7 @@ class ScoringEngine:
         """End-to-end entry: pinned host ids in, pinned host losses + key out (synchronises)."""
         B, T = ids_host.shape[0], target_ids.numel()
         S, row0 = self._tail_rows(plan, T)
+        self._check_length(S)
         self._ensure(max(self._cap_rows, min(B, 4096) * S, B * ids_host.shape[1]), self._cap_prefix)
         if self._prefix_stale:
             self.prefill(self._last_prefix)

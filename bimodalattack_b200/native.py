@@ -25,6 +25,7 @@ class ModelDesc(C.Structure):
         ("rms_eps", C.c_float), ("norm_mode", C.c_int), ("act", C.c_int),
         ("embed_scale", C.c_float), ("attn_scale", C.c_float),
         ("max_rows", C.c_int), ("max_prefix", C.c_int),
+        ("qk_norm", C.c_int), ("sandwich_norm", C.c_int),
     ]
 
 
@@ -33,6 +34,8 @@ class LayerWeights(C.Structure):
         ("w_qkv", C.c_void_p), ("w_o", C.c_void_p), ("w_gate_up", C.c_void_p),
         ("w_down", C.c_void_p), ("norm_attn", C.c_void_p), ("norm_mlp", C.c_void_p),
         ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p),
+        ("norm_post_attn", C.c_void_p), ("norm_post_mlp", C.c_void_p),
+        ("q_norm", C.c_void_p), ("k_norm", C.c_void_p),
     ]
 
 
@@ -62,8 +65,9 @@ SIGNATURES = {
     "bma_scorer_score_host": (_I, [_P, _P, _I, _I, _P, _P, _I, _P, _I, _I, _P, _P, _U32, _P]),
     "bma_gemm_bf16": (_I, [_P, _LL, _P, _LL, _P, _LL, _P, _LL, _I, _I, _I, _I, _P]),
     "bma_rmsnorm": (_I, [_P, _LL, _P, _P, _LL, _I, _I, _F, _I, _P]),
+    "bma_add_norm": (_I, [_P, _LL, _P, _P, _LL, _P, _P, _LL, _I, _I, _F, _I, _P]),
     "bma_attention": (_I, [_P, _LL, _P, _LL, _P, _LL, _P, _LL, _P, _LL, _P, _LL, _I, _I, _I, _I,
-                           _I, _F, _P]),
+                           _I, _I, _F, _P]),
 }
 
 _lib: Optional[C.CDLL] = None

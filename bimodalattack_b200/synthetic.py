@@ -177,9 +177,13 @@ def swap_in_robust_clip(llava, image_size: int = 224, seed: int = 7):
 
 
 def make_gemma3(size: str = "tiny", dtype=torch.float32, device=None, seed: int = 0,
-                head_gain: float = 1.0):
+                head_gain: float = 1.0, embed_gain: float = 1.0, randomize_norms: bool = False):
     """Gemma-3 (SigLIP tower, tied LM head). Random init leaves the multimodal projector at zero
-    (the image would have no effect), so it is re-initialised here."""
+    (the image would have no effect), so it is re-initialised here. ``embed_gain`` scales the tied
+    embedding / LM-head table (spreads the per-candidate losses like ``head_gain`` does for an
+    untied head); ``randomize_norms`` gives the (1 + w) RMSNorm weights non-zero values.
+    Sizes: 'tiny' (head_dim 128, CPU golden cases), 'tiny256' (head_dim 256, GQA 2, one local and
+    one global layer: the 4b attention geometry in miniature), '4b' (Gemma-3-4b-it arch)."""
     from transformers import Gemma3Config, Gemma3ForConditionalGeneration, Gemma3TextConfig, SiglipVisionConfig
 
     if size == "tiny":
@@ -187,6 +191,17 @@ def make_gemma3(size: str = "tiny", dtype=torch.float32, device=None, seed: int 
                               num_hidden_layers=2, num_attention_heads=2, num_key_value_heads=1,
                               head_dim=128, max_position_embeddings=2048, sliding_window=1024,
                               query_pre_attn_scalar=128)
+        vc = SiglipVisionConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=2,
+                                num_attention_heads=4, image_size=56, patch_size=14,
+                                vision_use_head=False)
+        cfg = Gemma3Config(text_config=tc, vision_config=vc, mm_tokens_per_image=4,
+                           image_token_index=4, boi_token_index=5, eoi_token_index=6)
+    elif size == "tiny256":
+        tc = Gemma3TextConfig(vocab_size=1024, hidden_size=256, intermediate_size=512,
+                              num_hidden_layers=2, num_attention_heads=2, num_key_value_heads=1,
+                              head_dim=256, max_position_embeddings=2048, sliding_window=1024,
+                              query_pre_attn_scalar=256,
+                              layer_types=["sliding_attention", "full_attention"])
         vc = SiglipVisionConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=2,
                                 num_attention_heads=4, image_size=56, patch_size=14,
                                 vision_use_head=False)
@@ -221,6 +236,13 @@ def make_gemma3(size: str = "tiny", dtype=torch.float32, device=None, seed: int 
         torch.manual_seed(seed + 1)
         proj.mm_input_projection_weight.copy_(
             torch.randn(proj.mm_input_projection_weight.shape) * 0.02)
+        if embed_gain != 1.0:
+            model.get_input_embeddings().weight.mul_(embed_gain)
+        if randomize_norms:
+            g = torch.Generator().manual_seed(seed + 2)
+            for name, p in model.model.language_model.named_parameters():
+                if "norm" in name:
+                    p.copy_((torch.rand(p.shape, generator=g) - 0.5).to(p.device, p.dtype))
     return _finish(model, dtype, device, head_gain, seed)
 
 

@@ -71,6 +71,9 @@ typedef struct {
   float attn_scale;   /* softmax scale, e.g. head_dim^-0.5 */
   int max_rows;       /* capacity in tail rows (candidates per pass = max_rows / S) */
   int max_prefix;     /* capacity in prefix rows */
+  int qk_norm;        /* 1: per-head RMSNorm (norm_mode) on Q and K before the rotation (Gemma-3) */
+  int sandwich_norm;  /* 1: Gemma-style layer  x += norm_post_attn(attn(norm_attn(x)));
+                            x += norm_post_mlp(mlp(norm_mlp(x)))   (4 norms per layer)         */
 } bma_model_desc;
 
 typedef struct {
@@ -80,8 +83,13 @@ typedef struct {
   const void* w_down;     /* [d, d_ff]                                                      */
   const void* norm_attn;  /* [d] */
   const void* norm_mlp;   /* [d] */
-  const float* rope_cos;  /* [max_pos, hd/2] fp32, values already rounded to the model dtype */
+  const float* rope_cos;  /* [max_pos, hd/2] fp32, values already rounded to the model dtype;
+                             per layer, so local/global layers can use different tables        */
   const float* rope_sin;
+  const void* norm_post_attn;  /* [d]   sandwich_norm only */
+  const void* norm_post_mlp;   /* [d]   sandwich_norm only */
+  const void* q_norm;          /* [hd]  qk_norm only */
+  const void* k_norm;          /* [hd]  qk_norm only */
 } bma_layer_weights;
 
 typedef struct bma_scorer bma_scorer;
@@ -135,12 +143,17 @@ int bma_gemm_bf16(const void* A, long long lda, const void* B, long long ldb, vo
                   int block_n, void* stream);
 int bma_rmsnorm(const void* x, long long ldx, const void* w, void* y, long long ldy, int rows,
                 int d, float eps, int mode, void* stream);
-/* Shared-prefix + causal-tail attention. q/k_* are row-major [rows, heads*128]; the value
- * operands are TRANSPOSED: vt_tail is [kv_heads*128, M] (row stride ldvt), vt_pre [kv_heads*128, P]. */
+/* x <- bf16(x + norm(y; w_post)); xn <- norm(x; w_next) when w_next != NULL (xn may alias y). */
+int bma_add_norm(const void* y, long long ldy, const void* w_post, void* x, long long ldx,
+                 const void* w_next, void* xn, long long ldxn, int rows, int d, float eps, int mode,
+                 void* stream);
+/* Shared-prefix + causal-tail attention, head_dim 128 or 256. q/k_* are row-major
+ * [rows, heads*head_dim]; the value operands are TRANSPOSED: vt_tail is [kv_heads*head_dim, M]
+ * (row stride ldvt), vt_pre [kv_heads*head_dim, P]. */
 int bma_attention(const void* q, long long ldq, const void* k_tail, long long ldk,
                   const void* vt_tail, long long ldvt, const void* k_pre, long long ldkp,
                   const void* vt_pre, long long ldvtp, void* out, long long ldo, int M, int S, int P,
-                  int n_heads, int kv_group, float scale, void* stream);
+                  int n_heads, int kv_group, int head_dim, float scale, void* stream);
 
 #ifdef __cplusplus
 }

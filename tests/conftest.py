@@ -19,3 +19,10 @@ def cuda_device():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="session")
+def lib(cuda_device):
+    from bimodalattack_b200 import native
+
+    return native.load()

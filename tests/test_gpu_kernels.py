@@ -13,12 +13,6 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def lib(cuda_device):
-    from bimodalattack_b200 import native
-    return native.load()
-
-
 def _stream():
     return torch.cuda.current_stream().cuda_stream
 
@@ -218,13 +212,15 @@ def _attn_reference(q, kt, vt, kp, vp, S, scale):
     return out
 
 
-@pytest.mark.parametrize("B,S,P,H,G", [(7, 42, 596, 4, 1), (3, 42, 0, 2, 1), (1, 596, 0, 2, 1), (5, 130, 70, 2, 1),
-                                       (64, 42, 24, 2, 1), (512, 41, 596, 1, 1), (6, 41, 300, 4, 2), (2, 300, 17, 2, 1)])
-def test_prefix_tail_attention(lib, cuda_device, B, S, P, H, G):
+@pytest.mark.parametrize("B,S,P,H,G,D", [
+    (7, 42, 596, 4, 1, 128), (3, 42, 0, 2, 1, 128), (1, 596, 0, 2, 1, 128), (5, 130, 70, 2, 1, 128),
+    (64, 42, 24, 2, 1, 128), (512, 41, 596, 1, 1, 128), (6, 41, 300, 4, 2, 128), (2, 300, 17, 2, 1, 128),
+    # head_dim 256 (Gemma-3: 64-key blocks, 256-column O accumulator), GQA 2
+    (7, 41, 20, 4, 2, 256), (3, 300, 4, 2, 2, 256), (1, 70, 0, 2, 1, 256), (40, 41, 200, 2, 2, 256)])
+def test_prefix_tail_attention(lib, cuda_device, B, S, P, H, G, D):
     """H query heads, H // G kv heads (G = GQA group). Values are handed over transposed
-    ([kv_heads*128, rows]) the way the fused QKV epilogue writes them."""
+    ([kv_heads*D, rows]) the way the fused QKV epilogue writes them."""
     from bimodalattack_b200 import native
-    D = 128
     Hkv = H // G
     g = torch.Generator(device="cpu").manual_seed(B * S + P)
     M = B * S
@@ -247,7 +243,7 @@ def test_prefix_tail_attention(lib, cuda_device, B, S, P, H, G):
     native.check(lib.bma_attention(q2.data_ptr(), q2.stride(0), k2.data_ptr(), k2.stride(0),
                                    vt_T.data_ptr(), vt_T.stride(0), kp_buf.data_ptr(), kp_buf.stride(0),
                                    vp_T.data_ptr(), vp_T.stride(0), out.data_ptr(), out.stride(0),
-                                   M, S, P, H, G, scale, _stream()), "attention")
+                                   M, S, P, H, G, D, scale, _stream()), "attention")
     torch.cuda.synchronize()
     rep = lambda t: t.repeat_interleave(G, dim=1)
     want = _attn_reference(q, rep(kt), rep(vt), rep(kp), rep(vp), S, scale).reshape(M, H * D)
