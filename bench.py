@@ -44,12 +44,16 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--model", default="7b", choices=["7b", "small128", "tiny128"])
+    ap.add_argument("--model", default="7b", choices=["7b", "small128", "tiny128", "gemma4b", "gemma-tiny256"],
+                    help="7b = BASELINE.json config 2 (the headline); gemma4b = config 4 (Gemma-3-4b GCG-only)")
     ap.add_argument("--search-width", type=int, default=512)
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="strong: search_width candidates in total; weak: search_width per GPU")
     ap.add_argument("--full-steps", type=int, default=3, help="full attack steps timed for steps/s (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-suffix-sharing", action="store_true",
+                    help="score every candidate's full tail (the north-star dataflow) instead of computing the "
+                         "rows it shares with the current suffix once")
     ap.add_argument("--cpu-sample", type=int, default=1, help="candidates per CPU-baseline step")
     return ap.parse_args()
 
@@ -108,55 +112,70 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def algorithmic_flops(d, d_ff, n_layers, heads, head_dim, vocab, P, S, T, n_cand):
+def algorithmic_flops(d, d_ff, n_layers, heads, head_dim, vocab, P, S, T, n_cand, kv_heads=None):
     """linear layers 2*params*rows, attention 4*rows*(keys)*d, LM head on
     the T target rows; prefix counted once (its last layer stops after the K/V projection)."""
     q = heads * head_dim
-    per_row = 2 * (d * 3 * q + q * d + 3 * d * d_ff)
+    kv = (kv_heads or heads) * head_dim
+    per_row = 2 * (d * (q + 2 * kv) + q * d + 3 * d * d_ff)
     tail = n_cand * (S * per_row * n_layers + 4 * S * (P + S / 2) * q * n_layers + 2 * T * d * vocab)
     prefix = P * per_row * n_layers + 4 * P * (P / 2) * q * n_layers
     return tail + prefix, tail / max(n_cand, 1)
 
 
+def oracle_scoring_fn(model, tok, proc, norm, cfg, messages, target, image, joint, segment_ids=None,
+                      target_ids=None):
+    """The reference's scoring dataflow (oracle/hotpath.py, pinned to the reference by tests/golden)
+    for n candidates: sw-fold repeat of the whole prompt, full sequence, full-vocab logits."""
+    from oracle import hotpath
+    ora = hotpath.OracleAttack(model, tok, proc, cfg, normalize=norm)
+    if segment_ids is None:
+        msgs = hotpath.build_messages(messages, joint)
+        prompt = proc.apply_chat_template(msgs, add_generation_prompt=True)
+        segment_ids = hotpath.split_prompt(prompt, tok, joint, ora.gemma_proc, "cpu")
+        target_ids = tok(target, add_special_tokens=False, return_tensors="pt")["input_ids"]
+        segment_ids["target"] = target_ids
+    ora.target_ids = target_ids.cpu()
+    ora.seg_embeds = {k: ora.emb(v.cpu()) for k, v in segment_ids.items()}
+    mtype = getattr(model.config, "model_type", "")
+    order = (hotpath.segment_order("pgd", mtype, single=True) if joint
+             else hotpath.segment_order("gcg", mtype, no_joint_eval=True))
+
+    def score(cand):
+        n = cand.shape[0]
+        with torch.no_grad():
+            feats = hotpath.image_features(model, norm(image), ora.gemma_proc) if joint else None
+            emb = hotpath.assemble(ora._parts(cand, feats), order, n)
+            loss, _ = hotpath.candidates_loss(model, emb, ora.target_ids, n)
+        return loss, emb.shape[1]
+    return score
+
+
 def run_reference(args):
-    """--impl reference: the reference's dataflow (oracle/hotpath.py, pinned to the reference by
-    tests/golden) on the host cores. Each step scores ``cpu_sample`` candidates the reference's
-    way: full 638-token sequence, full-vocabulary logits, CE in model dtype."""
+    """--impl reference: the reference's dataflow on the host cores. Each step scores
+    ``cpu_sample`` candidates the reference's way: full sequence, full-vocabulary logits, CE in
+    model dtype."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from bimodalattack_b200 import BimodalAttackConfig, synthetic as syn
-    from oracle import hotpath
+    from bimodalattack_b200 import BimodalAttackConfig
     torch.manual_seed(0)
-    vocab = {"7b": 32000, "small128": 4000, "tiny128": 1000}[args.model]
-    px = {"7b": 336, "small128": 56, "tiny128": 28}[args.model]
-    tok, proc, norm, image, messages, target, init = syn.headline_case(vocab, px)
     t0 = time.perf_counter()
-    model = syn.make_llava(args.model, dtype=torch.float32, device=None, head_gain=HEAD_GAIN[args.model],
-                           fast_init=(args.model == "7b"))
+    model, tok, proc, norm, image, messages, target, init, joint = build_case(args, torch.float32, None, fast_init=True)
     build_s = time.perf_counter() - t0
-    cfg = BimodalAttackConfig(num_steps=1, search_width=args.search_width, pgd_attack=True, gcg_attack=True,
-                              joint_eval=True, allow_non_ascii=True, optim_str_init=init, seed=1,
+    cfg = BimodalAttackConfig(num_steps=1, search_width=args.search_width, pgd_attack=joint, gcg_attack=True,
+                              joint_eval=joint, allow_non_ascii=True, optim_str_init=init, seed=1,
                               alpha=4 / 255, eps=64 / 255, verbosity="ERROR", images_folder=None)
-    ora = hotpath.OracleAttack(model, tok, proc, cfg, normalize=norm)
-    msgs = hotpath.build_messages(messages, True)
-    prompt = proc.apply_chat_template(msgs, add_generation_prompt=True)
-    seg = hotpath.split_prompt(prompt, tok, True, False, "cpu")
-    ora.target_ids = tok(target, add_special_tokens=False, return_tensors="pt")["input_ids"]
-    seg["target"] = ora.target_ids
-    ora.seg_embeds = {k: ora.emb(v) for k, v in seg.items()}
+    score = oracle_scoring_fn(model, tok, proc, norm, cfg, messages, target, image, joint)
     n = args.cpu_sample
     g = torch.Generator().manual_seed(3)
     n_tok = len(tok(init, add_special_tokens=False)["input_ids"])
-    order = hotpath.segment_order("pgd", "llava", single=True)
+    vocab = model.get_input_embeddings().num_embeddings
 
     def step():
-        sampled = torch.randint(8, vocab, (n, n_tok), generator=g)
-        with torch.no_grad():
-            feats = hotpath.image_features(model, norm(image), False)
-            emb = hotpath.assemble(ora._parts(sampled, feats), order, n)
-            loss, _ = hotpath.candidates_loss(model, emb, ora.target_ids, n)
-        return emb.shape[1], int(loss.argmin())
+        sampled = torch.randint(16, min(vocab, 32000), (n, n_tok), generator=g)
+        loss, seq_len = score(sampled)
+        return seq_len, int(loss.argmin())
 
     for _ in range(args.warmup):
         step()
@@ -168,11 +187,13 @@ def run_reference(args):
     cores = torch.get_num_threads()
     sample = (f"{n} candidate(s) per step through the reference dataflow (full {seq_len}-token sequence, "
               f"full-vocab logits, fp32), model {args.model}; search_width-{args.search_width} step extrapolates linearly")
+    T = len(tok(target, add_special_tokens=False)["input_ids"])
+    tail = n_tok + (6 + T if joint else seq_len - 20 - n_tok)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": workload_config(args, seq_len - n_tok - 22, n_tok + 22),
+        "data": "synthetic", "config": workload_config(args, seq_len - tail, tail),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                          "host_cpus": os.cpu_count(), "model_build_s": build_s},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -180,14 +201,43 @@ def run_reference(args):
     }))
 
 
+GEMMA = {"gemma4b": "4b", "gemma-tiny256": "tiny256"}
+LLAVA_PX = {"7b": 336, "small128": 56, "tiny128": 28}
+LLAVA_VOCAB = {"7b": 32000, "small128": 4000, "tiny128": 1000}
+
+
 def workload_config(args, P, S):
     sw = args.search_width * (args.gpus if args.scaling == "weak" else 1)
-    px = {"7b": 336, "small128": 56, "tiny128": 28}[args.model]
-    return {"workload": f"LLaVA-1.5-{args.model} arch random-init, joint GCG+PGD scoring phase, "
-                        f"search_width {sw} ({args.scaling} scaling), {px}x{px} synthetic image, topk 256, n_replace 1",
-            "search_width": sw, "prefix_rows": P, "tail_rows": S,
-            "parallelism": f"candidate-sharded dp{args.gpus}, replicated model",
-            "l2": "no flush needed: every step streams ~23 GB of weights (>> 126 MB L2)"}
+    if args.model in GEMMA:
+        what = (f"Gemma-3-{GEMMA[args.model]} arch random-init, GCG-only scoring phase (text-only order "
+                f"before|optim|after|target, 262k-vocab LM head fused with CE), search_width {sw} "
+                f"({args.scaling} scaling), topk 256, n_replace 1")
+        l2 = "no flush needed: every step streams the 7.8 GB of decoder weights + 1.3 GB LM head (>> 126 MB L2)"
+    else:
+        px = LLAVA_PX[args.model]
+        what = (f"LLaVA-1.5-{args.model} arch random-init, joint GCG+PGD scoring phase, "
+                f"search_width {sw} ({args.scaling} scaling), {px}x{px} synthetic image, topk 256, n_replace 1")
+        l2 = "no flush needed: every step streams ~23 GB of weights (>> 126 MB L2)"
+    return {"workload": what, "search_width": sw, "prefix_rows": P, "tail_rows": S,
+            "parallelism": f"candidate-sharded dp{args.gpus}, replicated model", "l2": l2}
+
+
+def build_case(args, dtype, device, fast_init=False):
+    """(model, tok, proc, norm, image_cpu, messages, target, init, joint) of the selected workload."""
+    from bimodalattack_b200 import synthetic as syn
+    if args.model in GEMMA:
+        size = GEMMA[args.model]
+        tok, proc, norm, image, messages, target, init = syn.gemma_case(262208 if size == "4b" else 1024,
+                                                                        896 if size == "4b" else 56)
+        model = syn.make_gemma3(size, dtype=dtype, device=device, seed=0, embed_gain=4.0 if size != "4b" else 1.5,
+                                fast_init=fast_init and size == "4b")
+        model.config._attn_implementation = "sdpa"
+        return model, tok, proc, norm, image, messages, target, init, False
+    tok, proc, norm, image, messages, target, init = syn.headline_case(LLAVA_VOCAB[args.model], LLAVA_PX[args.model])
+    kw = dict(fast_init=True) if fast_init and args.model == "7b" else {}
+    model = syn.make_llava(args.model, dtype=dtype, device=device, seed=0, head_gain=HEAD_GAIN[args.model],
+                           attn_implementation=None if device is None else "sdpa", **kw)
+    return model, tok, proc, norm, image, messages, target, init, True
 
 
 def main():
@@ -210,14 +260,11 @@ def main():
     lib = native.load()
     peaks = load_peaks()
 
-    vocab = {"7b": 32000, "small128": 4000, "tiny128": 1000}[args.model]
-    px = {"7b": 336, "small128": 56, "tiny128": 28}[args.model]
-    tok, proc, norm, image_cpu, messages, target, init = syn.headline_case(vocab, px)
-    model = syn.make_llava(args.model, dtype=torch.bfloat16, device=dev, seed=0, head_gain=HEAD_GAIN[args.model],
-                           attn_implementation="sdpa")
+    model, tok, proc, norm, image_cpu, messages, target, init, joint = build_case(args, torch.bfloat16, dev)
+    gemma = args.model in GEMMA
     sw = args.search_width * (world if args.scaling == "weak" else 1)
-    cfg = BimodalAttackConfig(num_steps=1, search_width=sw, topk=256, n_replace=1, pgd_attack=True,
-                              gcg_attack=True, joint_eval=True, allow_non_ascii=True, filter_ids=False,
+    cfg = BimodalAttackConfig(num_steps=1, search_width=sw, topk=256, n_replace=1, pgd_attack=joint,
+                              gcg_attack=True, joint_eval=joint, allow_non_ascii=True, filter_ids=False,
                               optim_str_init=init, seed=1, alpha=4 / 255, eps=64 / 255, verbosity="ERROR",
                               images_folder=None)
     atk = BimodalAttack(model, tok, proc, cfg, normalize=norm)
@@ -226,25 +273,35 @@ def main():
     image = image_cpu.to(dev)
     original = image.clone()
 
-    # one real gradient + PGD + sampling on rank 0 gives this step's inputs
+    # one real gradient (+ PGD) + sampling on rank 0 gives this step's inputs
     torch.manual_seed(1)
     optim_ids = tok(init, add_special_tokens=False, return_tensors="pt")["input_ids"].to(dev)
     n_tok = optim_ids.shape[1]
     sampled = None
     if rank == 0:
-        img = image.clone().requires_grad_()
+        img = image.clone().requires_grad_() if joint else None
         g_tok, g_img = atk.compute_gradient(optim_ids, img)
-        image = atk.perform_pgd_step(img, cfg.eps, cfg.alpha, g_img, original).detach()
+        if joint:
+            image = atk.perform_pgd_step(img, cfg.eps, cfg.alpha, g_img, original).detach()
         sampled, _, _, _ = atk.candidate_sampling(cfg, 0, optim_ids, g_tok, tok, [], 0.0)
     sampled = bdist.broadcast_candidates(sampled, n_tok, dev, w)
-    image = bdist.broadcast_tensor(image.contiguous(), w)
+    if joint:
+        image = bdist.broadcast_tensor(image.contiguous(), w)
     lo, hi = bdist.shard_bounds(sw, w)
+    base_ids = optim_ids.reshape(-1).to(torch.int64).contiguous()
+    atk.engine.share_suffix_head = not args.no_suffix_sharing
+    atk._base = (sampled, base_ids)          # the suffix the candidates were sampled from (all ranks)
+
+    def build_batch(img):
+        if joint:
+            feats = image_features(model, norm(img), gemma)
+            return atk._build_input_embeds_pgd(sampled, feats, search_width=sw, single=True)
+        return atk._build_input_embeds_gcg(sampled, search_width=sw, no_joint_eval=True)
 
     def scoring_step():
         with torch.no_grad():
-            feats = image_features(model, norm(image), False)
-            batch = atk._build_input_embeds_pgd(sampled, feats, search_width=sw, single=True)
-            atk._compute_candidates_loss_original(sw, batch)
+            atk._prefill_tag = None              # every step rebuilds the shared-prefix K/V (as a real step does)
+            atk._compute_candidates_loss_original(sw, build_batch(image))
         return atk._winner()                     # one 8-byte D2H: the step's result
 
     def barrier():
@@ -256,7 +313,8 @@ def main():
     for _ in range(args.warmup):
         scoring_step()
     P = atk.engine.prefix_len
-    plan = atk._plan(atk._build_input_embeds_pgd(sampled, image_features(model, norm(image), False), sw, single=True))
+    with torch.no_grad():
+        plan = atk._plan(build_batch(image))
     S, T = plan.n_tail, atk.target_ids.numel()
     atk.engine.profile(True)
     clocks = ClockSampler(local)
@@ -280,9 +338,11 @@ def main():
     value = sw / (ms_per_step * 1e-3)
     prof = atk.engine.profile_read()
     atk.engine.profile(False)
+    rows_run = atk.engine.last_rows          # tail rows of this rank's shard that went through the decoder
 
     # ---- e2e: host buffers through the C ABI ---------------------------------------------------
     ids_host = sampled.cpu().pin_memory()
+    base_host = base_ids.cpu().pin_memory()
     img_host = image.cpu().pin_memory()
     loss_host = torch.empty(sw, dtype=torch.float32).pin_memory()
     key_host = torch.empty(1, dtype=torch.int64).pin_memory()
@@ -291,12 +351,12 @@ def main():
 
     def e2e_step():
         with torch.no_grad():
-            img_dev.copy_(img_host, non_blocking=True)
-            feats = image_features(model, norm(img_dev), False)
-            batch = atk._build_input_embeds_pgd(sampled, feats, search_width=sw, single=True)
-            pl = atk._plan(batch)
+            if joint:
+                img_dev.copy_(img_host, non_blocking=True)
+            pl = atk._plan(build_batch(img_dev))
             atk.engine.prefill(pl.prefix)
-            atk.engine.score_host(ids_host[lo:hi], pl, atk.target_ids, loss_host[lo:hi], key_host, idx_base=lo)
+            atk.engine.score_host(ids_host[lo:hi], pl, atk.target_ids, loss_host[lo:hi], key_host, idx_base=lo,
+                                  base_ids_host=base_host)
             if world > 1:
                 key_dev.copy_(key_host, non_blocking=True)
                 td.all_reduce(key_dev, op=td.ReduceOp.MIN)
@@ -315,7 +375,7 @@ def main():
     if world > 1:
         td.all_reduce(ms2, op=td.ReduceOp.MAX)
     e2e_value = sw / (float(ms2.item()) / args.steps * 1e-3)
-    h2d = ids_host[lo:hi].numel() * 8 + img_host.numel() * 4
+    h2d = ids_host[lo:hi].numel() * 8 + base_host.numel() * 8 + (img_host.numel() * 4 if joint else 0)
     d2h = (hi - lo) * 4 + 8
 
     # ---- full attack steps through run() ---------------------------------------------------------
@@ -330,7 +390,7 @@ def main():
             torch.cuda.synchronize()
             marks.append(time.perf_counter())
         atk2.step_hook = hook
-        res = atk2.run(messages, "goal", target, image_cpu.to(dev))
+        res = atk2.run(messages, "goal", target, image_cpu.to(dev) if joint else None)
         if len(marks) >= 3:
             dt = torch.tensor([(marks[-1] - marks[1]) / (len(marks) - 2)], device=dev)
             if world > 1:
@@ -355,8 +415,9 @@ def main():
     total_prof_ms = sum(v["ms"] for v in prof.values())
     achieved = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
     total_flops, per_cand = algorithmic_flops(tc.hidden_size, tc.intermediate_size, tc.num_hidden_layers,
-                                              tc.num_attention_heads, 128, model.get_output_embeddings().weight.shape[0],
-                                              P, S, T, hi - lo)
+                                              tc.num_attention_heads, atk.engine.head_dim,
+                                              model.get_output_embeddings().weight.shape[0], P, S, T, hi - lo,
+                                              kv_heads=atk.engine.n_kv)
     roofline = {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel<*> (tcgen05, all epilogues)",
                 "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_sustained"], "frac_of_burst_peak": achieved / peaks["bf16_burst"],
@@ -365,32 +426,31 @@ def main():
                 "per_class": {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
                                   "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 and v["flops"] > 0 else None}
                               for k, v in prof.items()},
+                # SURVEY 8(d) numerator (every candidate's full tail) over the step time; with suffix-head
+                # sharing fewer rows are executed, so this is an EFFECTIVE rate, not a tensor-pipe rate:
                 "step_tflops_algorithmic": total_flops / (ms_per_step * 1e-3) / 1e12,
-                "gflop_per_candidate": per_cand / 1e9}
+                "gflop_per_candidate": per_cand / 1e9,
+                "suffix_head_sharing": {"enabled": bool(atk.engine.share_suffix_head), "tail_rows_full": (hi - lo) * S,
+                                        "tail_rows_executed": int(rows_run),
+                                        "note": "rows a candidate shares with the current suffix (before its first "
+                                                "replaced position) are computed once; SURVEY 8(f) rank 3"},
+                "gemm_tflops_executed_per_step": g_fl / args.steps / 1e12}
 
     # ---- CPU baseline: the oracle (reference dataflow) on the host cores, bounded sample ------------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         import copy
-        from oracle import hotpath
         t0 = time.perf_counter()
         twin = copy.deepcopy(model).to("cpu").float()
-        ora = hotpath.OracleAttack(twin, tok, proc, cfg, normalize=norm)
-        ora.target_ids = atk.target_ids.cpu()
-        ora.seg_embeds = {k: ora.emb(v.cpu()) for k, v in atk.segment_ids.items()}
+        score = oracle_scoring_fn(twin, tok, proc, norm, cfg, messages, target, image.cpu(), joint,
+                                  segment_ids=atk.segment_ids, target_ids=atk.target_ids)
         n = args.cpu_sample
-        cand = sampled[:n].cpu()
-        order = hotpath.segment_order("pgd", "llava", single=True)
-        img_c = image.cpu()
         t1 = time.perf_counter()
-        with torch.no_grad():
-            feats = hotpath.image_features(twin, norm(img_c), False)
-            emb = hotpath.assemble(ora._parts(cand, feats), order, n)
-            cl, _ = hotpath.candidates_loss(twin, emb, ora.target_ids, n)
+        cl, seq_len = score(sampled[:n].cpu())
         dt = time.perf_counter() - t1
         cpu = {"value": n / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                "host_cpus": os.cpu_count(),
-               "sample": f"{n} of {sw} candidates through the reference dataflow (full {emb.shape[1]}-token "
+               "sample": f"{n} of {sw} candidates through the reference dataflow (full {seq_len}-token "
                          f"sequence, full-vocab logits, fp32) in {dt:.1f}s; linear extrapolation to a full step",
                "loss_vs_gpu_abs_diff": float((cl - loss_host[:n]).abs().max()) if lo == 0 else None,
                "setup_s": t1 - t0}
@@ -403,8 +463,11 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu,
         "full_step": full, "winner": {"loss": win_loss, "index": win_idx, "e2e_key": e2e_key},
-        "a100_reference_published": {"cand_per_s": 10.7, "s_per_iter": 49.965,
-                                     "note": "BASELINE.md: LLaVA-1.5-7B joint_eval sw 512, A100-80GB, fp16"},
+        "a100_reference_published": (
+            {"cand_per_s": 128.0, "s_per_iter": 5.7641,
+             "note": "BASELINE.md: Gemma-3-4b-it GCG-only sw 512, A100-80GB, bf16"} if gemma else
+            {"cand_per_s": 10.7, "s_per_iter": 49.965,
+             "note": "BASELINE.md: LLaVA-1.5-7B joint_eval sw 512, A100-80GB, fp16"}),
     }
     print(json.dumps(out))
     if world > 1:

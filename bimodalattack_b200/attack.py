@@ -258,6 +258,8 @@ class BimodalAttack:
                                        config.topk, config.n_replace, mask_bits=self._mask_bits)
         if config.filter_ids:
             sampled = filter_ids(sampled, tokenizer)
+        # the scorer computes the rows a candidate shares with the suffix it was sampled from once
+        self._base = (sampled, optim_ids.reshape(-1).to(torch.int64).contiguous())
         dt = time.perf_counter() - t0
         sampling_times.append(dt)
         return sampled, sampled.shape[0], dt, total_sampling_time + dt
@@ -324,8 +326,11 @@ class BimodalAttack:
         lo, hi = bdist.shard_bounds(ids.shape[0], self.world)
         self.engine.reset_key()
         loss = torch.full((ids.shape[0],), float("inf"), dtype=torch.float32, device=self.device)
+        base = getattr(self, "_base", None)
+        base_ids = base[1] if base is not None and base[0] is ids else None
         if hi > lo:
-            loss[lo:hi] = self.engine.score(ids[lo:hi], plan, self.target_ids, idx_base=lo, reset=False)
+            loss[lo:hi] = self.engine.score(ids[lo:hi], plan, self.target_ids, idx_base=lo, reset=False,
+                                            base_ids=base_ids)
         bdist.reduce_winner(self.engine.key, self.engine.flag, self.world)
         if self.world.size > 1 and self.gather_all_losses:
             bdist.gather_losses(loss, lo, hi, self.world)
@@ -443,6 +448,8 @@ class BimodalAttack:
                 if cfg.pgd_attack and not cfg.pgd_after_gcg:
                     shared = bdist.broadcast_tensor(image.detach(), self.world)   # same storage on rank 0
                     image = image if lead else shared
+                if cfg.gcg_attack:      # every rank knows the current suffix: the scorer's sharing base
+                    self._base = (sampled, optim_ids.reshape(-1).to(torch.int64).contiguous())
 
             with torch.no_grad():
                 t0 = time.perf_counter()

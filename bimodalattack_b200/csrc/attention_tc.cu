@@ -55,6 +55,8 @@ struct AtcCfg {
 struct AtcParams {
   __nv_bfloat16* out; long long ldo;
   int M, S, P;
+  const int2* row_meta;      // ragged rows: (first row of the row's candidate, visible prefix keys)
+  int P_shared;              // prefix keys every row sees (== P without row_meta)
   int n_heads, kv_group;
   int q_col0, k_col0;        // column of head 0 inside the Q / K tensor maps
   float scale_log2;
@@ -76,7 +78,9 @@ struct BlockInfo { int pre; int key0; int nvalid; int n_mma; };
 // as the innermost TMA coordinate, whose byte address has to stay 16-byte aligned (an unaligned
 // coordinate faults with "illegal instruction"). The up-to-7 extra keys are masked like any other
 // key that belongs to an earlier candidate.
-__device__ __forceinline__ int tail_key_start(int r0, int S) { return ((r0 / S) * S) & ~7; }
+__device__ __forceinline__ int tail_key_start(int r0, int S, const int2* row_meta) {
+  return (row_meta != nullptr ? row_meta[r0].x : (r0 / S) * S) & ~7;
+}
 
 template <int BN>
 __device__ __forceinline__ BlockInfo block_info(int j, int n_pre, int P, int kt0, int r1) {
@@ -152,7 +156,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         const int head = item / m_tiles, tile = item - head * m_tiles;
         const int kvh = head / p.kv_group;
         const int r0 = tile * ATC_BM, r1 = min(p.M, r0 + ATC_BM);
-        const int kt0 = tail_key_start(r0, p.S);
+        const int kt0 = tail_key_start(r0, p.S, p.row_meta);
         const int nb = n_pre + (r1 - kt0 + BN - 1) / BN;
         mbar_wait(q_empty, (item_n & 1) ^ 1, 0x500);
         mbar_arrive_expect_tx(q_full, Cfg::kQTile);
@@ -200,7 +204,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
         const int head = item / m_tiles, tile = item - head * m_tiles;
         const int r0 = tile * ATC_BM, r1 = min(p.M, r0 + ATC_BM);
-        const int kt0 = tail_key_start(r0, p.S);
+        const int kt0 = tail_key_start(r0, p.S, p.row_meta);
         const int nb = n_pre + (r1 - kt0 + BN - 1) / BN;
         mbar_wait(q_full, item_n & 1, 0x600);
         int prev_n = 0;
@@ -238,10 +242,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
       const int head = item / m_tiles, tile = item - head * m_tiles;
       const int r0 = tile * ATC_BM, r1 = min(p.M, r0 + ATC_BM);
-      const int kt0 = tail_key_start(r0, p.S);
+      const int kt0 = tail_key_start(r0, p.S, p.row_meta);
       const int nb = n_pre + (r1 - kt0 + BN - 1) / BN;
       const int rq = r0 + row_in_tile;
-      const int cs = (rq / p.S) * p.S;
+      int cs = (rq / p.S) * p.S, plim = p.P;
+      if (p.row_meta != nullptr && rq < p.M) {
+        const int2 rm = p.row_meta[rq];
+        cs = rm.x; plim = rm.y;
+      }
       float m_ref = -INFINITY, l_run = 0.0f;
 
       for (int j = 0; j < nb; ++j, ++it) {
@@ -269,11 +277,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[st]);          // S_j is in registers: the buffer is free
-        if (!b.pre || b.nvalid < BN) {                 // masked blocks: last prefix block and the tail
+        if (!b.pre || b.key0 + BN > p.P_shared) {      // masked blocks: prefix keys past P_shared and the tail
 #pragma unroll
           for (int i = 0; i < BN; ++i) {
             const int key = b.key0 + i;
-            const bool vis = b.pre ? (key < p.P) : (key >= cs && key <= rq && key < r1);
+            const bool vis = b.pre ? (key < plim) : (key >= cs && key <= rq && key < r1);
             if (!vis) sv[i] = -INFINITY;
           }
         }
@@ -404,6 +412,8 @@ static cudaError_t launch_atc(const AttnParams& a, int n_heads, cudaStream_t str
   AtcParams p{};
   p.out = a.out; p.ldo = a.ldo;
   p.M = a.M; p.S = a.S; p.P = a.P;
+  p.row_meta = a.row_meta;
+  p.P_shared = a.row_meta != nullptr ? a.P_shared : a.P;
   p.n_heads = n_heads; p.kv_group = a.kv_group;
   p.q_col0 = 0; p.k_col0 = 0;
   p.scale_log2 = a.scale_log2;

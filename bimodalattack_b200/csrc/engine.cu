@@ -71,6 +71,13 @@ struct bma_scorer {
   __nv_bfloat16* prefix_vt = nullptr;    // [layers][kv_dim][ld_vtp]       V^T of the prefix
   float2* ce_part = nullptr;
   float* tgt_logit = nullptr;
+  // ragged-row plan (suffix-head sharing)
+  int2 *row_info = nullptr, *row_meta = nullptr;
+  int* cand_vstart = nullptr;
+  int* total_rows_dev = nullptr;
+  int* total_rows_host = nullptr;        // pinned
+  long long* base_dev = nullptr;         // staging for the *_host entry
+  long long last_rows = 0;
   long long* ids_dev = nullptr;          // staging for the *_host entry
   float* loss_dev = nullptr;
   unsigned long long* key_dev = nullptr;
@@ -117,10 +124,15 @@ bool dev_alloc(T** p, size_t count, size_t* total) {
 //   Gemma layer:  x += norm_post_attn(o(attn(norm_attn x))); x += norm_post_mlp(down(glu(norm_mlp x)))
 // In the Gemma form the residual adds cannot ride in the GEMM epilogue (a row norm sits in
 // between), so each (post-norm + add + next pre-norm) triple is one fused row kernel.
-int run_layers(bma_scorer* s, int rows, int seq, int pos_base, bool prefill, cudaStream_t st) {
+// n_share > 0: ragged rows (row_info / row_meta filled by plan_rows); tail rows [0, n_share) are the
+// base's suffix rows, whose K/V every layer appends to the prefix buffers at key index prefix_len
+// (append == false: a previous chunk of the same call already did).
+int run_layers(bma_scorer* s, int rows, int seq, int pos_base, bool prefill, cudaStream_t st,
+               int n_share = 0, bool append = false) {
   const bma_model_desc& D = s->desc;
   const int d = D.d_model;
   const int P = prefill ? 0 : s->prefix_len;
+  const bool ragged = n_share > 0;
   const bool sandwich = D.sandwich_norm != 0;
   for (int l = 0; l < D.n_layers; ++l) {
     const bma_layer_weights& W = s->layers[l];
@@ -133,7 +145,7 @@ int run_layers(bma_scorer* s, int rows, int seq, int pos_base, bool prefill, cud
     if (!sandwich || l == 0) {     // sandwich layers > 0 got xn from the previous layer's add_norm
       ProfScope ps(s, PC_NORM, 0, st);
       BMA_LAUNCH(launch_rmsnorm(s->x, d, bf(W.norm_attn), s->xn, d, rows, d, D.rms_eps, D.norm_mode,
-                                0, 0, 0, st), "rmsnorm(attn)");
+                                0, 0, 0, nullptr, st), "rmsnorm(attn)");
     }
     {
       GemmParams p{};
@@ -143,6 +155,7 @@ int run_layers(bma_scorer* s, int rows, int seq, int pos_base, bool prefill, cud
       p.rope_cos = W.rope_cos; p.rope_sin = W.rope_sin;
       p.rope_cols = s->qk_dim;
       p.rows_per_seq = seq; p.pos_base = pos_base;
+      if (ragged) p.row_info = s->row_info;
       if (D.qk_norm) {
         p.q_norm_w = bf(W.q_norm); p.k_norm_w = bf(W.k_norm);
         p.q_cols = s->q_dim; p.qk_norm_eps = D.rms_eps;
@@ -155,6 +168,11 @@ int run_layers(bma_scorer* s, int rows, int seq, int pos_base, bool prefill, cud
       }
     }
     if (prefill && l == D.n_layers - 1) break;   // only this layer's K/V are needed
+    if (ragged && append) {
+      ProfScope ps(s, PC_EMBED, 0, st);
+      BMA_LAUNCH(launch_append_prefix_kv(qk + s->q_dim, s->qk_dim, vt, ldvt, pre_qk + s->q_dim, s->qk_dim,
+                                         pre_vt, s->ld_vtp, n_share, s->kv_dim, P, st), "append_prefix_kv");
+    }
     {
       AttnParams a{};
       a.q = qk; a.ldq = s->qk_dim;
@@ -163,12 +181,13 @@ int run_layers(bma_scorer* s, int rows, int seq, int pos_base, bool prefill, cud
       a.k_pre = pre_qk + s->q_dim; a.ldkp = s->qk_dim;
       a.vt_pre = pre_vt; a.ldvtp = s->ld_vtp;
       a.out = s->attn; a.ldo = s->q_dim;
-      a.M = rows; a.S = seq; a.P = P;
+      a.M = rows; a.S = seq; a.P = P + n_share;
+      if (ragged) { a.row_meta = s->row_meta; a.P_shared = P; }
       a.kv_group = D.n_heads / D.n_kv_heads;
       a.head_dim = D.head_dim;
       a.scale_log2 = D.attn_scale * 1.4426950408889634f;
       // QK^T and PV over the visible keys: ~4 * rows * (P + seq/2) * q_dim
-      ProfScope ps(s, PC_ATTN, 4.0 * rows * (P + 0.5 * seq) * s->q_dim, st);
+      ProfScope ps(s, PC_ATTN, 4.0 * rows * (P + 0.5 * (seq + n_share)) * s->q_dim, st);
       BMA_LAUNCH(launch_prefix_tail_attention(a, D.n_heads, st), "attention");
     }
     {
@@ -187,7 +206,7 @@ int run_layers(bma_scorer* s, int rows, int seq, int pos_base, bool prefill, cud
                                    rows, d, D.rms_eps, D.norm_mode, st), "add_norm(post_attn, pre_mlp)");
       } else {
         BMA_LAUNCH(launch_rmsnorm(s->x, d, bf(W.norm_mlp), s->xn, d, rows, d, D.rms_eps, D.norm_mode,
-                                  0, 0, 0, st), "rmsnorm(mlp)");
+                                  0, 0, 0, nullptr, st), "rmsnorm(mlp)");
       }
     }
     {
@@ -315,6 +334,12 @@ bma_scorer* bma_scorer_create(const bma_model_desc* desc) {
   ok = ok && dev_alloc(&s->prefix_vt, static_cast<size_t>(D.n_layers) * s->kv_dim * s->ld_vtp, &s->ws_bytes);
   ok = ok && dev_alloc(&s->ce_part, static_cast<size_t>(n_ce_tiles) * s->ce_rows_cap, &s->ws_bytes);
   ok = ok && dev_alloc(&s->tgt_logit, static_cast<size_t>(s->ce_rows_cap), &s->ws_bytes);
+  ok = ok && dev_alloc(&s->row_info, static_cast<size_t>(D.max_rows), &s->ws_bytes);
+  ok = ok && dev_alloc(&s->row_meta, static_cast<size_t>(D.max_rows), &s->ws_bytes);
+  ok = ok && dev_alloc(&s->cand_vstart, static_cast<size_t>(D.max_rows), &s->ws_bytes);
+  ok = ok && dev_alloc(&s->total_rows_dev, 1, &s->ws_bytes);
+  ok = ok && dev_alloc(&s->base_dev, 4096, &s->ws_bytes);
+  ok = ok && cudaHostAlloc(reinterpret_cast<void**>(&s->total_rows_host), sizeof(int), cudaHostAllocDefault) == cudaSuccess;
   ok = ok && dev_alloc(&s->ids_dev, static_cast<size_t>(D.max_rows), &s->ws_bytes);
   ok = ok && dev_alloc(&s->loss_dev, static_cast<size_t>(D.max_rows), &s->ws_bytes);
   ok = ok && dev_alloc(&s->key_dev, 1, &s->ws_bytes);
@@ -331,6 +356,9 @@ void bma_scorer_destroy(bma_scorer* s) {
   if (s == nullptr) return;
   cudaFree(s->x); cudaFree(s->xn); cudaFree(s->qk); cudaFree(s->vt); cudaFree(s->attn); cudaFree(s->act);
   cudaFree(s->prefix_qk); cudaFree(s->prefix_vt); cudaFree(s->ce_part); cudaFree(s->tgt_logit);
+  cudaFree(s->row_info); cudaFree(s->row_meta); cudaFree(s->cand_vstart); cudaFree(s->total_rows_dev);
+  cudaFree(s->base_dev);
+  if (s->total_rows_host != nullptr) cudaFreeHost(s->total_rows_host);
   cudaFree(s->ids_dev); cudaFree(s->loss_dev); cudaFree(s->key_dev); cudaFree(s->flag_dev);
   for (cudaEvent_t e : s->ev_start) cudaEventDestroy(e);
   for (cudaEvent_t e : s->ev_stop) cudaEventDestroy(e);
@@ -408,10 +436,12 @@ int bma_scorer_reset_key(bma_scorer* s, unsigned long long* key, int* all_match,
   return 0;
 }
 
+long long bma_scorer_last_rows(const bma_scorer* s) { return s ? s->last_rows : 0; }
+
 int bma_scorer_score(bma_scorer* s, const long long* ids, int ids_stride, int B, const int* slot,
                      const void* fixed, int S, const long long* target_ids, int T, int ce_row0,
                      float* loss, unsigned long long* key, int* all_match, unsigned int idx_base,
-                     void* stream) {
+                     const long long* base_ids, void* stream) {
   if (s == nullptr) return fail(cudaErrorInvalidValue, "score: null scorer");
   const bma_model_desc& D = s->desc;
   if (B <= 0) return 0;
@@ -421,26 +451,55 @@ int bma_scorer_score(bma_scorer* s, const long long* ids, int ids_stride, int B,
   if (s->lm_head == nullptr || s->norm_final == nullptr || s->embed == nullptr)
     return fail(cudaErrorInvalidValue, "score: head weights not set");
   cudaStream_t st = as_stream(stream);
-  const int chunk = D.max_rows / S;
   const int d = D.d_model;
   const int n_ce_tiles = (D.vocab + kCeBlockN - 1) / kCeBlockN;
+  s->last_rows = 0;
+
+  // Suffix-head sharing: rows [0, n_share) of the tail can coincide with the base's rows; n_share
+  // is one past the last id-dependent tail position. Needs room for the base (one extra sequence
+  // per chunk, n_share extra prefix keys) and the shared rows must precede the scored rows.
+  int n_share = 0;
+  if (base_ids != nullptr) {
+    std::vector<int> slot_h(S);
+    BMA_CHECK(cudaMemcpyAsync(slot_h.data(), slot, sizeof(int) * S, cudaMemcpyDeviceToHost, st), "score: slot D2H");
+    BMA_CHECK(cudaStreamSynchronize(st), "score: sync");
+    for (int i = 0; i < S; ++i)
+      if (slot_h[i] >= 0) n_share = i + 1;
+    if (n_share > ce_row0) n_share = ce_row0;      // scored rows are always the candidate's own
+    if (s->prefix_len + n_share > D.max_prefix || 2 * S > D.max_rows) n_share = 0;
+  }
+  const bool ragged = n_share > 0;
+  const int chunk = ragged ? D.max_rows / S - 1 : D.max_rows / S;
   for (int b0 = 0; b0 < B; b0 += chunk) {
     const int nb = B - b0 < chunk ? B - b0 : chunk;
-    const int rows = nb * S;
+    int rows = nb * S;
+    const long long* ids_c = ids + (long long)b0 * ids_stride;
+    if (ragged) {
+      // every chunk carries the base as sequence 0: its rows are the keys [P, P+n_share) source
+      ProfScope ps(s, PC_EMBED, 0, st);
+      BMA_LAUNCH(launch_plan_rows(ids_c, ids_stride, base_ids, slot, S, n_share, nb, 1, s->prefix_len,
+                                  s->row_info, s->row_meta, s->cand_vstart, s->total_rows_dev, st), "plan_rows");
+      BMA_CHECK(cudaMemcpyAsync(s->total_rows_host, s->total_rows_dev, sizeof(int), cudaMemcpyDeviceToHost, st),
+                "score: row count D2H");
+      BMA_CHECK(cudaStreamSynchronize(st), "score: sync");
+      rows = *s->total_rows_host;
+      if (rows <= 0 || rows > D.max_rows) return fail(cudaErrorInvalidValue, "score: bad ragged row count");
+    }
+    s->last_rows += rows;
     {
       ProfScope ps(s, PC_EMBED, 0, st);
-      BMA_LAUNCH(launch_build_tail_embeds(ids + (long long)b0 * ids_stride, ids_stride, slot, bf(fixed),
-                                          s->embed, s->ld_embed, D.vocab, D.embed_scale, s->x, nb, S,
-                                          d, st), "build_tail_embeds");
+      BMA_LAUNCH(launch_build_tail_embeds(ids_c, ids_stride, slot, bf(fixed), s->embed, s->ld_embed, D.vocab,
+                                          D.embed_scale, s->x, rows, S, d, ragged ? s->row_info : nullptr,
+                                          base_ids, st), "build_tail_embeds");
     }
-    int rc = run_layers(s, rows, S, s->prefix_len, false, st);
+    int rc = run_layers(s, rows, S, s->prefix_len, false, st, n_share, ragged);
     if (rc != 0) return rc;
     // final norm on the T rows per candidate whose logits predict the target tokens
     const int ce_rows = nb * T;
     {
       ProfScope ps(s, PC_NORM, 0, st);
       BMA_LAUNCH(launch_rmsnorm(s->x, d, s->norm_final, s->xn, d, ce_rows, d, D.rms_eps, D.norm_mode,
-                                T, S, ce_row0, st), "rmsnorm(final, gathered)");
+                                T, S, ce_row0, ragged ? s->cand_vstart : nullptr, st), "rmsnorm(final, gathered)");
     }
     {
       GemmParams p{};
@@ -463,17 +522,21 @@ int bma_scorer_score(bma_scorer* s, const long long* ids, int ids_stride, int B,
 int bma_scorer_score_host(bma_scorer* s, const long long* ids_host, int ids_stride, int B,
                           const int* slot, const void* fixed, int S, const long long* target_ids,
                           int T, int ce_row0, float* loss_host, unsigned long long* key_host,
-                          unsigned int idx_base, void* stream) {
+                          unsigned int idx_base, const long long* base_ids_host, void* stream) {
   if (s == nullptr) return fail(cudaErrorInvalidValue, "score_host: null scorer");
-  if ((long long)B * ids_stride > s->desc.max_rows)
+  if ((long long)B * ids_stride > s->desc.max_rows || ids_stride > 4096)
     return fail(cudaErrorInvalidValue, "score_host: ids exceed staging capacity");
   cudaStream_t st = as_stream(stream);
   BMA_CHECK(cudaMemcpyAsync(s->ids_dev, ids_host, sizeof(long long) * B * ids_stride,
                             cudaMemcpyHostToDevice, st), "score_host: H2D ids");
+  if (base_ids_host != nullptr)
+    BMA_CHECK(cudaMemcpyAsync(s->base_dev, base_ids_host, sizeof(long long) * ids_stride,
+                              cudaMemcpyHostToDevice, st), "score_host: H2D base ids");
   int rc = bma_scorer_reset_key(s, s->key_dev, s->flag_dev, stream);
   if (rc != 0) return rc;
   rc = bma_scorer_score(s, s->ids_dev, ids_stride, B, slot, fixed, S, target_ids, T, ce_row0,
-                        s->loss_dev, s->key_dev, s->flag_dev, idx_base, stream);
+                        s->loss_dev, s->key_dev, s->flag_dev, idx_base,
+                        base_ids_host != nullptr ? s->base_dev : nullptr, stream);
   if (rc != 0) return rc;
   BMA_CHECK(cudaMemcpyAsync(loss_host, s->loss_dev, sizeof(float) * B, cudaMemcpyDeviceToHost, st),
             "score_host: D2H loss");
@@ -501,7 +564,7 @@ int bma_gemm_bf16(const void* A, long long lda, const void* B, long long ldb, vo
 
 int bma_rmsnorm(const void* x, long long ldx, const void* w, void* y, long long ldy, int rows,
                 int d, float eps, int mode, void* stream) {
-  BMA_LAUNCH(launch_rmsnorm(bf(x), ldx, bf(w), bf(y), ldy, rows, d, eps, mode, 0, 0, 0,
+  BMA_LAUNCH(launch_rmsnorm(bf(x), ldx, bf(w), bf(y), ldy, rows, d, eps, mode, 0, 0, 0, nullptr,
                             as_stream(stream)), "rmsnorm");
   return 0;
 }

@@ -29,12 +29,13 @@ struct GemmParams {
   long long ldc;
   const __nv_bfloat16* R;     // optional residual (EPI_STORE), same shape as C
   long long ldr;
-  // rotary (EPI_ROPE): tables [pos][64] fp32 (values already rounded to the model dtype)
+  // rotary (EPI_ROPE): tables [pos][head_dim/2] fp32 (values already rounded to the model dtype)
   const float* rope_cos;
   const float* rope_sin;
   int rope_cols;              // leading output columns that are Q/K heads (multiple of 128)
-  int rows_per_seq;           // position of row r is pos_base + (r % rows_per_seq)
-  int pos_base;
+  int rows_per_seq;           // position of row r is pos_base + (r % rows_per_seq), or
+  int pos_base;               //   pos_base + row_info[r].y when row_info != null (ragged rows)
+  const int2* row_info;
   __nv_bfloat16* Vt;          // EPI_ROPE: columns >= rope_cols (the V heads) go here TRANSPOSED,
   long long ldvt;             //   Vt[(col - rope_cols) * ldvt + row], for the K-major PV operand
   // optional per-head RMSNorm on Q and K before the rotation (Gemma-3 q_norm / k_norm):
@@ -246,7 +247,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
       } else if constexpr (EPI == EPI_ROPE) {
         static_assert(BN % HD == 0 && HD % 64 == 0, "a tile holds whole heads");
         constexpr int HALF = HD / 2;
-        const int pos = p.pos_base + (row_ok ? (row % p.rows_per_seq) : 0);
+        const int pos = p.pos_base + (!row_ok ? 0 : p.row_info != nullptr ? p.row_info[row].y
+                                                                          : (row % p.rows_per_seq));
         const float4* cosp = reinterpret_cast<const float4*>(p.rope_cos + (long long)pos * HALF);
         const float4* sinp = reinterpret_cast<const float4*>(p.rope_sin + (long long)pos * HALF);
 #pragma unroll 1

@@ -15,6 +15,10 @@ struct AttnParams {
   const __nv_bfloat16* vt_pre;  long long ldvtp;   // [Hkv*HD, P] prefix values, transposed
   __nv_bfloat16* out;           long long ldo;     // [M, H*HD]
   int M, S, P;
+  // ragged rows (suffix-head sharing): row_meta[r] = (first row of r's candidate, prefix keys
+  // visible to r); all rows see prefix keys < P_shared. null = uniform S-row candidates.
+  const int2* row_meta;
+  int P_shared;
   int kv_group;                 // query heads per kv head
   int head_dim;                 // 128 or 256
   float scale_log2;             // softmax scale * log2(e)
@@ -36,11 +40,21 @@ cudaError_t launch_sample_ids(const long long* ids, const void* grad, int grad_d
 
 cudaError_t launch_build_tail_embeds(const long long* ids, int ids_stride, const int* slot,
                                      const __nv_bfloat16* fixed, const __nv_bfloat16* W,
-                                     long long ldw, int V, float scale, __nv_bfloat16* out, int B,
-                                     int S, int d, cudaStream_t stream);
+                                     long long ldw, int V, float scale, __nv_bfloat16* out, int rows,
+                                     int S, int d, const int2* row_info, const long long* base_ids,
+                                     cudaStream_t stream);
+cudaError_t launch_plan_rows(const long long* ids, int ids_stride, const long long* base_ids,
+                             const int* slot, int S, int n_share, int B, int include_base, int P,
+                             int2* row_info, int2* row_meta, int* cand_vstart, int* total_rows,
+                             cudaStream_t stream);
+cudaError_t launch_append_prefix_kv(const __nv_bfloat16* k_tail, long long ldk, const __nv_bfloat16* vt_tail,
+                                    long long ldvt, __nv_bfloat16* k_pre, long long ldkp,
+                                    __nv_bfloat16* vt_pre, long long ldvtp, int n, int kv_dim, int P,
+                                    cudaStream_t stream);
 cudaError_t launch_rmsnorm(const __nv_bfloat16* x, long long ldx, const __nv_bfloat16* w,
                            __nv_bfloat16* y, long long ldy, int rows, int d, float eps, int mode,
-                           int gather_T, int gather_S, int gather_off, cudaStream_t stream);
+                           int gather_T, int gather_S, int gather_off, const int* gather_vstart,
+                           cudaStream_t stream);
 cudaError_t launch_add_norm(const __nv_bfloat16* y, long long ldy, const __nv_bfloat16* w_post,
                             __nv_bfloat16* x, long long ldx, const __nv_bfloat16* w_next,
                             __nv_bfloat16* xn, long long ldxn, int rows, int d, float eps, int mode,

@@ -11,16 +11,113 @@
 namespace bma {
 
 // ------------------------------------------------------------------------------------------------
-// out[b*S + s, :] = slot[s] >= 0 ? round_bf16(W[ids[b, slot[s]], :] * scale) : fixed[s, :]
+// Suffix-head sharing. A candidate equals the current suffix
+// ("base") up to its first replaced position j, so its tail rows [0, j) are the base's rows: they
+// are computed once (the base rides along as an extra candidate) and their K/V are appended to the
+// shared prefix. Candidate c then owns only rows [j_c, S): the flattened row space is ragged.
+//   row_info[r] = (candidate index in ids, or -1 for the base; tail position s)
+//   row_meta[r] = (first flattened row of the candidate; number of prefix keys the row may see,
+//                  = P + j_c)
+//   cand_vstart[c] = first row of candidate c minus j_c  (row of tail position s is vstart + s)
+// One block; candidates are spread over the threads, rows are numbered by a block-wide scan.
+__global__ void __launch_bounds__(1024)
+plan_rows_kernel(const long long* __restrict__ ids, int ids_stride, const long long* __restrict__ base_ids,
+                 const int* __restrict__ slot, int S, int n_share, int B, int include_base, int P,
+                 int2* __restrict__ row_info, int2* __restrict__ row_meta, int* __restrict__ cand_vstart,
+                 int* __restrict__ total_rows) {
+  __shared__ int part[1024];
+  const int t = threadIdx.x, nt = blockDim.x;
+  const int n = B + (include_base ? 1 : 0);            // entry 0 is the base when included
+  const int per = (n + nt - 1) / nt;
+  const int e0 = min(n, t * per), e1 = min(n, e0 + per);
+  auto first_diff = [&](int e) -> int {
+    if (include_base && e == 0) return 0;
+    const long long* row = ids + (long long)(e - (include_base ? 1 : 0)) * ids_stride;
+    for (int s = 0; s < n_share; ++s) {
+      const int sl = slot[s];
+      if (sl >= 0 && row[sl] != base_ids[sl]) return s;
+    }
+    return n_share;
+  };
+  int local = 0;
+  for (int e = e0; e < e1; ++e) local += S - first_diff(e);
+  part[t] = local;
+  __syncthreads();
+  for (int off = 1; off < nt; off <<= 1) {               // inclusive Hillis-Steele scan
+    const int v = t >= off ? part[t - off] : 0;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  int row = part[t] - local;
+  if (t == nt - 1) *total_rows = part[t];
+  for (int e = e0; e < e1; ++e) {
+    const int j = first_diff(e);
+    const int c = e - (include_base ? 1 : 0);           // -1 = base
+    if (c >= 0) cand_vstart[c] = row - j;
+    for (int s = j; s < S; ++s) {
+      row_info[row + s - j] = make_int2(c, s);
+      row_meta[row + s - j] = make_int2(row, P + j);
+    }
+    row += S - j;
+  }
+}
+
+cudaError_t launch_plan_rows(const long long* ids, int ids_stride, const long long* base_ids,
+                             const int* slot, int S, int n_share, int B, int include_base, int P,
+                             int2* row_info, int2* row_meta, int* cand_vstart, int* total_rows,
+                             cudaStream_t stream) {
+  plan_rows_kernel<<<1, 1024, 0, stream>>>(ids, ids_stride, base_ids, slot, S, n_share, B, include_base, P,
+                                           row_info, row_meta, cand_vstart, total_rows);
+  return cudaGetLastError();
+}
+
+// Appends the base's K rows / V^T columns [0, n) of one layer to the shared-prefix buffers at key
+// index P.. (K: row-major [key][kv_dim] slices with row strides ldk / ldkp; V^T: [kv_dim][key]).
+__global__ void __launch_bounds__(256)
+append_prefix_kv_kernel(const __nv_bfloat16* __restrict__ k_tail, long long ldk,
+                        const __nv_bfloat16* __restrict__ vt_tail, long long ldvt,
+                        __nv_bfloat16* __restrict__ k_pre, long long ldkp,
+                        __nv_bfloat16* __restrict__ vt_pre, long long ldvtp, int n, int kv_dim, int P) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * kv_dim) return;
+  const int key = i / kv_dim, c = i - key * kv_dim;     // K: consecutive threads -> consecutive columns
+  k_pre[(long long)(P + key) * ldkp + c] = k_tail[(long long)key * ldk + c];
+  const int dim = i / n, kk = i - dim * n;              // V^T: consecutive threads -> consecutive keys
+  vt_pre[(long long)dim * ldvtp + P + kk] = vt_tail[(long long)dim * ldvt + kk];
+}
+
+cudaError_t launch_append_prefix_kv(const __nv_bfloat16* k_tail, long long ldk, const __nv_bfloat16* vt_tail,
+                                    long long ldvt, __nv_bfloat16* k_pre, long long ldkp,
+                                    __nv_bfloat16* vt_pre, long long ldvtp, int n, int kv_dim, int P,
+                                    cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  const int total = n * kv_dim;
+  append_prefix_kv_kernel<<<(total + 255) / 256, 256, 0, stream>>>(k_tail, ldk, vt_tail, ldvt, k_pre, ldkp,
+                                                                   vt_pre, ldvtp, n, kv_dim, P);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// out[row, :] = slot[s] >= 0 ? round_bf16(W[ids[b, slot[s]], :] * scale) : fixed[s, :]
+// Uniform layout (row_info == null): row = b*S + s. Ragged layout: (b, s) = row_info[row], b = -1
+// reads the base ids.
 __global__ void __launch_bounds__(256)
 build_tail_embeds_kernel(const long long* __restrict__ ids, int ids_stride,
                          const int* __restrict__ slot, const __nv_bfloat16* __restrict__ fixed,
                          const __nv_bfloat16* __restrict__ W, long long ldw, int V, float scale,
-                         __nv_bfloat16* __restrict__ out, int B, int S, int d) {
+                         __nv_bfloat16* __restrict__ out, int rows, int S, int d,
+                         const int2* __restrict__ row_info, const long long* __restrict__ base_ids) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= B * S) return;
-  const int b = warp / S, s = warp - b * S;
+  if (warp >= rows) return;
+  int b, s;
+  if (row_info != nullptr) {
+    const int2 ri = row_info[warp];
+    b = ri.x; s = ri.y;
+  } else {
+    b = warp / S; s = warp - b * S;
+  }
   const int sl = slot[s];
   const int nvec = d >> 3;
   uint4* dst = reinterpret_cast<uint4*>(out + (long long)warp * d);
@@ -29,7 +126,7 @@ build_tail_embeds_kernel(const long long* __restrict__ ids, int ids_stride,
     for (int v = lane; v < nvec; v += 32) dst[v] = src[v];
     return;
   }
-  long long tok = ids[(long long)b * ids_stride + sl];
+  long long tok = b < 0 ? base_ids[sl] : ids[(long long)b * ids_stride + sl];
   if (tok < 0 || tok >= V) tok = 0;   // never read outside the table; host validates ids
   const uint4* src = reinterpret_cast<const uint4*>(W + tok * ldw);
   if (scale == 1.0f) {
@@ -48,30 +145,36 @@ build_tail_embeds_kernel(const long long* __restrict__ ids, int ids_stride,
 
 cudaError_t launch_build_tail_embeds(const long long* ids, int ids_stride, const int* slot,
                                      const __nv_bfloat16* fixed, const __nv_bfloat16* W,
-                                     long long ldw, int V, float scale, __nv_bfloat16* out, int B,
-                                     int S, int d, cudaStream_t stream) {
-  if (B <= 0 || S <= 0) return cudaSuccess;
+                                     long long ldw, int V, float scale, __nv_bfloat16* out, int rows,
+                                     int S, int d, const int2* row_info, const long long* base_ids,
+                                     cudaStream_t stream) {
+  if (rows <= 0 || S <= 0) return cudaSuccess;
   if ((d & 7) != 0) return cudaErrorInvalidValue;
-  const long long rows = (long long)B * S;
-  const int blocks = static_cast<int>((rows * 32 + 255) / 256);
+  const int blocks = static_cast<int>(((long long)rows * 32 + 255) / 256);
   build_tail_embeds_kernel<<<blocks, 256, 0, stream>>>(ids, ids_stride, slot, fixed, W, ldw, V,
-                                                       scale, out, B, S, d);
+                                                       scale, out, rows, S, d, row_info, base_ids);
   return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------
 // RMSNorm, one warp per output row. mode 0 (Llama): y = bf16(w * bf16(x * rstd));
 // mode 1 (Gemma): y = bf16(x * rstd * (1 + w)). Row gather: when gather_T > 0 output row r reads
-// input row (r / gather_T) * gather_S + gather_off + (r % gather_T).
+// input row start(r / gather_T) + gather_off + (r % gather_T), where start(c) = c * gather_S for
+// the uniform layout and gather_vstart[c] for the ragged one.
 __global__ void __launch_bounds__(256)
 rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
                const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ y, long long ldy,
-               int rows, int d, float eps, int mode, int gather_T, int gather_S, int gather_off) {
+               int rows, int d, float eps, int mode, int gather_T, int gather_S, int gather_off,
+               const int* __restrict__ gather_vstart) {
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (r >= rows) return;
   long long src_row = r;
-  if (gather_T > 0) src_row = (long long)(r / gather_T) * gather_S + gather_off + (r % gather_T);
+  if (gather_T > 0) {
+    const int c = r / gather_T;
+    const long long start = gather_vstart != nullptr ? gather_vstart[c] : (long long)c * gather_S;
+    src_row = start + gather_off + (r - c * gather_T);
+  }
   const uint4* src = reinterpret_cast<const uint4*>(x + src_row * ldx);
   const uint4* wv = reinterpret_cast<const uint4*>(w);
   uint4* dst = reinterpret_cast<uint4*>(y + (long long)r * ldy);
@@ -112,12 +215,13 @@ rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
 
 cudaError_t launch_rmsnorm(const __nv_bfloat16* x, long long ldx, const __nv_bfloat16* w,
                            __nv_bfloat16* y, long long ldy, int rows, int d, float eps, int mode,
-                           int gather_T, int gather_S, int gather_off, cudaStream_t stream) {
+                           int gather_T, int gather_S, int gather_off, const int* gather_vstart,
+                           cudaStream_t stream) {
   if (rows <= 0) return cudaSuccess;
   if ((d & 7) != 0 || (ldx & 7) != 0 || (ldy & 7) != 0) return cudaErrorInvalidValue;
   const int blocks = static_cast<int>(((long long)rows * 32 + 255) / 256);
   rmsnorm_kernel<<<blocks, 256, 0, stream>>>(x, ldx, w, y, ldy, rows, d, eps, mode, gather_T,
-                                             gather_S, gather_off);
+                                             gather_S, gather_off, gather_vstart);
   return cudaGetLastError();
 }
 
@@ -215,36 +319,58 @@ __global__ void init_key_kernel(unsigned long long* key, int* flag) {
   }
 }
 
-// One thread per candidate: T rows, n_tiles partials each. part is [n_tiles][M] so the reads of
-// neighbouring candidates' rows are contiguous.
-__global__ void __launch_bounds__(128)
+// One block per candidate, one warp per target row at a time: the lanes stride over the n_tiles
+// (max, sum-exp) partials of the row (part is [n_tiles][M]) and merge them with a fixed-order
+// shuffle tree, so the result does not depend on scheduling. Thread 0 then averages the T token
+// losses in order and publishes the candidate's loss and packed key.
+__device__ __forceinline__ void lse_merge(float& m, float& s, float om, float os) {
+  const float nm = fmaxf(m, om);
+  if (nm == -INFINITY) return;
+  s = s * __expf(m - nm) + os * __expf(om - nm);
+  m = nm;
+}
+
+__global__ void __launch_bounds__(256)
 ce_finalize_kernel(const float2* __restrict__ part, const float* __restrict__ tgt_logit,
                    int n_tiles, int B, int T, float* __restrict__ loss,
                    unsigned long long* __restrict__ key, int* __restrict__ all_match_flag,
                    unsigned int idx_base) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
+  extern __shared__ float ce_row[];              // [T] token losses, then [T] match flags
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
   const long long M = (long long)B * T;
-  float acc = 0.0f;
-  bool all_match = true;
-  for (int tt = 0; tt < T; ++tt) {
+  for (int tt = warp; tt < T; tt += n_warps) {
     const long long row = (long long)b * T + tt;
     float m = -INFINITY, s = 0.0f;
-    for (int nt = 0; nt < n_tiles; ++nt) {
+    for (int nt = lane; nt < n_tiles; nt += 32) {
       const float2 ps = part[(long long)nt * M + row];
-      const float nm = fmaxf(m, ps.x);
-      if (nm == -INFINITY) continue;
-      s = s * __expf(m - nm) + ps.y * __expf(ps.x - nm);
-      m = nm;
+      lse_merge(m, s, ps.x, ps.y);
     }
-    const float tl = tgt_logit[row];
-    acc += (m + logf(s)) - tl;
-    all_match = all_match && (tl >= m);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, m, o);
+      const float os = __shfl_xor_sync(0xffffffffu, s, o);
+      lse_merge(m, s, om, os);
+    }
+    if (lane == 0) {
+      const float tl = tgt_logit[row];
+      ce_row[tt] = (m + logf(s)) - tl;
+      ce_row[T + tt] = (tl >= m) ? 1.0f : 0.0f;
+    }
   }
-  const float l = acc / static_cast<float>(T);
-  loss[b] = l;
-  if (key != nullptr) atomicMin(key, pack_loss_key(l, idx_base + static_cast<unsigned int>(b)));
-  if (all_match_flag != nullptr && all_match) atomicOr(all_match_flag, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float acc = 0.0f;
+    bool all_match = true;
+    for (int tt = 0; tt < T; ++tt) {
+      acc += ce_row[tt];
+      all_match = all_match && (ce_row[T + tt] != 0.0f);
+    }
+    const float l = acc / static_cast<float>(T);
+    loss[b] = l;
+    if (key != nullptr) atomicMin(key, pack_loss_key(l, idx_base + static_cast<unsigned int>(b)));
+    if (all_match_flag != nullptr && all_match) atomicOr(all_match_flag, 1);
+  }
 }
 
 cudaError_t launch_init_key(unsigned long long* key, int* flag, cudaStream_t stream) {
@@ -256,9 +382,8 @@ cudaError_t launch_ce_finalize(const float2* part, const float* tgt_logit, int n
                                int T, float* loss, unsigned long long* key, int* all_match_flag,
                                unsigned int idx_base, cudaStream_t stream) {
   if (B <= 0) return cudaSuccess;
-  const int blocks = (B + 127) / 128;
-  ce_finalize_kernel<<<blocks, 128, 0, stream>>>(part, tgt_logit, n_tiles, B, T, loss, key,
-                                                 all_match_flag, idx_base);
+  ce_finalize_kernel<<<B, 256, 2 * T * sizeof(float), stream>>>(part, tgt_logit, n_tiles, B, T, loss, key,
+                                                                 all_match_flag, idx_base);
   return cudaGetLastError();
 }
 

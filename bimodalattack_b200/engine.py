@@ -102,6 +102,7 @@ class ScoringEngine:
         self.key = torch.empty(1, dtype=torch.int64, device=self.device)
         self.flag = torch.empty(1, dtype=torch.int32, device=self.device)
         self.prefix_len = 0
+        self.share_suffix_head = True    # compute tail rows shared with the base suffix once (see score())
         self._last_prefix: Optional[torch.Tensor] = None
         self._prefix_stale = False
 
@@ -216,7 +217,8 @@ class ScoringEngine:
     def prefill(self, prefix_embeds: Optional[torch.Tensor]):
         """Compute and keep the K/V of the shared prefix ([P, d] bf16; None/empty = no prefix)."""
         P = 0 if prefix_embeds is None else prefix_embeds.shape[0]
-        self._ensure(max(self._cap_rows, P, 1), P)
+        # room for the base suffix's keys behind the prefix (suffix-head sharing, see score())
+        self._ensure(max(self._cap_rows, P, 1), P + (64 if self.share_suffix_head else 0))
         if P > 0:
             if P + 1 > self._max_positions:
                 raise RuntimeError("bimodal_b200 scorer: sequence longer than the rotary table")
@@ -234,15 +236,18 @@ class ScoringEngine:
                                                        native.stream_ptr(self.device)), "scorer_reset_key")
 
     def score(self, ids: torch.Tensor, plan: TailPlan, target_ids: torch.Tensor, idx_base: int = 0,
-              reset: bool = True) -> torch.Tensor:
+              reset: bool = True, base_ids: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Per-candidate mean CE (fp32, [B]). ``self.key`` receives the packed (loss, index) minimum
-        and ``self.flag`` the early-stop indicator."""
+        and ``self.flag`` the early-stop indicator. ``base_ids`` ([n_optim] int64): the suffix the
+        candidates were sampled from; rows a candidate shares with it are computed once."""
         native.require_cuda(ids, "ids")
         B = ids.shape[0]
         T = target_ids.numel()
         S, row0 = self._tail_rows(plan, T)
         self._check_length(S)
-        self._ensure(max(self._cap_rows, min(B, 4096) * S), self._cap_prefix)
+        share = self._share_rows(ids, base_ids)
+        self._ensure(max(self._cap_rows, (min(B, 4096) + (1 if share else 0)) * S),
+                     max(self._cap_prefix, self.prefix_len + share))
         if self._prefix_stale:           # the workspace was re-created after the last prefill
             self.prefill(self._last_prefix)
         ids = ids.to(torch.int64).contiguous()
@@ -254,8 +259,22 @@ class ScoringEngine:
             native.check(self.lib.bma_scorer_score(
                 self._scorer, ids.data_ptr(), ids.stride(0), B, plan.slot.data_ptr(), plan.fixed.data_ptr(),
                 S, tgt.data_ptr(), T, row0, loss.data_ptr(), self.key.data_ptr(), self.flag.data_ptr(),
-                idx_base, native.stream_ptr(self.device)), "scorer_score")
+                idx_base, None if not share else base_ids.data_ptr(), native.stream_ptr(self.device)),
+                "scorer_score")
         return loss
+
+    def _share_rows(self, ids: torch.Tensor, base_ids: Optional[torch.Tensor]) -> int:
+        """Extra prefix keys suffix-head sharing needs (0 = sharing off)."""
+        if base_ids is None or not self.share_suffix_head:
+            return 0
+        if base_ids.dtype != torch.int64 or not base_ids.is_contiguous() or base_ids.numel() != ids.shape[1]:
+            raise RuntimeError("bimodal_b200 scorer: base_ids must be a contiguous int64 vector of the suffix length")
+        return int(ids.shape[1])
+
+    @property
+    def last_rows(self) -> int:
+        """Tail rows the last score call ran through the decoder."""
+        return 0 if self._scorer is None else int(self.lib.bma_scorer_last_rows(self._scorer))
 
     def _check_length(self, S: int):
         if self.prefix_len + S > self._max_positions:
@@ -273,16 +292,20 @@ class ScoringEngine:
         return S, S - T
 
     def score_host(self, ids_host: torch.Tensor, plan: TailPlan, target_ids: torch.Tensor,
-                   loss_host: torch.Tensor, key_host: torch.Tensor, idx_base: int = 0):
+                   loss_host: torch.Tensor, key_host: torch.Tensor, idx_base: int = 0,
+                   base_ids_host: Optional[torch.Tensor] = None):
         """End-to-end entry: pinned host ids in, pinned host losses + key out (synchronises)."""
         B, T = ids_host.shape[0], target_ids.numel()
         S, row0 = self._tail_rows(plan, T)
         self._check_length(S)
-        self._ensure(max(self._cap_rows, min(B, 4096) * S, B * ids_host.shape[1]), self._cap_prefix)
+        share = self._share_rows(ids_host, base_ids_host)
+        self._ensure(max(self._cap_rows, (min(B, 4096) + (1 if share else 0)) * S, B * ids_host.shape[1]),
+                     max(self._cap_prefix, self.prefix_len + share))
         if self._prefix_stale:
             self.prefill(self._last_prefix)
         with torch.cuda.device(self.device):
             native.check(self.lib.bma_scorer_score_host(
                 self._scorer, ids_host.data_ptr(), ids_host.stride(0), B, plan.slot.data_ptr(),
                 plan.fixed.data_ptr(), S, target_ids.data_ptr(), T, row0, loss_host.data_ptr(),
-                key_host.data_ptr(), idx_base, native.stream_ptr(self.device)), "scorer_score_host")
+                key_host.data_ptr(), idx_base, None if not share else base_ids_host.data_ptr(),
+                native.stream_ptr(self.device)), "scorer_score_host")

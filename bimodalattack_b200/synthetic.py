@@ -44,9 +44,10 @@ class Gemma3Processor:  # noqa: N801 - the reference dispatches on this exact cl
     """Minimal stand-in for HF's Gemma3Processor: the reference only reads the class name, the
     ``chat_template`` attribute and calls ``apply_chat_template``."""
 
-    def __init__(self, tokenizer):
+    def __init__(self, tokenizer, generation_prompt: str = " <end_of_turn> <start_of_turn>"):
         self.tokenizer = tokenizer
         self.chat_template = "gemma3-synthetic"
+        self.generation_prompt = generation_prompt
 
     def apply_chat_template(self, messages, add_generation_prompt=True, **_):
         content = messages[-1]["content"]
@@ -58,7 +59,7 @@ class Gemma3Processor:  # noqa: N801 - the reference dispatches on this exact cl
         out = "<start_of_turn> " + text
         if has_image:
             out += " <start_of_image>"
-        out += " <end_of_turn> <start_of_turn>"
+        out += self.generation_prompt
         return out
 
 
@@ -177,7 +178,8 @@ def swap_in_robust_clip(llava, image_size: int = 224, seed: int = 7):
 
 
 def make_gemma3(size: str = "tiny", dtype=torch.float32, device=None, seed: int = 0,
-                head_gain: float = 1.0, embed_gain: float = 1.0, randomize_norms: bool = False):
+                head_gain: float = 1.0, embed_gain: float = 1.0, randomize_norms: bool = False,
+                fast_init: bool = False):
     """Gemma-3 (SigLIP tower, tied LM head). Random init leaves the multimodal projector at zero
     (the image would have no effect), so it is re-initialised here. ``embed_gain`` scales the tied
     embedding / LM-head table (spreads the per-candidate losses like ``head_gain`` does for an
@@ -221,7 +223,16 @@ def make_gemma3(size: str = "tiny", dtype=torch.float32, device=None, seed: int 
     else:
         raise ValueError(size)
     torch.manual_seed(seed)
-    if device is not None and torch.device(device).type == "cuda":
+    if fast_init:
+        from transformers.initialization import no_init_weights
+        with no_init_weights():
+            model = Gemma3ForConditionalGeneration(cfg)
+        _tiled_init(model, seed)
+        with torch.no_grad():
+            for name, p in model.named_parameters():      # (1 + w) norms: w = 0 is the identity scale
+                if "norm" in name and p.dim() < 2:
+                    p.zero_()
+    elif device is not None and torch.device(device).type == "cuda":
         prev = torch.get_default_dtype()
         torch.set_default_dtype(dtype)
         try:
@@ -270,3 +281,21 @@ def headline_case(vocab: int = 32000, image_px: int = 336, n_optim: int = 20, n_
     target = synthetic_words(n_target, start=400)
     init = " ".join(["x"] * n_optim)
     return tok, proc, T.Normalize(CLIP_MEAN, CLIP_STD), image, messages, target, init
+
+
+def gemma_case(vocab: int = 262208, image_px: int = 896, n_optim: int = 20, n_target: int = 16,
+               seed: int = 1234):
+    """Synthetic inputs of BASELINE.json config 4: Gemma-3 text-only order
+    before 20 | optim 20 | after 6 | target 16. Returns (tokenizer, processor, normalize,
+    image [cpu fp32], messages, target, optim_str_init)."""
+    import torchvision.transforms as T
+
+    tok = make_tokenizer(vocab, image_token="<image_soft_token>",
+                         extra_tokens=["<start_of_image>", "<end_of_image>", "<start_of_turn>", "<end_of_turn>"])
+    proc = Gemma3Processor(tok, generation_prompt=" <end_of_turn> <start_of_turn> " + synthetic_words(4, start=100))
+    g = torch.Generator().manual_seed(seed)
+    image = torch.rand((1, 3, image_px, image_px), generator=g)
+    messages = [{"role": "user", "content": synthetic_words(18, start=200)}]     # + <s> <start_of_turn> = 20
+    target = synthetic_words(n_target, start=400)
+    init = " ".join(["x"] * n_optim)
+    return tok, proc, T.Normalize(GEMMA_MEAN, GEMMA_STD), image, messages, target, init

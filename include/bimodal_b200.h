@@ -112,19 +112,29 @@ int bma_scorer_prefill(bma_scorer* s, const void* prefix_embeds, int P, void* st
  * and ce_row0 = S - T. Outputs: loss[B]
  * fp32; *key = min over candidates of (orderable(loss) << 31 | idx_base + b) merged into the
  * existing value (call bma_scorer_reset_key first); *all_match != 0 if some candidate's argmax
- * equals the target everywhere (early_stop, :1300-1306). */
+ * equals the target everywhere (early_stop, :1300-1306).
+ *
+ * base_ids (device, [ids_stride] int64, or NULL) is the suffix the candidates were sampled from
+ * (the reference's optim_ids, :930-939). When given, tail rows a candidate shares with the base --
+ * everything before its first replaced position -- are computed once instead of once per
+ * candidate: the base is run as one extra sequence, its K/V are appended to the shared prefix and
+ * each candidate computes only the rows from its first difference on. Any base gives the same
+ * losses; one unrelated to the candidates merely saves nothing. The call then synchronises the
+ * stream once per chunk (the ragged row count comes back to the host). */
 int bma_scorer_reset_key(bma_scorer* s, unsigned long long* key, int* all_match, void* stream);
 int bma_scorer_score(bma_scorer* s, const long long* ids, int ids_stride, int B, const int* slot,
                      const void* fixed, int S, const long long* target_ids, int T, int ce_row0,
                      float* loss, unsigned long long* key, int* all_match, unsigned int idx_base,
-                     void* stream);
+                     const long long* base_ids, void* stream);
+/* Tail rows the last bma_scorer_score call ran through the decoder (B*S without base_ids). */
+long long bma_scorer_last_rows(const bma_scorer* s);
 
 /* Same call with HOST buffers for ids / loss / key (pinned recommended): copies in, scores,
  * copies out and synchronises the stream. This is the end-to-end entry the benchmark times. */
 int bma_scorer_score_host(bma_scorer* s, const long long* ids_host, int ids_stride, int B,
                           const int* slot, const void* fixed, int S, const long long* target_ids,
                           int T, int ce_row0, float* loss_host, unsigned long long* key_host,
-                          unsigned int idx_base, void* stream);
+                          unsigned int idx_base, const long long* base_ids_host, void* stream);
 
 /* Optional per-class CUDA-event profile of the scoring pass (events on the launching stream).
  * Classes: 0 tail-embed, 1 rmsnorm, 2 gemm qkv+rope, 3 attention, 4 gemm o_proj, 5 gemm gate/up+GLU,

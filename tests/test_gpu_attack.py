@@ -214,3 +214,67 @@ def test_small_model_joint_scoring_scale(cuda_device):
     assert bool(((got - want).abs() <= 2e-2 * want.abs() + 1e-3).all()), (got - want).abs().max()
     assert idx == int(got.argmin())
     assert float(want[idx]) <= float(want.min()) + 2e-2 * abs(float(want.min())) + 1e-3
+
+
+def _related_candidates(base, n, vocab_lo, vocab_hi, n_replace, seed, device):
+    """n candidates that differ from ``base`` ([L]) at n_replace random positions, plus the edge
+    cases: identical to the base, first position replaced, last position replaced."""
+    g = torch.Generator().manual_seed(seed)
+    L = base.numel()
+    cand = base.cpu().repeat(n, 1)
+    for i in range(n):
+        pos = torch.randperm(L, generator=g)[:n_replace]
+        cand[i, pos] = torch.randint(vocab_lo, vocab_hi, (n_replace,), generator=g)
+    cand[0] = base.cpu()
+    cand[1] = base.cpu(); cand[1, 0] = vocab_lo + 1
+    cand[2] = base.cpu(); cand[2, L - 1] = vocab_lo + 2
+    return cand.to(device)
+
+
+@pytest.mark.parametrize("mode,n,n_replace", [("joint", 300, 1), ("gcg_only", 64, 2), ("joint", 4300, 1)])
+def test_suffix_head_sharing_matches_full_tails(cuda_device, mode, n, n_replace):
+    """Rows a candidate shares with the suffix it was sampled from are computed once (SURVEY 8(f)
+    rank 3). Same losses as scoring every full tail (only the attention's key-block order differs)
+    and as the fp32 oracle; fewer decoder rows. n = 4300 exceeds one scorer chunk (4096)."""
+    from bimodalattack_b200 import BimodalAttack
+    from bimodalattack_b200.attack import image_features
+    from oracle import hotpath
+    model, tok, proc, norm, image, cfg = _setup(cuda_device, search_width=n, **MODES[mode])
+    atk = BimodalAttack(model, tok, proc, cfg, normalize=norm)
+    atk._prepare([{"role": "user", "content": PROMPT}], TARGET)
+    base = tok(INIT, add_special_tokens=False, return_tensors="pt")["input_ids"].to(cuda_device).reshape(-1)
+    cand = _related_candidates(base, n, 8, 1000, n_replace, seed=n, device=cuda_device)
+    with torch.no_grad():
+        feats = image_features(model, norm(image), False) if cfg.pgd_attack else None
+        if mode == "joint":
+            batch = atk._build_input_embeds_pgd(cand, feats, search_width=n, single=True)
+            order = hotpath.segment_order("pgd", "llava", single=True)
+        else:
+            batch = atk._build_input_embeds_gcg(cand, search_width=n, no_joint_eval=True)
+            order = hotpath.segment_order("gcg", "llava", no_joint_eval=True)
+        full = atk._compute_candidates_loss_original(n, batch).clone()
+        rows_full = atk.engine.last_rows
+        _, idx_full = atk._winner()
+        atk._base = (cand, base.to(torch.int64).contiguous())
+        shared = atk._compute_candidates_loss_original(n, batch).clone()
+        rows_shared = atk.engine.last_rows
+        key_loss, idx_shared = atk._winner()
+    S = atk._plan(batch).n_tail - 1
+    L = base.numel()
+    first_diff = torch.where((cand != base).any(1), (cand != base).float().argmax(1), torch.tensor(L, device=cuda_device))
+    first_diff = first_diff.clamp(max=S - atk.target_ids.numel())     # scored rows are never shared
+    n_chunks = (n + 4095) // 4096          # the engine sizes the workspace for 4096 candidates (+ the base) per chunk
+    assert rows_full == n * S
+    assert rows_shared == int((S - first_diff).sum()) + n_chunks * S          # + the base, once per chunk
+    assert rows_shared < 0.85 * rows_full
+    assert float((shared - full).abs().max()) <= 1e-2 * float(full.abs().max())
+    assert idx_shared == int(shared.argmin()) and key_loss == float(shared.min())
+    assert float(full[idx_shared]) <= float(full.min()) + 1e-2 * float(full.abs().max())
+    if n <= 300:
+        ora32 = hotpath.OracleAttack(_fp32_twin(model), tok, proc, cfg, normalize=norm)
+        ora32.target_ids = atk.target_ids
+        ora32.seg_embeds = {k: ora32.emb(v) for k, v in atk.segment_ids.items()}
+        f32 = feats.float() if feats is not None else None
+        want, _ = hotpath.candidates_loss(ora32.model, hotpath.assemble(ora32._parts(cand, f32), order, n),
+                                          atk.target_ids, 50)
+        assert bool(((shared - want).abs() <= 2e-2 * want.abs() + 1e-3).all()), (shared - want).abs().max()

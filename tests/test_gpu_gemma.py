@@ -158,3 +158,30 @@ def test_add_norm_kernel(lib, cuda_device):
     assert float((xs.float() - want_x.float()).abs().max()) <= 2 ** -7 * float(want_x.float().abs().max())
     assert float((xs != want_x).float().mean()) < 1e-3
     assert float((buf.float() - want_xn.float()).abs().max()) <= 2 ** -6 * float(want_xn.float().abs().max())
+
+
+def test_gemma_suffix_head_sharing(cuda_device):
+    """Gemma joint order puts the image AFTER the suffix, so the tail is long (optim | before_suffix
+    | image | after | target) and only its first rows can be shared with the base suffix."""
+    from bimodalattack_b200 import BimodalAttack
+    from bimodalattack_b200.attack import image_features
+    model, tok, proc, norm, image, cfg = _setup(cuda_device, **MODES["joint"])
+    atk = BimodalAttack(model, tok, proc, cfg, normalize=norm)
+    atk._prepare([{"role": "user", "content": PROMPT}], TARGET)
+    base = tok(INIT, add_special_tokens=False, return_tensors="pt")["input_ids"].to(cuda_device).reshape(-1)
+    g = torch.Generator().manual_seed(4)
+    cand = base.cpu().repeat(40, 1)
+    for i in range(1, 40):
+        cand[i, int(torch.randint(0, base.numel(), (1,), generator=g))] = int(torch.randint(12, 1000, (1,), generator=g))
+    cand = cand.to(cuda_device)
+    with torch.no_grad():
+        feats = image_features(model, norm(image), True)
+        batch = atk._build_input_embeds_pgd(cand, feats, search_width=40, single=True)
+        full = atk._compute_candidates_loss_original(40, batch).clone()
+        rows_full = atk.engine.last_rows
+        atk._base = (cand, base.to(torch.int64).contiguous())
+        shared = atk._compute_candidates_loss_original(40, batch).clone()
+        rows_shared = atk.engine.last_rows
+    assert rows_shared < rows_full + atk._plan(batch).n_tail
+    assert float((shared - full).abs().max()) <= 1e-2 * float(full.abs().max())
+    assert float(shared[0]) == float(shared[0]) and float((shared[1:] - shared[0]).abs().max()) > 0
