@@ -217,6 +217,72 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// ---------------------------------------------------------------- CTA pairs (cta_group::2)
+// Two CTAs of a cluster on one TPC issue ONE tcgen05.mma over M = 256: CTA r holds rows
+// [128 r, 128 r + 128) of A and of the accumulator (its own TMEM), and half of the B tile; the
+// leader (cluster rank 0) issues the instruction for both.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same smem location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA tile load whose completion bytes are credited to an mbarrier that may live in the PEER CTA
+// (bar_cluster_addr is a shared::cluster address, e.g. from mapa_shared).
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m,
+                                                 uint32_t bar_cluster_addr, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr),
+        "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(smem_result)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                                  uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrive on the mbarrier at this smem offset in BOTH CTAs of the pair once the MMAs issued so far
+// have completed.
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(mask)
+      : "memory");
+}
+
 // K-major, 128-byte-swizzled shared-memory operand descriptor for tcgen05.mma:
 // rows are 128 B apart, 8-row groups are 1024 B apart (SBO), version 1 (sm_100), layout 2.
 __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {

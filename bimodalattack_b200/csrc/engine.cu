@@ -162,9 +162,9 @@ int run_layers(bma_scorer* s, int rows, int seq, int pos_base, bool prefill, cud
       }
       ProfScope ps(s, PC_GEMM_QKV, gemm_flops(p), st);
       if (D.head_dim == 128) {
-        BMA_LAUNCH((launch_gemm<256, EPI_ROPE, 128>(s->xn, d, bf(W.w_qkv), d, p, st)), "gemm(qkv+rope)");
+        BMA_LAUNCH((launch_gemm_big<EPI_ROPE, 128>(s->xn, d, bf(W.w_qkv), d, p, st)), "gemm(qkv+rope)");
       } else {
-        BMA_LAUNCH((launch_gemm<256, EPI_ROPE, 256>(s->xn, d, bf(W.w_qkv), d, p, st)), "gemm(qkv+rope)");
+        BMA_LAUNCH((launch_gemm_big<EPI_ROPE, 256>(s->xn, d, bf(W.w_qkv), d, p, st)), "gemm(qkv+rope)");
       }
     }
     if (prefill && l == D.n_layers - 1) break;   // only this layer's K/V are needed
@@ -196,7 +196,7 @@ int run_layers(bma_scorer* s, int rows, int seq, int pos_base, bool prefill, cud
       if (sandwich) { p.C = s->xn; p.ldc = d; }                       // y: normed before the add
       else { p.C = s->x; p.ldc = d; p.R = s->x; p.ldr = d; }
       ProfScope ps(s, PC_GEMM_O, gemm_flops(p), st);
-      BMA_LAUNCH((launch_gemm<256, EPI_STORE>(s->attn, s->q_dim, bf(W.w_o), s->q_dim, p, st)),
+      BMA_LAUNCH((launch_gemm_big<EPI_STORE>(s->attn, s->q_dim, bf(W.w_o), s->q_dim, p, st)),
                  "gemm(o_proj)");
     }
     {
@@ -214,7 +214,7 @@ int run_layers(bma_scorer* s, int rows, int seq, int pos_base, bool prefill, cud
       p.M = rows; p.N = 2 * D.d_ff; p.K = d; p.group_m = 16;
       p.C = s->act; p.ldc = D.d_ff; p.act = D.act;
       ProfScope ps(s, PC_GEMM_GLU, gemm_flops(p), st);
-      BMA_LAUNCH((launch_gemm<256, EPI_GLU>(s->xn, d, bf(W.w_gate_up), d, p, st)), "gemm(gate_up)");
+      BMA_LAUNCH((launch_gemm_big<EPI_GLU>(s->xn, d, bf(W.w_gate_up), d, p, st)), "gemm(gate_up)");
     }
     {
       GemmParams p{};
@@ -222,7 +222,7 @@ int run_layers(bma_scorer* s, int rows, int seq, int pos_base, bool prefill, cud
       if (sandwich) { p.C = s->xn; p.ldc = d; }
       else { p.C = s->x; p.ldc = d; p.R = s->x; p.ldr = d; }
       ProfScope ps(s, PC_GEMM_DOWN, gemm_flops(p), st);
-      BMA_LAUNCH((launch_gemm<256, EPI_STORE>(s->act, D.d_ff, bf(W.w_down), D.d_ff, p, st)),
+      BMA_LAUNCH((launch_gemm_big<EPI_STORE>(s->act, D.d_ff, bf(W.w_down), D.d_ff, p, st)),
                  "gemm(down)");
     }
     if (sandwich) {
@@ -507,7 +507,7 @@ int bma_scorer_score(bma_scorer* s, const long long* ids, int ids_stride, int B,
       p.target_ids = target_ids; p.T = T;
       p.ce_part = s->ce_part; p.tgt_logit = s->tgt_logit;
       ProfScope ps(s, PC_GEMM_CE, gemm_flops(p), st);
-      BMA_LAUNCH((launch_gemm<kCeBlockN, EPI_CE>(s->xn, d, s->lm_head, d, p, st)), "gemm(lm_head+ce)");
+      BMA_LAUNCH((launch_gemm_big<EPI_CE>(s->xn, d, s->lm_head, d, p, st)), "gemm(lm_head+ce)");
     }
     {
       ProfScope ps(s, PC_FINAL, 0, st);
@@ -553,7 +553,7 @@ int bma_gemm_bf16(const void* A, long long lda, const void* B, long long ldb, vo
   p.M = M; p.N = N; p.K = K; p.group_m = 16;
   p.C = bf(C); p.ldc = ldc; p.R = bf(residual); p.ldr = ldr;
   if (block_n == 256) {
-    BMA_LAUNCH((launch_gemm<256, EPI_STORE>(bf(A), lda, bf(B), ldb, p, as_stream(stream))), "gemm");
+    BMA_LAUNCH((launch_gemm_big<EPI_STORE>(bf(A), lda, bf(B), ldb, p, as_stream(stream))), "gemm");
   } else if (block_n == 128) {
     BMA_LAUNCH((launch_gemm<128, EPI_STORE>(bf(A), lda, bf(B), ldb, p, as_stream(stream))), "gemm");
   } else {

@@ -4,6 +4,7 @@
 #include <cudaTypedefs.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -108,31 +109,65 @@ inline bool make_tmap_bf16(CUtensorMap* out, const void* ptr, long long rows, lo
   return true;
 }
 
-template <int BN, int EPI, int HD = 128>
+template <int BN, int EPI, int HD = 128, int CTAS = 1>
 inline cudaError_t launch_gemm(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B,
                                long long ldb, GemmParams p, cudaStream_t stream,
                                int max_ctas = 0) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CTAS>;
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) return cudaSuccess;
   watchdog_attach();
   CUtensorMap ta, tb;
   if (!make_tmap_bf16(&ta, A, p.M, p.K, lda, GEMM_BM)) return cudaErrorInvalidValue;
-  if (!make_tmap_bf16(&tb, B, p.N, p.K, ldb, BN)) return cudaErrorInvalidValue;
+  if (!make_tmap_bf16(&tb, B, p.N, p.K, ldb, BN / CTAS)) return cudaErrorInvalidValue;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, EPI, HD>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, EPI, HD, CTAS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
+  const int m_tiles = ((p.M + GEMM_BM - 1) / GEMM_BM + CTAS - 1) / CTAS;
   const int n_tiles = (p.N + BN - 1) / BN;
-  int grid = m_tiles * n_tiles;
-  const int cap = max_ctas > 0 ? max_ctas : num_sms();
+  int grid = m_tiles * n_tiles * CTAS;
+  const int cap = (max_ctas > 0 ? max_ctas : num_sms()) / CTAS * CTAS;
   if (grid > cap) grid = cap;
-  gemm_bf16_tn_kernel<BN, EPI, HD><<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, p);
-  return cudaGetLastError();
+  if constexpr (CTAS == 1) {
+    gemm_bf16_tn_kernel<BN, EPI, HD, 1><<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+    return cudaGetLastError();
+  } else {
+    // CTA pairs: clusters of 2 along x (both CTAs of a cluster share a TPC)
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CTAS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<BN, EPI, HD, CTAS>, ta, tb, p);
+  }
+}
+
+// The scorer's big GEMMs (BN = 256) run on CTA pairs unless BMA_GEMM_CTAS=1 is set (A/B switch).
+inline int gemm_ctas() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("BMA_GEMM_CTAS");
+    v = (e != nullptr && atoi(e) == 1) ? 1 : 2;
+  }
+  return v;
+}
+
+template <int EPI, int HD = 128>
+inline cudaError_t launch_gemm_big(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B,
+                                   long long ldb, GemmParams p, cudaStream_t stream) {
+  if (gemm_ctas() == 2) return launch_gemm<256, EPI, HD, 2>(A, lda, B, ldb, p, stream);
+  return launch_gemm<256, EPI, HD, 1>(A, lda, B, ldb, p, stream);
 }
 
 }  // namespace bma

@@ -57,12 +57,16 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 256;
 
-template <int BN>
+// CTAS = 2: a CTA pair computes a 256 x BN tile with one cta_group::2 MMA stream; each CTA stages
+// its own 128 rows of A and HALF of the B tile, so a stage is 32 KB instead of 48 KB at BN = 256
+// and the ring is 7 deep instead of 4 (3500 vs 2050 cycles of operand buffering at the MMA's
+// consumption rate) while L2->smem traffic per flop drops by a third.
+template <int BN, int CTAS = 1>
 struct GemmCfg {
   static constexpr int kStageBytesA = GEMM_BM * GEMM_BK * 2;
-  static constexpr int kStageBytesB = BN * GEMM_BK * 2;
+  static constexpr int kStageBytesB = (BN / CTAS) * GEMM_BK * 2;
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
-  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 10);
+  static constexpr int kStages = CTAS == 2 ? (BN >= 256 ? 7 : 9) : (BN >= 256) ? 4 : (BN >= 128 ? 6 : 10);
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
@@ -86,11 +90,12 @@ __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const uint32_t
   }
 }
 
-template <int BN, int EPI, int HD = 128>
+template <int BN, int EPI, int HD = 128, int CTAS = 1>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CTAS>;
+  static_assert(CTAS == 1 || CTAS == 2, "one CTA or a CTA pair");
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -107,11 +112,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
+  // Work units: CTAS == 1 -> 128 x BN tiles, one per CTA; CTAS == 2 -> 256 x BN tiles, one per
+  // CTA pair (this CTA owns rows [128 rank, 128 rank + 128) of it). Units are walked persistently.
+  const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+  const int unit0 = blockIdx.x / CTAS, unit_stride = gridDim.x / CTAS;
+  const int m_tiles = ((p.M + GEMM_BM - 1) / GEMM_BM + CTAS - 1) / CTAS;    // in units of CTAS*128 rows
   const int n_tiles = (p.N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
   const int k_blocks = (p.K + GEMM_BK - 1) / GEMM_BK;
-  const int group_m = p.group_m > 0 ? p.group_m : 16;
+  const int group_m = max(1, (p.group_m > 0 ? p.group_m : 16) / CTAS);
 
   auto tile_coords = [&](int tile, int& m_blk, int& n_blk) {
     const int per_group = group_m * n_tiles;
@@ -119,7 +129,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const int first_m = g * group_m;
     const int rows_in_group = min(group_m, m_tiles - first_m);
     const int r = tile - g * per_group;
-    m_blk = first_m + r % rows_in_group;
+    m_blk = (first_m + r % rows_in_group) * CTAS + static_cast<int>(cta_rank);   // this CTA's 128-row block
     n_blk = r / rows_in_group;
   };
 
@@ -134,16 +144,21 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_empty[i], 4 * CTAS);     // the epilogue warps of BOTH CTAs release the leader
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    tmem_relinquish();
+    if constexpr (CTAS == 2) {
+      tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -152,29 +167,38 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
         int m_blk, n_blk;
         tile_coords(tile, m_blk, n_blk);
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1, 0x100 + stage);
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_2d(smem_a + stage * Cfg::kStageBytesA, &tmap_a, &full_bar[stage],
-                      kb * GEMM_BK, m_blk * GEMM_BM);
-          tma_load_2d(smem_b + stage * Cfg::kStageBytesB, &tmap_b, &full_bar[stage],
-                      kb * GEMM_BK, n_blk * BN);
+          if constexpr (CTAS == 2) {
+            // both CTAs' bytes are credited to the LEADER's full barrier, which the MMA issuer waits on
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+            const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+            tma_load_2d_pair(smem_a + stage * Cfg::kStageBytesA, &tmap_a, bar, kb * GEMM_BK, m_blk * GEMM_BM);
+            tma_load_2d_pair(smem_b + stage * Cfg::kStageBytesB, &tmap_b, bar, kb * GEMM_BK,
+                             n_blk * BN + static_cast<int>(cta_rank) * (BN / 2));
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_2d(smem_a + stage * Cfg::kStageBytesA, &tmap_a, &full_bar[stage],
+                        kb * GEMM_BK, m_blk * GEMM_BM);
+            tma_load_2d(smem_b + stage * Cfg::kStageBytesB, &tmap_b, &full_bar[stage],
+                        kb * GEMM_BK, n_blk * BN);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM * CTAS, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 0x200 + acc);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
@@ -186,12 +210,15 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             // advance 16 elements (32 B) along K inside the 128-B swizzle atom: +2 in 16-B units
-            umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            if constexpr (CTAS == 2) umma_bf16_ss_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            else umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
           }
-          umma_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs retire
+          // frees the smem slot (in both CTAs of a pair) once these MMAs retire
+          if constexpr (CTAS == 2) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);       // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if constexpr (CTAS == 2) umma_commit_pair(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -200,7 +227,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const int sub = warp & 3;                 // TMEM sub-partition owned by this warp
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
       int m_blk, n_blk;
       tile_coords(tile, m_blk, n_blk);
       mbar_wait(&tmem_full[acc], acc_phase, 0x400 + acc);
@@ -412,16 +439,20 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if constexpr (CTAS == 2) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[acc]), 0));
+        else mbar_arrive(&tmem_empty[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();   // the peer's smem/TMEM stay alive
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if constexpr (CTAS == 2) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 

@@ -138,6 +138,8 @@ def _gemm(lib, A, B, res=None, block_n=256):
 @pytest.mark.parametrize("M,N,K,bn", [
     (128, 256, 64, 256), (128, 256, 256, 256), (256, 512, 4096, 256), (300, 776, 1088, 256),
     (42, 4096, 4096, 256), (1000, 1024, 512, 128), (4096, 4096, 11008, 256), (21504, 4096, 4096, 256),
+    # odd number of 128-row blocks (the second CTA of the last pair is all padding), ragged row count
+    (385, 512, 512, 256), (16157, 2560, 2560, 256), (129, 256, 64, 256),
 ])
 def test_gemm_tcgen05(lib, cuda_device, M, N, K, bn):
     g = torch.Generator(device="cpu").manual_seed(M + N + K)
