@@ -8,11 +8,12 @@
 //     rk <= rq (block-diagonal causal mask over the flattened rows).
 // With P = 0 and S = P_len the same kernel computes the prefix itself (plain causal attention).
 //
-//   warp 0      TMA producer: Q tile per item, then (K block, V^T block) pairs into a 2-stage ring
+//   warp 0      TMA producer: Q tile per item, then K blocks and V^T blocks into two 2-stage rings
 //   warp 1      MMA issuer:   S_j = Q K_j^T  and  O += P_j V_j   (tcgen05.mma, operands in smem,
 //                             accumulators in TMEM: 2 x S[128x128] + O[128x128])
 //   warp 2      TMEM allocator
-//   warps 4..7  softmax: one thread per query row pulls its S_j row from TMEM into registers in
+//   warps 4..11 softmax: TWO threads per query row (warps w and w+4 share a TMEM lane quadrant),
+//               each pulls its half of the S_j row from TMEM into registers in
 //               one pass, applies mask + online softmax and writes P_j (bf16) to smem in the UMMA
 //               K-major 128B-swizzled layout. O stays in TMEM across all key blocks; the running
 //               maximum is only raised when a block exceeds it by more than 2^8 (so P <= 256), and
@@ -30,7 +31,7 @@
 namespace bma {
 
 constexpr int ATC_BM = 128;        // query rows per work item
-constexpr int ATC_THREADS = 256;
+constexpr int ATC_THREADS = 384;     // 4 control warps + 8 softmax warps (two threads per query row)
 
 // Tile geometry for head dim HD and (at most) BN keys per block. Every operand is stored as
 // panels of [rows][64 bf16] with the 128-byte swizzle; a tile is a run of such panels.
@@ -45,7 +46,8 @@ struct AtcCfg {
   static constexpr int kKTile = (HD / 64) * kKPanel;
   static constexpr int kVTile = (BN / 64) * kVPanel;
   static constexpr int kPTile = (BN / 64) * kPPanel;
-  static constexpr int kSmem = kQTile + 2 * (kKTile + kVTile) + 2 * kPTile + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmem = kQTile + 2 * (kKTile + kVTile) + 2 * kPTile + 1024 /*align*/ + 256 /*barriers*/ +
+                               2 * ATC_BM * 4 /*row sum exchange*/;
   static constexpr int kTmemS = 0;                      // S_0 at +0, S_1 at +BN
   static constexpr int kTmemO = 2 * BN;                 // O: HD columns
   static_assert(2 * BN + HD <= 512, "TMEM budget");
@@ -109,14 +111,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * Cfg::kPTile);
   uint64_t* q_full = bars;            // [1]
   uint64_t* q_empty = bars + 1;       // [1]
-  uint64_t* kv_full = bars + 2;       // [2]
-  uint64_t* kv_empty = bars + 4;      // [2]
+  uint64_t* k_full = bars + 2;        // [2]  K and V^T blocks ride in SEPARATE rings: a K stage is
+  uint64_t* k_empty = bars + 4;       // [2]  released as soon as S_j = Q K_j^T has been computed, a V
+  uint64_t* v_full = bars + 16;       // [2]  stage when O += P_j V_j has, so the loads of block j+2
+  uint64_t* v_empty = bars + 18;      // [2]  are not serialised behind the softmax of block j
   uint64_t* s_full = bars + 6;        // [2]
   uint64_t* s_empty = bars + 8;       // [2]
   uint64_t* p_full = bars + 10;       // [2]
   uint64_t* p_empty = bars + 12;      // [2]
   uint64_t* o_empty = bars + 14;      // [1]  softmax has read the finished O of the item
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  float* xsum = reinterpret_cast<float*>(bars + 32);     // [2 halves][128 rows] partial row sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (p.M + ATC_BM - 1) / ATC_BM;
@@ -128,11 +133,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     tma_prefetch_desc(&tm_vt); tma_prefetch_desc(&tm_vp);
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(q_full, 1); mbar_init(q_empty, 1); mbar_init(o_empty, 4);
+    mbar_init(q_full, 1); mbar_init(q_empty, 1); mbar_init(o_empty, 8);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
-      mbar_init(&s_full[i], 1);  mbar_init(&s_empty[i], 4);
-      mbar_init(&p_full[i], 4);  mbar_init(&p_empty[i], 1);
+      mbar_init(&k_full[i], 1);  mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);  mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);  mbar_init(&s_empty[i], 8);
+      mbar_init(&p_full[i], 8);  mbar_init(&p_empty[i], 1);
     }
     fence_barrier_init();
   }
@@ -163,22 +169,38 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 #pragma unroll
         for (int c = 0; c < HD / 64; ++c)
           tma_load_2d(sQ + c * Cfg::kQPanel, &tm_q, q_full, p.q_col0 + head * HD + c * 64, r0);
-        for (int j = 0; j < nb; ++j, ++it) {
+        // issue order K_0, K_1, V_0, K_2, V_1, ...: K_{j+1} is requested before V_j, so every load
+        // has about two softmax periods of slack before its MMA
+        auto load_k = [&](int j) {
           const BlockInfo b = block_info<BN>(j, n_pre, p.P, kt0, r1);
-          const int st = it & 1;
-          mbar_wait(&kv_empty[st], ((it >> 1) & 1) ^ 1, 0x510 + st);
-          mbar_arrive_expect_tx(&kv_full[st], Cfg::kKTile + Cfg::kVTile);
+          const uint32_t g = it + j;
+          const int st = g & 1;
+          mbar_wait(&k_empty[st], ((g >> 1) & 1) ^ 1, 0x510 + st);
+          mbar_arrive_expect_tx(&k_full[st], Cfg::kKTile);
           const CUtensorMap* mk = b.pre ? &tm_kp : &tm_kt;
-          const CUtensorMap* mv = b.pre ? &tm_vp : &tm_vt;
           uint8_t* dk = sK + st * Cfg::kKTile;
-          uint8_t* dv = sV + st * Cfg::kVTile;
 #pragma unroll
           for (int c = 0; c < HD / 64; ++c)
-            tma_load_2d(dk + c * Cfg::kKPanel, mk, &kv_full[st], p.k_col0 + kvh * HD + c * 64, b.key0);
+            tma_load_2d(dk + c * Cfg::kKPanel, mk, &k_full[st], p.k_col0 + kvh * HD + c * 64, b.key0);
+        };
+        auto load_v = [&](int j) {
+          const BlockInfo b = block_info<BN>(j, n_pre, p.P, kt0, r1);
+          const uint32_t g = it + j;
+          const int st = g & 1;
+          mbar_wait(&v_empty[st], ((g >> 1) & 1) ^ 1, 0x520 + st);
+          mbar_arrive_expect_tx(&v_full[st], Cfg::kVTile);
+          const CUtensorMap* mv = b.pre ? &tm_vp : &tm_vt;
+          uint8_t* dv = sV + st * Cfg::kVTile;
 #pragma unroll
           for (int c = 0; c < BN / 64; ++c)
-            tma_load_2d(dv + c * Cfg::kVPanel, mv, &kv_full[st], b.key0 + c * 64, kvh * HD);
+            tma_load_2d(dv + c * Cfg::kVPanel, mv, &v_full[st], b.key0 + c * 64, kvh * HD);
+        };
+        load_k(0);
+        for (int j = 0; j < nb; ++j) {
+          if (j + 1 < nb) load_k(j + 1);
+          load_v(j);
         }
+        it += nb;
       }
     }
   } else if (warp == 1) {
@@ -187,6 +209,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       // O (+)= P_g V_g for the block with global index `g`; the first block of an item overwrites O
       auto issue_pv = [&](uint32_t g, int n_mma, bool first, uint32_t item_par) {
         const int st = g & 1;
+        mbar_wait(&v_full[st], (g >> 1) & 1, 0x660 + st);
         mbar_wait(&p_full[st], (g >> 1) & 1, 0x620 + st);
         if (first) mbar_wait(o_empty, item_par ^ 1, 0x630);     // previous item's O has been read out
         tc_fence_after();
@@ -198,7 +221,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           umma_bf16_ss(tmem_o, umma_desc_k_sw128(pa + off_p), umma_desc_k_sw128(vb + off_v), idesc,
                        !(first && kk == 0));
         }
-        umma_commit(&kv_empty[st]);
+        umma_commit(&v_empty[st]);
         umma_commit(&p_empty[st]);
       };
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
@@ -212,7 +235,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           const BlockInfo b = block_info<BN>(j, n_pre, p.P, kt0, r1);
           const int st = it & 1;
           const uint32_t par = (it >> 1) & 1;
-          mbar_wait(&kv_full[st], par, 0x640 + st);
+          mbar_wait(&k_full[st], par, 0x640 + st);
           mbar_wait(&s_empty[st], par ^ 1, 0x650 + st);
           tc_fence_after();
           const uint32_t idesc = umma_idesc_bf16(ATC_BM, b.n_mma);
@@ -225,6 +248,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                          ks != 0);
           }
           umma_commit(&s_full[st]);
+          umma_commit(&k_empty[st]);                    // K_j is free once S_j is complete
           if (j == nb - 1) umma_commit(q_empty);        // Q tile no longer needed after this MMA
           if (j > 0) issue_pv(it - 1, prev_n, j == 1, item_n & 1);
           prev_n = b.n_mma;
@@ -233,10 +257,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       }
     }
   } else if (warp >= 4) {
+    // Two threads per query row: warps 4-7 take the low half of every block's key columns (and of
+    // O's columns), warps 8-11 the high half; warp w may touch TMEM lanes 32*(w%4)..+31, so a
+    // row's two threads sit in warps w and w+4. They exchange their partial row maxima through
+    // smem (one named barrier per block) and then agree on every decision; the partial row sums
+    // are only combined at the end of the item.
+    constexpr int CH = BN / 2;                 // key columns per thread and block
+    constexpr int OH = HD / 2;                 // O columns per thread
     const int sub = warp & 3;
+    const int half = (warp - 4) >> 2;
     const int row_in_tile = sub * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(sub * 32) << 16;
-    const uint32_t to = tmem_o + lane_off;
+    const uint32_t to = tmem_o + lane_off + half * OH;
     constexpr float kRaise = 8.0f;         // raise the reference max only beyond 2^8: P stays <= 256
     uint32_t it = 0, item_n = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
@@ -256,15 +288,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         const BlockInfo b = block_info<BN>(j, n_pre, p.P, kt0, r1);
         const int st = it & 1;
         const uint32_t par = (it >> 1) & 1;
-        const uint32_t ts = tmem_s + lane_off + st * BN;
+        const uint32_t ts = tmem_s + lane_off + st * BN + half * CH;
+        const int kbase = b.key0 + half * CH;              // key of this thread's column 0
         mbar_wait(&s_full[st], par, 0x710 + st);
         tc_fence_after();
-        // ---- the whole S row into registers (columns >= n_mma were not computed: forced to -inf)
-        float sv[BN];
+        // ---- this thread's half of the S row into registers (columns >= n_mma were not computed)
+        float sv[CH];
 #pragma unroll
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = 0; c0 < CH; c0 += 32) {
           uint32_t r[32];
-          if (c0 < b.n_mma && !(p.debug & 4)) {
+          if (half * CH + c0 < b.n_mma && !(p.debug & 4)) {
             tmem_ld_32x32(ts + c0, r);
             tmem_ld_wait();
 #pragma unroll
@@ -279,21 +312,36 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         if (lane == 0) mbar_arrive(&s_empty[st]);          // S_j is in registers: the buffer is free
         if (!b.pre || b.key0 + BN > p.P_shared) {      // masked blocks: prefix keys past P_shared and the tail
 #pragma unroll
-          for (int i = 0; i < BN; ++i) {
-            const int key = b.key0 + i;
+          for (int i = 0; i < CH; ++i) {
+            const int key = kbase + i;
             const bool vis = b.pre ? (key < plim) : (key >= cs && key <= rq && key < r1);
             if (!vis) sv[i] = -INFINITY;
           }
         }
         float raw = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < BN; ++i) raw = fmaxf(raw, sv[i]);
+        for (int i = 0; i < CH; ++i) raw = fmaxf(raw, sv[i]);
+        // ---- row maximum over both halves. The two threads of a row swap their partial maxima
+        //      through the P tile they are about to fill: each writes into the 16-byte chunk the
+        //      OTHER one owns (and overwrites with P only after reading it), so no extra smem.
+        mbar_wait(&p_empty[st], par ^ 1, 0x720 + st);      // P_st is free: PV of block it-2 retired
+        uint8_t* prow = sP + st * Cfg::kPTile + row_in_tile * 128;
+        {
+          auto chunk_of = [&](int h) -> float* {           // first P chunk of half h's columns
+            const int col = h * CH;
+            return reinterpret_cast<float*>(prow + (col >> 6) * Cfg::kPPanel +
+                                            ((((col & 63) >> 3)) ^ (row_in_tile & 7)) * 16);
+          };
+          *chunk_of(half ^ 1) = raw;
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          raw = fmaxf(raw, *chunk_of(half));
+        }
         const float bm = raw * p.scale_log2;               // scale > 0; -inf stays -inf
         const bool raise = bm > m_ref + kRaise;            // also true for the first finite block
         const float m_new = raise ? bm : m_ref;
         const float m_use = (m_new == -INFINITY) ? 0.0f : m_new;
         const float factor = raise ? ex2(m_ref - m_use) : 1.0f;     // m_ref = -inf -> 0
-        // ---- rare: rescale this row of O in TMEM (all 32 lanes take part; others scale by 1)
+        // ---- rare: rescale this thread's half of the O row in TMEM (others scale by 1)
         const bool fix = raise && (m_ref != -INFINITY) && (j > 0);
         if (__any_sync(0xffffffffu, fix)) {
           const uint32_t g = it - 1;                       // PV_{j-1} must have retired
@@ -301,7 +349,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           tc_fence_after();
           const float f = fix ? factor : 1.0f;
 #pragma unroll
-          for (int c0 = 0; c0 < HD; c0 += 32) {
+          for (int c0 = 0; c0 < OH; c0 += 32) {
             uint32_t r[32];
             tmem_ld_32x32(to + c0, r);
             tmem_ld_wait();
@@ -312,13 +360,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           tmem_st_wait();
           tc_fence_before();
         }
-        // ---- P = exp2(s - m) as bf16 into the swizzled K-major P tile; row sum
-        mbar_wait(&p_empty[st], par ^ 1, 0x720 + st);
-        uint8_t* prow = sP + st * Cfg::kPTile + row_in_tile * 128;
+        // ---- P = exp2(s - m) as bf16 into the swizzled K-major P tile; partial row sum
         float rs = 0.0f;
 #pragma unroll
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          if (c0 < b.n_mma) {
+        for (int c0 = 0; c0 < CH; c0 += 32) {
+          const int col = half * CH + c0;                  // column inside the block
+          if (col < b.n_mma) {
             uint32_t pk[16];
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
@@ -327,8 +374,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
               rs += p0 + p1;
               pk[i >> 1] = pack_bf16x2(p0, p1);
             }
-            uint8_t* panel = prow + (c0 >> 6) * Cfg::kPPanel;
-            const int q0 = (c0 & 63) >> 3;                // first 16-byte chunk of this 32-key group
+            uint8_t* panel = prow + (col >> 6) * Cfg::kPPanel;
+            const int q0 = (col & 63) >> 3;               // first 16-byte chunk of this 32-key group
 #pragma unroll
             for (int q = 0; q < 4 && !(p.debug & 8); ++q) {
               const int phys = (q0 + q) ^ (row_in_tile & 7);
@@ -344,15 +391,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         m_ref = m_new;
       }
 
-      // ---- finished item: wait for the last PV, read O once, normalise, store
+      // ---- finished item: combine the two partial row sums, wait for the last PV, read this
+      //      thread's half of O once, normalise, store
       {
+        // (single buffer: the next write is separated from this read by a block-loop barrier)
+        xsum[half * ATC_BM + row_in_tile] = l_run;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float l_all = l_run + xsum[(half ^ 1) * ATC_BM + row_in_tile];
         const uint32_t g = it - 1;
         mbar_wait(&p_empty[g & 1], (g >> 1) & 1, 0x740);
         tc_fence_after();
-        const float inv = l_run > 0.0f ? 1.0f / l_run : 0.0f;
-        __nv_bfloat16* dst = p.out + (long long)rq * p.ldo + head * HD;
+        const float inv = l_all > 0.0f ? 1.0f / l_all : 0.0f;
+        __nv_bfloat16* dst = p.out + (long long)rq * p.ldo + head * HD + half * OH;
 #pragma unroll
-        for (int c0 = 0; c0 < HD; c0 += 32) {
+        for (int c0 = 0; c0 < OH; c0 += 32) {
           uint32_t r[32];
           if (p.debug & 16) {
 #pragma unroll

@@ -149,7 +149,7 @@ int run_layers(bma_scorer* s, int rows, int seq, int pos_base, bool prefill, cud
     }
     {
       GemmParams p{};
-      p.M = rows; p.N = s->qkv_dim; p.K = d; p.group_m = 16;
+      p.M = rows; p.N = s->qkv_dim; p.K = d; p.group_m = group_m_for(p.K);
       p.C = qk; p.ldc = s->qk_dim;
       p.Vt = vt; p.ldvt = ldvt;
       p.rope_cos = W.rope_cos; p.rope_sin = W.rope_sin;
@@ -192,7 +192,7 @@ int run_layers(bma_scorer* s, int rows, int seq, int pos_base, bool prefill, cud
     }
     {
       GemmParams p{};
-      p.M = rows; p.N = d; p.K = s->q_dim; p.group_m = 16;
+      p.M = rows; p.N = d; p.K = s->q_dim; p.group_m = group_m_for(p.K);
       if (sandwich) { p.C = s->xn; p.ldc = d; }                       // y: normed before the add
       else { p.C = s->x; p.ldc = d; p.R = s->x; p.ldr = d; }
       ProfScope ps(s, PC_GEMM_O, gemm_flops(p), st);
@@ -211,14 +211,14 @@ int run_layers(bma_scorer* s, int rows, int seq, int pos_base, bool prefill, cud
     }
     {
       GemmParams p{};
-      p.M = rows; p.N = 2 * D.d_ff; p.K = d; p.group_m = 16;
+      p.M = rows; p.N = 2 * D.d_ff; p.K = d; p.group_m = group_m_for(p.K);
       p.C = s->act; p.ldc = D.d_ff; p.act = D.act;
       ProfScope ps(s, PC_GEMM_GLU, gemm_flops(p), st);
       BMA_LAUNCH((launch_gemm_big<EPI_GLU>(s->xn, d, bf(W.w_gate_up), d, p, st)), "gemm(gate_up)");
     }
     {
       GemmParams p{};
-      p.M = rows; p.N = d; p.K = D.d_ff; p.group_m = 16;
+      p.M = rows; p.N = d; p.K = D.d_ff; p.group_m = group_m_for(p.K);
       if (sandwich) { p.C = s->xn; p.ldc = d; }
       else { p.C = s->x; p.ldc = d; p.R = s->x; p.ldr = d; }
       ProfScope ps(s, PC_GEMM_DOWN, gemm_flops(p), st);
@@ -503,7 +503,7 @@ int bma_scorer_score(bma_scorer* s, const long long* ids, int ids_stride, int B,
     }
     {
       GemmParams p{};
-      p.M = ce_rows; p.N = D.vocab; p.K = d; p.group_m = 16;
+      p.M = ce_rows; p.N = D.vocab; p.K = d; p.group_m = group_m_for(p.K);
       p.target_ids = target_ids; p.T = T;
       p.ce_part = s->ce_part; p.tgt_logit = s->tgt_logit;
       ProfScope ps(s, PC_GEMM_CE, gemm_flops(p), st);

@@ -153,6 +153,22 @@ inline cudaError_t launch_gemm(const __nv_bfloat16* A, long long lda, const __nv
   }
 }
 
+// L2 rasterisation: the M supergroup's A rows (group_m x 128 x K bf16) stay L2-resident while the B
+// (weight) tiles stream once per supergroup, so a larger group means fewer weight re-reads from
+// HBM. ~48 MB of A per supergroup leaves the rest of the 126 MB L2 to B and the output.
+// BMA_GROUP_M overrides (experiments).
+inline int group_m_for(int K) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("BMA_GROUP_M");
+    forced = e != nullptr ? atoi(e) : 0;
+  }
+  if (forced > 0) return forced;
+  int g = static_cast<int>((48ll << 20) / (128ll * K * 2));
+  g &= ~1;
+  return g < 8 ? 8 : (g > 64 ? 64 : g);
+}
+
 // The scorer's big GEMMs (BN = 256) run on CTA pairs unless BMA_GEMM_CTAS=1 is set (A/B switch).
 inline int gemm_ctas() {
   static int v = 0;
