@@ -47,8 +47,9 @@ def parse_args():
     ap.add_argument("--model", default="7b", choices=["7b", "small128", "tiny128", "gemma4b", "gemma-tiny256"],
                     help="7b = BASELINE.json config 2 (the headline); gemma4b = config 4 (Gemma-3-4b GCG-only)")
     ap.add_argument("--search-width", type=int, default=512)
-    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
-                    help="strong: search_width candidates in total; weak: search_width per GPU")
+    ap.add_argument("--scaling", default="weak", choices=["strong", "weak"],
+                    help="weak (default): search_width candidates PER GPU, i.e. the per-GPU work of the headline "
+                         "config is fixed as N grows; strong: search_width candidates in total, split over the GPUs")
     ap.add_argument("--full-steps", type=int, default=3, help="full attack steps timed for steps/s (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-suffix-sharing", action="store_true",
@@ -418,11 +419,33 @@ def main():
                                               tc.num_attention_heads, atk.engine.head_dim,
                                               model.get_output_embeddings().weight.shape[0], P, S, T, hi - lo,
                                               kv_heads=atk.engine.n_kv)
-    roofline = {"bound": "tensor", "kernel": "gemm_bf16_tn_kernel<*> (tcgen05, all epilogues)",
-                "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_sustained"], "frac_of_burst_peak": achieved / peaks["bf16_burst"],
+    # the dominant kernel: the gate/up projection with the SwiGLU (GeGLU) epilogue
+    top = prof["gemm_gate_up_glu"]
+    top_tf = top["flops"] / (top["ms"] * 1e-3) / 1e12 if top["ms"] > 0 else 0.0
+    rows_top = top["flops"] / max(top["launches"], 1) / (2.0 * 2 * tc.intermediate_size * tc.hidden_size)
+    alg_bytes = 2.0 * (2 * tc.intermediate_size * tc.hidden_size + rows_top * tc.hidden_size
+                       + rows_top * tc.intermediate_size)        # W + A + C, bf16, per launch
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(args.model, {}).get("gemm_gate_up_glu")
+    roofline = {"bound": "tensor",
+                "kernel": f"gemm_bf16_tn_kernel<256, EPI_GLU, 128, {1 if os.environ.get('BMA_GEMM_CTAS') == '1' else 2}> "
+                          "(gate/up projection + GLU epilogue, tcgen05)",
+                "achieved": top_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                "frac": top_tf / peaks["bf16_sustained"], "frac_of_burst_peak": top_tf / peaks["bf16_burst"],
                 "peak_source": peaks["source"] + " (sustained cuBLAS bf16; kernel timed inside a long step)",
-                "traffic": None, "share_of_scoring_kernels": g_ms / total_prof_ms if total_prof_ms else None,
+                "launches_per_step": top["launches"] / args.steps,
+                "avg_launch_ms": top["ms"] / max(top["launches"], 1),
+                "algorithmic_flops_per_launch": top["flops"] / max(top["launches"], 1),
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "all_tcgen05_gemms": {"achieved": achieved, "frac": achieved / peaks["bf16_sustained"],
+                                      "frac_of_burst_peak": achieved / peaks["bf16_burst"]},
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel from the committed
+                # `ncu --set full` capture (profiles/ncu_traffic.json); not measured in this run
+                "traffic": traffic, "share_of_step": top["ms"] / total_prof_ms if total_prof_ms else None,
+                "share_of_scoring_kernels": g_ms / total_prof_ms if total_prof_ms else None,
                 "per_class": {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
                                   "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 and v["flops"] > 0 else None}
                               for k, v in prof.items()},

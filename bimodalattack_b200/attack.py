@@ -59,6 +59,47 @@ def image_features(model, pixel_values: torch.Tensor, gemma_processor: bool) -> 
     return torch.stack(list(pooled), 0) if isinstance(pooled, (list, tuple)) else pooled
 
 
+def _patch_conv_as_gemm(conv: torch.nn.Conv2d):
+    """forward() for a patch-embedding Conv2d whose stride equals its kernel (CLIP / SigLIP): the
+    non-overlapping patches are unfolded by pure reshapes and multiplied by the [out, C*p*p] view
+    of the same weight. Same arithmetic as the convolution, but its input gradient -- which the PGD
+    step needs -- is a plain GEMM plus the inverse reshapes: deterministic and fast, whereas cuDNN's
+    deterministic dgrad for this shape takes 64 ms on a B200 (reference sets
+    torch.use_deterministic_algorithms, :267-269)."""
+    ph, pw = conv.kernel_size
+
+    def forward(x):
+        B, C, H, W = x.shape
+        gh, gw = H // ph, W // pw
+        x = x[..., :gh * ph, :gw * pw]
+        patches = x.reshape(B, C, gh, ph, gw, pw).permute(0, 2, 4, 1, 3, 5).reshape(B, gh * gw, C * ph * pw)
+        out = F.linear(patches, conv.weight.reshape(conv.out_channels, -1), conv.bias)
+        return out.transpose(1, 2).reshape(B, conv.out_channels, gh, gw)
+    return forward
+
+
+def install_patch_embed_gemm(model) -> int:
+    """Swap the forward of every eligible patch-embedding convolution of ``model`` (stride == kernel,
+    no padding, dilation 1, groups 1). Returns how many were swapped; ``conv._bma_orig_forward`` keeps
+    the original and ``restore_patch_embed`` puts it back."""
+    n = 0
+    for mod in model.modules():
+        if (isinstance(mod, torch.nn.Conv2d) and tuple(mod.stride) == tuple(mod.kernel_size)
+                and mod.padding in ((0, 0), "valid") and tuple(mod.dilation) == (1, 1) and mod.groups == 1
+                and not hasattr(mod, "_bma_orig_forward")):
+            mod._bma_orig_forward = mod.forward
+            mod.forward = _patch_conv_as_gemm(mod)
+            n += 1
+    return n
+
+
+def restore_patch_embed(model) -> None:
+    for mod in model.modules():
+        if hasattr(mod, "_bma_orig_forward"):
+            mod.forward = mod._bma_orig_forward
+            del mod._bma_orig_forward
+
+
 def sample_ids_from_grad(ids: torch.Tensor, grad: torch.Tensor, search_width: int, topk: int = 256,
                          n_replace: int = 1, not_allowed_ids: Optional[torch.Tensor] = None,
                          mask_bits: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -135,6 +176,12 @@ class BimodalAttack:
         self.world = bdist.world()
         self.gather_all_losses = False    # multi-rank: also all-reduce the per-candidate loss vector
         self.step_hook = None             # optional callable(step_index) run at the end of every step
+        self.graph_gradient = os.environ.get("BMA_GRAPH_GRADIENT", "1") != "0"
+        if config.pgd_attack and os.environ.get("BMA_PATCH_EMBED_GEMM", "1") != "0":
+            install_patch_embed_gemm(model)       # see _patch_conv_as_gemm; restore_patch_embed(model) undoes it
+        self._grad_graph = None
+        import inspect
+        self._keep_logits = "logits_to_keep" in inspect.signature(model.forward).parameters
 
     # ---------------------------------------------------------------------------------------------
     # prompt -> segments (:271-393)
@@ -193,10 +240,21 @@ class BimodalAttack:
             setattr(self, f"{k}_embeds", v)
         self._plans.clear()
         self._prefill_tag = None
+        self._grad_graph = None          # the captured gradient step references the old segment embeddings
 
     # ---------------------------------------------------------------------------------------------
     # phase A (:953-1028)
     def compute_gradient(self, optim_ids: torch.Tensor, image: Optional[torch.Tensor] = None):
+        """(one-hot gradient [1, L_s, V], image gradient) like the reference. The HF forward+backward
+        at batch 1 is ~1500 small kernels and CPU-launch bound, so after two eager calls it is replayed
+        from a CUDA graph (same kernels, same results); ``graph_gradient = False`` keeps it eager."""
+        if self.graph_gradient and self.device.type == "cuda":
+            out = self._gradient_graphed(optim_ids, image)
+            if out is not None:
+                return out
+        return self._gradient_eager(optim_ids, image)
+
+    def _gradient_eager(self, optim_ids: torch.Tensor, image: Optional[torch.Tensor]):
         cfg, model, emb = self.config, self.model, self.embedding_layer
         W = emb.weight
         # the reference multiplies a one-hot by W (:959-968): a row gather, and -- also for Gemma --
@@ -206,14 +264,20 @@ class BimodalAttack:
             optim_embeds.requires_grad_()
         e = self.segment_embeds
         if cfg.pgd_attack:
-            feats = image_features(model, self.normalize(image), self.gemma_processor)
+            feats = image_features(model, self._normalize_pixels(image), self.gemma_processor)
             seq = [e["before_img"], feats, e["before_suffix"], optim_embeds, e["after"], e["target"]]  # :981-991
         else:
             seq = [e["before"], optim_embeds, e["after"], e["target"]]
         x = torch.cat(seq, dim=1)
-        logits = model(inputs_embeds=x).logits
-        shift = x.shape[1] - self.target_ids.shape[1]
-        pred = logits[..., shift - 1:-1, :].contiguous()
+        T = self.target_ids.shape[1]
+        if self._keep_logits:
+            # only the T rows that predict the target are needed (the reference computes all L rows and
+            # slices, :1003-1008); row values do not depend on which other rows go through the head
+            pred = model(inputs_embeds=x, logits_to_keep=T + 1).logits[..., :-1, :].contiguous()
+        else:
+            logits = model(inputs_embeds=x).logits
+            shift = x.shape[1] - T
+            pred = logits[..., shift - 1:-1, :].contiguous()
         loss = F.cross_entropy(pred.view(-1, pred.size(-1)), self.target_ids.view(-1))
         g_embeds = g_image = None
         if cfg.pgd_attack and cfg.gcg_attack:
@@ -228,6 +292,50 @@ class BimodalAttack:
             onehot_grad = native.token_grad(g_embeds[0], W.detach()).unsqueeze(0)
         return onehot_grad, g_image
 
+    def _gradient_graphed(self, optim_ids: torch.Tensor, image: Optional[torch.Tensor]):
+        """CUDA-graph replay of ``_gradient_eager`` on static input/output buffers. Returns None
+        while warming up (first two calls) or when capture is not possible (then stays eager)."""
+        key = (tuple(optim_ids.shape), None if image is None else tuple(image.shape), id(self.segment_embeds))
+        st = self._grad_graph
+        if st is None or st.get("key") != key:
+            st = self._grad_graph = {"key": key, "calls": 0, "graph": None, "failed": False}
+        if st["failed"]:
+            return None
+        st["calls"] += 1
+        if st["graph"] is None:
+            if st["calls"] <= 2:
+                return None                            # eager warm-up (cuBLAS/cuDNN handles, TMA maps, allocator)
+            try:
+                ids_s = optim_ids.detach().clone()
+                img_s = None if image is None else image.detach().clone().requires_grad_()
+                side = torch.cuda.Stream(device=self.device)
+                side.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(side):
+                    self._gradient_eager(ids_s, img_s)     # once more on the capture stream's allocator pool
+                torch.cuda.current_stream(self.device).wait_stream(side)
+                torch.cuda.synchronize(self.device)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    out_tok, out_img = self._gradient_eager(ids_s, img_s)
+                st.update(graph=graph, ids=ids_s, img=img_s, out_tok=out_tok, out_img=out_img)
+            except Exception as exc:                   # noqa: BLE001 - any capture problem: stay eager
+                logger.warning(f"CUDA-graph capture of the gradient step failed ({type(exc).__name__}: {exc}); "
+                               "staying on the eager path")
+                if os.environ.get("BMA_GRAPH_DEBUG"):
+                    import traceback
+                    traceback.print_exc()
+                st["failed"] = True
+                torch.cuda.synchronize(self.device)
+                return None
+        with torch.no_grad():
+            st["ids"].copy_(optim_ids)
+            if image is not None:
+                st["img"].copy_(image.detach())
+        st["graph"].replay()
+        out_tok = None if st["out_tok"] is None else st["out_tok"].clone()
+        out_img = None if st["out_img"] is None else st["out_img"].clone()
+        return out_tok, out_img
+
     # phase B (:1030-1037)
     def perform_pgd_step(self, image: torch.Tensor, eps: float, alpha: float, image_grad: torch.Tensor,
                          image_original: torch.Tensor) -> torch.Tensor:
@@ -239,11 +347,25 @@ class BimodalAttack:
         self._pixel_values_of = new
         return new.requires_grad_()
 
+    def _normalize_pixels(self, image: torch.Tensor) -> torch.Tensor:
+        """``self.normalize(image)``. A torchvision ``Normalize`` builds its mean/std tensors from Python
+        lists on every call (a host-to-device copy, which also cannot be captured in a CUDA graph); here
+        they are cached on the device and applied with the same two ops (sub, then div)."""
+        mean, std = getattr(self.normalize, "mean", None), getattr(self.normalize, "std", None)
+        if mean is None or std is None or not image.is_floating_point():
+            return self.normalize(image)
+        cache = getattr(self, "_norm_consts", None)
+        if cache is None or cache[0].device != image.device or cache[0].dtype != image.dtype:
+            m = torch.as_tensor(mean, dtype=image.dtype, device=image.device).view(-1, 1, 1)
+            d = torch.as_tensor(std, dtype=image.dtype, device=image.device).view(-1, 1, 1)
+            cache = self._norm_consts = (m, d)
+        return (image - cache[0]) / cache[1]
+
     def _normalized(self, image: torch.Tensor) -> torch.Tensor:
         """Normalised pixels for the scoring phase; reuses the PGD kernel's fused output."""
         if getattr(self, "_pixel_values_of", None) is image and self._pixel_values is not None:
             return self._pixel_values
-        return self.normalize(image.detach())
+        return self._normalize_pixels(image.detach())
 
     # phase D sampling (:908-951)
     def candidate_sampling(self, config, i, optim_ids, optim_ids_onehot_grad, tokenizer, sampling_times,
@@ -386,7 +508,10 @@ class BimodalAttack:
         if cfg.seed is not None:
             from transformers import set_seed
             set_seed(cfg.seed)
-            torch.use_deterministic_algorithms(True, warn_only=True)
+            torch.use_deterministic_algorithms(True, warn_only=True)     # as the reference does (:267-269)
+            # ... but without torch's debug aid that memsets every freshly allocated tensor in this mode:
+            # it changes no result and doubles the kernel count of the batch-1 gradient step
+            torch.utils.deterministic.fill_uninitialized_memory = False
         if cfg.pgd_attack:
             if image is None:
                 raise ValueError("pgd_attack=True needs an image")

@@ -278,3 +278,25 @@ def test_suffix_head_sharing_matches_full_tails(cuda_device, mode, n, n_replace)
         want, _ = hotpath.candidates_loss(ora32.model, hotpath.assemble(ora32._parts(cand, f32), order, n),
                                           atk.target_ids, 50)
         assert bool(((shared - want).abs() <= 2e-2 * want.abs() + 1e-3).all()), (shared - want).abs().max()
+
+
+@pytest.mark.parametrize("mode", ["joint", "gcg_only"])
+def test_graphed_gradient_equals_eager(cuda_device, mode):
+    """The batch-1 gradient step is replayed from a CUDA graph after two eager calls: same kernels
+    on static buffers, so the results must equal the eager path for fresh inputs."""
+    from bimodalattack_b200 import BimodalAttack
+    model, tok, proc, norm, image, cfg = _setup(cuda_device, **MODES[mode])
+    atk = BimodalAttack(model, tok, proc, cfg, normalize=norm)
+    atk._prepare([{"role": "user", "content": PROMPT}], TARGET)
+    n_tok = len(tok(INIT, add_special_tokens=False)["input_ids"])
+    g = torch.Generator().manual_seed(11)
+    for call in range(5):
+        ids = torch.randint(8, 1000, (1, n_tok), generator=g).to(cuda_device)
+        img = (torch.rand(image.shape, generator=g).to(cuda_device).requires_grad_()) if cfg.pgd_attack else None
+        got_tok, got_img = atk.compute_gradient(ids, img)
+        img2 = img.detach().clone().requires_grad_() if img is not None else None
+        want_tok, want_img = atk._gradient_eager(ids, img2)
+        assert torch.equal(got_tok, want_tok), call
+        if cfg.pgd_attack:
+            assert torch.equal(got_img, want_img), call
+    assert atk._grad_graph["graph"] is not None and not atk._grad_graph["failed"]
