@@ -295,7 +295,7 @@ def main():
 
     def build_batch(img):
         if joint:
-            feats = image_features(model, norm(img), gemma)
+            feats = atk.scoring_features(img)      # normalise + vision tower + projector, as run() does
             return atk._build_input_embeds_pgd(sampled, feats, search_width=sw, single=True)
         return atk._build_input_embeds_gcg(sampled, search_width=sw, no_joint_eval=True)
 

@@ -180,6 +180,7 @@ class BimodalAttack:
         if config.pgd_attack and os.environ.get("BMA_PATCH_EMBED_GEMM", "1") != "0":
             install_patch_embed_gemm(model)       # see _patch_conv_as_gemm; restore_patch_embed(model) undoes it
         self._grad_graph = None
+        self._feat_graph = None
         import inspect
         self._keep_logits = "logits_to_keep" in inspect.signature(model.forward).parameters
 
@@ -361,6 +362,45 @@ class BimodalAttack:
             cache = self._norm_consts = (m, d)
         return (image - cache[0]) / cache[1]
 
+    def scoring_features(self, image: torch.Tensor) -> torch.Tensor:
+        """Image features for the scoring phase (no gradient): normalise (reusing the PGD kernel's fused
+        output when it is current), vision tower, projector. The tower at batch 1 is ~400 small launches,
+        so after two eager calls it is replayed from a CUDA graph on a static pixel buffer."""
+        pix = self._normalized(image)
+        st = self._feat_graph
+        key = (tuple(pix.shape), pix.dtype)
+        if not self.graph_gradient or st is None or st.get("key") != key:
+            st = self._feat_graph = {"key": key, "calls": 0, "graph": None, "failed": not self.graph_gradient}
+        st["calls"] += 1
+        if st["failed"] or st["calls"] <= 2:
+            with torch.no_grad():
+                return image_features(self.model, pix, self.gemma_processor)
+        if st["graph"] is None:
+            try:
+                with torch.no_grad():
+                    pix_s = pix.detach().clone()
+                    side = torch.cuda.Stream(device=self.device)
+                    side.wait_stream(torch.cuda.current_stream(self.device))
+                    with torch.cuda.stream(side):
+                        image_features(self.model, pix_s, self.gemma_processor)
+                    torch.cuda.current_stream(self.device).wait_stream(side)
+                    torch.cuda.synchronize(self.device)
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        out = image_features(self.model, pix_s, self.gemma_processor)
+                st.update(graph=graph, pix=pix_s, out=out)
+            except Exception as exc:                   # noqa: BLE001
+                logger.warning(f"CUDA-graph capture of the vision tower failed ({type(exc).__name__}: {exc}); "
+                               "staying on the eager path")
+                st["failed"] = True
+                torch.cuda.synchronize(self.device)
+                with torch.no_grad():
+                    return image_features(self.model, pix, self.gemma_processor)
+        with torch.no_grad():
+            st["pix"].copy_(pix)
+            st["graph"].replay()
+            return st["out"].clone()
+
     def _normalized(self, image: torch.Tensor) -> torch.Tensor:
         """Normalised pixels for the scoring phase; reuses the PGD kernel's fused output."""
         if getattr(self, "_pixel_values_of", None) is image and self._pixel_values is not None:
@@ -488,7 +528,7 @@ class BimodalAttack:
         n = max(1, cfg.buffer_size)
         with torch.no_grad():
             if cfg.pgd_attack:
-                feats = image_features(self.model, self._normalized(image), self.gemma_processor)
+                feats = self.scoring_features(image)
                 batch = self._build_input_embeds_gcg_pgd(init, feats, search_width=n, single=True)
             else:
                 batch = self._build_input_embeds_gcg(init, search_width=n, no_joint_eval=True)
@@ -580,7 +620,7 @@ class BimodalAttack:
                 t0 = time.perf_counter()
                 chunk = width if cfg.batch_size is None else cfg.batch_size
                 if cfg.pgd_attack:
-                    feats = image_features(model, self._normalized(image), self.gemma_processor)
+                    feats = self.scoring_features(image)
                     best_idx = 0
                     scored_with_image = False
                     if cfg.joint_eval:
@@ -628,7 +668,7 @@ class BimodalAttack:
                 image = image if lead else shared
                 with torch.no_grad():
                     t0 = time.perf_counter()
-                    feats = image_features(model, self._normalized(image), self.gemma_processor)
+                    feats = self.scoring_features(image)
                     full = self._build_input_embeds_gcg_pgd(chosen, feats)
                     self._compute_candidates_loss_original(1, full)
                     current, _ = self._winner()
@@ -642,7 +682,7 @@ class BimodalAttack:
             if cfg.debug_output and i % 10 == 0:
                 with torch.no_grad():
                     if cfg.pgd_attack:
-                        feats = image_features(model, self._normalized(image), self.gemma_processor)
+                        feats = self.scoring_features(image)
                         dbg = self._build_input_embeds_gcg_pgd(sampled, feats, search_width=width, no_target=True)
                     else:
                         dbg = self._build_input_embeds_gcg(sampled, search_width=width, no_target=True)
