@@ -44,7 +44,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--model", default="7b", choices=["7b", "small128", "tiny128", "gemma4b", "gemma-tiny256"],
+    ap.add_argument("--model", default="7b", choices=["7b", "small128", "tiny128", "gemma4b", "gemma-tiny256", "gemma4b-joint",
+                                                      "gemma-tiny256-joint"],
                     help="7b = BASELINE.json config 2 (the headline); gemma4b = config 4 (Gemma-3-4b GCG-only)")
     ap.add_argument("--search-width", type=int, default=512)
     ap.add_argument("--scaling", default="weak", choices=["strong", "weak"],
@@ -202,7 +203,7 @@ def run_reference(args):
     }))
 
 
-GEMMA = {"gemma4b": "4b", "gemma-tiny256": "tiny256"}
+GEMMA = {"gemma4b": "4b", "gemma-tiny256": "tiny256", "gemma4b-joint": "4b", "gemma-tiny256-joint": "tiny256"}
 LLAVA_PX = {"7b": 336, "small128": 56, "tiny128": 28}
 LLAVA_VOCAB = {"7b": 32000, "small128": 4000, "tiny128": 1000}
 
@@ -210,9 +211,14 @@ LLAVA_VOCAB = {"7b": 32000, "small128": 4000, "tiny128": 1000}
 def workload_config(args, P, S):
     sw = args.search_width * (args.gpus if args.scaling == "weak" else 1)
     if args.model in GEMMA:
-        what = (f"Gemma-3-{GEMMA[args.model]} arch random-init, GCG-only scoring phase (text-only order "
-                f"before|optim|after|target, 262k-vocab LM head fused with CE), search_width {sw} "
-                f"({args.scaling} scaling), topk 256, n_replace 1")
+        if args.model.endswith("-joint"):
+            what = (f"Gemma-3-{GEMMA[args.model]} arch random-init, joint GCG+PGD scoring phase (Gemma order "
+                    f"before_img|optim|before_suffix|image|after|target: the image tokens follow the suffix, so they "
+                    f"are part of every candidate's tail), search_width {sw} ({args.scaling} scaling), topk 256, n_replace 1")
+        else:
+            what = (f"Gemma-3-{GEMMA[args.model]} arch random-init, GCG-only scoring phase (text-only order "
+                    f"before|optim|after|target, 262k-vocab LM head fused with CE), search_width {sw} "
+                    f"({args.scaling} scaling), topk 256, n_replace 1")
         l2 = "no flush needed: every step streams the 7.8 GB of decoder weights + 1.3 GB LM head (>> 126 MB L2)"
     else:
         px = LLAVA_PX[args.model]
@@ -233,7 +239,7 @@ def build_case(args, dtype, device, fast_init=False):
         model = syn.make_gemma3(size, dtype=dtype, device=device, seed=0, embed_gain=4.0 if size != "4b" else 1.5,
                                 fast_init=fast_init and size == "4b")
         model.config._attn_implementation = "sdpa"
-        return model, tok, proc, norm, image, messages, target, init, False
+        return model, tok, proc, norm, image, messages, target, init, args.model.endswith("-joint")
     tok, proc, norm, image, messages, target, init = syn.headline_case(LLAVA_VOCAB[args.model], LLAVA_PX[args.model])
     kw = dict(fast_init=True) if fast_init and args.model == "7b" else {}
     model = syn.make_llava(args.model, dtype=dtype, device=device, seed=0, head_gain=HEAD_GAIN[args.model],
@@ -383,7 +389,8 @@ def main():
     full = None
     if args.full_steps > 0:
         import dataclasses
-        cfg2 = dataclasses.replace(cfg, num_steps=args.full_steps + 2)
+        warm_full = 4          # eager warm-up calls and the one-time CUDA-graph captures of phase A / vision tower
+        cfg2 = dataclasses.replace(cfg, num_steps=args.full_steps + warm_full)
         atk2 = BimodalAttack(model, tok, proc, cfg2, normalize=norm, engine=atk.engine)
         marks = []
 
@@ -392,12 +399,12 @@ def main():
             marks.append(time.perf_counter())
         atk2.step_hook = hook
         res = atk2.run(messages, "goal", target, image_cpu.to(dev) if joint else None)
-        if len(marks) >= 3:
-            dt = torch.tensor([(marks[-1] - marks[1]) / (len(marks) - 2)], device=dev)
+        if len(marks) > warm_full:
+            dt = torch.tensor([(marks[-1] - marks[warm_full - 1]) / (len(marks) - warm_full)], device=dev)
             if world > 1:
                 td.all_reduce(dt, op=td.ReduceOp.MAX)
             full = {"steps_per_sec": 1.0 / float(dt.item()), "ms_per_step": 1e3 * float(dt.item()),
-                    "timed_steps": len(marks) - 2, "losses": res.losses,
+                    "timed_steps": len(marks) - warm_full, "losses": res.losses,
                     "phase_s_last": {"gradient": res.gradient_times[-1] if res.gradient_times else None,
                                      "pgd": res.pgd_times[-1] if res.pgd_times else None,
                                      "sampling": res.sampling_times[-1] if res.sampling_times else None,
@@ -487,6 +494,8 @@ def main():
         "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu,
         "full_step": full, "winner": {"loss": win_loss, "index": win_idx, "e2e_key": e2e_key},
         "a100_reference_published": (
+            {"cand_per_s": 12.1, "s_per_iter": 43.9353,
+             "note": "BASELINE.md: Gemma-3-4b-it joint_eval sw 512, A100-80GB, bf16"} if gemma and joint else
             {"cand_per_s": 128.0, "s_per_iter": 5.7641,
              "note": "BASELINE.md: Gemma-3-4b-it GCG-only sw 512, A100-80GB, bf16"} if gemma else
             {"cand_per_s": 10.7, "s_per_iter": 49.965,

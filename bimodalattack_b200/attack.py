@@ -134,6 +134,43 @@ def filter_ids(ids: torch.Tensor, tokenizer) -> torch.Tensor:
     return ids[torch.tensor(keep, device=ids.device)]
 
 
+class _PngWriter:
+    """Background PNG encoder: (pinned uint8 HWC tensor, CUDA event, path) items from a queue."""
+
+    def __init__(self):
+        import queue
+        import threading
+        self.q = queue.Queue()
+        self.error = None
+        self.thread = threading.Thread(target=self._work, name="bma-png-writer", daemon=True)
+        self.thread.start()
+
+    def _work(self):
+        from PIL import Image
+        while True:
+            item = self.q.get()
+            try:
+                if item is None:
+                    return
+                host, done, path = item
+                if done is not None:
+                    done.synchronize()
+                Image.fromarray(host.numpy()).save(path)
+            except Exception as exc:                   # noqa: BLE001 - surfaced by flush()
+                self.error = exc
+            finally:
+                self.q.task_done()
+
+    def submit(self, host, done, path):
+        self.q.put((host, done, path))
+
+    def flush(self):
+        self.q.join()
+        if self.error is not None:
+            err, self.error = self.error, None
+            raise err
+
+
 @dataclass
 class CandidateBatch:
     """What ``_build_input_embeds*`` returns here instead of a materialised (sw, L, d) tensor: the
@@ -181,6 +218,7 @@ class BimodalAttack:
             install_patch_embed_gemm(model)       # see _patch_conv_as_gemm; restore_patch_embed(model) undoes it
         self._grad_graph = None
         self._feat_graph = None
+        self._png = None
         import inspect
         self._keep_logits = "logits_to_keep" in inspect.signature(model.forward).parameters
 
@@ -505,10 +543,25 @@ class BimodalAttack:
         return unpack_key(int(self.engine.key.item()))
 
     def _save_image(self, image, path):
-        import numpy as np
-        from PIL import Image
-        arr = image.squeeze(0).detach().cpu().numpy().transpose(1, 2, 0)
-        Image.fromarray((arr * 255).astype(np.uint8)).save(path)
+        """Per-step PNG of the adversarial image (:743-744, :1312-1317), off the critical path: the
+        uint8 conversion (same truncation as the reference's ``(arr * 255).astype(uint8)``) runs on
+        the device, the copy into pinned memory is asynchronous and a writer thread encodes the file."""
+        if self._png is None:
+            self._png = _PngWriter()
+        img = image.detach().squeeze(0)
+        u8 = (img * 255).to(torch.uint8).permute(1, 2, 0).contiguous()
+        host = torch.empty(u8.shape, dtype=torch.uint8, pin_memory=u8.is_cuda)
+        host.copy_(u8, non_blocking=True)
+        done = None
+        if u8.is_cuda:
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream(u8.device))
+        self._png.submit(host, done, path)
+
+    def flush_images(self):
+        """Block until every image handed to ``_save_image`` is on disk (called before run() returns)."""
+        if self._png is not None:
+            self._png.flush()
 
     # ---------------------------------------------------------------------------------------------
     def init_buffer(self, image) -> AttackBuffer:
@@ -700,6 +753,7 @@ class BimodalAttack:
             logger.info(f"[Iteration {i}] loss {current:.4f} | grad {grad_time:.4f}s sample {sampling_time:.4f}s "
                         f"pgd {pgd_time:.4f}s loss {loss_time:.4f}s")
 
+        self.flush_images()
         self.final_image = image
         self.final_optim_ids = optim_ids
         best = losses.index(min(losses))

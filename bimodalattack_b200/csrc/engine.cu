@@ -117,6 +117,24 @@ bool dev_alloc(T** p, size_t count, size_t* total) {
   return true;
 }
 
+// CE partials: [vocab tiles][rows] (max, sum-exp) + [rows] target logits, for `rows` scored rows of
+// one chunk. Grow-only; 262k-vocab models need 8 KB per scored row, so this is sized from B*T, not
+// from the tail-row capacity.
+int ensure_ce_rows(bma_scorer* s, int rows) {
+  if (rows <= s->ce_rows_cap) return 0;
+  const int n_ce_tiles = (s->desc.vocab + kCeBlockN - 1) / kCeBlockN;
+  BMA_CHECK(cudaDeviceSynchronize(), "ensure_ce_rows: sync");
+  cudaFree(s->ce_part); cudaFree(s->tgt_logit);
+  s->ce_part = nullptr; s->tgt_logit = nullptr; s->ce_rows_cap = 0;
+  size_t bytes = 0;
+  if (!dev_alloc(&s->ce_part, static_cast<size_t>(n_ce_tiles) * rows, &bytes) ||
+      !dev_alloc(&s->tgt_logit, static_cast<size_t>(rows), &bytes))
+    return fail(cudaGetLastError(), "ensure_ce_rows: cudaMalloc");
+  s->ws_bytes += bytes;
+  s->ce_rows_cap = rows;
+  return 0;
+}
+
 // One decoder pass over `rows` rows laid out as sequences of `seq` rows at positions
 // pos_base + (r % seq). prefill == true: rows are the prefix itself (their q/k/v land in
 // prefix_qkv and the last layer stops after its K/V are produced).
@@ -317,7 +335,6 @@ bma_scorer* bma_scorer_create(const bma_model_desc* desc) {
   s->qkv_dim = s->q_dim + 2 * s->kv_dim;
   s->qk_dim = s->q_dim + s->kv_dim;
   const size_t R = static_cast<size_t>(D.max_rows > D.max_prefix ? D.max_rows : D.max_prefix);
-  s->ce_rows_cap = D.max_rows;   // at most one target row per tail row
   const int n_ce_tiles = (D.vocab + kCeBlockN - 1) / kCeBlockN;
   bool ok = true;
   ok = ok && dev_alloc(&s->x, R * D.d_model, &s->ws_bytes);
@@ -332,8 +349,7 @@ bma_scorer* bma_scorer_create(const bma_model_desc* desc) {
                        static_cast<size_t>(D.n_layers) * (D.max_prefix > 0 ? D.max_prefix : 1) * s->qk_dim,
                        &s->ws_bytes);
   ok = ok && dev_alloc(&s->prefix_vt, static_cast<size_t>(D.n_layers) * s->kv_dim * s->ld_vtp, &s->ws_bytes);
-  ok = ok && dev_alloc(&s->ce_part, static_cast<size_t>(n_ce_tiles) * s->ce_rows_cap, &s->ws_bytes);
-  ok = ok && dev_alloc(&s->tgt_logit, static_cast<size_t>(s->ce_rows_cap), &s->ws_bytes);
+  (void)n_ce_tiles;   // the CE partial buffers are sized on first use (score knows T): ensure_ce_rows
   ok = ok && dev_alloc(&s->row_info, static_cast<size_t>(D.max_rows), &s->ws_bytes);
   ok = ok && dev_alloc(&s->row_meta, static_cast<size_t>(D.max_rows), &s->ws_bytes);
   ok = ok && dev_alloc(&s->cand_vstart, static_cast<size_t>(D.max_rows), &s->ws_bytes);
@@ -470,6 +486,10 @@ int bma_scorer_score(bma_scorer* s, const long long* ids, int ids_stride, int B,
   }
   const bool ragged = n_share > 0;
   const int chunk = ragged ? D.max_rows / S - 1 : D.max_rows / S;
+  {
+    const int rc = ensure_ce_rows(s, (B < chunk ? B : chunk) * T);
+    if (rc != 0) return rc;
+  }
   for (int b0 = 0; b0 < B; b0 += chunk) {
     const int nb = B - b0 < chunk ? B - b0 : chunk;
     int rows = nb * S;

@@ -300,3 +300,41 @@ def test_graphed_gradient_equals_eager(cuda_device, mode):
         if cfg.pgd_attack:
             assert torch.equal(got_img, want_img), call
     assert atk._grad_graph["graph"] is not None and not atk._grad_graph["failed"]
+
+
+def test_score_host_entry_and_degenerate_batches(cuda_device):
+    """The host-buffer entry (pinned ids in, losses + key out, with the sharing base) equals the
+    device entry; B = 1, all candidates identical to the base, and a base unrelated to the
+    candidates (nothing shared) all give the full-tail losses."""
+    from bimodalattack_b200 import BimodalAttack
+    from bimodalattack_b200.engine import unpack_key
+    model, tok, proc, norm, image, cfg = _setup(cuda_device, **MODES["joint"])
+    atk = BimodalAttack(model, tok, proc, cfg, normalize=norm)
+    atk._prepare([{"role": "user", "content": PROMPT}], TARGET)
+    base = tok(INIT, add_special_tokens=False, return_tensors="pt")["input_ids"].to(cuda_device).reshape(-1).contiguous()
+    cand = _related_candidates(base, 37, 8, 1000, 1, seed=9, device=cuda_device)
+    with torch.no_grad():
+        feats = atk.scoring_features(image)
+        batch = atk._build_input_embeds_pgd(cand, feats, search_width=37, single=True)
+        plan = atk._plan(batch)
+        atk.engine.prefill(plan.prefix)
+        full = atk.engine.score(cand, plan, atk.target_ids).clone()
+        shared = atk.engine.score(cand, plan, atk.target_ids, base_ids=base).clone()
+        key_dev = int(atk.engine.key.item())
+        loss_h = torch.empty(37, dtype=torch.float32).pin_memory()
+        key_h = torch.empty(1, dtype=torch.int64).pin_memory()
+        atk.engine.score_host(cand.cpu().pin_memory(), plan, atk.target_ids, loss_h, key_h,
+                              base_ids_host=base.cpu().pin_memory())
+        assert torch.equal(loss_h, shared.cpu()) and int(key_h.item()) == key_dev
+        assert unpack_key(key_dev)[1] == int(shared.argmin())
+        tol = 1e-2 * float(full.abs().max())
+        assert float((shared - full).abs().max()) <= tol
+        one = atk.engine.score(cand[5:6], plan, atk.target_ids, base_ids=base)
+        assert abs(float(one[0]) - float(full[5])) <= tol
+        same = atk.engine.score(base.repeat(6, 1), plan, atk.target_ids, base_ids=base)
+        assert float((same - full[0]).abs().max()) <= tol and float(same.max() - same.min()) == 0.0
+        unrelated = torch.randint(8, 1000, base.shape, generator=torch.Generator().manual_seed(2)).to(cuda_device)
+        rows_full = 37 * (plan.n_tail - 1)
+        none_shared = atk.engine.score(cand, plan, atk.target_ids, base_ids=unrelated.contiguous())
+        assert atk.engine.last_rows >= rows_full                        # nothing saved, one extra sequence
+        assert float((none_shared - full).abs().max()) <= tol

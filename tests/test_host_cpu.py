@@ -117,3 +117,46 @@ def test_attack_buffer_semantics():
     b = AttackBuffer(2)
     b.add(3.0, "a"); b.add(1.0, "b"); b.add(2.0, "c")
     assert [e[1] for e in b.buffer] == ["b", "c"] and b.get_highest_loss() == 2.0
+
+
+def test_png_writer_matches_reference_conversion(tmp_path):
+    """_save_image (reference :1312-1317) runs off-thread here; the bytes must be the reference's
+    ``(arr * 255).astype(uint8)`` in HWC order."""
+    import numpy as np
+    import torch
+    from PIL import Image
+    from bimodalattack_b200.attack import BimodalAttack
+
+    class Host:
+        _png = None
+    h = Host()
+    imgs = [torch.rand((1, 3, 9, 14), generator=torch.Generator().manual_seed(i)) for i in range(4)]
+    for i, img in enumerate(imgs):
+        BimodalAttack._save_image(h, img, str(tmp_path / f"{i}.png"))
+    BimodalAttack.flush_images(h)
+    for i, img in enumerate(imgs):
+        want = (img.squeeze(0).numpy().transpose(1, 2, 0) * 255).astype(np.uint8)
+        assert (np.array(Image.open(tmp_path / f"{i}.png")) == want).all()
+
+
+def test_patch_embed_gemm_equals_conv():
+    """The unfold+GEMM forward installed on the tower's patch-embedding convolution (and its input
+    gradient) equals the convolution; restore_patch_embed undoes it."""
+    import torch
+    from bimodalattack_b200.attack import install_patch_embed_gemm, restore_patch_embed
+    torch.manual_seed(0)
+    for bias in (False, True):
+        conv = torch.nn.Conv2d(3, 24, kernel_size=14, stride=14, bias=bias)
+        net = torch.nn.Sequential(conv)
+        x = torch.rand(2, 3, 56 + 5, 42, requires_grad=True)           # ragged height: the conv drops the remainder
+        want = net(x)
+        g_want, = torch.autograd.grad(want.square().sum(), x)
+        assert install_patch_embed_gemm(net) == 1 and install_patch_embed_gemm(net) == 0
+        got = net(x)
+        g_got, = torch.autograd.grad(got.square().sum(), x)
+        assert got.shape == want.shape and torch.allclose(got, want, atol=1e-5)
+        assert torch.allclose(g_got, g_want, atol=1e-4)
+        restore_patch_embed(net)
+        assert torch.equal(net(x), want)
+    other = torch.nn.Sequential(torch.nn.Conv2d(3, 8, kernel_size=3, stride=1, padding=1))
+    assert install_patch_embed_gemm(other) == 0                          # overlapping windows: left alone
