@@ -74,6 +74,8 @@ struct bma_scorer {
   // ragged-row plan (suffix-head sharing)
   int2 *row_info = nullptr, *row_meta = nullptr;
   int* cand_vstart = nullptr;
+  int2* cand_tmp = nullptr;
+  int dedupe = 1;                        // identical candidates share one set of rows (bma_scorer_set_dedupe)
   int* total_rows_dev = nullptr;
   int* total_rows_host = nullptr;        // pinned
   long long* base_dev = nullptr;         // staging for the *_host entry
@@ -352,7 +354,8 @@ bma_scorer* bma_scorer_create(const bma_model_desc* desc) {
   (void)n_ce_tiles;   // the CE partial buffers are sized on first use (score knows T): ensure_ce_rows
   ok = ok && dev_alloc(&s->row_info, static_cast<size_t>(D.max_rows), &s->ws_bytes);
   ok = ok && dev_alloc(&s->row_meta, static_cast<size_t>(D.max_rows), &s->ws_bytes);
-  ok = ok && dev_alloc(&s->cand_vstart, static_cast<size_t>(D.max_rows), &s->ws_bytes);
+  ok = ok && dev_alloc(&s->cand_vstart, static_cast<size_t>(D.max_rows) + 1, &s->ws_bytes);
+  ok = ok && dev_alloc(&s->cand_tmp, static_cast<size_t>(D.max_rows) + 1, &s->ws_bytes);
   ok = ok && dev_alloc(&s->total_rows_dev, 1, &s->ws_bytes);
   ok = ok && dev_alloc(&s->base_dev, 4096, &s->ws_bytes);
   ok = ok && cudaHostAlloc(reinterpret_cast<void**>(&s->total_rows_host), sizeof(int), cudaHostAllocDefault) == cudaSuccess;
@@ -372,7 +375,7 @@ void bma_scorer_destroy(bma_scorer* s) {
   if (s == nullptr) return;
   cudaFree(s->x); cudaFree(s->xn); cudaFree(s->qk); cudaFree(s->vt); cudaFree(s->attn); cudaFree(s->act);
   cudaFree(s->prefix_qk); cudaFree(s->prefix_vt); cudaFree(s->ce_part); cudaFree(s->tgt_logit);
-  cudaFree(s->row_info); cudaFree(s->row_meta); cudaFree(s->cand_vstart); cudaFree(s->total_rows_dev);
+  cudaFree(s->row_info); cudaFree(s->row_meta); cudaFree(s->cand_vstart); cudaFree(s->cand_tmp); cudaFree(s->total_rows_dev);
   cudaFree(s->base_dev);
   if (s->total_rows_host != nullptr) cudaFreeHost(s->total_rows_host);
   cudaFree(s->ids_dev); cudaFree(s->loss_dev); cudaFree(s->key_dev); cudaFree(s->flag_dev);
@@ -454,6 +457,12 @@ int bma_scorer_reset_key(bma_scorer* s, unsigned long long* key, int* all_match,
 
 long long bma_scorer_last_rows(const bma_scorer* s) { return s ? s->last_rows : 0; }
 
+int bma_scorer_set_dedupe(bma_scorer* s, int enable) {
+  if (s == nullptr) return fail(cudaErrorInvalidValue, "set_dedupe: null scorer");
+  s->dedupe = enable != 0;
+  return 0;
+}
+
 int bma_scorer_score(bma_scorer* s, const long long* ids, int ids_stride, int B, const int* slot,
                      const void* fixed, int S, const long long* target_ids, int T, int ce_row0,
                      float* loss, unsigned long long* key, int* all_match, unsigned int idx_base,
@@ -485,7 +494,8 @@ int bma_scorer_score(bma_scorer* s, const long long* ids, int ids_stride, int B,
     if (s->prefix_len + n_share > D.max_prefix || 2 * S > D.max_rows) n_share = 0;
   }
   const bool ragged = n_share > 0;
-  const int chunk = ragged ? D.max_rows / S - 1 : D.max_rows / S;
+  int chunk = ragged ? D.max_rows / S - 1 : D.max_rows / S;
+  if (ragged && chunk > 8190) chunk = 8190;              // plan_rows handles 8 entries per thread
   {
     const int rc = ensure_ce_rows(s, (B < chunk ? B : chunk) * T);
     if (rc != 0) return rc;
@@ -497,8 +507,9 @@ int bma_scorer_score(bma_scorer* s, const long long* ids, int ids_stride, int B,
     if (ragged) {
       // every chunk carries the base as sequence 0: its rows are the keys [P, P+n_share) source
       ProfScope ps(s, PC_EMBED, 0, st);
-      BMA_LAUNCH(launch_plan_rows(ids_c, ids_stride, base_ids, slot, S, n_share, nb, 1, s->prefix_len,
-                                  s->row_info, s->row_meta, s->cand_vstart, s->total_rows_dev, st), "plan_rows");
+      BMA_LAUNCH(launch_plan_rows(ids_c, ids_stride, base_ids, slot, S, n_share, nb, 1, s->prefix_len, s->dedupe,
+                                  s->row_info, s->row_meta, s->cand_vstart, s->cand_tmp, s->total_rows_dev, st),
+                 "plan_rows");
       BMA_CHECK(cudaMemcpyAsync(s->total_rows_host, s->total_rows_dev, sizeof(int), cudaMemcpyDeviceToHost, st),
                 "score: row count D2H");
       BMA_CHECK(cudaStreamSynchronize(st), "score: sync");

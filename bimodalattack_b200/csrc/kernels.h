@@ -44,9 +44,9 @@ cudaError_t launch_build_tail_embeds(const long long* ids, int ids_stride, const
                                      int S, int d, const int2* row_info, const long long* base_ids,
                                      cudaStream_t stream);
 cudaError_t launch_plan_rows(const long long* ids, int ids_stride, const long long* base_ids,
-                             const int* slot, int S, int n_share, int B, int include_base, int P,
-                             int2* row_info, int2* row_meta, int* cand_vstart, int* total_rows,
-                             cudaStream_t stream);
+                             const int* slot, int S, int n_share, int B, int include_base, int P, int dedupe,
+                             int2* row_info, int2* row_meta, int* cand_vstart, int2* cand_tmp,
+                             int* total_rows, cudaStream_t stream);
 cudaError_t launch_append_prefix_kv(const __nv_bfloat16* k_tail, long long ldk, const __nv_bfloat16* vt_tail,
                                     long long ldvt, __nv_bfloat16* k_pre, long long ldkp,
                                     __nv_bfloat16* vt_pre, long long ldvtp, int n, int kv_dim, int P,

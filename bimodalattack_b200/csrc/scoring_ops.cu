@@ -19,28 +19,64 @@ namespace bma {
 //   row_meta[r] = (first flattened row of the candidate; number of prefix keys the row may see,
 //                  = P + j_c)
 //   cand_vstart[c] = first row of candidate c minus j_c  (row of tail position s is vstart + s)
+// Candidates that are IDENTICAL to an earlier candidate of the chunk (or to the base) own no rows at
+// all: their cand_vstart points at the representative's rows, so the LM head scores the same hidden
+// states again and their loss is the representative's (the reference scores duplicates redundantly;
+// at sw 512 about 5 % of the draws repeat a (position, token) pair).
 // One block; candidates are spread over the threads, rows are numbered by a block-wide scan.
 __global__ void __launch_bounds__(1024)
 plan_rows_kernel(const long long* __restrict__ ids, int ids_stride, const long long* __restrict__ base_ids,
-                 const int* __restrict__ slot, int S, int n_share, int B, int include_base, int P,
+                 const int* __restrict__ slot, int S, int n_share, int B, int include_base, int P, int dedupe,
                  int2* __restrict__ row_info, int2* __restrict__ row_meta, int* __restrict__ cand_vstart,
-                 int* __restrict__ total_rows) {
+                 int2* __restrict__ cand_tmp, int* __restrict__ total_rows) {
   __shared__ int part[1024];
   const int t = threadIdx.x, nt = blockDim.x;
-  const int n = B + (include_base ? 1 : 0);            // entry 0 is the base when included
+  const int nbase = include_base ? 1 : 0;
+  const int n = B + nbase;                               // entry 0 is the base when included
   const int per = (n + nt - 1) / nt;
   const int e0 = min(n, t * per), e1 = min(n, e0 + per);
-  auto first_diff = [&](int e) -> int {
-    if (include_base && e == 0) return 0;
-    const long long* row = ids + (long long)(e - (include_base ? 1 : 0)) * ids_stride;
-    for (int s = 0; s < n_share; ++s) {
-      const int sl = slot[s];
-      if (sl >= 0 && row[sl] != base_ids[sl]) return s;
+  // (first differing tail position, token there) of every entry
+  for (int e = e0; e < e1; ++e) {
+    int jd = n_share, tk = -1;
+    if (e < nbase) {
+      jd = 0;
+    } else {
+      const long long* row = ids + (long long)(e - nbase) * ids_stride;
+      for (int s = 0; s < n_share; ++s) {
+        const int sl = slot[s];
+        if (sl >= 0 && row[sl] != base_ids[sl]) { jd = s; tk = static_cast<int>(row[sl]); break; }
+      }
     }
-    return n_share;
-  };
+    cand_tmp[e] = make_int2(jd, tk);
+  }
+  __syncthreads();
+  // representative of every entry (itself unless an identical earlier entry exists)
   int local = 0;
-  for (int e = e0; e < e1; ++e) local += S - first_diff(e);
+  for (int e = e0; e < e1; ++e) {
+    const int2 me = cand_tmp[e];
+    int rep = e;
+    if (dedupe && e >= nbase) {
+      const long long* row = ids + (long long)(e - nbase) * ids_stride;
+      auto same_from = [&](const long long* other, int s0) {
+        for (int s = s0; s < S; ++s) {
+          const int sl = slot[s];
+          if (sl >= 0 && row[sl] != other[sl]) return false;
+        }
+        return true;
+      };
+      if (me.x == n_share && nbase == 1 && same_from(base_ids, n_share)) {
+        rep = 0;                                         // the candidate IS the base
+      } else if (me.x < n_share) {
+        for (int o = nbase; o < e; ++o) {
+          const int2 ot = cand_tmp[o];
+          if (ot.x == me.x && ot.y == me.y &&
+              same_from(ids + (long long)(o - nbase) * ids_stride, me.x + 1)) { rep = o; break; }
+        }
+      }
+    }
+    cand_vstart[e] = rep;                                // staged: entry -> representative entry
+    local += rep == e ? S - me.x : 0;
+  }
   part[t] = local;
   __syncthreads();
   for (int off = 1; off < nt; off <<= 1) {               // inclusive Hillis-Steele scan
@@ -52,23 +88,33 @@ plan_rows_kernel(const long long* __restrict__ ids, int ids_stride, const long l
   int row = part[t] - local;
   if (t == nt - 1) *total_rows = part[t];
   for (int e = e0; e < e1; ++e) {
-    const int j = first_diff(e);
-    const int c = e - (include_base ? 1 : 0);           // -1 = base
-    if (c >= 0) cand_vstart[c] = row - j;
-    for (int s = j; s < S; ++s) {
-      row_info[row + s - j] = make_int2(c, s);
-      row_meta[row + s - j] = make_int2(row, P + j);
+    if (cand_vstart[e] != e) continue;                   // duplicates are resolved below
+    const int jd = cand_tmp[e].x;
+    const int c = e - nbase;                             // -1 = base
+    cand_tmp[e].y = row - jd;                            // virtual start of this representative
+    for (int s = jd; s < S; ++s) {
+      row_info[row + s - jd] = make_int2(c, s);
+      row_meta[row + s - jd] = make_int2(row, P + jd);
     }
-    row += S - j;
+    row += S - jd;
   }
+  __syncthreads();
+  // cand_vstart is indexed by CANDIDATE (entry - nbase) for the CE gather; entries were staged in
+  // place, so resolve through a register and re-synchronise before the shifted write
+  int vs[8];
+  for (int e = e0, k = 0; e < e1 && k < 8; ++e, ++k) vs[k] = cand_tmp[cand_vstart[e]].y;
+  __syncthreads();
+  for (int e = e0, k = 0; e < e1 && k < 8; ++e, ++k)
+    if (e >= nbase) cand_vstart[e - nbase] = vs[k];
 }
 
 cudaError_t launch_plan_rows(const long long* ids, int ids_stride, const long long* base_ids,
-                             const int* slot, int S, int n_share, int B, int include_base, int P,
-                             int2* row_info, int2* row_meta, int* cand_vstart, int* total_rows,
-                             cudaStream_t stream) {
+                             const int* slot, int S, int n_share, int B, int include_base, int P, int dedupe,
+                             int2* row_info, int2* row_meta, int* cand_vstart, int2* cand_tmp,
+                             int* total_rows, cudaStream_t stream) {
+  if (B + 1 > 8 * 1024) return cudaErrorInvalidValue;    // 8 entries per thread at most
   plan_rows_kernel<<<1, 1024, 0, stream>>>(ids, ids_stride, base_ids, slot, S, n_share, B, include_base, P,
-                                           row_info, row_meta, cand_vstart, total_rows);
+                                           dedupe, row_info, row_meta, cand_vstart, cand_tmp, total_rows);
   return cudaGetLastError();
 }
 

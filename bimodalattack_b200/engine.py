@@ -103,6 +103,7 @@ class ScoringEngine:
         self.flag = torch.empty(1, dtype=torch.int32, device=self.device)
         self.prefix_len = 0
         self.share_suffix_head = True    # compute tail rows shared with the base suffix once (see score())
+        self.dedupe_candidates = True    # ... and the rows of identical candidates once
         self._last_prefix: Optional[torch.Tensor] = None
         self._prefix_stale = False
 
@@ -155,6 +156,7 @@ class ScoringEngine:
             raise RuntimeError("bimodal_b200: scorer_create failed: " +
                                self.lib.bma_last_error().decode("utf-8", "replace"))
         self._scorer = handle
+        native.check(self.lib.bma_scorer_set_dedupe(handle, int(self.dedupe_candidates)), "scorer_set_dedupe")
         self._cap_rows, self._cap_prefix = cap_rows, cap_prefix
         self._prefix_stale = True        # a new scorer has no prefix K/V yet
         for i, layer in enumerate(self.lm.layers):

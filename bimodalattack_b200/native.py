@@ -63,6 +63,7 @@ SIGNATURES = {
     "bma_scorer_reset_key": (_I, [_P, _P, _P, _P]),
     "bma_scorer_score": (_I, [_P, _P, _I, _I, _P, _P, _I, _P, _I, _I, _P, _P, _P, _U32, _P, _P]),
     "bma_scorer_last_rows": (_LL, [_P]),
+    "bma_scorer_set_dedupe": (_I, [_P, _I]),
     "bma_scorer_score_host": (_I, [_P, _P, _I, _I, _P, _P, _I, _P, _I, _I, _P, _P, _U32, _P, _P]),
     "bma_gemm_bf16": (_I, [_P, _LL, _P, _LL, _P, _LL, _P, _LL, _I, _I, _I, _I, _P]),
     "bma_rmsnorm": (_I, [_P, _LL, _P, _P, _LL, _I, _I, _F, _I, _P]),

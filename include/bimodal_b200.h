@@ -128,6 +128,9 @@ int bma_scorer_score(bma_scorer* s, const long long* ids, int ids_stride, int B,
                      const long long* base_ids, void* stream);
 /* Tail rows the last bma_scorer_score call ran through the decoder (B*S without base_ids). */
 long long bma_scorer_last_rows(const bma_scorer* s);
+/* With base_ids: candidates identical to an earlier candidate of the chunk (or to the base) reuse its
+ * rows instead of recomputing them (default on); their loss is the representative's. */
+int bma_scorer_set_dedupe(bma_scorer* s, int enable);
 
 /* Same call with HOST buffers for ids / loss / key (pinned recommended): copies in, scores,
  * copies out and synchronises the stream. This is the end-to-end entry the benchmark times. */

@@ -228,6 +228,9 @@ def _related_candidates(base, n, vocab_lo, vocab_hi, n_replace, seed, device):
     cand[0] = base.cpu()
     cand[1] = base.cpu(); cand[1, 0] = vocab_lo + 1
     cand[2] = base.cpu(); cand[2, L - 1] = vocab_lo + 2
+    if n > 12:                               # exact duplicates: of another candidate and of the base
+        cand[9] = cand[4]
+        cand[11] = base.cpu()
     return cand.to(device)
 
 
@@ -265,7 +268,18 @@ def test_suffix_head_sharing_matches_full_tails(cuda_device, mode, n, n_replace)
     first_diff = first_diff.clamp(max=S - atk.target_ids.numel())     # scored rows are never shared
     n_chunks = (n + 4095) // 4096          # the engine sizes the workspace for 4096 candidates (+ the base) per chunk
     assert rows_full == n * S
-    assert rows_shared == int((S - first_diff).sum()) + n_chunks * S          # + the base, once per chunk
+    # identical candidates (within a chunk) and copies of the base own no rows; + the base, once per chunk
+    want_rows = n_chunks * S
+    for lo in range(0, n, 4096):
+        chunk = cand[lo:lo + 4096]
+        uniq, first = [], {}
+        for i, row in enumerate(chunk.tolist()):
+            if tuple(row) not in first and row != base.tolist():
+                first[tuple(row)] = i
+                uniq.append(lo + i)
+        want_rows += int((S - first_diff[torch.tensor(uniq, device=cuda_device)]).sum())
+    assert rows_shared == want_rows
+    assert float(shared[9]) == float(shared[4]) and float(shared[11]) == float(shared[0])   # exact copies
     assert rows_shared < 0.85 * rows_full
     assert float((shared - full).abs().max()) <= 1e-2 * float(full.abs().max())
     assert idx_shared == int(shared.argmin()) and key_loss == float(shared.min())
@@ -334,7 +348,8 @@ def test_score_host_entry_and_degenerate_batches(cuda_device):
         same = atk.engine.score(base.repeat(6, 1), plan, atk.target_ids, base_ids=base)
         assert float((same - full[0]).abs().max()) <= tol and float(same.max() - same.min()) == 0.0
         unrelated = torch.randint(8, 1000, base.shape, generator=torch.Generator().manual_seed(2)).to(cuda_device)
-        rows_full = 37 * (plan.n_tail - 1)
         none_shared = atk.engine.score(cand, plan, atk.target_ids, base_ids=unrelated.contiguous())
-        assert atk.engine.last_rows >= rows_full                        # nothing saved, one extra sequence
+        # no shared suffix head; only the two exact duplicates inside the batch (rows 9 and 11) are saved,
+        # and the (unrelated) base rides along as one extra sequence
+        assert atk.engine.last_rows == (37 - 2 + 1) * (plan.n_tail - 1)
         assert float((none_shared - full).abs().max()) <= tol
