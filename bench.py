@@ -56,7 +56,8 @@ def parse_args():
     ap.add_argument("--no-suffix-sharing", action="store_true",
                     help="score every candidate's full tail (the north-star dataflow) instead of computing the "
                          "rows it shares with the current suffix once")
-    ap.add_argument("--cpu-sample", type=int, default=1, help="candidates per CPU-baseline step")
+    ap.add_argument("--cpu-sample", type=int, default=0,
+                    help="candidates per CPU-baseline step (0 = 3 for the in-run cpu_baseline, 1 per step for --impl reference)")
     return ap.parse_args()
 
 
@@ -169,7 +170,7 @@ def run_reference(args):
                               joint_eval=joint, allow_non_ascii=True, optim_str_init=init, seed=1,
                               alpha=4 / 255, eps=64 / 255, verbosity="ERROR", images_folder=None)
     score = oracle_scoring_fn(model, tok, proc, norm, cfg, messages, target, image, joint)
-    n = args.cpu_sample
+    n = args.cpu_sample or 1
     g = torch.Generator().manual_seed(3)
     n_tok = len(tok(init, add_special_tokens=False)["input_ids"])
     vocab = model.get_input_embeddings().num_embeddings
@@ -474,7 +475,7 @@ def main():
         twin = copy.deepcopy(model).to("cpu").float()
         score = oracle_scoring_fn(twin, tok, proc, norm, cfg, messages, target, image.cpu(), joint,
                                   segment_ids=atk.segment_ids, target_ids=atk.target_ids)
-        n = args.cpu_sample
+        n = args.cpu_sample or 3
         t1 = time.perf_counter()
         cl, seq_len = score(sampled[:n].cpu())
         dt = time.perf_counter() - t1

@@ -1,0 +1,152 @@
+"""Parity at BASELINE.json's full sizes (config 2: LLaVA-1.5-7B architecture, search_width 512,
+596-row prefix, 42-row tail; config 4: Gemma-3-4b architecture, 262k vocabulary).
+
+The oracle (the reference's dataflow: full 638-token sequence, full-vocabulary logits, loss in bf16)
+is too slow to score 512 candidates per test, so it scores a sample of them on the GPU and the rest
+of the batch is covered by size-independent properties of the scorer: sharing on/off equivalence,
+permutation equivariance, exact duplicates, batch-1 re-scoring of the winner (what the reference
+does after every step, bimodal_attack.py:605-612) and the packed-key argmin.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _sample_candidates(atk, tok, init, sw, device):
+    """Real candidates: gradient -> device sampler, as a step of run() produces them."""
+    from bimodalattack_b200 import synthetic  # noqa: F401
+    optim_ids = tok(init, add_special_tokens=False, return_tensors="pt")["input_ids"].to(device)
+    return optim_ids
+
+
+@pytest.fixture(scope="module")
+def llava7b(cuda_device):
+    from bimodalattack_b200 import BimodalAttack, BimodalAttackConfig, synthetic as syn
+    tok, proc, norm, image_cpu, messages, target, init = syn.headline_case(32000, 336)
+    model = syn.make_llava("7b", dtype=torch.bfloat16, device=cuda_device, seed=0, head_gain=2.0,
+                           attn_implementation="sdpa")
+    cfg = BimodalAttackConfig(num_steps=1, search_width=512, topk=256, n_replace=1, pgd_attack=True, gcg_attack=True,
+                              joint_eval=True, allow_non_ascii=True, filter_ids=False, optim_str_init=init, seed=1,
+                              alpha=4 / 255, eps=64 / 255, verbosity="ERROR", images_folder=None)
+    atk = BimodalAttack(model, tok, proc, cfg, normalize=norm)
+    atk._prepare(messages, target)
+    image = image_cpu.to(cuda_device)
+    torch.manual_seed(1)
+    optim_ids = tok(init, add_special_tokens=False, return_tensors="pt")["input_ids"].to(cuda_device)
+    g_tok, g_img = atk.compute_gradient(optim_ids, image.clone().requires_grad_())
+    image = atk.perform_pgd_step(image.clone().requires_grad_(), cfg.eps, cfg.alpha, g_img, image.clone()).detach()
+    sampled, _, _, _ = atk.candidate_sampling(cfg, 0, optim_ids, g_tok, tok, [], 0.0)
+    yield dict(atk=atk, model=model, tok=tok, proc=proc, norm=norm, cfg=cfg, image=image, sampled=sampled,
+               base=optim_ids.reshape(-1).contiguous())
+    atk.engine.close()
+
+
+def _score(atk, cand, feats, base=None):
+    batch = atk._build_input_embeds_pgd(cand, feats, search_width=cand.shape[0], single=True)
+    atk._base = None if base is None else (cand, base)
+    loss = atk._compute_candidates_loss_original(cand.shape[0], batch).clone()
+    return loss, atk._winner(), atk.engine.last_rows
+
+
+def test_headline_scoring_properties(llava7b):
+    h = llava7b
+    atk, sampled, base = h["atk"], h["sampled"], h["base"]
+    assert sampled.shape == (512, 20)
+    with torch.no_grad():
+        feats = atk.scoring_features(h["image"])
+        full, (lf, wf), rows_full = _score(atk, sampled, feats)
+        shared, (ls, ws), rows_shared = _score(atk, sampled, feats, base)
+        assert rows_full == 512 * 41 and rows_shared < 0.8 * rows_full
+        # Tolerance for every comparison below: 2 bf16 ulps of the loss value (0.0625 for losses in
+        # [4, 8), 0.125 in [8, 16)) -- the resolution of the reference's own bf16 loss. Re-ordering the
+        # attention's key blocks perturbs bf16 roundings that 32 layers of bf16 activations amplify.
+        tol = 2 * float(2.0 ** (torch.floor(torch.log2(full.abs().max())) - 7))
+        # (1) sharing the suffix head changes nothing but the attention's key-block order
+        assert float((shared - full).abs().max()) <= tol
+        # (2) packed-key argmin == argmin of the returned losses, lowest index on ties
+        assert ws == int(shared.argmin()) and ls == float(shared.min())
+        assert float(full[ws]) <= float(full.min()) + tol
+        # (3) permutation equivariance
+        perm = torch.randperm(512, generator=torch.Generator().manual_seed(3)).to(sampled.device)
+        permuted, (lp, wp), _ = _score(atk, sampled[perm].contiguous(), feats, base)
+        assert float((permuted - shared[perm]).abs().max()) <= tol
+        assert float(shared[perm[wp]]) <= float(shared.min()) + tol
+        # (4) exact duplicates score exactly alike
+        rows = [tuple(r) for r in sampled.tolist()]
+        first, dups = {}, []
+        for i, r in enumerate(rows):
+            if r in first:
+                dups.append((first[r], i))
+            else:
+                first[r] = i
+        assert len(dups) >= 1            # ~25 expected: 512 draws over 20 x 256 (position, token) pairs
+        for a, b in dups:
+            assert float(shared[a]) == float(shared[b])
+        # (5) the winner re-scored alone at batch 1 (reference :605-612)
+        alone, _, _ = _score(atk, sampled[ws:ws + 1].contiguous(), feats)
+        assert abs(float(alone[0]) - ls) <= tol
+        # the scores really differ between candidates
+        assert float(shared.max() - shared.min()) > 0.05
+
+
+def test_headline_losses_match_oracle_sample(llava7b):
+    """16 of the 512 candidates through the reference's dataflow on the GPU (bf16 model, loss in
+    bf16): |diff| <= 2 bf16 ulps of the reference value; and against an fp32 evaluation of the same
+    logits-from-bf16-forward the relative error stays below 2e-2."""
+    from oracle import hotpath
+    h = llava7b
+    atk, sampled, base, model = h["atk"], h["sampled"], h["base"], h["model"]
+    with torch.no_grad():
+        feats = atk.scoring_features(h["image"])
+        got, _, _ = _score(atk, sampled, feats, base)
+        pick = torch.arange(0, 512, 32, device=sampled.device)
+        ora = hotpath.OracleAttack(model, h["tok"], h["proc"], h["cfg"], normalize=h["norm"])
+        ora.target_ids = atk.target_ids
+        ora.seg_embeds = {k: ora.emb(v) for k, v in atk.segment_ids.items()}
+        order = hotpath.segment_order("pgd", "llava", single=True)
+        want, _ = hotpath.candidates_loss(model, hotpath.assemble(ora._parts(sampled[pick], feats), order, pick.numel()),
+                                          atk.target_ids, 4)
+    want = want.float()
+    ulp = 2.0 ** (torch.floor(torch.log2(want.abs().clamp_min(1e-3))) - 7)
+    diff = (got[pick] - want).abs()
+    assert bool((diff <= 2 * ulp + 1e-3).all()), (diff / ulp).max()
+    # the oracle's own argmin over the sample is (tie-aware) the scorer's
+    assert float(want[int(got[pick].argmin())]) <= float(want.min()) + 2 * float(ulp.max())
+
+
+def test_gemma4b_losses_match_oracle_sample(cuda_device):
+    """Config 4 at full size: Gemma-3-4b architecture (34 layers, head_dim 256, 262 208-row tied
+    head), GCG-only order, search_width 512; 8 candidates against the reference's dataflow."""
+    from bimodalattack_b200 import BimodalAttack, BimodalAttackConfig, synthetic as syn
+    from oracle import hotpath
+    tok, proc, norm, image, messages, target, init = syn.gemma_case(262208, 56)
+    model = syn.make_gemma3("4b", dtype=torch.bfloat16, device=cuda_device, seed=0, embed_gain=1.5)
+    model.config._attn_implementation = "sdpa"
+    cfg = BimodalAttackConfig(num_steps=1, search_width=512, topk=256, n_replace=1, pgd_attack=False, gcg_attack=True,
+                              allow_non_ascii=True, filter_ids=False, optim_str_init=init, seed=1, verbosity="ERROR",
+                              images_folder=None)
+    atk = BimodalAttack(model, tok, proc, cfg, normalize=norm)
+    atk._prepare(messages, target)
+    torch.manual_seed(1)
+    optim_ids = tok(init, add_special_tokens=False, return_tensors="pt")["input_ids"].to(cuda_device)
+    g_tok, _ = atk.compute_gradient(optim_ids, None)
+    sampled, _, _, _ = atk.candidate_sampling(cfg, 0, optim_ids, g_tok, tok, [], 0.0)
+    with torch.no_grad():
+        batch = atk._build_input_embeds_gcg(sampled, search_width=512, no_joint_eval=True)
+        got = atk._compute_candidates_loss_original(512, batch).clone()
+        rows = atk.engine.last_rows
+        _, widx = atk._winner()
+        pick = torch.arange(0, 512, 64, device=cuda_device)
+        ora = hotpath.OracleAttack(model, tok, proc, cfg, normalize=norm)
+        ora.target_ids = atk.target_ids
+        ora.seg_embeds = {k: ora.emb(v) for k, v in atk.segment_ids.items()}
+        order = hotpath.segment_order("gcg", "gemma3", no_joint_eval=True)
+        want, _ = hotpath.candidates_loss(model, hotpath.assemble(ora._parts(sampled[pick]), order, pick.numel()),
+                                          atk.target_ids, 4)
+    assert rows < 0.85 * 512 * 41 and widx == int(got.argmin())
+    want = want.float()
+    ulp = 2.0 ** (torch.floor(torch.log2(want.abs().clamp_min(1e-3))) - 7)
+    diff = (got[pick] - want).abs()
+    assert bool((diff <= 2 * ulp + 1e-3).all()), (diff / ulp).max()
+    atk.engine.close()
