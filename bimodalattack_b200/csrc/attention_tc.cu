@@ -8,7 +8,8 @@
 //     rk <= rq (block-diagonal causal mask over the flattened rows).
 // With P = 0 and S = P_len the same kernel computes the prefix itself (plain causal attention).
 //
-//   warp 0      TMA producer: Q tile per item, then K blocks and V^T blocks into two 2-stage rings
+//   warp 0      TMA producer: Q tile per item (double-buffered for head_dim 128: the next item's Q is
+//               fetched while this one runs), then K blocks and V^T blocks into two 2-stage rings
 //   warp 1      MMA issuer:   S_j = Q K_j^T  and  O += P_j V_j   (tcgen05.mma, operands in smem,
 //                             accumulators in TMEM: 2 x S[128x128] + O[128x128])
 //   warp 2      TMEM allocator
@@ -46,8 +47,12 @@ struct AtcCfg {
   static constexpr int kKTile = (HD / 64) * kKPanel;
   static constexpr int kVTile = (BN / 64) * kVPanel;
   static constexpr int kPTile = (BN / 64) * kPPanel;
-  static constexpr int kSmem = kQTile + 2 * (kKTile + kVTile) + 2 * kPTile + 1024 /*align*/ + 256 /*barriers*/ +
-                               2 * ATC_BM * 4 /*row sum exchange*/;
+  // head_dim 128: TWO Q tiles (the next item's Q is fetched while this item runs) and ONE P tile
+  // (P_j is written late in the softmax of block j, long after PV_{j-1} has drained the tile);
+  // head_dim 256: one Q tile, there is no room for a second one
+  static constexpr int kQBuf = (HD <= 128) ? 2 : 1;
+  static constexpr int kXchg = 2 * 2 * ATC_BM * 4;       // [2 rotating buffers][2 halves][128 rows] floats
+  static constexpr int kSmem = kQBuf * kQTile + 2 * (kKTile + kVTile) + kPTile + 256 /*barriers*/ + kXchg;
   static constexpr int kTmemS = 0;                      // S_0 at +0, S_1 at +BN
   static constexpr int kTmemO = 2 * BN;                 // O: HD columns
   static_assert(2 * BN + HD <= 512, "TMEM budget");
@@ -100,28 +105,32 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kt,
                     const __grid_constant__ CUtensorMap tm_kp, const __grid_constant__ CUtensorMap tm_vt,
                     const __grid_constant__ CUtensorMap tm_vp, const AtcParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  // The swizzled tiles need 1024-byte alignment. The whole 227 KB budget is used, so there is no
+  // slack for rounding the base up: the dynamic segment is declared 1024-aligned (it is the only
+  // shared allocation of the kernel) and checked.
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
   using Cfg = AtcCfg<HD, BN>;
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + Cfg::kQTile;              // [2 stages][tile]
+  constexpr int QB = Cfg::kQBuf;
+  uint8_t* sQ = smem;                          // [QB][tile]
+  uint8_t* sK = sQ + QB * Cfg::kQTile;         // [2 stages][tile]
   uint8_t* sV = sK + 2 * Cfg::kKTile;          // [2 stages][tile]  (V^T: [HD dims][keys])
-  uint8_t* sP = sV + 2 * Cfg::kVTile;          // [2][tile]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * Cfg::kPTile);
-  uint64_t* q_full = bars;            // [1]
-  uint64_t* q_empty = bars + 1;       // [1]
+  uint8_t* sP = sV + 2 * Cfg::kVTile;          // [tile]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::kPTile);
+  uint64_t* q_full = bars + 22;       // [2]
+  uint64_t* q_empty = bars + 24;      // [2]
   uint64_t* k_full = bars + 2;        // [2]  K and V^T blocks ride in SEPARATE rings: a K stage is
   uint64_t* k_empty = bars + 4;       // [2]  released as soon as S_j = Q K_j^T has been computed, a V
   uint64_t* v_full = bars + 16;       // [2]  stage when O += P_j V_j has, so the loads of block j+2
   uint64_t* v_empty = bars + 18;      // [2]  are not serialised behind the softmax of block j
   uint64_t* s_full = bars + 6;        // [2]
   uint64_t* s_empty = bars + 8;       // [2]
-  uint64_t* p_full = bars + 10;       // [2]
-  uint64_t* p_empty = bars + 12;      // [2]
+  uint64_t* p_full = bars + 10;       // [1]
+  uint64_t* p_empty = bars + 12;      // [1]
   uint64_t* o_empty = bars + 14;      // [1]  softmax has read the finished O of the item
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
-  float* xsum = reinterpret_cast<float*>(bars + 32);     // [2 halves][128 rows] partial row sums
+  float* xchg = reinterpret_cast<float*>(bars + 32);     // [2 rotating][2 halves][128 rows] row max / row sum swaps
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (p.M + ATC_BM - 1) / ATC_BM;
@@ -133,12 +142,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     tma_prefetch_desc(&tm_vt); tma_prefetch_desc(&tm_vp);
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(q_full, 1); mbar_init(q_empty, 1); mbar_init(o_empty, 8);
+    mbar_init(o_empty, 8);
+    mbar_init(p_full, 8); mbar_init(p_empty, 1);
     for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);  mbar_init(&q_empty[i], 1);
       mbar_init(&k_full[i], 1);  mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1);  mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);  mbar_init(&s_empty[i], 8);
-      mbar_init(&p_full[i], 8);  mbar_init(&p_empty[i], 1);
     }
     fence_barrier_init();
   }
@@ -164,11 +174,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         const int r0 = tile * ATC_BM, r1 = min(p.M, r0 + ATC_BM);
         const int kt0 = tail_key_start(r0, p.S, p.row_meta);
         const int nb = n_pre + (r1 - kt0 + BN - 1) / BN;
-        mbar_wait(q_empty, (item_n & 1) ^ 1, 0x500);
-        mbar_arrive_expect_tx(q_full, Cfg::kQTile);
+        {
+          const int qb = item_n % QB;
+          const uint32_t qpar = (item_n / QB) & 1;
+          mbar_wait(&q_empty[qb], qpar ^ 1, 0x500 + qb);
+          mbar_arrive_expect_tx(&q_full[qb], Cfg::kQTile);
 #pragma unroll
-        for (int c = 0; c < HD / 64; ++c)
-          tma_load_2d(sQ + c * Cfg::kQPanel, &tm_q, q_full, p.q_col0 + head * HD + c * 64, r0);
+          for (int c = 0; c < HD / 64; ++c)
+            tma_load_2d(sQ + qb * Cfg::kQTile + c * Cfg::kQPanel, &tm_q, &q_full[qb],
+                        p.q_col0 + head * HD + c * 64, r0);
+        }
         // issue order K_0, K_1, V_0, K_2, V_1, ...: K_{j+1} is requested before V_j, so every load
         // has about two softmax periods of slack before its MMA
         auto load_k = [&](int j) {
@@ -210,11 +225,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       auto issue_pv = [&](uint32_t g, int n_mma, bool first, uint32_t item_par) {
         const int st = g & 1;
         mbar_wait(&v_full[st], (g >> 1) & 1, 0x660 + st);
-        mbar_wait(&p_full[st], (g >> 1) & 1, 0x620 + st);
+        mbar_wait(p_full, g & 1, 0x620);
         if (first) mbar_wait(o_empty, item_par ^ 1, 0x630);     // previous item's O has been read out
         tc_fence_after();
         const uint32_t idesc = umma_idesc_bf16(ATC_BM, HD);
-        const uint32_t pa = smem_u32(sP + st * Cfg::kPTile), vb = smem_u32(sV + st * Cfg::kVTile);
+        const uint32_t pa = smem_u32(sP), vb = smem_u32(sV + st * Cfg::kVTile);
         for (int kk = 0; kk < n_mma / 16 && !(p.debug & 2); ++kk) {
           const uint32_t off_p = (kk >> 2) * Cfg::kPPanel + (kk & 3) * 32;
           const uint32_t off_v = (kk >> 2) * Cfg::kVPanel + (kk & 3) * 32;
@@ -222,15 +237,26 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
                        !(first && kk == 0));
         }
         umma_commit(&v_empty[st]);
-        umma_commit(&p_empty[st]);
+        umma_commit(p_empty);
       };
+      // One flat stream of blocks across work items: S_g is issued BEFORE the PV of block g-1, also
+      // when g is the first block of the next item, so the softmax warps always find their next S
+      // ready (the PV of an item's last block is issued after the next item's first QK).
+      bool have_pending = false;
+      uint32_t pend_g = 0, pend_item_par = 0;
+      int pend_n = 0;
+      bool pend_first = false;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
         const int head = item / m_tiles, tile = item - head * m_tiles;
         const int r0 = tile * ATC_BM, r1 = min(p.M, r0 + ATC_BM);
         const int kt0 = tail_key_start(r0, p.S, p.row_meta);
         const int nb = n_pre + (r1 - kt0 + BN - 1) / BN;
-        mbar_wait(q_full, item_n & 1, 0x600);
-        int prev_n = 0;
+        const int qb = item_n % QB;
+        if (QB == 1 && have_pending) {                  // a single Q tile cannot be prefetched: do not hold
+          issue_pv(pend_g, pend_n, pend_first, pend_item_par);   // the last PV back behind the Q reload
+          have_pending = false;
+        }
+        mbar_wait(&q_full[qb], (item_n / QB) & 1, 0x600 + qb);
         for (int j = 0; j < nb; ++j, ++it) {
           const BlockInfo b = block_info<BN>(j, n_pre, p.P, kt0, r1);
           const int st = it & 1;
@@ -239,7 +265,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           mbar_wait(&s_empty[st], par ^ 1, 0x650 + st);
           tc_fence_after();
           const uint32_t idesc = umma_idesc_bf16(ATC_BM, b.n_mma);
-          const uint32_t qa = smem_u32(sQ), kb = smem_u32(sK + st * Cfg::kKTile);
+          const uint32_t qa = smem_u32(sQ + qb * Cfg::kQTile), kb = smem_u32(sK + st * Cfg::kKTile);
 #pragma unroll
           for (int ks = 0; ks < HD / 16 && !(p.debug & 1); ++ks) {
             const uint32_t off_q = (ks >> 2) * Cfg::kQPanel + (ks & 3) * 32;
@@ -249,12 +275,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           }
           umma_commit(&s_full[st]);
           umma_commit(&k_empty[st]);                    // K_j is free once S_j is complete
-          if (j == nb - 1) umma_commit(q_empty);        // Q tile no longer needed after this MMA
-          if (j > 0) issue_pv(it - 1, prev_n, j == 1, item_n & 1);
-          prev_n = b.n_mma;
+          if (j == nb - 1) umma_commit(&q_empty[qb]);   // Q tile no longer needed after this MMA
+          if (have_pending) issue_pv(pend_g, pend_n, pend_first, pend_item_par);
+          have_pending = true;
+          pend_g = it; pend_n = b.n_mma; pend_first = (j == 0); pend_item_par = item_n & 1;
         }
-        issue_pv(it - 1, prev_n, nb == 1, item_n & 1);
       }
+      if (have_pending) issue_pv(pend_g, pend_n, pend_first, pend_item_par);
     }
   } else if (warp >= 4) {
     // Two threads per query row: warps 4-7 take the low half of every block's key columns (and of
@@ -270,7 +297,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     const uint32_t lane_off = static_cast<uint32_t>(sub * 32) << 16;
     const uint32_t to = tmem_o + lane_off + half * OH;
     constexpr float kRaise = 8.0f;         // raise the reference max only beyond 2^8: P stays <= 256
-    uint32_t it = 0, item_n = 0;
+    uint32_t it = 0, item_n = 0, xn = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
       const int head = item / m_tiles, tile = item - head * m_tiles;
       const int r0 = tile * ATC_BM, r1 = min(p.M, r0 + ATC_BM);
@@ -321,20 +348,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         float raw = -INFINITY;
 #pragma unroll
         for (int i = 0; i < CH; ++i) raw = fmaxf(raw, sv[i]);
-        // ---- row maximum over both halves. The two threads of a row swap their partial maxima
-        //      through the P tile they are about to fill: each writes into the 16-byte chunk the
-        //      OTHER one owns (and overwrites with P only after reading it), so no extra smem.
-        mbar_wait(&p_empty[st], par ^ 1, 0x720 + st);      // P_st is free: PV of block it-2 retired
-        uint8_t* prow = sP + st * Cfg::kPTile + row_in_tile * 128;
+        // ---- row maximum over both halves: the two threads of a row swap their partial maxima
+        //      through one of two rotating smem buffers (one named barrier per swap; a buffer is
+        //      rewritten two swaps later, i.e. after a barrier that follows every read of it)
         {
-          auto chunk_of = [&](int h) -> float* {           // first P chunk of half h's columns
-            const int col = h * CH;
-            return reinterpret_cast<float*>(prow + (col >> 6) * Cfg::kPPanel +
-                                            ((((col & 63) >> 3)) ^ (row_in_tile & 7)) * 16);
-          };
-          *chunk_of(half ^ 1) = raw;
+          float* xb = xchg + (xn & 1) * 2 * ATC_BM;
+          ++xn;
+          xb[half * ATC_BM + row_in_tile] = raw;
           asm volatile("bar.sync 1, 256;" ::: "memory");
-          raw = fmaxf(raw, *chunk_of(half));
+          raw = fmaxf(raw, xb[(half ^ 1) * ATC_BM + row_in_tile]);
         }
         const float bm = raw * p.scale_log2;               // scale > 0; -inf stays -inf
         const bool raise = bm > m_ref + kRaise;            // also true for the first finite block
@@ -344,8 +366,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         // ---- rare: rescale this thread's half of the O row in TMEM (others scale by 1)
         const bool fix = raise && (m_ref != -INFINITY) && (j > 0);
         if (__any_sync(0xffffffffu, fix)) {
-          const uint32_t g = it - 1;                       // PV_{j-1} must have retired
-          mbar_wait(&p_empty[g & 1], (g >> 1) & 1, 0x730);
+          mbar_wait(p_empty, (it - 1) & 1, 0x730);        // PV_{j-1} must have retired
           tc_fence_after();
           const float f = fix ? factor : 1.0f;
 #pragma unroll
@@ -361,6 +382,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           tc_fence_before();
         }
         // ---- P = exp2(s - m) as bf16 into the swizzled K-major P tile; partial row sum
+        mbar_wait(p_empty, (it & 1) ^ 1, 0x720);           // the P tile is free: PV of block it-1 retired
+        uint8_t* prow = sP + row_in_tile * 128;
         float rs = 0.0f;
 #pragma unroll
         for (int c0 = 0; c0 < CH; c0 += 32) {
@@ -386,7 +409,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         }
         fence_proxy_async_smem();                         // P visible to the tensor-core (async) proxy
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[st]);
+        if (lane == 0) mbar_arrive(p_full);
         l_run = l_run * factor + rs;
         m_ref = m_new;
       }
@@ -394,12 +417,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       // ---- finished item: combine the two partial row sums, wait for the last PV, read this
       //      thread's half of O once, normalise, store
       {
-        // (single buffer: the next write is separated from this read by a block-loop barrier)
-        xsum[half * ATC_BM + row_in_tile] = l_run;
+        float* xb = xchg + (xn & 1) * 2 * ATC_BM;
+        ++xn;
+        xb[half * ATC_BM + row_in_tile] = l_run;
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        const float l_all = l_run + xsum[(half ^ 1) * ATC_BM + row_in_tile];
-        const uint32_t g = it - 1;
-        mbar_wait(&p_empty[g & 1], (g >> 1) & 1, 0x740);
+        const float l_all = l_run + xb[(half ^ 1) * ATC_BM + row_in_tile];
+        mbar_wait(p_empty, (it - 1) & 1, 0x740);          // the item's last PV has retired
         tc_fence_after();
         const float inv = l_all > 0.0f ? 1.0f / l_all : 0.0f;
         __nv_bfloat16* dst = p.out + (long long)rq * p.ldo + head * HD + half * OH;
