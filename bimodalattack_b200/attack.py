@@ -22,6 +22,7 @@ import copy
 import logging
 import os
 import time
+import types
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple, Union
 
@@ -59,23 +60,21 @@ def image_features(model, pixel_values: torch.Tensor, gemma_processor: bool) -> 
     return torch.stack(list(pooled), 0) if isinstance(pooled, (list, tuple)) else pooled
 
 
-def _patch_conv_as_gemm(conv: torch.nn.Conv2d):
+def _patch_conv_forward(conv: torch.nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
     """forward() for a patch-embedding Conv2d whose stride equals its kernel (CLIP / SigLIP): the
     non-overlapping patches are unfolded by pure reshapes and multiplied by the [out, C*p*p] view
     of the same weight. Same arithmetic as the convolution, but its input gradient -- which the PGD
     step needs -- is a plain GEMM plus the inverse reshapes: deterministic and fast, whereas cuDNN's
     deterministic dgrad for this shape takes 64 ms on a B200 (reference sets
-    torch.use_deterministic_algorithms, :267-269)."""
+    torch.use_deterministic_algorithms, :267-269). Bound to the module as a method, so copies of the
+    model (``copy.deepcopy``, ``.to()``) keep working on their own weights."""
     ph, pw = conv.kernel_size
-
-    def forward(x):
-        B, C, H, W = x.shape
-        gh, gw = H // ph, W // pw
-        x = x[..., :gh * ph, :gw * pw]
-        patches = x.reshape(B, C, gh, ph, gw, pw).permute(0, 2, 4, 1, 3, 5).reshape(B, gh * gw, C * ph * pw)
-        out = F.linear(patches, conv.weight.reshape(conv.out_channels, -1), conv.bias)
-        return out.transpose(1, 2).reshape(B, conv.out_channels, gh, gw)
-    return forward
+    B, C, H, W = x.shape
+    gh, gw = H // ph, W // pw
+    x = x[..., :gh * ph, :gw * pw]
+    patches = x.reshape(B, C, gh, ph, gw, pw).permute(0, 2, 4, 1, 3, 5).reshape(B, gh * gw, C * ph * pw)
+    out = F.linear(patches, conv.weight.reshape(conv.out_channels, -1), conv.bias)
+    return out.transpose(1, 2).reshape(B, conv.out_channels, gh, gw)
 
 
 def install_patch_embed_gemm(model) -> int:
@@ -88,7 +87,7 @@ def install_patch_embed_gemm(model) -> int:
                 and mod.padding in ((0, 0), "valid") and tuple(mod.dilation) == (1, 1) and mod.groups == 1
                 and not hasattr(mod, "_bma_orig_forward")):
             mod._bma_orig_forward = mod.forward
-            mod.forward = _patch_conv_as_gemm(mod)
+            mod.forward = types.MethodType(_patch_conv_forward, mod)
             n += 1
     return n
 
@@ -215,7 +214,7 @@ class BimodalAttack:
         self.step_hook = None             # optional callable(step_index) run at the end of every step
         self.graph_gradient = os.environ.get("BMA_GRAPH_GRADIENT", "1") != "0"
         if config.pgd_attack and os.environ.get("BMA_PATCH_EMBED_GEMM", "1") != "0":
-            install_patch_embed_gemm(model)       # see _patch_conv_as_gemm; restore_patch_embed(model) undoes it
+            install_patch_embed_gemm(model)       # see _patch_conv_forward; restore_patch_embed(model) undoes it
         self._grad_graph = None
         self._feat_graph = None
         self._png = None

@@ -156,6 +156,9 @@ def test_patch_embed_gemm_equals_conv():
         g_got, = torch.autograd.grad(got.square().sum(), x)
         assert got.shape == want.shape and torch.allclose(got, want, atol=1e-5)
         assert torch.allclose(g_got, g_want, atol=1e-4)
+        import copy
+        twin = copy.deepcopy(net).double()                               # a copy runs on ITS OWN weights
+        assert twin(x.double()).dtype == torch.float64
         restore_patch_embed(net)
         assert torch.equal(net(x), want)
     other = torch.nn.Sequential(torch.nn.Conv2d(3, 8, kernel_size=3, stride=1, padding=1))
