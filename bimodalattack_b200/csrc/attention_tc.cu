@@ -355,7 +355,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           float* xb = xchg + (xn & 1) * 2 * ATC_BM;
           ++xn;
           xb[half * ATC_BM + row_in_tile] = raw;
-          asm volatile("bar.sync 1, 256;" ::: "memory");
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + sub) : "memory");   // only this row quadrant's two warps
           raw = fmaxf(raw, xb[(half ^ 1) * ATC_BM + row_in_tile]);
         }
         const float bm = raw * p.scale_log2;               // scale > 0; -inf stays -inf
@@ -420,7 +420,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         float* xb = xchg + (xn & 1) * 2 * ATC_BM;
         ++xn;
         xb[half * ATC_BM + row_in_tile] = l_run;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + sub) : "memory");
         const float l_all = l_run + xb[(half ^ 1) * ATC_BM + row_in_tile];
         mbar_wait(p_empty, (it - 1) & 1, 0x740);          // the item's last PV has retired
         tc_fence_after();
