@@ -505,7 +505,15 @@ static cudaError_t launch_atc(const AttnParams& a, int n_heads, cudaStream_t str
 cudaError_t launch_prefix_tail_attention(const AttnParams& a, int n_heads, cudaStream_t stream) {
   if (a.M <= 0) return cudaSuccess;
   if (a.S <= 0 || a.P < 0 || a.kv_group <= 0) return cudaErrorInvalidValue;
-  if (a.head_dim == 128) return launch_atc<128, 128>(a, n_heads, stream);
+  if (a.head_dim == 128) {
+    // default: split-key kernel (attention_split.cu); BMA_ATTN_SPLIT=0 keeps this file's kernel (A/B runs)
+    static int use_split = -1;
+    if (use_split < 0) {
+      const char* e = getenv("BMA_ATTN_SPLIT");
+      use_split = (e != nullptr && atoi(e) == 0) ? 0 : 1;
+    }
+    return use_split ? launch_attention_split(a, n_heads, stream) : launch_atc<128, 128>(a, n_heads, stream);
+  }
   if (a.head_dim == 256) return launch_atc<256, 64>(a, n_heads, stream);
   return cudaErrorInvalidValue;
 }
