@@ -11,6 +11,14 @@
 // so a block needs no communication at all; the halves are merged once per work item,
 //     out = (O_lo f_lo + O_hi f_hi) / (l_lo f_lo + l_hi f_hi),   f_h = 2^(m_h - max(m_lo, m_hi)),
 // each thread producing 64 of the 128 output columns. TMEM: S_0 S_1 O_lo O_hi = 4 x 128 columns.
+//
+// P never touches shared memory: a thread packs its 64 probabilities to bf16 and writes them with
+// tcgen05.st over the S columns it has just read (P_lo at columns 0..31, P_hi at 64..95 of S_st), and
+// the PV MMAs take their A operand from tensor memory (tcgen05.mma [d], [a_tmem], b_desc). With both
+// operands in smem a key block costs 224 KB of smem traffic (TMA 64 + QK 64 + PV 64 + P 32) against
+// 128 B/clk -- 1750 cycles, more than the 1024 cycles of MMA or MUFU work; this way it is 160 KB.
+// The S buffer needs no "empty" barrier any more: S_{g+2} is issued after the PVs of block g, the
+// tensor pipe executes in order, and those PVs wait for the softmax threads that read S_g.
 //   warp 0  TMA producer: Q (double-buffered) per item; K and V^T blocks in separate 2-stage rings
 //   warp 1  MMA issuer, one flat stream over items: S_g before the PVs of block g-1
 //   warp 2  TMEM allocator
@@ -28,7 +36,7 @@ namespace spl {
 constexpr int BM = 128, BN = 128, HD = 128, THREADS = 384, CH = 64;
 constexpr int PANEL = 128 * 128;              // [128 rows][64 bf16], 128-byte swizzle
 constexpr int TILE = 2 * PANEL;               // 128 x 128 bf16
-constexpr int SMEM = 2 * TILE /*Q*/ + 2 * TILE /*K*/ + 2 * TILE /*V^T*/ + TILE /*P*/ + 256 /*barriers*/ +
+constexpr int SMEM = 2 * TILE /*Q*/ + 2 * TILE /*K*/ + 2 * TILE /*V^T*/ + 256 /*barriers*/ +
                      2 * BM * 8 /*(max, sum) swap*/;
 
 struct Params {
@@ -72,8 +80,7 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   uint8_t* sQ = smem;                          // [2][tile]
   uint8_t* sK = sQ + 2 * TILE;                 // [2][tile]
   uint8_t* sV = sK + 2 * TILE;                 // [2][tile]   V^T: [128 dims][keys]
-  uint8_t* sP = sV + 2 * TILE;                 // [tile]      panel h = key half h
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + TILE);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * TILE);
   uint64_t* q_full = bars;            // [2]
   uint64_t* q_empty = bars + 2;       // [2]
   uint64_t* k_full = bars + 4;        // [2]
@@ -81,7 +88,6 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   uint64_t* v_full = bars + 8;        // [2]
   uint64_t* v_empty = bars + 10;      // [2]
   uint64_t* s_full = bars + 12;       // [2]
-  uint64_t* s_empty = bars + 14;      // [2]  8 softmax warps
   uint64_t* p_full = bars + 16;       // [2]  per key half: its 4 warps
   uint64_t* p_empty = bars + 18;      // [2]  per key half
   uint64_t* o_empty = bars + 20;      // [1]  8 warps: the item's output has left TMEM
@@ -103,7 +109,7 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       mbar_init(&q_full[i], 1);  mbar_init(&q_empty[i], 1);
       mbar_init(&k_full[i], 1);  mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1);  mbar_init(&v_empty[i], 1);
-      mbar_init(&s_full[i], 1);  mbar_init(&s_empty[i], 8);
+      mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);  mbar_init(&p_empty[i], 1);
     }
     fence_barrier_init();
@@ -182,10 +188,10 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
           const bool fst = (first >> h) & 1;
           if (fst) mbar_wait(o_empty, item_par ^ 1, 0x630);      // the previous item's output was read out
           tc_fence_after();
-          const uint32_t pa = smem_u32(sP + h * PANEL), vb = smem_u32(sV + st * TILE + h * PANEL);
+          const uint32_t pa = tmem_s + st * 128 + h * CH;       // P_h: bf16 pairs, 8 columns per 16 keys
+          const uint32_t vb = smem_u32(sV + st * TILE + h * PANEL);
           for (int kk = 0; kk < keys / 16; ++kk)
-            umma_bf16_ss(tmem_o + h * 128, umma_desc_k_sw128(pa + kk * 32), umma_desc_k_sw128(vb + kk * 32), idesc,
-                         !(fst && kk == 0));
+            umma_bf16_ts(tmem_o + h * 128, pa + kk * 8, umma_desc_k_sw128(vb + kk * 32), idesc, !(fst && kk == 0));
           umma_commit(&p_empty[h]);
           ++cnt[h];
         }
@@ -206,8 +212,7 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
           const Block b = block_of(j, n_pre, p.P, kt0, r1);
           const int st = it & 1;
           const uint32_t par = (it >> 1) & 1;
-          mbar_wait(&k_full[st], par, 0x640 + st);
-          mbar_wait(&s_empty[st], par ^ 1, 0x650 + st);
+          mbar_wait(&k_full[st], par, 0x640 + st);          // (S_st is free: the PVs of block it-2 precede this MMA)
           tc_fence_after();
           const uint32_t idesc = umma_idesc_bf16(BM, b.n_mma);
           const uint32_t qa = smem_u32(sQ + qb * TILE), kb = smem_u32(sK + st * TILE);
@@ -277,9 +282,6 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
             for (int i = 0; i < 32; ++i) sv[c0 + i] = -INFINITY;
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[st]);          // S is in registers (or not needed): buffer free
         if (keys == 0) continue;                           // this half has no keys in the block
         const int kbase = b.key0 + h * CH;
         if (!b.pre || b.key0 + BN > p.P_shared) {
@@ -298,10 +300,9 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         const float m_new = raise ? bm : m_ref;
         const float m_use = (m_new == -INFINITY) ? 0.0f : m_new;
         const float factor = raise ? ex2(m_ref - m_use) : 1.0f;
-        // this half's P panel is free and O_h quiescent once its previous PV has retired
-        mbar_wait(&p_empty[h], (cnt_mine & 1) ^ 1, 0x720 + h);
         const bool fix = raise && (m_ref != -INFINITY) && (mine > 0);
         if (__any_sync(0xffffffffu, fix)) {                // rare: rescale this row of O_h in TMEM
+          mbar_wait(&p_empty[h], (cnt_mine - 1) & 1, 0x720 + h);     // O_h is quiescent: its last PV retired
           tc_fence_after();
           const float f = fix ? factor : 1.0f;
 #pragma unroll
@@ -314,31 +315,20 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
             tmem_st_32x32(to_mine + c0, r);
           }
           tmem_st_wait();
-          tc_fence_before();
         }
-        uint8_t* panel = sP + h * PANEL + row_in_tile * 128;
+        // P = exp2(s - m) as packed bf16 pairs over this half's own S columns (already in registers)
         float rs = 0.0f;
+        uint32_t pk[32];
 #pragma unroll
-        for (int c0 = 0; c0 < CH; c0 += 32) {
-          if (c0 < keys) {
-            uint32_t pk[16];
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const float p0 = ex2(fmaf(sv[c0 + i], p.scale_log2, -m_use));
-              const float p1 = ex2(fmaf(sv[c0 + i + 1], p.scale_log2, -m_use));
-              rs += p0 + p1;
-              pk[i >> 1] = pack_bf16x2(p0, p1);
-            }
-            const int q0 = c0 >> 3;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int phys = (q0 + q) ^ (row_in_tile & 7);
-              *reinterpret_cast<uint4*>(panel + phys * 16) =
-                  make_uint4(pk[q * 4 + 0], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
-            }
-          }
+        for (int i = 0; i < CH; i += 2) {
+          const float p0 = ex2(fmaf(sv[i], p.scale_log2, -m_use));         // -inf -> 0
+          const float p1 = ex2(fmaf(sv[i + 1], p.scale_log2, -m_use));
+          rs += p0 + p1;
+          pk[i >> 1] = pack_bf16x2(p0, p1);
         }
-        fence_proxy_async_smem();
+        tmem_st_32x32(tmem_s + lane_off + st * 128 + h * CH, pk);
+        tmem_st_wait();
+        tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[h]);
         l_run = l_run * factor + rs;
