@@ -8,6 +8,10 @@
 //     rk <= rq (block-diagonal causal mask over the flattened rows).
 // With P = 0 and S = P_len the same kernel computes the prefix itself (plain causal attention).
 //
+// This file is the kernel for head_dim 256 (Gemma-3; 64-key blocks) and the A/B fallback for
+// head_dim 128 (BMA_ATTN_SPLIT=0); head_dim 128 normally runs attention_split.cu (per-half
+// accumulators, P in tensor memory).
+//
 //   warp 0      TMA producer: Q tile per item (double-buffered for head_dim 128: the next item's Q is
 //               fetched while this one runs), then K blocks and V^T blocks into two 2-stage rings
 //   warp 1      MMA issuer:   S_j = Q K_j^T  and  O += P_j V_j   (tcgen05.mma, operands in smem,
