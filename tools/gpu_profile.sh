@@ -13,5 +13,5 @@ ncu --nvtx --nvtx-include "bench_timed/" --set full --clock-control none --impor
     -k regex:gemm_bf16_tn -s 133 -c 5 -o gpurun_out/prof_gemm $CMD > gpurun_out/ncu_gemm.log 2>&1
 echo "gemm capture rc=$?"
 ncu --nvtx --nvtx-include "bench_timed/" --set full --clock-control none --import-source on \
-    -k regex:attention_tc -s 40 -c 1 -o gpurun_out/prof_attn $CMD > gpurun_out/ncu_attn.log 2>&1
+    -k regex:attention -s 40 -c 1 -o gpurun_out/prof_attn $CMD > gpurun_out/ncu_attn.log 2>&1
 echo "attn capture rc=$?"
