@@ -70,6 +70,7 @@ struct bma_scorer {
   __nv_bfloat16* prefix_qk = nullptr;    // [layers][max_prefix][qk_dim]   Q|K rows of the prefix
   __nv_bfloat16* prefix_vt = nullptr;    // [layers][kv_dim][ld_vtp]       V^T of the prefix
   float2* ce_part = nullptr;
+  __nv_bfloat16 *x_c = nullptr, *attn_c = nullptr;   // the scored rows of the last layer, made contiguous
   float* tgt_logit = nullptr;
   // ragged-row plan (suffix-head sharing)
   int2 *row_info = nullptr, *row_meta = nullptr;
@@ -126,11 +127,13 @@ int ensure_ce_rows(bma_scorer* s, int rows) {
   if (rows <= s->ce_rows_cap) return 0;
   const int n_ce_tiles = (s->desc.vocab + kCeBlockN - 1) / kCeBlockN;
   BMA_CHECK(cudaDeviceSynchronize(), "ensure_ce_rows: sync");
-  cudaFree(s->ce_part); cudaFree(s->tgt_logit);
-  s->ce_part = nullptr; s->tgt_logit = nullptr; s->ce_rows_cap = 0;
+  cudaFree(s->ce_part); cudaFree(s->tgt_logit); cudaFree(s->x_c); cudaFree(s->attn_c);
+  s->ce_part = nullptr; s->tgt_logit = nullptr; s->x_c = nullptr; s->attn_c = nullptr; s->ce_rows_cap = 0;
   size_t bytes = 0;
   if (!dev_alloc(&s->ce_part, static_cast<size_t>(n_ce_tiles) * rows, &bytes) ||
-      !dev_alloc(&s->tgt_logit, static_cast<size_t>(rows), &bytes))
+      !dev_alloc(&s->tgt_logit, static_cast<size_t>(rows), &bytes) ||
+      !dev_alloc(&s->x_c, static_cast<size_t>(rows) * s->desc.d_model, &bytes) ||
+      !dev_alloc(&s->attn_c, static_cast<size_t>(rows) * s->q_dim, &bytes))
     return fail(cudaGetLastError(), "ensure_ce_rows: cudaMalloc");
   s->ws_bytes += bytes;
   s->ce_rows_cap = rows;
@@ -147,13 +150,21 @@ int ensure_ce_rows(bma_scorer* s, int rows) {
 // n_share > 0: ragged rows (row_info / row_meta filled by plan_rows); tail rows [0, n_share) are the
 // base's suffix rows, whose K/V every layer appends to the prefix buffers at key index prefix_len
 // (append == false: a previous chunk of the same call already did).
+// scored != null (candidate pass): only the T rows per candidate that predict the target are needed
+// after the LAST layer's attention -- no later layer reads the other rows -- so that layer's o_proj,
+// norms and MLP run on those rows alone, gathered into x_c / attn_c (they stay the residual stream
+// for the final norm and the LM head).
+struct ScoredRows { int n, T, ce_row0; const int* vstart; };
+
 int run_layers(bma_scorer* s, int rows, int seq, int pos_base, bool prefill, cudaStream_t st,
-               int n_share = 0, bool append = false) {
+               int n_share = 0, bool append = false, const ScoredRows* scored = nullptr) {
   const bma_model_desc& D = s->desc;
   const int d = D.d_model;
   const int P = prefill ? 0 : s->prefix_len;
   const bool ragged = n_share > 0;
   const bool sandwich = D.sandwich_norm != 0;
+  __nv_bfloat16* xres = s->x;                 // residual stream
+  const __nv_bfloat16* attn_in = s->attn;     // o_proj input
   for (int l = 0; l < D.n_layers; ++l) {
     const bma_layer_weights& W = s->layers[l];
     __nv_bfloat16* pre_qk = s->prefix_qk + (size_t)l * D.max_prefix * s->qk_dim;
@@ -210,22 +221,32 @@ int run_layers(bma_scorer* s, int rows, int seq, int pos_base, bool prefill, cud
       ProfScope ps(s, PC_ATTN, 4.0 * rows * (P + 0.5 * (seq + n_share)) * s->q_dim, st);
       BMA_LAUNCH(launch_prefix_tail_attention(a, D.n_heads, st), "attention");
     }
+    if (scored != nullptr && l == D.n_layers - 1) {
+      ProfScope ps(s, PC_EMBED, 0, st);
+      BMA_LAUNCH(launch_gather_rows(s->attn, s->q_dim, s->attn_c, s->q_dim, scored->n, s->q_dim, scored->T, seq,
+                                    scored->ce_row0, scored->vstart, st), "gather(attn rows)");
+      BMA_LAUNCH(launch_gather_rows(s->x, d, s->x_c, d, scored->n, d, scored->T, seq, scored->ce_row0,
+                                    scored->vstart, st), "gather(residual rows)");
+      rows = scored->n;
+      xres = s->x_c;
+      attn_in = s->attn_c;
+    }
     {
       GemmParams p{};
       p.M = rows; p.N = d; p.K = s->q_dim; p.group_m = group_m_for(p.K);
       if (sandwich) { p.C = s->xn; p.ldc = d; }                       // y: normed before the add
-      else { p.C = s->x; p.ldc = d; p.R = s->x; p.ldr = d; }
+      else { p.C = xres; p.ldc = d; p.R = xres; p.ldr = d; }
       ProfScope ps(s, PC_GEMM_O, gemm_flops(p), st);
-      BMA_LAUNCH((launch_gemm_big<EPI_STORE>(s->attn, s->q_dim, bf(W.w_o), s->q_dim, p, st)),
+      BMA_LAUNCH((launch_gemm_big<EPI_STORE>(attn_in, s->q_dim, bf(W.w_o), s->q_dim, p, st)),
                  "gemm(o_proj)");
     }
     {
       ProfScope ps(s, PC_NORM, 0, st);
       if (sandwich) {
-        BMA_LAUNCH(launch_add_norm(s->xn, d, bf(W.norm_post_attn), s->x, d, bf(W.norm_mlp), s->xn, d,
+        BMA_LAUNCH(launch_add_norm(s->xn, d, bf(W.norm_post_attn), xres, d, bf(W.norm_mlp), s->xn, d,
                                    rows, d, D.rms_eps, D.norm_mode, st), "add_norm(post_attn, pre_mlp)");
       } else {
-        BMA_LAUNCH(launch_rmsnorm(s->x, d, bf(W.norm_mlp), s->xn, d, rows, d, D.rms_eps, D.norm_mode,
+        BMA_LAUNCH(launch_rmsnorm(xres, d, bf(W.norm_mlp), s->xn, d, rows, d, D.rms_eps, D.norm_mode,
                                   0, 0, 0, nullptr, st), "rmsnorm(mlp)");
       }
     }
@@ -240,7 +261,7 @@ int run_layers(bma_scorer* s, int rows, int seq, int pos_base, bool prefill, cud
       GemmParams p{};
       p.M = rows; p.N = d; p.K = D.d_ff; p.group_m = group_m_for(p.K);
       if (sandwich) { p.C = s->xn; p.ldc = d; }
-      else { p.C = s->x; p.ldc = d; p.R = s->x; p.ldr = d; }
+      else { p.C = xres; p.ldc = d; p.R = xres; p.ldr = d; }
       ProfScope ps(s, PC_GEMM_DOWN, gemm_flops(p), st);
       BMA_LAUNCH((launch_gemm_big<EPI_STORE>(s->act, D.d_ff, bf(W.w_down), D.d_ff, p, st)),
                  "gemm(down)");
@@ -248,7 +269,7 @@ int run_layers(bma_scorer* s, int rows, int seq, int pos_base, bool prefill, cud
     if (sandwich) {
       const __nv_bfloat16* next = (l + 1 < D.n_layers) ? bf(s->layers[l + 1].norm_attn) : nullptr;
       ProfScope ps(s, PC_NORM, 0, st);
-      BMA_LAUNCH(launch_add_norm(s->xn, d, bf(W.norm_post_mlp), s->x, d, next, s->xn, d, rows, d,
+      BMA_LAUNCH(launch_add_norm(s->xn, d, bf(W.norm_post_mlp), xres, d, next, s->xn, d, rows, d,
                                  D.rms_eps, D.norm_mode, st), "add_norm(post_mlp, next input)");
     }
   }
@@ -375,6 +396,7 @@ void bma_scorer_destroy(bma_scorer* s) {
   if (s == nullptr) return;
   cudaFree(s->x); cudaFree(s->xn); cudaFree(s->qk); cudaFree(s->vt); cudaFree(s->attn); cudaFree(s->act);
   cudaFree(s->prefix_qk); cudaFree(s->prefix_vt); cudaFree(s->ce_part); cudaFree(s->tgt_logit);
+  cudaFree(s->x_c); cudaFree(s->attn_c);
   cudaFree(s->row_info); cudaFree(s->row_meta); cudaFree(s->cand_vstart); cudaFree(s->cand_tmp); cudaFree(s->total_rows_dev);
   cudaFree(s->base_dev);
   if (s->total_rows_host != nullptr) cudaFreeHost(s->total_rows_host);
@@ -523,14 +545,15 @@ int bma_scorer_score(bma_scorer* s, const long long* ids, int ids_stride, int B,
                                           D.embed_scale, s->x, rows, S, d, ragged ? s->row_info : nullptr,
                                           base_ids, st), "build_tail_embeds");
     }
-    int rc = run_layers(s, rows, S, s->prefix_len, false, st, n_share, ragged);
-    if (rc != 0) return rc;
-    // final norm on the T rows per candidate whose logits predict the target tokens
+    // the T rows per candidate whose logits predict the target tokens
     const int ce_rows = nb * T;
-    {
+    const ScoredRows scored{ce_rows, T, ce_row0, ragged ? s->cand_vstart : nullptr};
+    int rc = run_layers(s, rows, S, s->prefix_len, false, st, n_share, ragged, &scored);
+    if (rc != 0) return rc;
+    {                                            // final norm: the scored rows are contiguous in x_c
       ProfScope ps(s, PC_NORM, 0, st);
-      BMA_LAUNCH(launch_rmsnorm(s->x, d, s->norm_final, s->xn, d, ce_rows, d, D.rms_eps, D.norm_mode,
-                                T, S, ce_row0, ragged ? s->cand_vstart : nullptr, st), "rmsnorm(final, gathered)");
+      BMA_LAUNCH(launch_rmsnorm(s->x_c, d, s->norm_final, s->xn, d, ce_rows, d, D.rms_eps, D.norm_mode,
+                                0, 0, 0, nullptr, st), "rmsnorm(final)");
     }
     {
       GemmParams p{};

@@ -57,6 +57,9 @@ cudaError_t launch_rmsnorm(const __nv_bfloat16* x, long long ldx, const __nv_bfl
                            __nv_bfloat16* y, long long ldy, int rows, int d, float eps, int mode,
                            int gather_T, int gather_S, int gather_off, const int* gather_vstart,
                            cudaStream_t stream);
+cudaError_t launch_gather_rows(const __nv_bfloat16* src, long long lds, __nv_bfloat16* dst, long long ldd,
+                               int rows, int width, int T, int S, int off, const int* vstart,
+                               cudaStream_t stream);
 cudaError_t launch_add_norm(const __nv_bfloat16* y, long long ldy, const __nv_bfloat16* w_post,
                             __nv_bfloat16* x, long long ldx, const __nv_bfloat16* w_next,
                             __nv_bfloat16* xn, long long ldxn, int rows, int d, float eps, int mode,

@@ -272,6 +272,32 @@ cudaError_t launch_rmsnorm(const __nv_bfloat16* x, long long ldx, const __nv_bfl
 }
 
 // ------------------------------------------------------------------------------------------------
+// Row gather: dst[r, :] = src[start(r / T) + off + r % T, :] with start(c) = c * S (uniform tails)
+// or vstart[c] (ragged tails) -- the T scored rows of every candidate, made contiguous.
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const __nv_bfloat16* __restrict__ src, long long lds, __nv_bfloat16* __restrict__ dst,
+                   long long ldd, int rows, int width, int T, int S, int off, const int* __restrict__ vstart) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const int c = r / T;
+  const long long start = vstart != nullptr ? vstart[c] : (long long)c * S;
+  const uint4* s4 = reinterpret_cast<const uint4*>(src + (start + off + (r - c * T)) * lds);
+  uint4* d4 = reinterpret_cast<uint4*>(dst + (long long)r * ldd);
+  for (int v = lane; v < (width >> 3); v += 32) d4[v] = s4[v];
+}
+
+cudaError_t launch_gather_rows(const __nv_bfloat16* src, long long lds, __nv_bfloat16* dst, long long ldd,
+                               int rows, int width, int T, int S, int off, const int* vstart,
+                               cudaStream_t stream) {
+  if (rows <= 0) return cudaSuccess;
+  if ((width & 7) != 0 || (lds & 7) != 0 || (ldd & 7) != 0 || T <= 0) return cudaErrorInvalidValue;
+  const int blocks = static_cast<int>(((long long)rows * 32 + 255) / 256);
+  gather_rows_kernel<<<blocks, 256, 0, stream>>>(src, lds, dst, ldd, rows, width, T, S, off, vstart);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 // Sandwich-norm step of a Gemma-style layer, one warp per row:
 //   x  <- bf16(x + norm(y; w_post))            (post_attention / post_feedforward norm + residual)
 //   xn <- norm(x; w_next)   if w_next != null  (the next pre-norm: pre_feedforward / input norm)
