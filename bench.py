@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 
 # LM-head scale of the random-init models: logit std ~ 0.02 * gain * sqrt(d), chosen so per-candidate
 # losses are spread over a few nats instead of all being ln(V) (SURVEY.md section 7 "Ties")
-HEAD_GAIN = {"7b": 2.0, "small128": 10.0, "tiny128": 20.0}
+HEAD_GAIN = {"7b": 2.0, "small128": 10.0, "tiny128": 20.0, "tiny": 20.0}
 METRIC = "gcg_pgd_candidates_scored_per_sec"
 UNIT = "candidates/s"
 
@@ -44,9 +44,10 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--model", default="7b", choices=["7b", "small128", "tiny128", "gemma4b", "gemma-tiny256", "gemma4b-joint",
+    ap.add_argument("--model", default="7b", choices=["7b", "small128", "tiny128", "tiny", "gemma4b", "gemma-tiny256", "gemma4b-joint",
                                                       "gemma-tiny256-joint"],
-                    help="7b = BASELINE.json config 2 (the headline); gemma4b = config 4 (Gemma-3-4b GCG-only)")
+                    help="7b = BASELINE.json config 2 (the headline); gemma4b = config 4 (Gemma-3-4b GCG-only); "
+                         "tiny = the CPU-sized model of config 1 (use --search-width 64)")
     ap.add_argument("--search-width", type=int, default=512)
     ap.add_argument("--scaling", default="weak", choices=["strong", "weak"],
                     help="weak (default): search_width candidates PER GPU, i.e. the per-GPU work of the headline "
@@ -205,8 +206,8 @@ def run_reference(args):
 
 
 GEMMA = {"gemma4b": "4b", "gemma-tiny256": "tiny256", "gemma4b-joint": "4b", "gemma-tiny256-joint": "tiny256"}
-LLAVA_PX = {"7b": 336, "small128": 56, "tiny128": 28}
-LLAVA_VOCAB = {"7b": 32000, "small128": 4000, "tiny128": 1000}
+LLAVA_PX = {"7b": 336, "small128": 56, "tiny128": 28, "tiny": 28}
+LLAVA_VOCAB = {"7b": 32000, "small128": 4000, "tiny128": 1000, "tiny": 990}
 
 
 def workload_config(args, P, S):

@@ -519,6 +519,7 @@ cudaError_t launch_prefix_tail_attention(const AttnParams& a, int n_heads, cudaS
     return use_split ? launch_attention_split(a, n_heads, stream) : launch_atc<128, 128>(a, n_heads, stream);
   }
   if (a.head_dim == 256) return launch_atc<256, 64>(a, n_heads, stream);
+  if (a.head_dim == 64) return launch_atc<64, 128>(a, n_heads, stream);
   return cudaErrorInvalidValue;
 }
 

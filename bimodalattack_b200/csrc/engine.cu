@@ -194,6 +194,8 @@ int run_layers(bma_scorer* s, int rows, int seq, int pos_base, bool prefill, cud
       ProfScope ps(s, PC_GEMM_QKV, gemm_flops(p), st);
       if (D.head_dim == 128) {
         BMA_LAUNCH((launch_gemm_big<EPI_ROPE, 128>(s->xn, d, bf(W.w_qkv), d, p, st)), "gemm(qkv+rope)");
+      } else if (D.head_dim == 64) {
+        BMA_LAUNCH((launch_gemm_big<EPI_ROPE, 64>(s->xn, d, bf(W.w_qkv), d, p, st)), "gemm(qkv+rope)");
       } else {
         BMA_LAUNCH((launch_gemm_big<EPI_ROPE, 256>(s->xn, d, bf(W.w_qkv), d, p, st)), "gemm(qkv+rope)");
       }
@@ -341,8 +343,8 @@ int bma_sample_ids(const long long* ids, const void* grad, int grad_dtype, long 
 bma_scorer* bma_scorer_create(const bma_model_desc* desc) {
   if (desc == nullptr) return nullptr;
   const bma_model_desc& D = *desc;
-  if (D.head_dim != 128 && D.head_dim != 256) {
-    g_last_error = "scorer: head_dim must be 128 or 256";
+  if (D.head_dim != 64 && D.head_dim != 128 && D.head_dim != 256) {
+    g_last_error = "scorer: head_dim must be 64, 128 or 256";
     return nullptr;
   }
   if (D.n_layers <= 0 || D.d_model % 64 != 0 || D.d_ff % 128 != 0 || D.n_heads % D.n_kv_heads != 0 ||

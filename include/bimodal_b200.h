@@ -160,7 +160,7 @@ int bma_rmsnorm(const void* x, long long ldx, const void* w, void* y, long long 
 int bma_add_norm(const void* y, long long ldy, const void* w_post, void* x, long long ldx,
                  const void* w_next, void* xn, long long ldxn, int rows, int d, float eps, int mode,
                  void* stream);
-/* Shared-prefix + causal-tail attention, head_dim 128 or 256. q/k_* are row-major
+/* Shared-prefix + causal-tail attention, head_dim 64, 128 or 256. q/k_* are row-major
  * [rows, heads*head_dim]; the value operands are TRANSPOSED: vt_tail is [kv_heads*head_dim, M]
  * (row stride ldvt), vt_pre [kv_heads*head_dim, P]. */
 int bma_attention(const void* q, long long ldq, const void* k_tail, long long ldk,

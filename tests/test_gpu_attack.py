@@ -353,3 +353,38 @@ def test_score_host_entry_and_degenerate_batches(cuda_device):
         # and the (unrelated) base rides along as one extra sequence
         assert atk.engine.last_rows == (37 - 2 + 1) * (plan.n_tail - 1)
         assert float((none_shared - full).abs().max()) <= tol
+
+
+def test_config1_tiny_model(cuda_device):
+    """BASELINE.json config 1 -- the reference's CPU-sized case (2 layers, hidden 256, 4 heads of 64,
+    V = 1000, 4 image tokens; joint GCG+PGD, 20 steps, search_width 64) -- on the native path in
+    bf16: candidate losses against the oracle, then the full 20-step run."""
+    import torchvision.transforms as T
+    import bimodalattack_b200 as bma
+    from bimodalattack_b200 import synthetic as syn
+    from oracle import hotpath
+    tok = syn.make_tokenizer(1000)
+    proc = syn.make_llava_processor(tok, 28)
+    model = syn.make_llava("tiny", dtype=torch.bfloat16, device=cuda_device, head_gain=20.0, attn_implementation="sdpa")
+    norm = T.Normalize(syn.CLIP_MEAN, syn.CLIP_STD)
+    image = torch.rand((1, 3, 28, 28), generator=torch.Generator().manual_seed(5)).to(cuda_device)
+    cfg = bma.BimodalAttackConfig(num_steps=20, search_width=64, topk=32, seed=1, allow_non_ascii=True, alpha=4 / 255,
+                                  eps=64 / 255, pgd_attack=True, gcg_attack=True, joint_eval=True,
+                                  optim_str_init="x x x x x x x x", verbosity="ERROR", images_folder=None)
+    msgs = [{"role": "user", "content": "w10 w11 w12 w13"}]
+    atk = bma.BimodalAttack(model, tok, proc, cfg, normalize=norm)
+    assert atk.engine.head_dim == 64
+    atk._prepare(msgs, "w20 w21 w22 w23 w24")
+    cand = torch.randint(8, 990, (64, 8), generator=torch.Generator().manual_seed(2)).to(cuda_device)
+    with torch.no_grad():
+        feats = atk.scoring_features(image)
+        got = atk._compute_candidates_loss_original(64, atk._build_input_embeds_pgd(cand, feats, 64, single=True))
+        ora32 = hotpath.OracleAttack(_fp32_twin(model), tok, proc, cfg, normalize=norm)
+        ora32.target_ids = atk.target_ids
+        ora32.seg_embeds = {k: ora32.emb(v) for k, v in atk.segment_ids.items()}
+        order = hotpath.segment_order("pgd", "llava", single=True)
+        want, _ = hotpath.candidates_loss(ora32.model, hotpath.assemble(ora32._parts(cand, feats.float()), order, 64),
+                                          atk.target_ids, 64)
+    assert bool(((got - want).abs() <= 2e-2 * want.abs() + 1e-3).all()), (got - want).abs().max()
+    res = bma.BimodalAttack(model, tok, proc, cfg, normalize=norm).run(msgs, "goal", "w20 w21 w22 w23 w24", image.clone())
+    assert len(res.losses) == 20 and res.best_loss == min(res.losses) and res.losses[-1] < res.losses[0]

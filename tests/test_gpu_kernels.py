@@ -218,7 +218,9 @@ def _attn_reference(q, kt, vt, kp, vp, S, scale):
     (7, 42, 596, 4, 1, 128), (3, 42, 0, 2, 1, 128), (1, 596, 0, 2, 1, 128), (5, 130, 70, 2, 1, 128),
     (64, 42, 24, 2, 1, 128), (512, 41, 596, 1, 1, 128), (6, 41, 300, 4, 2, 128), (2, 300, 17, 2, 1, 128),
     # head_dim 256 (Gemma-3: 64-key blocks, 256-column O accumulator), GQA 2
-    (7, 41, 20, 4, 2, 256), (3, 300, 4, 2, 2, 256), (1, 70, 0, 2, 1, 256), (40, 41, 200, 2, 2, 256)])
+    (7, 41, 20, 4, 2, 256), (3, 300, 4, 2, 2, 256), (1, 70, 0, 2, 1, 256), (40, 41, 200, 2, 2, 256),
+    # head_dim 64 (the tiny CPU-sized model of BASELINE.json config 1)
+    (5, 42, 24, 4, 1, 64), (3, 130, 0, 2, 2, 64)])
 def test_prefix_tail_attention(lib, cuda_device, B, S, P, H, G, D):
     """H query heads, H // G kv heads (G = GQA group). Values are handed over transposed
     ([kv_heads*D, rows]) the way the fused QKV epilogue writes them."""
