@@ -18,7 +18,9 @@
 // operands in smem a key block costs 224 KB of smem traffic (TMA 64 + QK 64 + PV 64 + P 32) against
 // 128 B/clk -- 1750 cycles, more than the 1024 cycles of MMA or MUFU work; this way it is 160 KB.
 // The S buffer needs no "empty" barrier any more: S_{g+2} is issued after the PVs of block g, the
-// tensor pipe executes in order, and those PVs wait for the softmax threads that read S_g.
+// tensor pipe executes in order, and those PVs wait for the softmax threads that read S_g. What
+// keeps the four warps of a half within one block of each other is the p_empty wait before P is
+// written (see the softmax loop).
 //   warp 0  TMA producer: Q (double-buffered) per item; K and V^T blocks in separate 2-stage rings
 //   warp 1  MMA issuer, one flat stream over items: S_g before the PVs of block g-1
 //   warp 2  TMEM allocator
@@ -300,9 +302,14 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         const float m_new = raise ? bm : m_ref;
         const float m_use = (m_new == -INFINITY) ? 0.0f : m_new;
         const float factor = raise ? ex2(m_ref - m_use) : 1.0f;
+        // Back-pressure: this half's previous PV has retired, i.e. ALL FOUR warps of the half had
+        // delivered their part of the previous P. Without it a fast warp could arrive on p_full for two
+        // consecutive blocks before a slow one has arrived for the first (the two S/P buffers would let
+        // it), completing a phase with a row quarter of P missing and desynchronising the barrier.
+        // (It also makes O_h quiescent for the rescale below.) Usually satisfied long before.
+        mbar_wait(&p_empty[h], (cnt_mine & 1) ^ 1, 0x720 + h);
         const bool fix = raise && (m_ref != -INFINITY) && (mine > 0);
         if (__any_sync(0xffffffffu, fix)) {                // rare: rescale this row of O_h in TMEM
-          mbar_wait(&p_empty[h], (cnt_mine - 1) & 1, 0x720 + h);     // O_h is quiescent: its last PV retired
           tc_fence_after();
           const float f = fix ? factor : 1.0f;
 #pragma unroll

@@ -26,3 +26,20 @@ def lib(cuda_device):
     from bimodalattack_b200 import native
 
     return native.load()
+
+
+@pytest.hookimpl(hookwrapper=True)
+def pytest_runtest_makereport(item, call):
+    """On a failing GPU test, show the device-side watchdog word (csrc/common.cuh): a pipeline wait
+    that timed out leaves its barrier code there even after the CUDA context has died."""
+    outcome = yield
+    rep = outcome.get_result()
+    if rep.when == "call" and rep.failed and item.get_closest_marker("gpu") is not None:
+        try:
+            import ctypes
+            from bimodalattack_b200 import native
+            code = ctypes.c_uint(0)
+            native.load().bma_watchdog_code(ctypes.byref(code))
+            rep.sections.append(("bimodal_b200 watchdog", f"code 0x{code.value:x} (0 = no pipeline wait timed out)"))
+        except Exception as exc:  # noqa: BLE001
+            rep.sections.append(("bimodal_b200 watchdog", f"unavailable: {exc}"))
