@@ -163,3 +163,28 @@ def test_patch_embed_gemm_equals_conv():
         assert torch.equal(net(x), want)
     other = torch.nn.Sequential(torch.nn.Conv2d(3, 8, kernel_size=3, stride=1, padding=1))
     assert install_patch_embed_gemm(other) == 0                          # overlapping windows: left alone
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the oracle on the host cores) prints ONE JSON line with the keys
+    the driver reads; here on the CPU-sized model of BASELINE.json config 1."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--model", "tiny",
+                        "--search-width", "64", "--cpu-sample", "4", "--steps", "2", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "gcg_pgd_candidates_scored_per_sec"
+    assert d["unit"] == "candidates/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["steps"] == 2 and d["warmup"] == 1 and d["n_gpus"] == 1 and d["vs_baseline"] is None
+    assert "workload" in d["config"] and d["config"]["search_width"] == 64
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "candidate" in cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0
