@@ -49,11 +49,12 @@ def parse_args():
                     help="7b = BASELINE.json config 2 (the headline); gemma4b = config 4 (Gemma-3-4b GCG-only); "
                          "tiny = the CPU-sized model of config 1 (use --search-width 64)")
     ap.add_argument("--search-width", type=int, default=512)
-    ap.add_argument("--scaling", default="weak", choices=["strong", "weak"],
-                    help="weak (default): search_width candidates PER GPU, i.e. the per-GPU work of the headline "
-                         "config is fixed as N grows; strong: search_width candidates in total, split over the GPUs")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong (default, BASELINE.json north_star): search_width candidates in TOTAL, each of the N "
+                         "GPUs scores search_width/N of them; weak: search_width candidates PER GPU")
     ap.add_argument("--full-steps", type=int, default=3, help="full attack steps timed for steps/s (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-hbm-kernels", action="store_true", help="skip the HBM-bound kernel rooflines (roofline_hbm)")
     ap.add_argument("--no-suffix-sharing", action="store_true",
                     help="score every candidate's full tail (the north-star dataflow) instead of computing the "
                          "rows it shares with the current suffix once")
@@ -163,6 +164,8 @@ def run_reference(args):
     if rank != 0:
         return
     from bimodalattack_b200 import BimodalAttackConfig
+    # torchrun exports OMP_NUM_THREADS=1 for nproc > 1: the CPU arm must still use every host core
+    torch.set_num_threads(os.cpu_count() or 1)
     torch.manual_seed(0)
     t0 = time.perf_counter()
     model, tok, proc, norm, image, messages, target, init, joint = build_case(args, torch.float32, None, fast_init=True)
@@ -249,6 +252,80 @@ def build_case(args, dtype, device, fast_init=False):
     return model, tok, proc, norm, image, messages, target, init, True
 
 
+def hbm_bound_kernels(atk, model, sampled, optim_ids, image, original, cfg, peaks):
+    """Roofline entries of the HBM-bound kernels of the path: token-gradient GEMM, sampler
+    (top-k + replacement), PGD step, RMSNorm. Each is timed alone with CUDA events, L2 flushed (a 512 MB
+    write) between iterations; bytes are the ALGORITHMIC bytes per launch. `traffic` comes from the
+    committed ncu captures (profiles/ncu_traffic.json) when present."""
+    import ctypes as C
+    from bimodalattack_b200 import native
+    dev = image.device if image is not None else sampled.device
+    lib = native.load()
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("hbm_kernels", {})
+
+    def timeit(fn, iters=10, warm=3, back_to_back=False):
+        for _ in range(warm):
+            fn()
+        if back_to_back:      # working set > L2 (126 MB): consecutive launches cannot reuse it, no flush needed,
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)   # and launch latency amortises
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(iters):
+                fn()
+            b.record()
+            b.synchronize()
+            return a.elapsed_time(b) * 1e-3 / iters
+        ts = []
+        for _ in range(iters):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            b.synchronize()
+            ts.append(a.elapsed_time(b))
+        return statistics.median(ts) * 1e-3
+
+    def entry(name, kernel, secs, nbytes, launches=1):
+        gbs = nbytes / secs / 1e9
+        return {"kernel": kernel, "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": gbs / peaks["hbm_gbs"], "us": secs * 1e6, "algorithmic_bytes": nbytes, "launches": launches,
+                "traffic": traffic.get(name), "peak_source": peaks["source"] + " (copy bandwidth; kernel timed alone, L2 flushed)"}
+
+    out = {}
+    W = model.get_input_embeddings().weight.detach()
+    V, d = W.shape
+    n_tok = optim_ids.shape[1]
+    g = (torch.randn(n_tok, d, device=dev) * 1e-3).to(torch.bfloat16)
+    secs = timeit(lambda: native.token_grad(g, W), back_to_back=True)
+    out["token_grad"] = entry("token_grad", "gemm_bf16_tn_kernel<*, EPI_STORE_T> (W streamed once as the A operand)", secs,
+                              2 * (V * d + n_tok * d + n_tok * V))
+    grad = native.token_grad(g, W)
+    ids = optim_ids.reshape(-1)
+    secs = timeit(lambda: native.sample_ids(ids, grad, cfg.search_width, cfg.topk, cfg.n_replace, None, 1, 0))
+    out["sampler"] = entry("sampler", "topk_chunk + topk_merge + sample_replace", secs,
+                           n_tok * V * 2 + n_tok * cfg.topk * 8 + cfg.search_width * n_tok * 8, launches=3)
+    if image is not None:
+        x = image.clone()
+        gi = torch.randn_like(x)
+        secs = timeit(lambda: native.pgd_step_(x, gi, original, cfg.alpha * cfg.eps, cfg.eps))
+        out["pgd_step"] = entry("pgd_step", "pgd_step_kernel (sign/step/project/clamp fused)", secs, 4 * x.numel() * 4)
+    rows = 16384
+    xr = torch.randn(rows, d, device=dev).to(torch.bfloat16)
+    yr = torch.empty_like(xr)
+    wn = torch.ones(d, dtype=torch.bfloat16, device=dev)
+    st = native.stream_ptr(dev)
+    secs = timeit(lambda: native.check(lib.bma_rmsnorm(xr.data_ptr(), d, wn.data_ptr(), yr.data_ptr(), d, rows, d,
+                                                       C.c_float(1e-5), 0, st), "rmsnorm"), back_to_back=True)
+    out["rmsnorm"] = entry("rmsnorm", f"rmsnorm_kernel ({rows} rows x {d})", secs, 2 * rows * d * 2)
+    return out
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -309,7 +386,7 @@ def main():
 
     def scoring_step():
         with torch.no_grad():
-            atk._prefill_tag = None              # every step rebuilds the shared-prefix K/V (as a real step does)
+            atk.engine.prefill_tag = None        # every step rebuilds the shared-prefix K/V (as a real step does)
             atk._compute_candidates_loss_original(sw, build_batch(image))
         return atk._winner()                     # one 8-byte D2H: the step's result
 
@@ -318,14 +395,13 @@ def main():
             td.barrier()
         torch.cuda.synchronize()
 
-    # ---- value: device-resident inputs -------------------------------------------------------
+    # ---- value: device-resident inputs (profiler OFF) ---------------------------------------------
     for _ in range(args.warmup):
         scoring_step()
     P = atk.engine.prefix_len
     with torch.no_grad():
         plan = atk._plan(build_batch(image))
     S, T = plan.n_tail, atk.target_ids.numel()
-    atk.engine.profile(True)
     clocks = ClockSampler(local)
     barrier()
     launches0 = lib.bma_launch_count()
@@ -345,9 +421,16 @@ def main():
         td.all_reduce(ms, op=td.ReduceOp.MAX)
     ms_per_step = float(ms.item()) / args.steps
     value = sw / (ms_per_step * 1e-3)
+    rows_run = atk.engine.last_rows          # tail (+ fused prefix) rows of this rank's shard that went through the decoder
+
+    # ---- per-class profile: a SEPARATE pass with an event pair around every launch -----------------
+    prof_steps = max(1, min(args.steps, 5))
+    atk.engine.profile(True)
+    for _ in range(prof_steps):
+        scoring_step()
+    torch.cuda.synchronize()
     prof = atk.engine.profile_read()
     atk.engine.profile(False)
-    rows_run = atk.engine.last_rows          # tail rows of this rank's shard that went through the decoder
 
     # ---- e2e: host buffers through the C ABI ---------------------------------------------------
     ids_host = sampled.cpu().pin_memory()
@@ -364,12 +447,9 @@ def main():
                 img_dev.copy_(img_host, non_blocking=True)
             pl = atk._plan(build_batch(img_dev))
             atk.engine.prefill(pl.prefix)
+            # multi-rank: the library reduces the winner key (one NCCL all-reduce) before it leaves the device
             atk.engine.score_host(ids_host[lo:hi], pl, atk.target_ids, loss_host[lo:hi], key_host, idx_base=lo,
                                   base_ids_host=base_host)
-            if world > 1:
-                key_dev.copy_(key_host, non_blocking=True)
-                td.all_reduce(key_dev, op=td.ReduceOp.MIN)
-                return int(key_dev.item())
         return int(key_host.item())
 
     for _ in range(max(1, args.warmup // 2)):
@@ -412,10 +492,28 @@ def main():
                                      "sampling": res.sampling_times[-1] if res.sampling_times else None,
                                      "scoring": res.loss_times[-1]}}
 
+    # ---- multi-rank parity: rank 0 scores ALL candidates alone; the sharded winner must be that winner ----
+    unsharded = None
+    if world > 1:
+        barrier()
+        if rank == 0:
+            with torch.no_grad():
+                eng = atk.engine
+                eng.attach_comm(None)
+                pl = atk._plan(build_batch(image))
+                eng.prefill(pl.prefix, deferred=False)
+                all_loss = eng.score(sampled, pl, atk.target_ids, base_ids=base_ids)
+                u_loss, u_idx = atk._winner()
+                eng.attach_comm(bdist.native_comm(dev, w))
+            unsharded = {"loss": u_loss, "index": u_idx, "matches_sharded": bool(u_idx == win_idx and u_loss == win_loss)}
+        barrier()
+
     if rank != 0:
         if world > 1:
             td.destroy_process_group()
         return
+
+    hbm = hbm_bound_kernels(atk, model, sampled, optim_ids, image, original, cfg, peaks) if not args.no_hbm_kernels else None
 
     # ---- roofline of the dominant kernel class (tcgen05 GEMMs), from in-run CUDA events ----------
     tc = model.config.text_config
@@ -445,7 +543,7 @@ def main():
                 "achieved": top_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": top_tf / peaks["bf16_sustained"], "frac_of_burst_peak": top_tf / peaks["bf16_burst"],
                 "peak_source": peaks["source"] + " (sustained cuBLAS bf16; kernel timed inside a long step)",
-                "launches_per_step": top["launches"] / args.steps,
+                "launches_per_step": top["launches"] / prof_steps,
                 "avg_launch_ms": top["ms"] / max(top["launches"], 1),
                 "algorithmic_flops_per_launch": top["flops"] / max(top["launches"], 1),
                 "algorithmic_bytes_per_launch": alg_bytes,
@@ -455,7 +553,7 @@ def main():
                 # `ncu --set full` capture (profiles/ncu_traffic.json); not measured in this run
                 "traffic": traffic, "share_of_step": top["ms"] / total_prof_ms if total_prof_ms else None,
                 "share_of_scoring_kernels": g_ms / total_prof_ms if total_prof_ms else None,
-                "per_class": {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
+                "per_class": {k: {"ms_per_step": v["ms"] / prof_steps, "launches_per_step": v["launches"] / prof_steps,
                                   "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["ms"] > 0 and v["flops"] > 0 else None}
                               for k, v in prof.items()},
                 # SURVEY 8(d) numerator (every candidate's full tail) over the step time; with suffix-head
@@ -466,7 +564,8 @@ def main():
                                         "tail_rows_executed": int(rows_run),
                                         "note": "rows a candidate shares with the current suffix (before its first "
                                                 "replaced position) are computed once; SURVEY 8(f) rank 3"},
-                "gemm_tflops_executed_per_step": g_fl / args.steps / 1e12}
+                "gemm_tflops_executed_per_step": g_fl / prof_steps / 1e12,
+                "profile_pass": f"{prof_steps} extra steps with an event pair around every launch (value and e2e are timed without)"}
 
     # ---- CPU baseline: the oracle (reference dataflow) on the host cores, bounded sample ------------
     cpu = None
@@ -494,7 +593,8 @@ def main():
         "config": workload_config(args, P, S),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu,
-        "full_step": full, "winner": {"loss": win_loss, "index": win_idx, "e2e_key": e2e_key},
+        "roofline_hbm": hbm,
+        "full_step": full, "winner": {"loss": win_loss, "index": win_idx, "e2e_key": e2e_key, "unsharded_rank0": unsharded},
         "a100_reference_published": (
             {"cand_per_s": 12.1, "s_per_iter": 43.9353,
              "note": "BASELINE.md: Gemma-3-4b-it joint_eval sw 512, A100-80GB, bf16"} if gemma and joint else

@@ -170,6 +170,39 @@ class _PngWriter:
             raise err
 
 
+class _PhaseClock:
+    """CUDA-event stopwatch for the phases of one step: ``mark(name)`` closes the interval since the
+    previous mark and files it under ``name`` (None = not a phase); ``read()`` returns
+    {name: [seconds, ...]} once the events have completed. Falls back to perf_counter off-GPU."""
+
+    def __init__(self, device):
+        self.cuda = torch.device(device).type == "cuda"
+        self.device = device
+        self.marks = []
+
+    def _now(self):
+        if not self.cuda:
+            return time.perf_counter()
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream(self.device))
+        return ev
+
+    def start(self):
+        self.marks = [(None, self._now())]
+
+    def mark(self, name):
+        self.marks.append((name, self._now()))
+
+    def read(self) -> Dict[str, List[float]]:
+        out: Dict[str, List[float]] = {}
+        if self.cuda and self.marks:
+            self.marks[-1][1].synchronize()
+        for (_, a), (name, b) in zip(self.marks, self.marks[1:]):
+            if name is not None:
+                out.setdefault(name, []).append(a.elapsed_time(b) * 1e-3 if self.cuda else b - a)
+        return out
+
+
 @dataclass
 class CandidateBatch:
     """What ``_build_input_embeds*`` returns here instead of a materialised (sw, L, d) tensor: the
@@ -208,13 +241,16 @@ class BimodalAttack:
         # between attacks on the same model (one per (goal, target) pair in the reference's driver)
         self.engine = engine if engine is not None else ScoringEngine(model)
         self._plans: Dict[Tuple[str, ...], TailPlan] = {}
-        self._prefill_tag = None
         self.world = bdist.world()
+        if self.world.size > 1:
+            # the library's own NCCL communicator: split prefill + the winner all-reduce on the scorer's stream
+            self.engine.attach_comm(bdist.native_comm(self.device, self.world))
         self.gather_all_losses = False    # multi-rank: also all-reduce the per-candidate loss vector
         self.step_hook = None             # optional callable(step_index) run at the end of every step
         self.graph_gradient = os.environ.get("BMA_GRAPH_GRADIENT", "1") != "0"
-        if config.pgd_attack and os.environ.get("BMA_PATCH_EMBED_GEMM", "1") != "0":
-            install_patch_embed_gemm(model)       # see _patch_conv_forward; restore_patch_embed(model) undoes it
+        # patch-embedding convolutions run as unfold + GEMM while run() is active (see _patch_conv_forward);
+        # run() puts the model's own forward back before it returns
+        self.patch_embed_gemm = config.pgd_attack and os.environ.get("BMA_PATCH_EMBED_GEMM", "1") != "0"
         self._grad_graph = None
         self._feat_graph = None
         self._png = None
@@ -277,7 +313,7 @@ class BimodalAttack:
         for k, v in self.segment_embeds.items():
             setattr(self, f"{k}_embeds", v)
         self._plans.clear()
-        self._prefill_tag = None
+        self.engine.prefill_tag = None
         self._grad_graph = None          # the captured gradient step references the old segment embeddings
 
     # ---------------------------------------------------------------------------------------------
@@ -514,26 +550,29 @@ class BimodalAttack:
 
     # scoring (:1278-1310). search_batch_size is accepted for interface compatibility; the native
     # workspace is sized up front, so no OOM-driven chunk search is needed.
-    def _compute_candidates_loss_original(self, search_batch_size: int, batch: CandidateBatch) -> torch.Tensor:
+    def _compute_candidates_loss_original(self, search_batch_size: int, batch: CandidateBatch,
+                                          gather: bool = False) -> torch.Tensor:
         plan = self._plan(batch)
-        tag = (tuple(batch.order), None if batch.image is None else (batch.image.data_ptr(), batch.image._version),
-               plan.n_prefix)
-        if tag != self._prefill_tag or "image" in batch.order:
-            self.engine.prefill(plan.prefix)
-            self._prefill_tag = tag
+        eng = self.engine
+        tag = (id(self), tuple(batch.order),
+               None if batch.image is None else (batch.image.data_ptr(), batch.image._version), plan.n_prefix)
+        if tag != eng.prefill_tag or "image" in batch.order:
+            eng.prefill(plan.prefix)      # deferred: rides in the first chunk of the score call below
+            eng.prefill_tag = tag
         ids = batch.sampled_ids
         lo, hi = bdist.shard_bounds(ids.shape[0], self.world)
-        self.engine.reset_key()
+        eng.want_all_match = bool(self.config.early_stop)
+        eng.reset_key()
         loss = torch.full((ids.shape[0],), float("inf"), dtype=torch.float32, device=self.device)
         base = getattr(self, "_base", None)
         base_ids = base[1] if base is not None and base[0] is ids else None
-        if hi > lo:
-            loss[lo:hi] = self.engine.score(ids[lo:hi], plan, self.target_ids, idx_base=lo, reset=False,
-                                            base_ids=base_ids)
-        bdist.reduce_winner(self.engine.key, self.engine.flag, self.world)
-        if self.world.size > 1 and self.gather_all_losses:
+        # with a split prefill every rank takes part in the per-layer exchange, candidates or not
+        if hi > lo or (self.world.size > 1 and base_ids is not None):
+            loss[lo:hi] = eng.score(ids[lo:hi], plan, self.target_ids, idx_base=lo, reset=False, base_ids=base_ids)
+        bdist.reduce_winner(eng.key, eng.flag if self.config.early_stop else None, self.world)
+        if self.world.size > 1 and (gather or self.gather_all_losses):
             bdist.gather_losses(loss, lo, hi, self.world)
-        if self.config.early_stop and int(self.engine.flag.item()) != 0:
+        if self.config.early_stop and int(eng.flag.item()) != 0:
             self.stop_flag = True
         return loss
 
@@ -584,7 +623,8 @@ class BimodalAttack:
                 batch = self._build_input_embeds_gcg_pgd(init, feats, search_width=n, single=True)
             else:
                 batch = self._build_input_embeds_gcg(init, search_width=n, no_joint_eval=True)
-            losses = self._compute_candidates_loss_original(n, batch)
+            # every rank needs every entry's loss: the buffer (and the first suffix) must agree across ranks
+            losses = self._compute_candidates_loss_original(n, batch, gather=True)
         for j, value in enumerate(losses.tolist()):
             buf.add(value, init[[j]])
         buf.log_buffer(tok, logger)
@@ -593,6 +633,18 @@ class BimodalAttack:
     # ---------------------------------------------------------------------------------------------
     def run(self, messages: Union[str, List[dict]], goal: str, target: str,
             image: Optional[torch.Tensor] = None) -> BimodalAttackResult:
+        """The step loop (:441-794). Process- and model-wide switches this path flips for speed are put
+        back before returning: torch's fill_uninitialized_memory flag and the patch-embedding forward."""
+        fill_flag = torch.utils.deterministic.fill_uninitialized_memory
+        patched = install_patch_embed_gemm(self.model) if self.patch_embed_gemm else 0
+        try:
+            return self._run(messages, goal, target, image)
+        finally:
+            torch.utils.deterministic.fill_uninitialized_memory = fill_flag
+            if patched:
+                restore_patch_embed(self.model)
+
+    def _run(self, messages, goal: str, target: str, image: Optional[torch.Tensor]) -> BimodalAttackResult:
         cfg, model, tok = self.config, self.model, self.tokenizer
         self.initial_prompt = goal
         if cfg.pgd_attack and cfg.images_folder:
@@ -638,38 +690,38 @@ class BimodalAttack:
 
         lead = self.world.rank == 0         # gradient, PGD and sampling run on rank 0 only
         n_tok = optim_ids.shape[1]
+        # Phase times are DEVICE times: CUDA events on the launching stream bracket every phase and are
+        # read once per step, after the step's last host sync (the reference's perf_counter deltas measure
+        # launch time only once work is asynchronous or replayed from a graph).
+        clock = _PhaseClock(self.device)
         i = -1
         for i in range(cfg.num_steps):
             grad_time = pgd_time = sampling_time = 0.0
             sampled, width = None, 0
+            clock.start()
             if lead:
-                t0 = time.perf_counter()
                 onehot_grad, image_grad = self.compute_gradient(optim_ids, image if cfg.pgd_attack else None)
-                grad_time = time.perf_counter() - t0
-                g_times.append(grad_time)
+                clock.mark("gradient")
                 if cfg.pgd_attack and not cfg.pgd_after_gcg:
-                    t0 = time.perf_counter()
                     image = self.perform_pgd_step(image, cfg.eps, cfg.alpha, image_grad, original)
-                    pgd_time = time.perf_counter() - t0
-                    p_times.append(pgd_time)
+                    clock.mark("pgd")
                     if cfg.gcg_attack and not cfg.joint_eval:        # phase C (:481-491)
-                        t0 = time.perf_counter()
                         onehot_grad, image_grad = self.compute_gradient(optim_ids, image)
-                        grad_time = time.perf_counter() - t0
-                        g_times.append(grad_time)
-                sampled, width, sampling_time, tot_s = self.candidate_sampling(cfg, i, optim_ids, onehot_grad, tok,
-                                                                              s_times, tot_s)
+                        clock.mark("gradient")
+                sampled, width, _, _ = self.candidate_sampling(cfg, i, optim_ids, onehot_grad, tok, [], 0.0)
+                clock.mark("sampling")
             if self.world.size > 1:
                 sampled = bdist.broadcast_candidates(sampled, n_tok, self.device, self.world)
                 width = sampled.shape[0]
                 if cfg.pgd_attack and not cfg.pgd_after_gcg:
-                    shared = bdist.broadcast_tensor(image.detach(), self.world)   # same storage on rank 0
+                    # rank 0 sends its own storage; the others receive into a copy, never into the caller's tensor
+                    shared = bdist.broadcast_tensor(image.detach() if lead else image.detach().clone(), self.world)
                     image = image if lead else shared
                 if cfg.gcg_attack:      # every rank knows the current suffix: the scorer's sharing base
                     self._base = (sampled, optim_ids.reshape(-1).to(torch.int64).contiguous())
 
+            clock.mark(None)                # broadcasts belong to no phase
             with torch.no_grad():
-                t0 = time.perf_counter()
                 chunk = width if cfg.batch_size is None else cfg.batch_size
                 if cfg.pgd_attack:
                     feats = self.scoring_features(image)
@@ -703,30 +755,34 @@ class BimodalAttack:
                     current, best_idx = self._winner()
                     optim_ids = sampled[best_idx].unsqueeze(0)
                     record(current, optim_ids, None)
-                loss_time = time.perf_counter() - t0
-                l_times.append(loss_time)
+                clock.mark("loss")
 
             if cfg.pgd_after_gcg and cfg.pgd_attack:             # phases E, F (:668-740)
                 if lead:
-                    t0 = time.perf_counter()
                     _, image_grad = self.compute_gradient(optim_ids, image)   # still the previous suffix (:673)
-                    grad_time = time.perf_counter() - t0
-                    g_times.append(grad_time)
-                    t0 = time.perf_counter()
+                    clock.mark("gradient")
                     image = self.perform_pgd_step(image, cfg.eps, cfg.alpha, image_grad, original)
-                    pgd_time = time.perf_counter() - t0
-                    p_times.append(pgd_time)
-                shared = bdist.broadcast_tensor(image.detach(), self.world)
+                    clock.mark("pgd")
+                shared = bdist.broadcast_tensor(image.detach() if lead else image.detach().clone(), self.world)
                 image = image if lead else shared
+                clock.mark(None)
                 with torch.no_grad():
-                    t0 = time.perf_counter()
                     feats = self.scoring_features(image)
                     full = self._build_input_embeds_gcg_pgd(chosen, feats)
                     self._compute_candidates_loss_original(1, full)
                     current, _ = self._winner()
                     optim_ids = chosen
-                    l_times.append(time.perf_counter() - t0)
                     record(current, optim_ids, image)
+                clock.mark("loss")
+
+            # one read per step: every phase's events are complete after the winner came back to the host
+            phases = clock.read()
+            for name, dst in (("gradient", g_times), ("pgd", p_times), ("sampling", s_times), ("loss", l_times)):
+                dst.extend(phases.get(name, []))
+            grad_time = phases["gradient"][-1] if phases.get("gradient") else 0.0
+            pgd_time = phases["pgd"][-1] if phases.get("pgd") else 0.0
+            sampling_time = sum(phases.get("sampling", []))
+            loss_time = sum(phases.get("loss", []))
 
             if cfg.pgd_attack and cfg.images_folder:
                 self._save_image(image, os.path.join(cfg.images_folder, f"{i}.png"))

@@ -44,8 +44,10 @@ constexpr int SMEM = 2 * TILE /*Q*/ + 2 * TILE /*K*/ + 2 * TILE /*V^T*/ + 256 /*
 struct Params {
   __nv_bfloat16* out; long long ldo;
   int M, S, P;
+  const int* M_dev;
   const int2* row_meta;
   int P_shared;
+  int pre_rows;              // leading rows that are shared-prefix positions (fused prefill): they see fewer keys
   int n_heads, kv_group;
   float scale_log2;
 };
@@ -97,7 +99,8 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   float2* swap = reinterpret_cast<float2*>(bars + 32);     // [2 halves][128 rows] (max, sum)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_tiles = (p.M + BM - 1) / BM;
+  const int M = p.M_dev != nullptr ? min(p.M, __ldg(p.M_dev)) : p.M;   // live row count (ragged pass)
+  const int m_tiles = (M + BM - 1) / BM;
   const int n_items = m_tiles * p.n_heads;
   const int n_pre = (p.P + BN - 1) / BN;
 
@@ -134,7 +137,7 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
         const int head = item / m_tiles, tile = item - head * m_tiles;
         const int kvh = head / p.kv_group;
-        const int r0 = tile * BM, r1 = min(p.M, r0 + BM);
+        const int r0 = tile * BM, r1 = min(M, r0 + BM);
         const int kt0 = tail_start(r0, p.S, p.row_meta);
         const int nb = n_pre + (r1 - kt0 + BN - 1) / BN;
         {
@@ -204,7 +207,7 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       int pend_n = 0, pend_first = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
         const int head = item / m_tiles, tile = item - head * m_tiles;
-        const int r0 = tile * BM, r1 = min(p.M, r0 + BM);
+        const int r0 = tile * BM, r1 = min(M, r0 + BM);
         const int kt0 = tail_start(r0, p.S, p.row_meta);
         const int nb = n_pre + (r1 - kt0 + BN - 1) / BN;
         const int qb = item_n & 1;
@@ -248,12 +251,12 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
                                                  // an array indexed by h would live in local memory)
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
       const int head = item / m_tiles, tile = item - head * m_tiles;
-      const int r0 = tile * BM, r1 = min(p.M, r0 + BM);
+      const int r0 = tile * BM, r1 = min(M, r0 + BM);
       const int kt0 = tail_start(r0, p.S, p.row_meta);
       const int nb = n_pre + (r1 - kt0 + BN - 1) / BN;
       const int rq = r0 + row_in_tile;
       int cs = (rq / p.S) * p.S, plim = p.P;
-      if (p.row_meta != nullptr && rq < p.M) {
+      if (p.row_meta != nullptr && rq < M) {
         const int2 rm = p.row_meta[rq];
         cs = rm.x; plim = rm.y;
       }
@@ -286,7 +289,7 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         }
         if (keys == 0) continue;                           // this half has no keys in the block
         const int kbase = b.key0 + h * CH;
-        if (!b.pre || b.key0 + BN > p.P_shared) {
+        if (!b.pre || b.key0 + BN > (r0 < p.pre_rows ? 0 : p.P_shared)) {
 #pragma unroll
           for (int i = 0; i < CH; ++i) {
             const int key = kbase + i;
@@ -384,7 +387,7 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
 #pragma unroll
             for (int i = 0; i < 32; ++i) o[i] = fmaf(__uint_as_float(a[i]), s1, o[i]);
           }
-          if (rq < p.M) {
+          if (rq < M) {
 #pragma unroll
             for (int v4 = 0; v4 < 4; ++v4) {
               reinterpret_cast<uint4*>(dst + c0)[v4] = make_uint4(
@@ -433,9 +436,10 @@ cudaError_t launch_attention_split(const AttnParams& a, int n_heads, cudaStream_
   }
   Params p{};
   p.out = a.out; p.ldo = a.ldo;
-  p.M = a.M; p.S = a.S; p.P = a.P;
+  p.M = a.M; p.S = a.S; p.P = a.P; p.M_dev = a.M_dev;
   p.row_meta = a.row_meta;
   p.P_shared = a.row_meta != nullptr ? a.P_shared : a.P;
+  p.pre_rows = a.row_meta != nullptr ? a.pre_rows : 0;
   p.n_heads = n_heads; p.kv_group = a.kv_group;
   p.scale_log2 = a.scale_log2;
   watchdog_attach();

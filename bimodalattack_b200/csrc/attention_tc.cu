@@ -66,8 +66,10 @@ struct AtcCfg {
 struct AtcParams {
   __nv_bfloat16* out; long long ldo;
   int M, S, P;
+  const int* M_dev;
   const int2* row_meta;      // ragged rows: (first row of the row's candidate, visible prefix keys)
   int P_shared;              // prefix keys every row sees (== P without row_meta)
+  int pre_rows;              // leading rows that are shared-prefix positions (fused prefill): they see fewer keys
   int n_heads, kv_group;
   int q_col0, k_col0;        // column of head 0 inside the Q / K tensor maps
   float scale_log2;
@@ -137,7 +139,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   float* xchg = reinterpret_cast<float*>(bars + 32);     // [2 rotating][2 halves][128 rows] row max / row sum swaps
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_tiles = (p.M + ATC_BM - 1) / ATC_BM;
+  const int M = p.M_dev != nullptr ? min(p.M, __ldg(p.M_dev)) : p.M;   // live row count (ragged pass)
+  const int m_tiles = (M + ATC_BM - 1) / ATC_BM;
   const int n_items = m_tiles * p.n_heads;
   const int n_pre = (p.P + BN - 1) / BN;
 
@@ -175,7 +178,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
         const int head = item / m_tiles, tile = item - head * m_tiles;
         const int kvh = head / p.kv_group;
-        const int r0 = tile * ATC_BM, r1 = min(p.M, r0 + ATC_BM);
+        const int r0 = tile * ATC_BM, r1 = min(M, r0 + ATC_BM);
         const int kt0 = tail_key_start(r0, p.S, p.row_meta);
         const int nb = n_pre + (r1 - kt0 + BN - 1) / BN;
         {
@@ -252,7 +255,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       bool pend_first = false;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
         const int head = item / m_tiles, tile = item - head * m_tiles;
-        const int r0 = tile * ATC_BM, r1 = min(p.M, r0 + ATC_BM);
+        const int r0 = tile * ATC_BM, r1 = min(M, r0 + ATC_BM);
         const int kt0 = tail_key_start(r0, p.S, p.row_meta);
         const int nb = n_pre + (r1 - kt0 + BN - 1) / BN;
         const int qb = item_n % QB;
@@ -304,12 +307,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     uint32_t it = 0, item_n = 0, xn = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
       const int head = item / m_tiles, tile = item - head * m_tiles;
-      const int r0 = tile * ATC_BM, r1 = min(p.M, r0 + ATC_BM);
+      const int r0 = tile * ATC_BM, r1 = min(M, r0 + ATC_BM);
       const int kt0 = tail_key_start(r0, p.S, p.row_meta);
       const int nb = n_pre + (r1 - kt0 + BN - 1) / BN;
       const int rq = r0 + row_in_tile;
       int cs = (rq / p.S) * p.S, plim = p.P;
-      if (p.row_meta != nullptr && rq < p.M) {
+      if (p.row_meta != nullptr && rq < M) {
         const int2 rm = p.row_meta[rq];
         cs = rm.x; plim = rm.y;
       }
@@ -341,7 +344,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[st]);          // S_j is in registers: the buffer is free
-        if (!b.pre || b.key0 + BN > p.P_shared) {      // masked blocks: prefix keys past P_shared and the tail
+        if (!b.pre || b.key0 + BN > (r0 < p.pre_rows ? 0 : p.P_shared)) {      // masked blocks: prefix keys past P_shared and the tail
 #pragma unroll
           for (int i = 0; i < CH; ++i) {
             const int key = kbase + i;
@@ -440,7 +443,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             tmem_ld_32x32(to + c0, r);
             tmem_ld_wait();
           }
-          if (rq < p.M) {
+          if (rq < M) {
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
               reinterpret_cast<uint4*>(dst + c0)[v] = make_uint4(
@@ -490,9 +493,10 @@ static cudaError_t launch_atc(const AttnParams& a, int n_heads, cudaStream_t str
   }
   AtcParams p{};
   p.out = a.out; p.ldo = a.ldo;
-  p.M = a.M; p.S = a.S; p.P = a.P;
+  p.M = a.M; p.S = a.S; p.P = a.P; p.M_dev = a.M_dev;
   p.row_meta = a.row_meta;
   p.P_shared = a.row_meta != nullptr ? a.P_shared : a.P;
+  p.pre_rows = a.row_meta != nullptr ? a.pre_rows : 0;
   p.n_heads = n_heads; p.kv_group = a.kv_group;
   p.q_col0 = 0; p.k_col0 = 0;
   p.scale_log2 = a.scale_log2;

@@ -54,6 +54,8 @@ constexpr int kCeBlockN = 256;
 
 }  // namespace
 
+struct bma_comm;   // comm.cu: NCCL communicator owned by this library (one rank per process)
+
 struct bma_scorer {
   bma_model_desc desc;
   std::vector<bma_layer_weights> layers;
@@ -65,11 +67,22 @@ struct bma_scorer {
   int qk_dim = 0;                        // row stride of the Q|K buffers (V is stored transposed)
   long long ld_vt = 0, ld_vtp = 0;       // row strides (in keys) of the transposed V buffers
   int prefix_len = 0;
+  // fused prefill: the prefix embeddings handed to bma_scorer_prefill_deferred wait here until the
+  // next score call runs them inside its first chunk (or an explicit prefill consumes them)
+  const __nv_bfloat16* pending_prefix = nullptr;
+  int pending_P = 0;
+  // multi-rank (one process per GPU): prefix rows are split over the ranks of `comm`, their K/V
+  // all-gathered per layer; the emulated group (tests) uses vrank/vsize with local copies instead
+  bma_comm* comm = nullptr;
+  int vrank = 0, vsize = 1;
+  __nv_bfloat16 *xchg_send = nullptr, *xchg_recv = nullptr;
+  size_t xchg_elems = 0;
   // workspace
   __nv_bfloat16 *x = nullptr, *xn = nullptr, *qk = nullptr, *vt = nullptr, *attn = nullptr, *act = nullptr;
   __nv_bfloat16* prefix_qk = nullptr;    // [layers][max_prefix][qk_dim]   Q|K rows of the prefix
   __nv_bfloat16* prefix_vt = nullptr;    // [layers][kv_dim][ld_vtp]       V^T of the prefix
   float2* ce_part = nullptr;
+  int* ce_arg = nullptr;
   __nv_bfloat16 *x_c = nullptr, *attn_c = nullptr;   // the scored rows of the last layer, made contiguous
   float* tgt_logit = nullptr;
   // ragged-row plan (suffix-head sharing)
@@ -77,10 +90,11 @@ struct bma_scorer {
   int* cand_vstart = nullptr;
   int2* cand_tmp = nullptr;
   int dedupe = 1;                        // identical candidates share one set of rows (bma_scorer_set_dedupe)
-  int* total_rows_dev = nullptr;
+  int* total_rows_dev = nullptr;         // live row count of the current chunk (read by every kernel of the pass)
   int* total_rows_host = nullptr;        // pinned
+  unsigned long long* rows_accum_dev = nullptr;   // rows run by the ragged chunks of the last score call
   long long* base_dev = nullptr;         // staging for the *_host entry
-  long long last_rows = 0;
+  long long last_rows = 0;               // rows of the uniform (non-ragged) chunks of the last score call
   long long* ids_dev = nullptr;          // staging for the *_host entry
   float* loss_dev = nullptr;
   unsigned long long* key_dev = nullptr;
@@ -95,11 +109,21 @@ struct bma_scorer {
   size_t ev_used = 0;
 };
 
+int comm_allgather_bytes(bma_comm* c, const void* send, void* recv, size_t bytes_per_rank, cudaStream_t st);
+int comm_rank(const bma_comm* c);
+int comm_size(const bma_comm* c);
+
 namespace {
 struct ProfScope {
   bma_scorer* s; cudaStream_t st; size_t slot; bool on;
   ProfScope(bma_scorer* s_, int cls, double flops, cudaStream_t st_) : s(s_), st(st_), slot(0), on(false) {
-    if (!s->profiling || s->ev_used >= s->ev_start.size()) return;
+    if (!s->profiling) return;
+    if (s->ev_used >= s->ev_start.size()) {       // grow instead of silently dropping launches
+      const size_t n = s->ev_start.size() + 4096;
+      const size_t old = s->ev_start.size();
+      s->ev_start.resize(n); s->ev_stop.resize(n); s->ev_class.resize(n); s->ev_flops.resize(n);
+      for (size_t i = old; i < n; ++i) { cudaEventCreate(&s->ev_start[i]); cudaEventCreate(&s->ev_stop[i]); }
+    }
     on = true;
     slot = s->ev_used++;
     s->ev_class[slot] = cls;
@@ -116,6 +140,9 @@ namespace {
 template <typename T>
 bool dev_alloc(T** p, size_t count, size_t* total) {
   if (cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T)) != cudaSuccess) return false;
+  // zero once: a ragged pass bounds its TMA maps by the row CAPACITY, so tiles may touch rows past
+  // the live count; those must hold finite values (0 * NaN would poison P.V in the attention)
+  if (cudaMemset(*p, 0, count * sizeof(T)) != cudaSuccess) return false;
   *total += count * sizeof(T);
   return true;
 }
@@ -127,10 +154,12 @@ int ensure_ce_rows(bma_scorer* s, int rows) {
   if (rows <= s->ce_rows_cap) return 0;
   const int n_ce_tiles = (s->desc.vocab + kCeBlockN - 1) / kCeBlockN;
   BMA_CHECK(cudaDeviceSynchronize(), "ensure_ce_rows: sync");
-  cudaFree(s->ce_part); cudaFree(s->tgt_logit); cudaFree(s->x_c); cudaFree(s->attn_c);
-  s->ce_part = nullptr; s->tgt_logit = nullptr; s->x_c = nullptr; s->attn_c = nullptr; s->ce_rows_cap = 0;
+  cudaFree(s->ce_part); cudaFree(s->ce_arg); cudaFree(s->tgt_logit); cudaFree(s->x_c); cudaFree(s->attn_c);
+  s->ce_part = nullptr; s->ce_arg = nullptr; s->tgt_logit = nullptr; s->x_c = nullptr; s->attn_c = nullptr;
+  s->ce_rows_cap = 0;
   size_t bytes = 0;
   if (!dev_alloc(&s->ce_part, static_cast<size_t>(n_ce_tiles) * rows, &bytes) ||
+      !dev_alloc(&s->ce_arg, static_cast<size_t>(n_ce_tiles) * rows, &bytes) ||
       !dev_alloc(&s->tgt_logit, static_cast<size_t>(rows), &bytes) ||
       !dev_alloc(&s->x_c, static_cast<size_t>(rows) * s->desc.d_model, &bytes) ||
       !dev_alloc(&s->attn_c, static_cast<size_t>(rows) * s->q_dim, &bytes))
@@ -140,140 +169,249 @@ int ensure_ce_rows(bma_scorer* s, int rows) {
   return 0;
 }
 
-// One decoder pass over `rows` rows laid out as sequences of `seq` rows at positions
+// One decoder pass over `rows` rows. Uniform layout: sequences of `seq` rows at positions
 // pos_base + (r % seq). prefill == true: rows are the prefix itself (their q/k/v land in
 // prefix_qkv and the last layer stops after its K/V are produced).
 //   Llama layer:  x += o(attn(norm_attn x));                x += down(glu(norm_mlp x))
 //   Gemma layer:  x += norm_post_attn(o(attn(norm_attn x))); x += norm_post_mlp(down(glu(norm_mlp x)))
 // In the Gemma form the residual adds cannot ride in the GEMM epilogue (a row norm sits in
 // between), so each (post-norm + add + next pre-norm) triple is one fused row kernel.
-// n_share > 0: ragged rows (row_info / row_meta filled by plan_rows); tail rows [0, n_share) are the
-// base's suffix rows, whose K/V every layer appends to the prefix buffers at key index prefix_len
-// (append == false: a previous chunk of the same call already did).
+// Ragged layout (n_share > 0; row_info / row_meta filled by plan_rows): rows are
+//   [ pre_n prefix positions (fused prefill) | the base suffix's n_share.. rows | candidates' own rows ].
+// Every layer publishes the K/V of the prefix rows and of the base's first n_share rows into the
+// per-layer prefix buffers before its attention runs (`publish`): a local copy on one rank, a pack +
+// all-gather + unpack when the prefix positions are split over ranks. `rows` is then an upper bound
+// and `rows_dev` the live count every kernel reads on the device -- no host round trip per chunk.
 // scored != null (candidate pass): only the T rows per candidate that predict the target are needed
 // after the LAST layer's attention -- no later layer reads the other rows -- so that layer's o_proj,
 // norms and MLP run on those rows alone, gathered into x_c / attn_c (they stay the residual stream
 // for the final norm and the LM head).
 struct ScoredRows { int n, T, ce_row0; const int* vstart; };
 
-int run_layers(bma_scorer* s, int rows, int seq, int pos_base, bool prefill, cudaStream_t st,
-               int n_share = 0, bool append = false, const ScoredRows* scored = nullptr) {
+struct Pass {
+  int rows = 0;                    // rows (upper bound when rows_dev != null)
+  const int* rows_dev = nullptr;
+  int seq = 1, pos_base = 0;
+  bool prefill = false;
+  int n_share = 0;                 // > 0: ragged rows
+  bool publish = false;            // this chunk carries prefix rows / the base: publish their K/V per layer
+  int pre0 = 0, pre_n = 0;         // fused prefill: prefix positions [pre0, pre0 + pre_n) are rows [0, pre_n)
+  int pre_chunk = 0;               // prefix positions per rank (split prefill), 0 = not split
+  const ScoredRows* scored = nullptr;
+  // running state of the pass
+  int cur_rows = 0;
+  const int* cur_rows_dev = nullptr;
+  __nv_bfloat16* xres = nullptr;
+  const __nv_bfloat16* attn_in = nullptr;
+};
+
+inline void pass_start(bma_scorer* s, Pass& ps) {
+  ps.cur_rows = ps.rows; ps.cur_rows_dev = ps.rows_dev;
+  ps.xres = s->x; ps.attn_in = s->attn;
+}
+inline __nv_bfloat16* layer_pre_qk(bma_scorer* s, int l) {
+  return s->prefix_qk + (size_t)l * s->desc.max_prefix * s->qk_dim;
+}
+inline __nv_bfloat16* layer_pre_vt(bma_scorer* s, int l) {
+  return s->prefix_vt + (size_t)l * s->kv_dim * s->ld_vtp;
+}
+
+// pre-norm + fused QKV projection (+ q/k-norm + rotary, V transposed)
+int layer_front(bma_scorer* s, int l, Pass& ps, cudaStream_t st) {
   const bma_model_desc& D = s->desc;
   const int d = D.d_model;
-  const int P = prefill ? 0 : s->prefix_len;
-  const bool ragged = n_share > 0;
+  const bma_layer_weights& W = s->layers[l];
   const bool sandwich = D.sandwich_norm != 0;
-  __nv_bfloat16* xres = s->x;                 // residual stream
-  const __nv_bfloat16* attn_in = s->attn;     // o_proj input
-  for (int l = 0; l < D.n_layers; ++l) {
-    const bma_layer_weights& W = s->layers[l];
-    __nv_bfloat16* pre_qk = s->prefix_qk + (size_t)l * D.max_prefix * s->qk_dim;
-    __nv_bfloat16* pre_vt = s->prefix_vt + (size_t)l * s->kv_dim * s->ld_vtp;
-    __nv_bfloat16* qk = prefill ? pre_qk : s->qk;
-    __nv_bfloat16* vt = prefill ? pre_vt : s->vt;
-    const long long ldvt = prefill ? s->ld_vtp : s->ld_vt;
+  __nv_bfloat16* qk = ps.prefill ? layer_pre_qk(s, l) : s->qk;
+  __nv_bfloat16* vt = ps.prefill ? layer_pre_vt(s, l) : s->vt;
+  const long long ldvt = ps.prefill ? s->ld_vtp : s->ld_vt;
+  if (!sandwich || l == 0) {     // sandwich layers > 0 got xn from the previous layer's add_norm
+    ProfScope pr(s, PC_NORM, 0, st);
+    BMA_LAUNCH(launch_rmsnorm(s->x, d, bf(W.norm_attn), s->xn, d, ps.cur_rows, d, D.rms_eps, D.norm_mode,
+                              0, 0, 0, nullptr, st, ps.cur_rows_dev), "rmsnorm(attn)");
+  }
+  GemmParams p{};
+  p.M = ps.cur_rows; p.M_dev = ps.cur_rows_dev; p.N = s->qkv_dim; p.K = d; p.group_m = group_m_for(p.K);
+  p.C = qk; p.ldc = s->qk_dim;
+  p.Vt = vt; p.ldvt = ldvt;
+  p.rope_cos = W.rope_cos; p.rope_sin = W.rope_sin;
+  p.rope_cols = s->qk_dim;
+  p.rows_per_seq = ps.seq; p.pos_base = ps.pos_base;
+  if (ps.n_share > 0) p.row_info = s->row_info;
+  if (D.qk_norm) {
+    p.q_norm_w = bf(W.q_norm); p.k_norm_w = bf(W.k_norm);
+    p.q_cols = s->q_dim; p.qk_norm_eps = D.rms_eps;
+  }
+  ProfScope pr(s, PC_GEMM_QKV, gemm_flops(p), st);
+  if (D.head_dim == 128) {
+    BMA_LAUNCH((launch_gemm_big<EPI_ROPE, 128>(s->xn, d, bf(W.w_qkv), d, p, st)), "gemm(qkv+rope)");
+  } else if (D.head_dim == 64) {
+    BMA_LAUNCH((launch_gemm_big<EPI_ROPE, 64>(s->xn, d, bf(W.w_qkv), d, p, st)), "gemm(qkv+rope)");
+  } else {
+    BMA_LAUNCH((launch_gemm_big<EPI_ROPE, 256>(s->xn, d, bf(W.w_qkv), d, p, st)), "gemm(qkv+rope)");
+  }
+  return 0;
+}
 
-    if (!sandwich || l == 0) {     // sandwich layers > 0 got xn from the previous layer's add_norm
-      ProfScope ps(s, PC_NORM, 0, st);
-      BMA_LAUNCH(launch_rmsnorm(s->x, d, bf(W.norm_attn), s->xn, d, rows, d, D.rms_eps, D.norm_mode,
-                                0, 0, 0, nullptr, st), "rmsnorm(attn)");
-    }
-    {
-      GemmParams p{};
-      p.M = rows; p.N = s->qkv_dim; p.K = d; p.group_m = group_m_for(p.K);
-      p.C = qk; p.ldc = s->qk_dim;
-      p.Vt = vt; p.ldvt = ldvt;
-      p.rope_cos = W.rope_cos; p.rope_sin = W.rope_sin;
-      p.rope_cols = s->qk_dim;
-      p.rows_per_seq = seq; p.pos_base = pos_base;
-      if (ragged) p.row_info = s->row_info;
-      if (D.qk_norm) {
-        p.q_norm_w = bf(W.q_norm); p.k_norm_w = bf(W.k_norm);
-        p.q_cols = s->q_dim; p.qk_norm_eps = D.rms_eps;
-      }
-      ProfScope ps(s, PC_GEMM_QKV, gemm_flops(p), st);
-      if (D.head_dim == 128) {
-        BMA_LAUNCH((launch_gemm_big<EPI_ROPE, 128>(s->xn, d, bf(W.w_qkv), d, p, st)), "gemm(qkv+rope)");
-      } else if (D.head_dim == 64) {
-        BMA_LAUNCH((launch_gemm_big<EPI_ROPE, 64>(s->xn, d, bf(W.w_qkv), d, p, st)), "gemm(qkv+rope)");
-      } else {
-        BMA_LAUNCH((launch_gemm_big<EPI_ROPE, 256>(s->xn, d, bf(W.w_qkv), d, p, st)), "gemm(qkv+rope)");
-      }
-    }
-    if (prefill && l == D.n_layers - 1) break;   // only this layer's K/V are needed
-    if (ragged && append) {
-      ProfScope ps(s, PC_EMBED, 0, st);
-      BMA_LAUNCH(launch_append_prefix_kv(qk + s->q_dim, s->qk_dim, vt, ldvt, pre_qk + s->q_dim, s->qk_dim,
-                                         pre_vt, s->ld_vtp, n_share, s->kv_dim, P, st), "append_prefix_kv");
-    }
-    {
-      AttnParams a{};
-      a.q = qk; a.ldq = s->qk_dim;
-      a.k_tail = qk + s->q_dim; a.ldk = s->qk_dim;
-      a.vt_tail = vt; a.ldvt = ldvt;
-      a.k_pre = pre_qk + s->q_dim; a.ldkp = s->qk_dim;
-      a.vt_pre = pre_vt; a.ldvtp = s->ld_vtp;
-      a.out = s->attn; a.ldo = s->q_dim;
-      a.M = rows; a.S = seq; a.P = P + n_share;
-      if (ragged) { a.row_meta = s->row_meta; a.P_shared = P; }
-      a.kv_group = D.n_heads / D.n_kv_heads;
-      a.head_dim = D.head_dim;
-      a.scale_log2 = D.attn_scale * 1.4426950408889634f;
-      // QK^T and PV over the visible keys: ~4 * rows * (P + seq/2) * q_dim
-      ProfScope ps(s, PC_ATTN, 4.0 * rows * (P + 0.5 * (seq + n_share)) * s->q_dim, st);
-      BMA_LAUNCH(launch_prefix_tail_attention(a, D.n_heads, st), "attention");
-    }
-    if (scored != nullptr && l == D.n_layers - 1) {
-      ProfScope ps(s, PC_EMBED, 0, st);
-      BMA_LAUNCH(launch_gather_rows(s->attn, s->q_dim, s->attn_c, s->q_dim, scored->n, s->q_dim, scored->T, seq,
-                                    scored->ce_row0, scored->vstart, st), "gather(attn rows)");
-      BMA_LAUNCH(launch_gather_rows(s->x, d, s->x_c, d, scored->n, d, scored->T, seq, scored->ce_row0,
-                                    scored->vstart, st), "gather(residual rows)");
-      rows = scored->n;
-      xres = s->x_c;
-      attn_in = s->attn_c;
-    }
-    {
-      GemmParams p{};
-      p.M = rows; p.N = d; p.K = s->q_dim; p.group_m = group_m_for(p.K);
-      if (sandwich) { p.C = s->xn; p.ldc = d; }                       // y: normed before the add
-      else { p.C = xres; p.ldc = d; p.R = xres; p.ldr = d; }
-      ProfScope ps(s, PC_GEMM_O, gemm_flops(p), st);
-      BMA_LAUNCH((launch_gemm_big<EPI_STORE>(attn_in, s->q_dim, bf(W.w_o), s->q_dim, p, st)),
-                 "gemm(o_proj)");
-    }
-    {
-      ProfScope ps(s, PC_NORM, 0, st);
-      if (sandwich) {
-        BMA_LAUNCH(launch_add_norm(s->xn, d, bf(W.norm_post_attn), xres, d, bf(W.norm_mlp), s->xn, d,
-                                   rows, d, D.rms_eps, D.norm_mode, st), "add_norm(post_attn, pre_mlp)");
-      } else {
-        BMA_LAUNCH(launch_rmsnorm(xres, d, bf(W.norm_mlp), s->xn, d, rows, d, D.rms_eps, D.norm_mode,
-                                  0, 0, 0, nullptr, st), "rmsnorm(mlp)");
-      }
-    }
-    {
-      GemmParams p{};
-      p.M = rows; p.N = 2 * D.d_ff; p.K = d; p.group_m = group_m_for(p.K);
-      p.C = s->act; p.ldc = D.d_ff; p.act = D.act;
-      ProfScope ps(s, PC_GEMM_GLU, gemm_flops(p), st);
-      BMA_LAUNCH((launch_gemm_big<EPI_GLU>(s->xn, d, bf(W.w_gate_up), d, p, st)), "gemm(gate_up)");
-    }
-    {
-      GemmParams p{};
-      p.M = rows; p.N = d; p.K = D.d_ff; p.group_m = group_m_for(p.K);
-      if (sandwich) { p.C = s->xn; p.ldc = d; }
-      else { p.C = xres; p.ldc = d; p.R = xres; p.ldr = d; }
-      ProfScope ps(s, PC_GEMM_DOWN, gemm_flops(p), st);
-      BMA_LAUNCH((launch_gemm_big<EPI_STORE>(s->act, D.d_ff, bf(W.w_down), D.d_ff, p, st)),
-                 "gemm(down)");
-    }
+// K rows / V^T columns [0, n) of (k_src, vt_src) -> keys [at, at + n) of (k_dst, vt_dst)
+int copy_kv(bma_scorer* s, const __nv_bfloat16* k_src, long long ldk, const __nv_bfloat16* vt_src, long long ldvt,
+            __nv_bfloat16* k_dst, long long ldkd, __nv_bfloat16* vt_dst, long long ldvtd, int n, int at,
+            cudaStream_t st) {
+  if (n <= 0) return 0;
+  BMA_LAUNCH(launch_append_prefix_kv(k_src, ldk, vt_src, ldvt, k_dst, ldkd, vt_dst, ldvtd, n, s->kv_dim, at, st),
+             "append_prefix_kv");
+  return 0;
+}
+
+// Split prefill, step 1: this rank's prefix-position K/V of layer l -> its contiguous send block
+// [pre_chunk x kv_dim K rows | kv_dim x pre_chunk V^T].
+int layer_pack(bma_scorer* s, int l, const Pass& ps, cudaStream_t st) {
+  (void)l;
+  ProfScope pr(s, PC_EMBED, 0, st);
+  return copy_kv(s, s->qk + s->q_dim, s->qk_dim, s->vt, s->ld_vt, s->xchg_send, s->kv_dim,
+                 s->xchg_send + (size_t)ps.pre_chunk * s->kv_dim, ps.pre_chunk, ps.pre_n, 0, st);
+}
+// Split prefill, step 2: rank q's send block -> prefix keys [q pre_chunk, ...) of layer l.
+int layer_unpack(bma_scorer* s, int l, const Pass& ps, const __nv_bfloat16* block, int q, int P, cudaStream_t st) {
+  const int at = q * ps.pre_chunk;
+  const int n = P - at < ps.pre_chunk ? P - at : ps.pre_chunk;
+  ProfScope pr(s, PC_EMBED, 0, st);
+  return copy_kv(s, block, s->kv_dim, block + (size_t)ps.pre_chunk * s->kv_dim, ps.pre_chunk,
+                 layer_pre_qk(s, l) + s->q_dim, s->qk_dim, layer_pre_vt(s, l), s->ld_vtp, n, at, st);
+}
+// The base suffix's first n_share rows (they follow the prefix rows) -> prefix keys [P, P + n_share).
+int layer_publish_base(bma_scorer* s, int l, const Pass& ps, int P, cudaStream_t st) {
+  ProfScope pr(s, PC_EMBED, 0, st);
+  return copy_kv(s, s->qk + (size_t)ps.pre_n * s->qk_dim + s->q_dim, s->qk_dim, s->vt + ps.pre_n, s->ld_vt,
+                 layer_pre_qk(s, l) + s->q_dim, s->qk_dim, layer_pre_vt(s, l), s->ld_vtp, ps.n_share, P, st);
+}
+// Everything a single rank publishes in one copy: prefix rows [0, pre_n) (pre0 == 0) + the base rows.
+int layer_publish_local(bma_scorer* s, int l, const Pass& ps, int P, cudaStream_t st) {
+  ProfScope pr(s, PC_EMBED, 0, st);
+  return copy_kv(s, s->qk + s->q_dim, s->qk_dim, s->vt, s->ld_vt, layer_pre_qk(s, l) + s->q_dim, s->qk_dim,
+                 layer_pre_vt(s, l), s->ld_vtp, ps.pre_n + ps.n_share, P - ps.pre_n, st);
+}
+
+// attention, o_proj, MLP. Returns 1 when the pass is complete after this layer's front half
+// (prefill of the last layer).
+int layer_back(bma_scorer* s, int l, Pass& ps, cudaStream_t st) {
+  const bma_model_desc& D = s->desc;
+  const int d = D.d_model;
+  const bma_layer_weights& W = s->layers[l];
+  const bool sandwich = D.sandwich_norm != 0;
+  const bool ragged = ps.n_share > 0;
+  const int P = ps.prefill ? 0 : s->prefix_len;
+  __nv_bfloat16* pre_qk = layer_pre_qk(s, l);
+  __nv_bfloat16* pre_vt = layer_pre_vt(s, l);
+  __nv_bfloat16* qk = ps.prefill ? pre_qk : s->qk;
+  __nv_bfloat16* vt = ps.prefill ? pre_vt : s->vt;
+  const long long ldvt = ps.prefill ? s->ld_vtp : s->ld_vt;
+  {
+    AttnParams a{};
+    a.q = qk; a.ldq = s->qk_dim;
+    a.k_tail = qk + s->q_dim; a.ldk = s->qk_dim;
+    a.vt_tail = vt; a.ldvt = ldvt;
+    a.k_pre = pre_qk + s->q_dim; a.ldkp = s->qk_dim;
+    a.vt_pre = pre_vt; a.ldvtp = s->ld_vtp;
+    a.out = s->attn; a.ldo = s->q_dim;
+    a.M = ps.cur_rows; a.M_dev = ps.cur_rows_dev; a.S = ps.seq; a.P = P + ps.n_share;
+    if (ragged) { a.row_meta = s->row_meta; a.P_shared = P; a.pre_rows = ps.pre_n; }
+    a.kv_group = D.n_heads / D.n_kv_heads;
+    a.head_dim = D.head_dim;
+    a.scale_log2 = D.attn_scale * 1.4426950408889634f;
+    // QK^T and PV over the visible keys: ~4 * rows * (P + seq/2) * q_dim
+    ProfScope pr(s, PC_ATTN, 4.0 * ps.cur_rows * (P + 0.5 * (ps.seq + ps.n_share)) * s->q_dim, st);
+    BMA_LAUNCH(launch_prefix_tail_attention(a, D.n_heads, st), "attention");
+  }
+  const ScoredRows* scored = ps.scored;
+  if (scored != nullptr && l == D.n_layers - 1) {
+    ProfScope pr(s, PC_EMBED, 0, st);
+    BMA_LAUNCH(launch_gather_rows(s->attn, s->q_dim, s->attn_c, s->q_dim, scored->n, s->q_dim, scored->T, ps.seq,
+                                  scored->ce_row0, scored->vstart, st), "gather(attn rows)");
+    BMA_LAUNCH(launch_gather_rows(s->x, d, s->x_c, d, scored->n, d, scored->T, ps.seq, scored->ce_row0,
+                                  scored->vstart, st), "gather(residual rows)");
+    ps.cur_rows = scored->n; ps.cur_rows_dev = nullptr;
+    ps.xres = s->x_c;
+    ps.attn_in = s->attn_c;
+  }
+  const int rows = ps.cur_rows;
+  const int* rows_dev = ps.cur_rows_dev;
+  __nv_bfloat16* xres = ps.xres;
+  {
+    GemmParams p{};
+    p.M = rows; p.M_dev = rows_dev; p.N = d; p.K = s->q_dim; p.group_m = group_m_for(p.K);
+    if (sandwich) { p.C = s->xn; p.ldc = d; }                       // y: normed before the add
+    else { p.C = xres; p.ldc = d; p.R = xres; p.ldr = d; }
+    ProfScope pr(s, PC_GEMM_O, gemm_flops(p), st);
+    BMA_LAUNCH((launch_gemm_big<EPI_STORE>(ps.attn_in, s->q_dim, bf(W.w_o), s->q_dim, p, st)),
+               "gemm(o_proj)");
+  }
+  {
+    ProfScope pr(s, PC_NORM, 0, st);
     if (sandwich) {
-      const __nv_bfloat16* next = (l + 1 < D.n_layers) ? bf(s->layers[l + 1].norm_attn) : nullptr;
-      ProfScope ps(s, PC_NORM, 0, st);
-      BMA_LAUNCH(launch_add_norm(s->xn, d, bf(W.norm_post_mlp), xres, d, next, s->xn, d, rows, d,
-                                 D.rms_eps, D.norm_mode, st), "add_norm(post_mlp, next input)");
+      BMA_LAUNCH(launch_add_norm(s->xn, d, bf(W.norm_post_attn), xres, d, bf(W.norm_mlp), s->xn, d,
+                                 rows, d, D.rms_eps, D.norm_mode, st, rows_dev), "add_norm(post_attn, pre_mlp)");
+    } else {
+      BMA_LAUNCH(launch_rmsnorm(xres, d, bf(W.norm_mlp), s->xn, d, rows, d, D.rms_eps, D.norm_mode,
+                                0, 0, 0, nullptr, st, rows_dev), "rmsnorm(mlp)");
     }
+  }
+  {
+    GemmParams p{};
+    p.M = rows; p.M_dev = rows_dev; p.N = 2 * D.d_ff; p.K = d; p.group_m = group_m_for(p.K);
+    p.C = s->act; p.ldc = D.d_ff; p.act = D.act;
+    ProfScope pr(s, PC_GEMM_GLU, gemm_flops(p), st);
+    BMA_LAUNCH((launch_gemm_big<EPI_GLU>(s->xn, d, bf(W.w_gate_up), d, p, st)), "gemm(gate_up)");
+  }
+  {
+    GemmParams p{};
+    p.M = rows; p.M_dev = rows_dev; p.N = d; p.K = D.d_ff; p.group_m = group_m_for(p.K);
+    if (sandwich) { p.C = s->xn; p.ldc = d; }
+    else { p.C = xres; p.ldc = d; p.R = xres; p.ldr = d; }
+    ProfScope pr(s, PC_GEMM_DOWN, gemm_flops(p), st);
+    BMA_LAUNCH((launch_gemm_big<EPI_STORE>(s->act, D.d_ff, bf(W.w_down), D.d_ff, p, st)),
+               "gemm(down)");
+  }
+  if (sandwich) {
+    const __nv_bfloat16* next = (l + 1 < D.n_layers) ? bf(s->layers[l + 1].norm_attn) : nullptr;
+    ProfScope pr(s, PC_NORM, 0, st);
+    BMA_LAUNCH(launch_add_norm(s->xn, d, bf(W.norm_post_mlp), xres, d, next, s->xn, d, rows, d,
+                               D.rms_eps, D.norm_mode, st, rows_dev), "add_norm(post_mlp, next input)");
+  }
+  return 0;
+}
+
+// A whole pass on ONE scorer (no other scorer takes part in the prefix exchange except through `comm`).
+int run_layers(bma_scorer* s, Pass& ps, cudaStream_t st) {
+  const bma_model_desc& D = s->desc;
+  pass_start(s, ps);
+  const int P = s->prefix_len;
+  for (int l = 0; l < D.n_layers; ++l) {
+    int rc = layer_front(s, l, ps, st);
+    if (rc != 0) return rc;
+    if (ps.prefill && l == D.n_layers - 1) break;   // only this layer's K/V are needed
+    if (ps.publish) {
+      if (ps.pre_chunk > 0) {                        // prefix positions split over the ranks of comm
+        rc = layer_pack(s, l, ps, st);
+        if (rc != 0) return rc;
+        const size_t blk = 2 * (size_t)ps.pre_chunk * s->kv_dim;
+        {
+          ProfScope pr(s, PC_EMBED, 0, st);
+          rc = comm_allgather_bytes(s->comm, s->xchg_send, s->xchg_recv, blk * sizeof(__nv_bfloat16), st);
+          if (rc != 0) return fail(cudaErrorUnknown, "prefix K/V all-gather (NCCL)");
+        }
+        for (int q = 0; q < comm_size(s->comm); ++q) {
+          rc = layer_unpack(s, l, ps, s->xchg_recv + q * blk, q, P, st);
+          if (rc != 0) return rc;
+        }
+        rc = layer_publish_base(s, l, ps, P, st);
+      } else {
+        rc = layer_publish_local(s, l, ps, P, st);
+      }
+      if (rc != 0) return rc;
+    }
+    rc = layer_back(s, l, ps, st);
+    if (rc != 0) return rc;
   }
   return 0;
 }
@@ -380,6 +518,7 @@ bma_scorer* bma_scorer_create(const bma_model_desc* desc) {
   ok = ok && dev_alloc(&s->cand_vstart, static_cast<size_t>(D.max_rows) + 1, &s->ws_bytes);
   ok = ok && dev_alloc(&s->cand_tmp, static_cast<size_t>(D.max_rows) + 1, &s->ws_bytes);
   ok = ok && dev_alloc(&s->total_rows_dev, 1, &s->ws_bytes);
+  ok = ok && dev_alloc(&s->rows_accum_dev, 1, &s->ws_bytes);
   ok = ok && dev_alloc(&s->base_dev, 4096, &s->ws_bytes);
   ok = ok && cudaHostAlloc(reinterpret_cast<void**>(&s->total_rows_host), sizeof(int), cudaHostAllocDefault) == cudaSuccess;
   ok = ok && dev_alloc(&s->ids_dev, static_cast<size_t>(D.max_rows), &s->ws_bytes);
@@ -397,7 +536,8 @@ bma_scorer* bma_scorer_create(const bma_model_desc* desc) {
 void bma_scorer_destroy(bma_scorer* s) {
   if (s == nullptr) return;
   cudaFree(s->x); cudaFree(s->xn); cudaFree(s->qk); cudaFree(s->vt); cudaFree(s->attn); cudaFree(s->act);
-  cudaFree(s->prefix_qk); cudaFree(s->prefix_vt); cudaFree(s->ce_part); cudaFree(s->tgt_logit);
+  cudaFree(s->prefix_qk); cudaFree(s->prefix_vt); cudaFree(s->ce_part); cudaFree(s->ce_arg); cudaFree(s->tgt_logit);
+  cudaFree(s->xchg_send); cudaFree(s->xchg_recv); cudaFree(s->rows_accum_dev);
   cudaFree(s->x_c); cudaFree(s->attn_c);
   cudaFree(s->row_info); cudaFree(s->row_meta); cudaFree(s->cand_vstart); cudaFree(s->cand_tmp); cudaFree(s->total_rows_dev);
   cudaFree(s->base_dev);
@@ -465,12 +605,24 @@ int bma_scorer_set_head(bma_scorer* s, const void* norm_final, const void* lm_he
 int bma_scorer_prefill(bma_scorer* s, const void* prefix_embeds, int P, void* stream) {
   if (s == nullptr) return fail(cudaErrorInvalidValue, "prefill: null scorer");
   if (P < 0 || P > s->desc.max_prefix) return fail(cudaErrorInvalidValue, "prefill: P exceeds max_prefix");
+  s->pending_prefix = nullptr; s->pending_P = 0;
   s->prefix_len = P;
   if (P == 0) return 0;
   cudaStream_t st = as_stream(stream);
   BMA_CHECK(cudaMemcpyAsync(s->x, prefix_embeds, (size_t)P * s->desc.d_model * sizeof(__nv_bfloat16),
                             cudaMemcpyDeviceToDevice, st), "prefill: copy embeds");
-  return run_layers(s, P, P, 0, true, st);
+  Pass ps;
+  ps.rows = P; ps.seq = P; ps.pos_base = 0; ps.prefill = true;
+  return run_layers(s, ps, st);
+}
+
+int bma_scorer_prefill_deferred(bma_scorer* s, const void* prefix_embeds, int P) {
+  if (s == nullptr) return fail(cudaErrorInvalidValue, "prefill_deferred: null scorer");
+  if (P < 0 || P > s->desc.max_prefix) return fail(cudaErrorInvalidValue, "prefill_deferred: P exceeds max_prefix");
+  s->prefix_len = P;
+  s->pending_prefix = P > 0 ? bf(prefix_embeds) : nullptr;
+  s->pending_P = P > 0 ? P : 0;
+  return 0;
 }
 
 int bma_scorer_reset_key(bma_scorer* s, unsigned long long* key, int* all_match, void* stream) {
@@ -479,7 +631,12 @@ int bma_scorer_reset_key(bma_scorer* s, unsigned long long* key, int* all_match,
   return 0;
 }
 
-long long bma_scorer_last_rows(const bma_scorer* s) { return s ? s->last_rows : 0; }
+long long bma_scorer_last_rows(const bma_scorer* s) {
+  if (s == nullptr) return 0;
+  unsigned long long ragged = 0;     // synchronising read: the ragged chunks counted their rows on the device
+  if (cudaMemcpy(&ragged, s->rows_accum_dev, sizeof(ragged), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return s->last_rows + static_cast<long long>(ragged);
+}
 
 int bma_scorer_set_dedupe(bma_scorer* s, int enable) {
   if (s == nullptr) return fail(cudaErrorInvalidValue, "set_dedupe: null scorer");
@@ -487,89 +644,295 @@ int bma_scorer_set_dedupe(bma_scorer* s, int enable) {
   return 0;
 }
 
-int bma_scorer_score(bma_scorer* s, const long long* ids, int ids_stride, int B, const int* slot,
-                     const void* fixed, int S, const long long* target_ids, int T, int ce_row0,
-                     float* loss, unsigned long long* key, int* all_match, unsigned int idx_base,
-                     const long long* base_ids, void* stream) {
-  if (s == nullptr) return fail(cudaErrorInvalidValue, "score: null scorer");
-  const bma_model_desc& D = s->desc;
-  if (B <= 0) return 0;
-  if (S <= 0 || T <= 0 || ce_row0 < 0 || ce_row0 + T > S)
-    return fail(cudaErrorInvalidValue, "score: target rows [ce_row0, ce_row0+T) must lie inside the tail");
-  if (S > D.max_rows) return fail(cudaErrorInvalidValue, "score: S exceeds max_rows");
-  if (s->lm_head == nullptr || s->norm_final == nullptr || s->embed == nullptr)
-    return fail(cudaErrorInvalidValue, "score: head weights not set");
-  cudaStream_t st = as_stream(stream);
-  const int d = D.d_model;
-  const int n_ce_tiles = (D.vocab + kCeBlockN - 1) / kCeBlockN;
-  s->last_rows = 0;
+}  // extern "C"
 
-  // Suffix-head sharing: rows [0, n_share) of the tail can coincide with the base's rows; n_share
-  // is one past the last id-dependent tail position. Needs room for the base (one extra sequence
-  // per chunk, n_share extra prefix keys) and the shared rows must precede the scored rows.
+namespace {
+
+struct ScoreArgs {
+  const long long* ids; int ids_stride; int B; const int* slot; const void* fixed; int S;
+  const long long* target_ids; int T; int ce_row0; float* loss; unsigned long long* key; int* all_match;
+  unsigned int idx_base; const long long* base_ids; int n_id_rows;
+};
+
+// Ragged-mode geometry of one score call on one scorer.
+struct ScorePlan {
   int n_share = 0;
-  if (base_ids != nullptr) {
-    std::vector<int> slot_h(S);
-    BMA_CHECK(cudaMemcpyAsync(slot_h.data(), slot, sizeof(int) * S, cudaMemcpyDeviceToHost, st), "score: slot D2H");
-    BMA_CHECK(cudaStreamSynchronize(st), "score: sync");
-    for (int i = 0; i < S; ++i)
-      if (slot_h[i] >= 0) n_share = i + 1;
-    if (n_share > ce_row0) n_share = ce_row0;      // scored rows are always the candidate's own
-    if (s->prefix_len + n_share > D.max_prefix || 2 * S > D.max_rows) n_share = 0;
+  bool ragged = false, fused = false;
+  int chunk = 0;            // candidates per chunk
+  int pre0 = 0, pre_n = 0, pre_chunk = 0;
+};
+
+int plan_score(bma_scorer* s, const ScoreArgs& a, ScorePlan& sp, int rank, int size) {
+  const bma_model_desc& D = s->desc;
+  // Suffix-head sharing: rows [0, n_share) of the tail can coincide with the base's rows; n_share is
+  // one past the last id-dependent tail position (the host knows its slot table). Needs room for the
+  // base (one extra sequence per chunk, n_share extra prefix keys); shared rows precede the scored rows.
+  int n_share = 0;
+  if (a.base_ids != nullptr) {
+    n_share = a.n_id_rows < 0 ? 0 : a.n_id_rows;
+    if (n_share > a.ce_row0) n_share = a.ce_row0;      // scored rows are always the candidate's own
+    if (s->prefix_len + n_share > D.max_prefix || 2 * a.S > D.max_rows) n_share = 0;
   }
-  const bool ragged = n_share > 0;
-  int chunk = ragged ? D.max_rows / S - 1 : D.max_rows / S;
-  if (ragged && chunk > 8190) chunk = 8190;              // plan_rows handles 8 entries per thread
-  {
-    const int rc = ensure_ce_rows(s, (B < chunk ? B : chunk) * T);
-    if (rc != 0) return rc;
+  sp.n_share = n_share;
+  sp.ragged = n_share > 0;
+  sp.fused = sp.ragged && s->pending_prefix != nullptr;
+  if (sp.fused) {
+    const int P = s->pending_P;
+    if (size > 1) {
+      sp.pre_chunk = (P + size - 1) / size;
+      sp.pre0 = rank * sp.pre_chunk < P ? rank * sp.pre_chunk : P;
+      sp.pre_n = P - sp.pre0 < sp.pre_chunk ? P - sp.pre0 : sp.pre_chunk;
+    } else {
+      sp.pre0 = 0; sp.pre_n = P;
+    }
+    if (sp.pre_n + 2 * a.S > D.max_rows) { sp.fused = false; sp.pre0 = sp.pre_n = sp.pre_chunk = 0; }
   }
-  for (int b0 = 0; b0 < B; b0 += chunk) {
-    const int nb = B - b0 < chunk ? B - b0 : chunk;
-    int rows = nb * S;
-    const long long* ids_c = ids + (long long)b0 * ids_stride;
-    if (ragged) {
-      // every chunk carries the base as sequence 0: its rows are the keys [P, P+n_share) source
-      ProfScope ps(s, PC_EMBED, 0, st);
-      BMA_LAUNCH(launch_plan_rows(ids_c, ids_stride, base_ids, slot, S, n_share, nb, 1, s->prefix_len, s->dedupe,
-                                  s->row_info, s->row_meta, s->cand_vstart, s->cand_tmp, s->total_rows_dev, st),
-                 "plan_rows");
+  sp.chunk = sp.ragged ? (D.max_rows - sp.pre_n) / a.S - 1 : D.max_rows / a.S;
+  if (sp.ragged && sp.chunk > 8190) sp.chunk = 8190;              // plan_rows handles 8 entries per thread
+  if (sp.chunk < 1) return fail(cudaErrorInvalidValue, "score: workspace too small for one candidate");
+  return 0;
+}
+
+int ensure_xchg(bma_scorer* s, int pre_chunk, int size) {
+  const size_t need = 2 * (size_t)pre_chunk * s->kv_dim;
+  if (need <= s->xchg_elems) return 0;
+  BMA_CHECK(cudaDeviceSynchronize(), "ensure_xchg: sync");
+  cudaFree(s->xchg_send); cudaFree(s->xchg_recv);
+  s->xchg_send = s->xchg_recv = nullptr; s->xchg_elems = 0;
+  size_t bytes = 0;
+  if (!dev_alloc(&s->xchg_send, need, &bytes) || !dev_alloc(&s->xchg_recv, need * size, &bytes))
+    return fail(cudaGetLastError(), "ensure_xchg: cudaMalloc");
+  s->ws_bytes += bytes;
+  s->xchg_elems = need;
+  return 0;
+}
+
+// Rows + embeddings of chunk [b0, b0 + nb) (nb may be 0 on a rank that only contributes prefix rows).
+int chunk_begin(bma_scorer* s, const ScoreArgs& a, const ScorePlan& sp, int b0, int nb, bool first, Pass& ps,
+                ScoredRows& scored, cudaStream_t st) {
+  const bma_model_desc& D = s->desc;
+  const int d = D.d_model;
+  const long long* ids_c = a.ids + (long long)b0 * a.ids_stride;
+  const bool fused = sp.fused && first;
+  ps = Pass{};
+  ps.seq = a.S; ps.pos_base = s->prefix_len;
+  ps.rows = nb * a.S;
+  if (sp.ragged) {
+    ps.n_share = sp.n_share;
+    ps.publish = true;          // every chunk carries the base as its first sequence
+    if (fused) { ps.pre0 = sp.pre0; ps.pre_n = sp.pre_n; ps.pre_chunk = sp.pre_chunk; }
+    ProfScope pr(s, PC_EMBED, 0, st);
+    BMA_LAUNCH(launch_plan_rows(ids_c, a.ids_stride, a.base_ids, a.slot, a.S, sp.n_share, nb, 1, s->prefix_len,
+                                s->dedupe, ps.pre0, ps.pre_n, s->row_info, s->row_meta, s->cand_vstart,
+                                s->cand_tmp, s->total_rows_dev, s->rows_accum_dev, st), "plan_rows");
+    ps.rows = ps.pre_n + (nb + 1) * a.S;               // upper bound; the live count stays on the device
+    ps.rows_dev = s->total_rows_dev;
+    if (s->profiling) {
+      // the per-class profile wants exact FLOPs: fetch the row count (profiling passes only)
       BMA_CHECK(cudaMemcpyAsync(s->total_rows_host, s->total_rows_dev, sizeof(int), cudaMemcpyDeviceToHost, st),
                 "score: row count D2H");
       BMA_CHECK(cudaStreamSynchronize(st), "score: sync");
-      rows = *s->total_rows_host;
-      if (rows <= 0 || rows > D.max_rows) return fail(cudaErrorInvalidValue, "score: bad ragged row count");
+      ps.rows = *s->total_rows_host;
+      if (ps.rows <= 0 || ps.rows > D.max_rows) return fail(cudaErrorInvalidValue, "score: bad ragged row count");
     }
-    s->last_rows += rows;
-    {
-      ProfScope ps(s, PC_EMBED, 0, st);
-      BMA_LAUNCH(launch_build_tail_embeds(ids_c, ids_stride, slot, bf(fixed), s->embed, s->ld_embed, D.vocab,
-                                          D.embed_scale, s->x, rows, S, d, ragged ? s->row_info : nullptr,
-                                          base_ids, st), "build_tail_embeds");
-    }
-    // the T rows per candidate whose logits predict the target tokens
-    const int ce_rows = nb * T;
-    const ScoredRows scored{ce_rows, T, ce_row0, ragged ? s->cand_vstart : nullptr};
-    int rc = run_layers(s, rows, S, s->prefix_len, false, st, n_share, ragged, &scored);
+  } else {
+    s->last_rows += ps.rows;
+  }
+  {
+    ProfScope pr(s, PC_EMBED, 0, st);
+    BMA_LAUNCH(launch_build_tail_embeds(ids_c, a.ids_stride, a.slot, bf(a.fixed), s->embed, s->ld_embed, D.vocab,
+                                        D.embed_scale, s->x, ps.rows, a.S, d, sp.ragged ? s->row_info : nullptr,
+                                        a.base_ids, fused ? s->pending_prefix : nullptr, s->prefix_len,
+                                        ps.rows_dev, st), "build_tail_embeds");
+  }
+  scored = ScoredRows{nb * a.T, a.T, a.ce_row0, sp.ragged ? s->cand_vstart : nullptr};
+  ps.scored = nb > 0 ? &scored : nullptr;
+  return 0;
+}
+
+// final norm + LM head fused with CE + per-candidate finalise of chunk [b0, b0 + nb)
+int chunk_end(bma_scorer* s, const ScoreArgs& a, int b0, int nb, cudaStream_t st) {
+  if (nb <= 0) return 0;
+  const bma_model_desc& D = s->desc;
+  const int d = D.d_model;
+  const int n_ce_tiles = (D.vocab + kCeBlockN - 1) / kCeBlockN;
+  const int ce_rows = nb * a.T;
+  {                                            // final norm: the scored rows are contiguous in x_c
+    ProfScope pr(s, PC_NORM, 0, st);
+    BMA_LAUNCH(launch_rmsnorm(s->x_c, d, s->norm_final, s->xn, d, ce_rows, d, D.rms_eps, D.norm_mode,
+                              0, 0, 0, nullptr, st), "rmsnorm(final)");
+  }
+  {
+    GemmParams p{};
+    p.M = ce_rows; p.N = D.vocab; p.K = d; p.group_m = group_m_for(p.K);
+    p.target_ids = a.target_ids; p.T = a.T;
+    p.ce_part = s->ce_part; p.tgt_logit = s->tgt_logit;
+    p.ce_arg = a.all_match != nullptr ? s->ce_arg : nullptr;
+    ProfScope pr(s, PC_GEMM_CE, gemm_flops(p), st);
+    BMA_LAUNCH((launch_gemm_big<EPI_CE>(s->xn, d, s->lm_head, d, p, st)), "gemm(lm_head+ce)");
+  }
+  {
+    ProfScope pr(s, PC_FINAL, 0, st);
+    BMA_LAUNCH(launch_ce_finalize(s->ce_part, s->tgt_logit, a.all_match != nullptr ? s->ce_arg : nullptr,
+                                  a.target_ids, n_ce_tiles, nb, a.T, a.loss + b0, a.key,
+                                  a.all_match, a.idx_base + static_cast<unsigned int>(b0), st),
+               "ce_finalize");
+  }
+  return 0;
+}
+
+int check_score_args(bma_scorer* s, const ScoreArgs& a) {
+  if (s == nullptr) return fail(cudaErrorInvalidValue, "score: null scorer");
+  const bma_model_desc& D = s->desc;
+  if (a.S <= 0 || a.T <= 0 || a.ce_row0 < 0 || a.ce_row0 + a.T > a.S)
+    return fail(cudaErrorInvalidValue, "score: target rows [ce_row0, ce_row0+T) must lie inside the tail");
+  if (a.S > D.max_rows) return fail(cudaErrorInvalidValue, "score: S exceeds max_rows");
+  if (s->lm_head == nullptr || s->norm_final == nullptr || s->embed == nullptr)
+    return fail(cudaErrorInvalidValue, "score: head weights not set");
+  return 0;
+}
+
+// The score call of ONE scorer (rank `rank` of `size` when a communicator is attached).
+int score_one(bma_scorer* s, const ScoreArgs& a, cudaStream_t st, bool reset_counters = true) {
+  int rc = check_score_args(s, a);
+  if (rc != 0) return rc;
+  const int size = s->comm != nullptr ? comm_size(s->comm) : 1;
+  const int rank = s->comm != nullptr ? comm_rank(s->comm) : 0;
+  if (a.B <= 0 && !(size > 1 && s->pending_prefix != nullptr && a.base_ids != nullptr)) return 0;
+  if (reset_counters) {
+    s->last_rows = 0;
+    BMA_CHECK(cudaMemsetAsync(s->rows_accum_dev, 0, sizeof(unsigned long long), st), "score: reset row counter");
+  }
+  ScorePlan sp;
+  rc = plan_score(s, a, sp, rank, size);
+  if (rc != 0) return rc;
+  if (s->pending_prefix != nullptr && !sp.fused) {      // no ragged pass to ride in: prefill now
+    rc = bma_scorer_prefill(s, s->pending_prefix, s->pending_P, st);
     if (rc != 0) return rc;
-    {                                            // final norm: the scored rows are contiguous in x_c
-      ProfScope ps(s, PC_NORM, 0, st);
-      BMA_LAUNCH(launch_rmsnorm(s->x_c, d, s->norm_final, s->xn, d, ce_rows, d, D.rms_eps, D.norm_mode,
-                                0, 0, 0, nullptr, st), "rmsnorm(final)");
+  }
+  if (sp.fused && sp.pre_chunk > 0) {
+    rc = ensure_xchg(s, sp.pre_chunk, size);
+    if (rc != 0) return rc;
+  }
+  {
+    const int most = a.B < sp.chunk ? a.B : sp.chunk;
+    rc = ensure_ce_rows(s, (most > 0 ? most : 1) * a.T);
+    if (rc != 0) return rc;
+  }
+  bool first = true;
+  for (int b0 = 0; b0 < a.B || first; b0 += sp.chunk) {
+    const int nb = a.B - b0 < sp.chunk ? a.B - b0 : sp.chunk;
+    Pass ps; ScoredRows scored;
+    rc = chunk_begin(s, a, sp, b0, nb, first, ps, scored, st);
+    if (rc != 0) return rc;
+    rc = run_layers(s, ps, st);
+    if (rc != 0) return rc;
+    rc = chunk_end(s, a, b0, nb, st);
+    if (rc != 0) return rc;
+    first = false;
+  }
+  if (sp.fused) { s->pending_prefix = nullptr; s->pending_P = 0; }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bma_scorer_score(bma_scorer* s, const long long* ids, int ids_stride, int B, const int* slot,
+                     const void* fixed, int S, const long long* target_ids, int T, int ce_row0,
+                     float* loss, unsigned long long* key, int* all_match, unsigned int idx_base,
+                     const long long* base_ids, int n_id_rows, void* stream) {
+  const ScoreArgs a{ids, ids_stride, B, slot, fixed, S, target_ids, T, ce_row0, loss, key, all_match,
+                    idx_base, base_ids, n_id_rows};
+  return score_one(s, a, as_stream(stream));
+}
+
+// Test / single-process form of the multi-rank path: `n` scorers (same model, same deferred prefix)
+// act as the ranks of one box on ONE device. Rank r scores the contiguous shard r of the B candidates
+// (first ranks take the extras, like bimodalattack_b200.dist.shard_bounds) and computes the r-th slice
+// of the prefix positions; the per-layer K/V exchange is a set of local copies instead of an NCCL
+// all-gather. Everything else is the code path of a real rank.
+int bma_scorer_group_score(bma_scorer** group, int n, const long long* ids, int ids_stride, int B,
+                           const int* slot, const void* fixed, int S, const long long* target_ids, int T,
+                           int ce_row0, float* loss, unsigned long long* key, int* all_match,
+                           const long long* base_ids, int n_id_rows, void* stream) {
+  if (group == nullptr || n <= 0) return fail(cudaErrorInvalidValue, "group_score: empty group");
+  cudaStream_t st = as_stream(stream);
+  std::vector<ScoreArgs> args(n);
+  std::vector<ScorePlan> plans(n);
+  std::vector<Pass> pass(n);
+  std::vector<ScoredRows> scored(n);
+  std::vector<int> nb0(n);
+  const int base = B / n, extra = B % n;
+  bool fused = true;
+  for (int r = 0; r < n; ++r) {
+    bma_scorer* s = group[r];
+    const int lo = r * base + (r < extra ? r : extra), cnt = base + (r < extra ? 1 : 0);
+    args[r] = ScoreArgs{ids + (long long)lo * ids_stride, ids_stride, cnt, slot, fixed, S, target_ids, T, ce_row0,
+                        loss + lo, key, all_match, static_cast<unsigned int>(lo), base_ids, n_id_rows};
+    int rc = check_score_args(s, args[r]);
+    if (rc != 0) return rc;
+    s->last_rows = 0;
+    BMA_CHECK(cudaMemsetAsync(s->rows_accum_dev, 0, sizeof(unsigned long long), st), "group_score: reset");
+    rc = plan_score(s, args[r], plans[r], r, n);
+    if (rc != 0) return rc;
+    fused = fused && plans[r].fused && plans[r].pre_chunk == plans[0].pre_chunk;
+  }
+  if (!fused || n == 1) {                     // nothing to exchange: every scorer runs on its own
+    for (int r = 0; r < n; ++r) {
+      if (n > 1 && group[r]->pending_prefix != nullptr) {
+        int rc = bma_scorer_prefill(group[r], group[r]->pending_prefix, group[r]->pending_P, stream);
+        if (rc != 0) return rc;
+      }
+      int rc = score_one(group[r], args[r], st);
+      if (rc != 0) return rc;
     }
-    {
-      GemmParams p{};
-      p.M = ce_rows; p.N = D.vocab; p.K = d; p.group_m = group_m_for(p.K);
-      p.target_ids = target_ids; p.T = T;
-      p.ce_part = s->ce_part; p.tgt_logit = s->tgt_logit;
-      ProfScope ps(s, PC_GEMM_CE, gemm_flops(p), st);
-      BMA_LAUNCH((launch_gemm_big<EPI_CE>(s->xn, d, s->lm_head, d, p, st)), "gemm(lm_head+ce)");
+    return 0;
+  }
+  const int P = group[0]->pending_P;
+  for (int r = 0; r < n; ++r) {
+    bma_scorer* s = group[r];
+    int rc = ensure_xchg(s, plans[r].pre_chunk, 1);
+    if (rc != 0) return rc;
+    const int most = args[r].B < plans[r].chunk ? args[r].B : plans[r].chunk;
+    rc = ensure_ce_rows(s, (most > 0 ? most : 1) * T);
+    if (rc != 0) return rc;
+    nb0[r] = most > 0 ? most : 0;
+    rc = chunk_begin(s, args[r], plans[r], 0, nb0[r], true, pass[r], scored[r], st);
+    if (rc != 0) return rc;
+    pass_start(s, pass[r]);
+  }
+  const int L = group[0]->desc.n_layers;
+  for (int l = 0; l < L; ++l) {
+    for (int r = 0; r < n; ++r) {
+      int rc = layer_front(group[r], l, pass[r], st);
+      if (rc != 0) return rc;
+      rc = layer_pack(group[r], l, pass[r], st);
+      if (rc != 0) return rc;
     }
-    {
-      ProfScope ps(s, PC_FINAL, 0, st);
-      BMA_LAUNCH(launch_ce_finalize(s->ce_part, s->tgt_logit, n_ce_tiles, nb, T, loss + b0, key,
-                                    all_match, idx_base + static_cast<unsigned int>(b0), st),
-                 "ce_finalize");
+    for (int r = 0; r < n; ++r) {
+      for (int q = 0; q < n; ++q) {           // the all-gather, as local copies
+        int rc = layer_unpack(group[r], l, pass[r], group[q]->xchg_send, q, P, st);
+        if (rc != 0) return rc;
+      }
+      int rc = layer_publish_base(group[r], l, pass[r], P, st);
+      if (rc != 0) return rc;
+      rc = layer_back(group[r], l, pass[r], st);
+      if (rc != 0) return rc;
+    }
+  }
+  for (int r = 0; r < n; ++r) {
+    bma_scorer* s = group[r];
+    int rc = chunk_end(s, args[r], 0, nb0[r], st);
+    if (rc != 0) return rc;
+    s->pending_prefix = nullptr; s->pending_P = 0;
+    if (args[r].B > nb0[r]) {                 // remaining chunks of this rank need no exchange
+      ScoreArgs rest = args[r];
+      rest.ids += (long long)nb0[r] * ids_stride; rest.B -= nb0[r]; rest.loss += nb0[r];
+      rest.idx_base += static_cast<unsigned int>(nb0[r]);
+      rc = score_one(s, rest, st, false);
+      if (rc != 0) return rc;
     }
   }
   return 0;
@@ -578,7 +941,7 @@ int bma_scorer_score(bma_scorer* s, const long long* ids, int ids_stride, int B,
 int bma_scorer_score_host(bma_scorer* s, const long long* ids_host, int ids_stride, int B,
                           const int* slot, const void* fixed, int S, const long long* target_ids,
                           int T, int ce_row0, float* loss_host, unsigned long long* key_host,
-                          unsigned int idx_base, const long long* base_ids_host, void* stream) {
+                          unsigned int idx_base, const long long* base_ids_host, int n_id_rows, void* stream) {
   if (s == nullptr) return fail(cudaErrorInvalidValue, "score_host: null scorer");
   if ((long long)B * ids_stride > s->desc.max_rows || ids_stride > 4096)
     return fail(cudaErrorInvalidValue, "score_host: ids exceed staging capacity");
@@ -591,14 +954,24 @@ int bma_scorer_score_host(bma_scorer* s, const long long* ids_host, int ids_stri
   int rc = bma_scorer_reset_key(s, s->key_dev, s->flag_dev, stream);
   if (rc != 0) return rc;
   rc = bma_scorer_score(s, s->ids_dev, ids_stride, B, slot, fixed, S, target_ids, T, ce_row0,
-                        s->loss_dev, s->key_dev, s->flag_dev, idx_base,
-                        base_ids_host != nullptr ? s->base_dev : nullptr, stream);
+                        s->loss_dev, s->key_dev, nullptr, idx_base,
+                        base_ids_host != nullptr ? s->base_dev : nullptr, n_id_rows, stream);
   if (rc != 0) return rc;
+  if (s->comm != nullptr) {                    // multi-rank: the winner key is reduced before it leaves the device
+    rc = bma_comm_allreduce_min_packed(s->comm, s->key_dev, 1, stream);
+    if (rc != 0) return rc;
+  }
   BMA_CHECK(cudaMemcpyAsync(loss_host, s->loss_dev, sizeof(float) * B, cudaMemcpyDeviceToHost, st),
             "score_host: D2H loss");
   BMA_CHECK(cudaMemcpyAsync(key_host, s->key_dev, sizeof(unsigned long long),
                             cudaMemcpyDeviceToHost, st), "score_host: D2H key");
   BMA_CHECK(cudaStreamSynchronize(st), "score_host: sync");
+  return 0;
+}
+
+int bma_scorer_set_comm(bma_scorer* s, bma_comm* comm) {
+  if (s == nullptr) return fail(cudaErrorInvalidValue, "set_comm: null scorer");
+  s->comm = comm;
   return 0;
 }
 

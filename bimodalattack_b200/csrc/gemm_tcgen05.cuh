@@ -23,6 +23,8 @@ enum : int { EPI_STORE = 0, EPI_ROPE = 1, EPI_GLU = 2, EPI_CE = 3, EPI_STORE_T =
 
 struct GemmParams {
   int M, N, K;
+  const int* M_dev;           // optional: the live row count on the device (<= M). M then only bounds
+                              // the grid and the TMA maps, so a ragged pass needs no host round trip
   int group_m;                // rasterisation: m-blocks per L2 supergroup
   // output
   __nv_bfloat16* C;           // EPI_STORE/ROPE/GLU/STORE_T
@@ -51,6 +53,7 @@ struct GemmParams {
   int T;
   float2* ce_part;            // [n_tiles][M] (running max, sum of exp)
   float* tgt_logit;           // [M]
+  int* ce_arg;                // [n_tiles][M] first column attaining the tile maximum (torch.argmax order)
 };
 
 constexpr int GEMM_BM = 128;
@@ -117,7 +120,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0u;
   const bool leader = cta_rank == 0;
   const int unit0 = blockIdx.x / CTAS, unit_stride = gridDim.x / CTAS;
-  const int m_tiles = ((p.M + GEMM_BM - 1) / GEMM_BM + CTAS - 1) / CTAS;    // in units of CTAS*128 rows
+  const int M = p.M_dev != nullptr ? min(p.M, __ldg(p.M_dev)) : p.M;
+  const int m_tiles = ((M + GEMM_BM - 1) / GEMM_BM + CTAS - 1) / CTAS;    // in units of CTAS*128 rows
   const int n_tiles = (p.N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
   const int k_blocks = (p.K + GEMM_BK - 1) / GEMM_BK;
@@ -234,7 +238,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * BN;
       const int row = m_blk * GEMM_BM + sub * 32 + lane;
-      const bool row_ok = row < p.M;
+      const bool row_ok = row < M;
       const int n0 = n_blk * BN;
 
       if constexpr (EPI == EPI_STORE) {
@@ -391,6 +395,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
       } else if constexpr (EPI == EPI_CE) {
         const int tcol = row_ok ? static_cast<int>(p.target_ids[row % p.T]) : -1;
         float run_m = -INFINITY, run_s = 0.0f;
+        int run_arg = n0;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
           uint32_t r[32];
@@ -406,6 +411,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
             v[j] = (j < valid) ? bf16_round(__uint_as_float(r[j])) : -INFINITY;
             cm = fmaxf(cm, v[j]);
           }
+          if (cm > run_m) {                       // strictly: an earlier column keeps a tie
+            int first = 0;
+#pragma unroll
+            for (int j = 31; j >= 0; --j)
+              if (v[j] == cm) first = j;
+            run_arg = col + first;
+          }
           if (tcol >= col && tcol < col + valid) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
@@ -418,7 +430,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
           run_s = run_s * __expf(run_m - nm) + s;
           run_m = nm;
         }
-        if (row_ok) p.ce_part[(long long)n_blk * p.M + row] = make_float2(run_m, run_s);
+        if (row_ok) {
+          p.ce_part[(long long)n_blk * p.M + row] = make_float2(run_m, run_s);
+          if (p.ce_arg != nullptr) p.ce_arg[(long long)n_blk * p.M + row] = run_arg;
+        }
       } else if constexpr (EPI == EPI_STORE_T) {
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {

@@ -15,10 +15,12 @@ struct AttnParams {
   const __nv_bfloat16* vt_pre;  long long ldvtp;   // [Hkv*HD, P] prefix values, transposed
   __nv_bfloat16* out;           long long ldo;     // [M, H*HD]
   int M, S, P;
+  const int* M_dev;             // optional live row count on the device (<= M; M bounds grid and TMA maps)
   // ragged rows (suffix-head sharing): row_meta[r] = (first row of r's candidate, prefix keys
   // visible to r); all rows see prefix keys < P_shared. null = uniform S-row candidates.
   const int2* row_meta;
   int P_shared;
+  int pre_rows;                 // leading rows that are prefix positions themselves (fused prefill)
   int kv_group;                 // query heads per kv head
   int head_dim;                 // 128 or 256
   float scale_log2;             // softmax scale * log2(e)
@@ -44,11 +46,12 @@ cudaError_t launch_build_tail_embeds(const long long* ids, int ids_stride, const
                                      const __nv_bfloat16* fixed, const __nv_bfloat16* W,
                                      long long ldw, int V, float scale, __nv_bfloat16* out, int rows,
                                      int S, int d, const int2* row_info, const long long* base_ids,
+                                     const __nv_bfloat16* prefix_embeds, int P, const int* rows_dev,
                                      cudaStream_t stream);
 cudaError_t launch_plan_rows(const long long* ids, int ids_stride, const long long* base_ids,
                              const int* slot, int S, int n_share, int B, int include_base, int P, int dedupe,
-                             int2* row_info, int2* row_meta, int* cand_vstart, int2* cand_tmp,
-                             int* total_rows, cudaStream_t stream);
+                             int pre0, int pre_n, int2* row_info, int2* row_meta, int* cand_vstart, int2* cand_tmp,
+                             int* total_rows, unsigned long long* rows_accum, cudaStream_t stream);
 cudaError_t launch_append_prefix_kv(const __nv_bfloat16* k_tail, long long ldk, const __nv_bfloat16* vt_tail,
                                     long long ldvt, __nv_bfloat16* k_pre, long long ldkp,
                                     __nv_bfloat16* vt_pre, long long ldvtp, int n, int kv_dim, int P,
@@ -56,16 +59,17 @@ cudaError_t launch_append_prefix_kv(const __nv_bfloat16* k_tail, long long ldk, 
 cudaError_t launch_rmsnorm(const __nv_bfloat16* x, long long ldx, const __nv_bfloat16* w,
                            __nv_bfloat16* y, long long ldy, int rows, int d, float eps, int mode,
                            int gather_T, int gather_S, int gather_off, const int* gather_vstart,
-                           cudaStream_t stream);
+                           cudaStream_t stream, const int* rows_dev = nullptr);
 cudaError_t launch_gather_rows(const __nv_bfloat16* src, long long lds, __nv_bfloat16* dst, long long ldd,
                                int rows, int width, int T, int S, int off, const int* vstart,
                                cudaStream_t stream);
 cudaError_t launch_add_norm(const __nv_bfloat16* y, long long ldy, const __nv_bfloat16* w_post,
                             __nv_bfloat16* x, long long ldx, const __nv_bfloat16* w_next,
                             __nv_bfloat16* xn, long long ldxn, int rows, int d, float eps, int mode,
-                            cudaStream_t stream);
+                            cudaStream_t stream, const int* rows_dev = nullptr);
 cudaError_t launch_init_key(unsigned long long* key, int* flag, cudaStream_t stream);
-cudaError_t launch_ce_finalize(const float2* part, const float* tgt_logit, int n_tiles, int B,
+cudaError_t launch_ce_finalize(const float2* part, const float* tgt_logit, const int* arg,
+                               const long long* target_ids, int n_tiles, int B,
                                int T, float* loss, unsigned long long* key, int* all_match_flag,
                                unsigned int idx_base, cudaStream_t stream);
 

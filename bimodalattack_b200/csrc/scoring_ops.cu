@@ -27,10 +27,20 @@ namespace bma {
 __global__ void __launch_bounds__(1024)
 plan_rows_kernel(const long long* __restrict__ ids, int ids_stride, const long long* __restrict__ base_ids,
                  const int* __restrict__ slot, int S, int n_share, int B, int include_base, int P, int dedupe,
+                 int pre0, int pre_n,
                  int2* __restrict__ row_info, int2* __restrict__ row_meta, int* __restrict__ cand_vstart,
-                 int2* __restrict__ cand_tmp, int* __restrict__ total_rows) {
+                 int2* __restrict__ cand_tmp, int* __restrict__ total_rows,
+                 unsigned long long* __restrict__ rows_accum) {
   __shared__ int part[1024];
   const int t = threadIdx.x, nt = blockDim.x;
+  // Fused prefill: rows [0, pre_n) are the shared-prefix positions [pre0, pre0 + pre_n) themselves
+  // (candidate -2, tail position relative to P so the rotary position pos_base + y comes out right).
+  // Their K/V reach the prefix buffers before this layer's attention, so row i sees prefix keys
+  // [0, i) there and itself as its only tail key.
+  for (int i = t; i < pre_n; i += nt) {
+    row_info[i] = make_int2(-2, pre0 + i - P);
+    row_meta[i] = make_int2(i, pre0 + i);
+  }
   const int nbase = include_base ? 1 : 0;
   const int n = B + nbase;                               // entry 0 is the base when included
   const int per = (n + nt - 1) / nt;
@@ -85,8 +95,11 @@ plan_rows_kernel(const long long* __restrict__ ids, int ids_stride, const long l
     part[t] += v;
     __syncthreads();
   }
-  int row = part[t] - local;
-  if (t == nt - 1) *total_rows = part[t];
+  int row = pre_n + part[t] - local;
+  if (t == nt - 1) {
+    *total_rows = pre_n + part[t];
+    if (rows_accum != nullptr) *rows_accum += static_cast<unsigned long long>(part[t]);   // tail rows only
+  }
   for (int e = e0; e < e1; ++e) {
     if (cand_vstart[e] != e) continue;                   // duplicates are resolved below
     const int jd = cand_tmp[e].x;
@@ -110,11 +123,13 @@ plan_rows_kernel(const long long* __restrict__ ids, int ids_stride, const long l
 
 cudaError_t launch_plan_rows(const long long* ids, int ids_stride, const long long* base_ids,
                              const int* slot, int S, int n_share, int B, int include_base, int P, int dedupe,
+                             int pre0, int pre_n,
                              int2* row_info, int2* row_meta, int* cand_vstart, int2* cand_tmp,
-                             int* total_rows, cudaStream_t stream) {
+                             int* total_rows, unsigned long long* rows_accum, cudaStream_t stream) {
   if (B + 1 > 8 * 1024) return cudaErrorInvalidValue;    // 8 entries per thread at most
   plan_rows_kernel<<<1, 1024, 0, stream>>>(ids, ids_stride, base_ids, slot, S, n_share, B, include_base, P,
-                                           dedupe, row_info, row_meta, cand_vstart, cand_tmp, total_rows);
+                                           dedupe, pre0, pre_n, row_info, row_meta, cand_vstart, cand_tmp,
+                                           total_rows, rows_accum);
   return cudaGetLastError();
 }
 
@@ -153,10 +168,12 @@ build_tail_embeds_kernel(const long long* __restrict__ ids, int ids_stride,
                          const int* __restrict__ slot, const __nv_bfloat16* __restrict__ fixed,
                          const __nv_bfloat16* __restrict__ W, long long ldw, int V, float scale,
                          __nv_bfloat16* __restrict__ out, int rows, int S, int d,
-                         const int2* __restrict__ row_info, const long long* __restrict__ base_ids) {
+                         const int2* __restrict__ row_info, const long long* __restrict__ base_ids,
+                         const __nv_bfloat16* __restrict__ prefix_embeds, int P,
+                         const int* __restrict__ rows_dev) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= rows) return;
+  if (warp >= rows || (rows_dev != nullptr && warp >= *rows_dev)) return;
   int b, s;
   if (row_info != nullptr) {
     const int2 ri = row_info[warp];
@@ -164,9 +181,14 @@ build_tail_embeds_kernel(const long long* __restrict__ ids, int ids_stride,
   } else {
     b = warp / S; s = warp - b * S;
   }
-  const int sl = slot[s];
   const int nvec = d >> 3;
   uint4* dst = reinterpret_cast<uint4*>(out + (long long)warp * d);
+  if (b == -2) {                                   // a shared-prefix position (fused prefill)
+    const uint4* src = reinterpret_cast<const uint4*>(prefix_embeds + (long long)(P + s) * d);
+    for (int v = lane; v < nvec; v += 32) dst[v] = src[v];
+    return;
+  }
+  const int sl = slot[s];
   if (sl < 0) {
     const uint4* src = reinterpret_cast<const uint4*>(fixed + (long long)s * d);
     for (int v = lane; v < nvec; v += 32) dst[v] = src[v];
@@ -193,12 +215,14 @@ cudaError_t launch_build_tail_embeds(const long long* ids, int ids_stride, const
                                      const __nv_bfloat16* fixed, const __nv_bfloat16* W,
                                      long long ldw, int V, float scale, __nv_bfloat16* out, int rows,
                                      int S, int d, const int2* row_info, const long long* base_ids,
+                                     const __nv_bfloat16* prefix_embeds, int P, const int* rows_dev,
                                      cudaStream_t stream) {
   if (rows <= 0 || S <= 0) return cudaSuccess;
   if ((d & 7) != 0) return cudaErrorInvalidValue;
   const int blocks = static_cast<int>(((long long)rows * 32 + 255) / 256);
   build_tail_embeds_kernel<<<blocks, 256, 0, stream>>>(ids, ids_stride, slot, fixed, W, ldw, V,
-                                                       scale, out, rows, S, d, row_info, base_ids);
+                                                       scale, out, rows, S, d, row_info, base_ids,
+                                                       prefix_embeds, P, rows_dev);
   return cudaGetLastError();
 }
 
@@ -211,10 +235,10 @@ __global__ void __launch_bounds__(256)
 rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
                const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ y, long long ldy,
                int rows, int d, float eps, int mode, int gather_T, int gather_S, int gather_off,
-               const int* __restrict__ gather_vstart) {
+               const int* __restrict__ gather_vstart, const int* __restrict__ rows_dev) {
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (r >= rows) return;
+  if (r >= rows || (rows_dev != nullptr && r >= *rows_dev)) return;
   long long src_row = r;
   if (gather_T > 0) {
     const int c = r / gather_T;
@@ -262,12 +286,12 @@ rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
 cudaError_t launch_rmsnorm(const __nv_bfloat16* x, long long ldx, const __nv_bfloat16* w,
                            __nv_bfloat16* y, long long ldy, int rows, int d, float eps, int mode,
                            int gather_T, int gather_S, int gather_off, const int* gather_vstart,
-                           cudaStream_t stream) {
+                           cudaStream_t stream, const int* rows_dev) {
   if (rows <= 0) return cudaSuccess;
   if ((d & 7) != 0 || (ldx & 7) != 0 || (ldy & 7) != 0) return cudaErrorInvalidValue;
   const int blocks = static_cast<int>(((long long)rows * 32 + 255) / 256);
   rmsnorm_kernel<<<blocks, 256, 0, stream>>>(x, ldx, w, y, ldy, rows, d, eps, mode, gather_T,
-                                             gather_S, gather_off, gather_vstart);
+                                             gather_S, gather_off, gather_vstart, rows_dev);
   return cudaGetLastError();
 }
 
@@ -309,10 +333,11 @@ __device__ __forceinline__ float norm_apply(float v, float rstd, float w, int mo
 __global__ void __launch_bounds__(256)
 add_norm_kernel(const __nv_bfloat16* y, long long ldy, const __nv_bfloat16* __restrict__ w_post,
                 __nv_bfloat16* x, long long ldx, const __nv_bfloat16* __restrict__ w_next,
-                __nv_bfloat16* xn, long long ldxn, int rows, int d, float eps, int mode) {
+                __nv_bfloat16* xn, long long ldxn, int rows, int d, float eps, int mode,
+                const int* __restrict__ rows_dev) {
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (r >= rows) return;
+  if (r >= rows || (rows_dev != nullptr && r >= *rows_dev)) return;
   const uint4* yv = reinterpret_cast<const uint4*>(y + (long long)r * ldy);
   uint4* xv = reinterpret_cast<uint4*>(x + (long long)r * ldx);
   const int nvec = d >> 3;
@@ -369,11 +394,12 @@ add_norm_kernel(const __nv_bfloat16* y, long long ldy, const __nv_bfloat16* __re
 cudaError_t launch_add_norm(const __nv_bfloat16* y, long long ldy, const __nv_bfloat16* w_post,
                             __nv_bfloat16* x, long long ldx, const __nv_bfloat16* w_next,
                             __nv_bfloat16* xn, long long ldxn, int rows, int d, float eps, int mode,
-                            cudaStream_t stream) {
+                            cudaStream_t stream, const int* rows_dev) {
   if (rows <= 0) return cudaSuccess;
   if ((d & 7) != 0 || (ldx & 7) != 0 || (ldy & 7) != 0 || (ldxn & 7) != 0) return cudaErrorInvalidValue;
   const int blocks = static_cast<int>(((long long)rows * 32 + 255) / 256);
-  add_norm_kernel<<<blocks, 256, 0, stream>>>(y, ldy, w_post, x, ldx, w_next, xn, ldxn, rows, d, eps, mode);
+  add_norm_kernel<<<blocks, 256, 0, stream>>>(y, ldy, w_post, x, ldx, w_next, xn, ldxn, rows, d, eps, mode,
+                                              rows_dev);
   return cudaGetLastError();
 }
 
@@ -404,6 +430,7 @@ __device__ __forceinline__ void lse_merge(float& m, float& s, float om, float os
 
 __global__ void __launch_bounds__(256)
 ce_finalize_kernel(const float2* __restrict__ part, const float* __restrict__ tgt_logit,
+                   const int* __restrict__ arg, const long long* __restrict__ target_ids,
                    int n_tiles, int B, int T, float* __restrict__ loss,
                    unsigned long long* __restrict__ key, int* __restrict__ all_match_flag,
                    unsigned int idx_base) {
@@ -414,20 +441,27 @@ ce_finalize_kernel(const float2* __restrict__ part, const float* __restrict__ tg
   for (int tt = warp; tt < T; tt += n_warps) {
     const long long row = (long long)b * T + tt;
     float m = -INFINITY, s = 0.0f;
+    float am = -INFINITY;                        // running maximum and the FIRST column attaining it:
+    int ai = 0x7fffffff;                         // torch.argmax's answer (reference :1300-1306)
     for (int nt = lane; nt < n_tiles; nt += 32) {
       const float2 ps = part[(long long)nt * M + row];
       lse_merge(m, s, ps.x, ps.y);
+      if (arg != nullptr && ps.x > am) { am = ps.x; ai = arg[(long long)nt * M + row]; }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const float om = __shfl_xor_sync(0xffffffffu, m, o);
       const float os = __shfl_xor_sync(0xffffffffu, s, o);
       lse_merge(m, s, om, os);
+      const float oam = __shfl_xor_sync(0xffffffffu, am, o);
+      const int oai = __shfl_xor_sync(0xffffffffu, ai, o);
+      if (oam > am || (oam == am && oai < ai)) { am = oam; ai = oai; }
     }
     if (lane == 0) {
       const float tl = tgt_logit[row];
       ce_row[tt] = (m + logf(s)) - tl;
-      ce_row[T + tt] = (tl >= m) ? 1.0f : 0.0f;
+      const bool hit = arg != nullptr ? (ai == static_cast<int>(target_ids[tt])) : (tl >= m);
+      ce_row[T + tt] = hit ? 1.0f : 0.0f;
     }
   }
   __syncthreads();
@@ -450,12 +484,13 @@ cudaError_t launch_init_key(unsigned long long* key, int* flag, cudaStream_t str
   return cudaGetLastError();
 }
 
-cudaError_t launch_ce_finalize(const float2* part, const float* tgt_logit, int n_tiles, int B,
+cudaError_t launch_ce_finalize(const float2* part, const float* tgt_logit, const int* arg,
+                               const long long* target_ids, int n_tiles, int B,
                                int T, float* loss, unsigned long long* key, int* all_match_flag,
                                unsigned int idx_base, cudaStream_t stream) {
   if (B <= 0) return cudaSuccess;
-  ce_finalize_kernel<<<B, 256, 2 * T * sizeof(float), stream>>>(part, tgt_logit, n_tiles, B, T, loss, key,
-                                                                 all_match_flag, idx_base);
+  ce_finalize_kernel<<<B, 256, 2 * T * sizeof(float), stream>>>(part, tgt_logit, arg, target_ids, n_tiles, B, T,
+                                                                 loss, key, all_match_flag, idx_base);
   return cudaGetLastError();
 }
 

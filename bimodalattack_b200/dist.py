@@ -45,9 +45,50 @@ def pack_key(loss: float, index: int) -> int:
     return (order << 31) | (index & 0x7FFFFFFF)
 
 
+_native_comm = None          # (handle, world size) of the library-owned NCCL communicator
+
+
+def native_comm(device, w: Optional[World] = None):
+    """The C library's own NCCL communicator for this process (created once; None on one rank or on
+    CPU). Rank 0 makes the 128-byte unique id, torch.distributed carries it to the other ranks."""
+    global _native_comm
+    w = w or world()
+    if w.size == 1 or torch.device(device).type != "cuda":
+        return None
+    if _native_comm is not None and _native_comm[1] == w.size:
+        return _native_comm[0]
+    import ctypes as C
+    from . import native
+    lib = native.load()
+    uid = torch.zeros(128, dtype=torch.uint8)
+    if w.rank == 0:
+        buf = (C.c_ubyte * 128)()
+        native.check(lib.bma_comm_unique_id(buf), "comm_unique_id")
+        uid = torch.tensor(list(buf), dtype=torch.uint8)
+    uid = uid.to(device)
+    td.broadcast(uid, src=0)
+    raw = bytes(uid.cpu().tolist())
+    with torch.cuda.device(device):
+        handle = lib.bma_comm_create(raw, w.size, w.rank)
+    if not handle:
+        raise RuntimeError("bimodal_b200: NCCL communicator creation failed: " +
+                           lib.bma_comm_last_error().decode("utf-8", "replace"))
+    _native_comm = (handle, w.size)
+    return handle
+
+
 def reduce_winner(key: torch.Tensor, flag: Optional[torch.Tensor], w: World) -> None:
-    """In-place MIN all-reduce of the int64 key (and MAX of the early-stop flag)."""
+    """In-place MIN all-reduce of the int64 key (and MAX of the early-stop flag when given): ONE NCCL
+    launch on the scorer's stream through the library's communicator; torch.distributed (gloo in
+    the CPU tests) otherwise."""
     if w.size == 1:
+        return
+    if key.is_cuda and _native_comm is not None:
+        from . import native
+        with torch.cuda.device(key.device):
+            native.check(native.load().bma_comm_reduce_winner(
+                _native_comm[0], key.data_ptr(), None if flag is None else flag.data_ptr(),
+                native.stream_ptr(key.device)), "comm_reduce_winner")
         return
     td.all_reduce(key, op=td.ReduceOp.MIN)
     if flag is not None:

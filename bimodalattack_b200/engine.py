@@ -100,10 +100,16 @@ class ScoringEngine:
         self._max_positions = max_positions or 4096
         self._build_rope(self._max_positions)
         self.key = torch.empty(1, dtype=torch.int64, device=self.device)
-        self.flag = torch.empty(1, dtype=torch.int32, device=self.device)
+        self.flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.want_all_match = True       # track the early-stop flag (reference :1300-1306); off saves the argmax pass
         self.prefix_len = 0
         self.share_suffix_head = True    # compute tail rows shared with the base suffix once (see score())
         self.dedupe_candidates = True    # ... and the rows of identical candidates once
+        # fused prefill: the prefix positions ride in the first chunk of the next score() call as extra
+        # rows (one [prefix | base | candidates] row space per layer) instead of a separate pass
+        self.fused_prefill = True
+        self.prefill_tag = None          # what the resident prefix K/V were computed from (set by the attack)
+        self.comm = None                 # native NCCL communicator (dist.native_comm) for multi-rank runs
         self._last_prefix: Optional[torch.Tensor] = None
         self._prefix_stale = False
 
@@ -157,6 +163,8 @@ class ScoringEngine:
                                self.lib.bma_last_error().decode("utf-8", "replace"))
         self._scorer = handle
         native.check(self.lib.bma_scorer_set_dedupe(handle, int(self.dedupe_candidates)), "scorer_set_dedupe")
+        if self.comm is not None:
+            native.check(self.lib.bma_scorer_set_comm(handle, self.comm), "scorer_set_comm")
         self._cap_rows, self._cap_prefix = cap_rows, cap_prefix
         self._prefix_stale = True        # a new scorer has no prefix K/V yet
         for i, layer in enumerate(self.lm.layers):
@@ -196,7 +204,7 @@ class ScoringEngine:
     PROFILE_CLASSES = ("tail_embed", "rmsnorm", "gemm_qkv_rope", "attention", "gemm_o_proj",
                        "gemm_gate_up_glu", "gemm_down", "gemm_lm_head_ce", "ce_finalize")
 
-    def profile(self, enable: bool, max_events: int = 8192):
+    def profile(self, enable: bool, max_events: int = 16384):
         """Per-kernel-class CUDA-event timing inside the scoring pass (used by bench.py's roofline)."""
         self._ensure(max(self._cap_rows, 1), self._cap_prefix)
         native.check(self.lib.bma_scorer_profile(self._scorer, int(enable), max_events), "scorer_profile")
@@ -216,9 +224,18 @@ class ScoringEngine:
     def reserve(self, rows: int, prefix: int):
         self._ensure(rows, prefix)
 
-    def prefill(self, prefix_embeds: Optional[torch.Tensor]):
-        """Compute and keep the K/V of the shared prefix ([P, d] bf16; None/empty = no prefix)."""
+    def attach_comm(self, comm):
+        """Native communicator (``dist.native_comm``): the fused prefill is then split over its ranks."""
+        self.comm = comm
+        if self._scorer is not None:
+            native.check(self.lib.bma_scorer_set_comm(self._scorer, comm), "scorer_set_comm")
+
+    def prefill(self, prefix_embeds: Optional[torch.Tensor], deferred: Optional[bool] = None):
+        """Compute and keep the K/V of the shared prefix ([P, d] bf16; None/empty = no prefix). With
+        ``fused_prefill`` (default) the work is deferred into the next ``score`` call that carries
+        ``base_ids``; any other score call consumes it with a plain prefill pass first."""
         P = 0 if prefix_embeds is None else prefix_embeds.shape[0]
+        deferred = self.fused_prefill if deferred is None else deferred
         # room for the base suffix's keys behind the prefix (suffix-head sharing, see score())
         self._ensure(max(self._cap_rows, P, 1), P + (64 if self.share_suffix_head else 0))
         if P > 0:
@@ -226,8 +243,13 @@ class ScoringEngine:
                 raise RuntimeError("bimodal_b200 scorer: sequence longer than the rotary table")
             pe = prefix_embeds.to(self.dtype).contiguous()
         with torch.cuda.device(self.device):
-            native.check(self.lib.bma_scorer_prefill(self._scorer, None if P == 0 else pe.data_ptr(), P,
-                                                     native.stream_ptr(self.device)), "scorer_prefill")
+            if deferred:
+                native.check(self.lib.bma_scorer_prefill_deferred(self._scorer, None if P == 0 else pe.data_ptr(), P),
+                             "scorer_prefill_deferred")
+            else:
+                native.check(self.lib.bma_scorer_prefill(self._scorer, None if P == 0 else pe.data_ptr(), P,
+                                                         native.stream_ptr(self.device)), "scorer_prefill")
+        self._pending_rows = P if deferred else 0
         self.prefix_len = P
         self._last_prefix = None if P == 0 else pe
         self._prefix_stale = False
@@ -248,7 +270,7 @@ class ScoringEngine:
         S, row0 = self._tail_rows(plan, T)
         self._check_length(S)
         share = self._share_rows(ids, base_ids)
-        self._ensure(max(self._cap_rows, (min(B, 4096) + (1 if share else 0)) * S),
+        self._ensure(max(self._cap_rows, (min(B, 4096) + (1 if share else 0)) * S + self._fused_rows(share)),
                      max(self._cap_prefix, self.prefix_len + share))
         if self._prefix_stale:           # the workspace was re-created after the last prefill
             self.prefill(self._last_prefix)
@@ -260,10 +282,16 @@ class ScoringEngine:
         with torch.cuda.device(self.device):
             native.check(self.lib.bma_scorer_score(
                 self._scorer, ids.data_ptr(), ids.stride(0), B, plan.slot.data_ptr(), plan.fixed.data_ptr(),
-                S, tgt.data_ptr(), T, row0, loss.data_ptr(), self.key.data_ptr(), self.flag.data_ptr(),
-                idx_base, None if not share else base_ids.data_ptr(), native.stream_ptr(self.device)),
-                "scorer_score")
+                S, tgt.data_ptr(), T, row0, loss.data_ptr(), self.key.data_ptr(),
+                self.flag.data_ptr() if self.want_all_match else None,
+                idx_base, None if not share else base_ids.data_ptr(), plan.n_id_rows,
+                native.stream_ptr(self.device)), "scorer_score")
+        self._pending_rows = 0
         return loss
+
+    def _fused_rows(self, share: int) -> int:
+        """Extra row capacity the deferred prefix needs inside the next ragged chunk."""
+        return getattr(self, "_pending_rows", 0) if share else 0
 
     def _share_rows(self, ids: torch.Tensor, base_ids: Optional[torch.Tensor]) -> int:
         """Extra prefix keys suffix-head sharing needs (0 = sharing off)."""
@@ -301,7 +329,8 @@ class ScoringEngine:
         S, row0 = self._tail_rows(plan, T)
         self._check_length(S)
         share = self._share_rows(ids_host, base_ids_host)
-        self._ensure(max(self._cap_rows, (min(B, 4096) + (1 if share else 0)) * S, B * ids_host.shape[1]),
+        self._ensure(max(self._cap_rows, (min(B, 4096) + (1 if share else 0)) * S + self._fused_rows(share),
+                         B * ids_host.shape[1]),
                      max(self._cap_prefix, self.prefix_len + share))
         if self._prefix_stale:
             self.prefill(self._last_prefix)
@@ -309,5 +338,38 @@ class ScoringEngine:
             native.check(self.lib.bma_scorer_score_host(
                 self._scorer, ids_host.data_ptr(), ids_host.stride(0), B, plan.slot.data_ptr(),
                 plan.fixed.data_ptr(), S, target_ids.data_ptr(), T, row0, loss_host.data_ptr(),
-                key_host.data_ptr(), idx_base, None if not share else base_ids_host.data_ptr(),
+                key_host.data_ptr(), idx_base, None if not share else base_ids_host.data_ptr(), plan.n_id_rows,
                 native.stream_ptr(self.device)), "scorer_score_host")
+        self._pending_rows = 0
+
+
+def group_score(engines, ids: torch.Tensor, plan: TailPlan, target_ids: torch.Tensor,
+                base_ids: torch.Tensor) -> torch.Tensor:
+    """Single-process form of the multi-rank scoring path (C ABI ``bma_scorer_group_score``): the
+    engines act as the ranks of one box on one device -- contiguous candidate shards, the deferred
+    prefix split over them, the per-layer K/V all-gather done as local copies. Every engine must have
+    been given the same prefix with ``prefill(..., deferred=True)``. Returns the [B] losses; the winner
+    key / early-stop flag land in ``engines[0].key`` / ``.flag``."""
+    e0 = engines[0]
+    B, T = ids.shape[0], target_ids.numel()
+    S, row0 = e0._tail_rows(plan, T)
+    share = e0._share_rows(ids, base_ids)
+    for e in engines:
+        e._check_length(S)
+        e._ensure(max(e._cap_rows, (min(B, 4096) + 1) * S + e._fused_rows(share)),
+                  max(e._cap_prefix, e.prefix_len + share))
+        if e._prefix_stale:
+            e.prefill(e._last_prefix, deferred=True)
+    ids = ids.to(torch.int64).contiguous()
+    tgt = target_ids.reshape(-1).to(torch.int64).contiguous()
+    loss = torch.empty(B, dtype=torch.float32, device=e0.device)
+    e0.reset_key()
+    handles = (C.c_void_p * len(engines))(*[e._scorer for e in engines])
+    with torch.cuda.device(e0.device):
+        native.check(e0.lib.bma_scorer_group_score(
+            handles, len(engines), ids.data_ptr(), ids.stride(0), B, plan.slot.data_ptr(), plan.fixed.data_ptr(),
+            S, tgt.data_ptr(), T, row0, loss.data_ptr(), e0.key.data_ptr(), e0.flag.data_ptr(),
+            base_ids.data_ptr(), plan.n_id_rows, native.stream_ptr(e0.device)), "scorer_group_score")
+    for e in engines:
+        e._pending_rows = 0
+    return loss

@@ -60,11 +60,22 @@ SIGNATURES = {
     "bma_scorer_profile": (_I, [_P, _I, _I]),
     "bma_scorer_profile_read": (_I, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_LL), _I]),
     "bma_scorer_prefill": (_I, [_P, _P, _I, _P]),
+    "bma_scorer_prefill_deferred": (_I, [_P, _P, _I]),
     "bma_scorer_reset_key": (_I, [_P, _P, _P, _P]),
-    "bma_scorer_score": (_I, [_P, _P, _I, _I, _P, _P, _I, _P, _I, _I, _P, _P, _P, _U32, _P, _P]),
+    "bma_scorer_score": (_I, [_P, _P, _I, _I, _P, _P, _I, _P, _I, _I, _P, _P, _P, _U32, _P, _I, _P]),
+    "bma_scorer_group_score": (_I, [C.POINTER(_P), _I, _P, _I, _I, _P, _P, _I, _P, _I, _I, _P, _P, _P, _P, _I, _P]),
+    "bma_scorer_set_comm": (_I, [_P, _P]),
+    "bma_comm_unique_id": (_I, [_P]),
+    "bma_comm_create": (_P, [_P, _I, _I]),
+    "bma_comm_destroy": (None, [_P]),
+    "bma_comm_rank": (_I, [_P]),
+    "bma_comm_size": (_I, [_P]),
+    "bma_comm_last_error": (C.c_char_p, []),
+    "bma_comm_allreduce_min_packed": (_I, [_P, _P, _I, _P]),
+    "bma_comm_reduce_winner": (_I, [_P, _P, _P, _P]),
     "bma_scorer_last_rows": (_LL, [_P]),
     "bma_scorer_set_dedupe": (_I, [_P, _I]),
-    "bma_scorer_score_host": (_I, [_P, _P, _I, _I, _P, _P, _I, _P, _I, _I, _P, _P, _U32, _P, _P]),
+    "bma_scorer_score_host": (_I, [_P, _P, _I, _I, _P, _P, _I, _P, _I, _I, _P, _P, _U32, _P, _I, _P]),
     "bma_gemm_bf16": (_I, [_P, _LL, _P, _LL, _P, _LL, _P, _LL, _I, _I, _I, _I, _P]),
     "bma_rmsnorm": (_I, [_P, _LL, _P, _P, _LL, _I, _I, _F, _I, _P]),
     "bma_add_norm": (_I, [_P, _LL, _P, _P, _LL, _P, _P, _LL, _I, _I, _F, _I, _P]),

@@ -48,6 +48,7 @@ class TailPlan:
     fixed: torch.Tensor              # [S, d] model dtype (device); rows at slot>=0 are unused
     n_prefix: int
     n_tail: int
+    n_id_rows: int = 0               # one past the last tail row that depends on the candidate's ids
 
 
 def plan_tail(order: Sequence[str], parts: Dict[str, torch.Tensor], n_optim: int) -> TailPlan:
@@ -70,5 +71,6 @@ def plan_tail(order: Sequence[str], parts: Dict[str, torch.Tensor], n_optim: int
             slot += [-1] * t.shape[0]
             rows.append(t)
     fixed = torch.cat(rows, 0).contiguous()
+    n_id_rows = max(i for i, v in enumerate(slot) if v >= 0) + 1
     return TailPlan(prefix=prefix, slot=torch.tensor(slot, dtype=torch.int32, device=dev), fixed=fixed,
-                    n_prefix=0 if prefix is None else prefix.shape[0], n_tail=len(slot))
+                    n_prefix=0 if prefix is None else prefix.shape[0], n_tail=len(slot), n_id_rows=n_id_rows)

@@ -103,6 +103,14 @@ size_t bma_scorer_workspace_bytes(const bma_scorer* s);
 
 /* Run the shared prefix (image tokens + prompt) once; its K/V stay resident in the scorer. */
 int bma_scorer_prefill(bma_scorer* s, const void* prefix_embeds, int P, void* stream);
+/* Fused prefill: only RECORD the prefix ([P, d] bf16, must stay valid until it has been consumed).
+ * The next bma_scorer_score call that carries base_ids runs the P prefix positions as extra rows of
+ * its first chunk -- one row space [prefix | base suffix | candidates] per layer, every weight matrix
+ * streamed once instead of twice and half the launches -- and publishes their K/V to the per-layer
+ * prefix buffers before that layer's attention. With a communicator attached (bma_scorer_set_comm)
+ * the prefix positions are split over the ranks and each layer's K/V slices are all-gathered. A score
+ * call without base_ids (or bma_scorer_prefill) consumes the recorded prefix with a plain prefill. */
+int bma_scorer_prefill_deferred(bma_scorer* s, const void* prefix_embeds, int P);
 
 /* Score B candidates. ids is [B, ids_stride] int64; tail position s takes the embedding of
  * ids[b, slot[s]] when slot[s] >= 0, else row s of fixed ([S, d] bf16). The loss of candidate b is
@@ -119,14 +127,16 @@ int bma_scorer_prefill(bma_scorer* s, const void* prefix_embeds, int P, void* st
  * everything before its first replaced position -- are computed once instead of once per
  * candidate: the base is run as one extra sequence, its K/V are appended to the shared prefix and
  * each candidate computes only the rows from its first difference on. Any base gives the same
- * losses; one unrelated to the candidates merely saves nothing. The call then synchronises the
- * stream once per chunk (the ragged row count comes back to the host). */
+ * losses; one unrelated to the candidates merely saves nothing. n_id_rows is one past the last tail
+ * position whose slot is >= 0 (the host knows its slot table); the ragged row count stays on the
+ * device (every kernel of the pass reads it there), so the call never synchronises the stream. */
 int bma_scorer_reset_key(bma_scorer* s, unsigned long long* key, int* all_match, void* stream);
 int bma_scorer_score(bma_scorer* s, const long long* ids, int ids_stride, int B, const int* slot,
                      const void* fixed, int S, const long long* target_ids, int T, int ce_row0,
                      float* loss, unsigned long long* key, int* all_match, unsigned int idx_base,
-                     const long long* base_ids, void* stream);
-/* Tail rows the last bma_scorer_score call ran through the decoder (B*S without base_ids). */
+                     const long long* base_ids, int n_id_rows, void* stream);
+/* Tail rows the last bma_scorer_score call ran through the decoder (B*S without base_ids). Reads a
+ * device counter: synchronises. */
 long long bma_scorer_last_rows(const bma_scorer* s);
 /* With base_ids: candidates identical to an earlier candidate of the chunk (or to the base) reuse its
  * rows instead of recomputing them (default on); their loss is the representative's. */
@@ -137,7 +147,37 @@ int bma_scorer_set_dedupe(bma_scorer* s, int enable);
 int bma_scorer_score_host(bma_scorer* s, const long long* ids_host, int ids_stride, int B,
                           const int* slot, const void* fixed, int S, const long long* target_ids,
                           int T, int ce_row0, float* loss_host, unsigned long long* key_host,
-                          unsigned int idx_base, const long long* base_ids_host, void* stream);
+                          unsigned int idx_base, const long long* base_ids_host, int n_id_rows,
+                          void* stream);
+
+/* ---- multi-GPU ------------------------------------------------------
+ * One process per GPU. Candidates are sharded over the ranks (the host passes each rank its slice
+ * and idx_base); the library owns an NCCL communicator for the two exchanges of the path: the
+ * per-layer all-gather of the split prefix K/V (fused prefill) and ONE all-reduce(MIN) over the packed
+ * winner key. NCCL is resolved at run time from the libnccl.so.2 already loaded in the process.
+ * bma_comm_unique_id fills 128 bytes on rank 0; the host hands them to every rank (the reference
+ * has no multi-GPU path; its winner selection is loss.min()/argmin(), :550-551). */
+typedef struct bma_comm bma_comm;
+int bma_comm_unique_id(void* out128);
+bma_comm* bma_comm_create(const void* id128, int size, int rank);
+void bma_comm_destroy(bma_comm* c);
+int bma_comm_rank(const bma_comm* c);
+int bma_comm_size(const bma_comm* c);
+const char* bma_comm_last_error(void);
+/* In-place MIN over n packed keys on `stream`. */
+int bma_comm_allreduce_min_packed(bma_comm* c, unsigned long long* keys, int n, void* stream);
+/* Winner key (MIN) and, when all_match != NULL, the early-stop flag (MAX) in one NCCL launch. */
+int bma_comm_reduce_winner(bma_comm* c, unsigned long long* key, int* all_match, void* stream);
+/* Attach (or detach with NULL) the communicator the scorer splits its fused prefill over. */
+int bma_scorer_set_comm(bma_scorer* s, bma_comm* comm);
+/* Single-process form of the multi-rank path for tests: the n scorers act as the ranks of one box on
+ * one device (contiguous candidate shards, split prefix, the all-gather done as local copies). Each
+ * scorer must hold the same deferred prefix. loss is [B]; key / all_match are merged like
+ * bma_scorer_score does. */
+int bma_scorer_group_score(bma_scorer** group, int n, const long long* ids, int ids_stride, int B,
+                           const int* slot, const void* fixed, int S, const long long* target_ids, int T,
+                           int ce_row0, float* loss, unsigned long long* key, int* all_match,
+                           const long long* base_ids, int n_id_rows, void* stream);
 
 /* Optional per-class CUDA-event profile of the scoring pass (events on the launching stream).
  * Classes: 0 tail-embed, 1 rmsnorm, 2 gemm qkv+rope, 3 attention, 4 gemm o_proj, 5 gemm gate/up+GLU,

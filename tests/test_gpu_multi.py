@@ -15,18 +15,22 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.timeout(600)
-def test_two_rank_run_matches_single_rank(cuda_device, tmp_path):
+@pytest.mark.parametrize("buffer_size", [0, 3])
+def test_two_rank_run_matches_single_rank(cuda_device, tmp_path, buffer_size):
+    """buffer_size 3: the initial buffer is scored sharded too -- every rank must still see every entry's
+    loss and start from the same suffix (the per-candidate vector is gathered for init_buffer)."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     worker = os.path.join(ROOT, "tests", "_multi_worker.py")
     env = dict(os.environ, PYTHONPATH=ROOT)
-    subprocess.run([sys.executable, worker, str(tmp_path)], check=True, env=env, timeout=300)
+    b = str(buffer_size)
+    subprocess.run([sys.executable, worker, str(tmp_path), b], check=True, env=env, timeout=300)
     subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                    "--master-addr", "127.0.0.1", "--master-port", "29541", worker, str(tmp_path)],
+                    "--master-addr", "127.0.0.1", "--master-port", str(29541 + buffer_size), worker, str(tmp_path), b],
                    check=True, env=env, timeout=300)
-    one = json.load(open(tmp_path / "rank0_of1.json"))
-    r0 = json.load(open(tmp_path / "rank0_of2.json"))
-    r1 = json.load(open(tmp_path / "rank1_of2.json"))
+    one = json.load(open(tmp_path / f"rank0_of1_b{b}.json"))
+    r0 = json.load(open(tmp_path / f"rank0_of2_b{b}.json"))
+    r1 = json.load(open(tmp_path / f"rank1_of2_b{b}.json"))
     assert r0 == r1                                              # every rank holds the same result
     assert len(r0["losses"]) == 4
     # sharding moves candidates to other tiles: last-bit differences only (2 bf16 ulps of the loss)
