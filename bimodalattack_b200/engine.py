@@ -250,6 +250,7 @@ class ScoringEngine:
                 native.check(self.lib.bma_scorer_prefill(self._scorer, None if P == 0 else pe.data_ptr(), P,
                                                          native.stream_ptr(self.device)), "scorer_prefill")
         self._pending_rows = P if deferred else 0
+        self._last_deferred = deferred
         self.prefix_len = P
         self._last_prefix = None if P == 0 else pe
         self._prefix_stale = False
@@ -273,7 +274,7 @@ class ScoringEngine:
         self._ensure(max(self._cap_rows, (min(B, 4096) + (1 if share else 0)) * S + self._fused_rows(share)),
                      max(self._cap_prefix, self.prefix_len + share))
         if self._prefix_stale:           # the workspace was re-created after the last prefill
-            self.prefill(self._last_prefix)
+            self.prefill(self._last_prefix, deferred=getattr(self, "_last_deferred", None))
         ids = ids.to(torch.int64).contiguous()
         tgt = target_ids.reshape(-1).to(torch.int64).contiguous()   # validated by the caller
         loss = torch.empty(B, dtype=torch.float32, device=self.device)
@@ -290,8 +291,9 @@ class ScoringEngine:
         return loss
 
     def _fused_rows(self, share: int) -> int:
-        """Extra row capacity the deferred prefix needs inside the next ragged chunk."""
-        return getattr(self, "_pending_rows", 0) if share else 0
+        """Extra row capacity a deferred prefix needs inside a ragged chunk (reserved whenever the fused
+        prefill is on, so a workspace re-created between prefill() and score() keeps its chunk size)."""
+        return self.prefix_len if (share and self.fused_prefill) else 0
 
     def _share_rows(self, ids: torch.Tensor, base_ids: Optional[torch.Tensor]) -> int:
         """Extra prefix keys suffix-head sharing needs (0 = sharing off)."""
@@ -333,7 +335,7 @@ class ScoringEngine:
                          B * ids_host.shape[1]),
                      max(self._cap_prefix, self.prefix_len + share))
         if self._prefix_stale:
-            self.prefill(self._last_prefix)
+            self.prefill(self._last_prefix, deferred=getattr(self, "_last_deferred", None))
         with torch.cuda.device(self.device):
             native.check(self.lib.bma_scorer_score_host(
                 self._scorer, ids_host.data_ptr(), ids_host.stride(0), B, plan.slot.data_ptr(),

@@ -331,7 +331,10 @@ def test_score_host_entry_and_degenerate_batches(cuda_device):
         feats = atk.scoring_features(image)
         batch = atk._build_input_embeds_pgd(cand, feats, search_width=37, single=True)
         plan = atk._plan(batch)
-        atk.engine.prefill(plan.prefix)
+        # size the workspace once, so both entries below run the same (non-fused) ragged pass on the same
+        # prefix K/V and can be compared bit for bit
+        atk.engine.reserve(40 * plan.n_tail + plan.n_prefix, plan.n_prefix + 64)
+        atk.engine.prefill(plan.prefix, deferred=False)
         full = atk.engine.score(cand, plan, atk.target_ids).clone()
         shared = atk.engine.score(cand, plan, atk.target_ids, base_ids=base).clone()
         key_dev = int(atk.engine.key.item())
