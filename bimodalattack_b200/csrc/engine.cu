@@ -271,20 +271,6 @@ int layer_pack(bma_scorer* s, int l, const Pass& ps, cudaStream_t st) {
   return copy_kv(s, s->qk + s->q_dim, s->qk_dim, s->vt, s->ld_vt, s->xchg_send, s->kv_dim,
                  s->xchg_send + (size_t)ps.pre_chunk * s->kv_dim, ps.pre_chunk, ps.pre_n, 0, st);
 }
-// Split prefill, step 2: rank q's send block -> prefix keys [q pre_chunk, ...) of layer l.
-int layer_unpack(bma_scorer* s, int l, const Pass& ps, const __nv_bfloat16* block, int q, int P, cudaStream_t st) {
-  const int at = q * ps.pre_chunk;
-  const int n = P - at < ps.pre_chunk ? P - at : ps.pre_chunk;
-  ProfScope pr(s, PC_EMBED, 0, st);
-  return copy_kv(s, block, s->kv_dim, block + (size_t)ps.pre_chunk * s->kv_dim, ps.pre_chunk,
-                 layer_pre_qk(s, l) + s->q_dim, s->qk_dim, layer_pre_vt(s, l), s->ld_vtp, n, at, st);
-}
-// The base suffix's first n_share rows (they follow the prefix rows) -> prefix keys [P, P + n_share).
-int layer_publish_base(bma_scorer* s, int l, const Pass& ps, int P, cudaStream_t st) {
-  ProfScope pr(s, PC_EMBED, 0, st);
-  return copy_kv(s, s->qk + (size_t)ps.pre_n * s->qk_dim + s->q_dim, s->qk_dim, s->vt + ps.pre_n, s->ld_vt,
-                 layer_pre_qk(s, l) + s->q_dim, s->qk_dim, layer_pre_vt(s, l), s->ld_vtp, ps.n_share, P, st);
-}
 // Everything a single rank publishes in one copy: prefix rows [0, pre_n) (pre0 == 0) + the base rows.
 int layer_publish_local(bma_scorer* s, int l, const Pass& ps, int P, cudaStream_t st) {
   ProfScope pr(s, PC_EMBED, 0, st);
@@ -400,11 +386,13 @@ int run_layers(bma_scorer* s, Pass& ps, cudaStream_t st) {
           rc = comm_allgather_bytes(s->comm, s->xchg_send, s->xchg_recv, blk * sizeof(__nv_bfloat16), st);
           if (rc != 0) return fail(cudaErrorUnknown, "prefix K/V all-gather (NCCL)");
         }
-        for (int q = 0; q < comm_size(s->comm); ++q) {
-          rc = layer_unpack(s, l, ps, s->xchg_recv + q * blk, q, P, st);
-          if (rc != 0) return rc;
+        {                                            // every rank's slice + the base rows in ONE launch
+          ProfScope pr(s, PC_EMBED, 0, st);
+          BMA_LAUNCH(launch_unpack_prefix_kv(s->xchg_recv, static_cast<long long>(blk), ps.pre_chunk,
+                                             comm_size(s->comm), P, s->qk + s->q_dim, s->qk_dim, s->vt, s->ld_vt,
+                                             ps.pre_n, ps.n_share, layer_pre_qk(s, l) + s->q_dim, s->qk_dim,
+                                             layer_pre_vt(s, l), s->ld_vtp, s->kv_dim, st), "unpack_prefix_kv");
         }
-        rc = layer_publish_base(s, l, ps, P, st);
       } else {
         rc = layer_publish_local(s, l, ps, P, st);
       }
@@ -694,13 +682,13 @@ int plan_score(bma_scorer* s, const ScoreArgs& a, ScorePlan& sp, int rank, int s
 }
 
 int ensure_xchg(bma_scorer* s, int pre_chunk, int size) {
-  const size_t need = 2 * (size_t)pre_chunk * s->kv_dim;
+  const size_t need = 2 * (size_t)pre_chunk * s->kv_dim * size;     // receive side: one block per rank
   if (need <= s->xchg_elems) return 0;
   BMA_CHECK(cudaDeviceSynchronize(), "ensure_xchg: sync");
   cudaFree(s->xchg_send); cudaFree(s->xchg_recv);
   s->xchg_send = s->xchg_recv = nullptr; s->xchg_elems = 0;
   size_t bytes = 0;
-  if (!dev_alloc(&s->xchg_send, need, &bytes) || !dev_alloc(&s->xchg_recv, need * size, &bytes))
+  if (!dev_alloc(&s->xchg_send, need / size, &bytes) || !dev_alloc(&s->xchg_recv, need, &bytes))
     return fail(cudaGetLastError(), "ensure_xchg: cudaMalloc");
   s->ws_bytes += bytes;
   s->xchg_elems = need;
@@ -893,7 +881,7 @@ int bma_scorer_group_score(bma_scorer** group, int n, const long long* ids, int 
   const int P = group[0]->pending_P;
   for (int r = 0; r < n; ++r) {
     bma_scorer* s = group[r];
-    int rc = ensure_xchg(s, plans[r].pre_chunk, 1);
+    int rc = ensure_xchg(s, plans[r].pre_chunk, n);
     if (rc != 0) return rc;
     const int most = args[r].B < plans[r].chunk ? args[r].B : plans[r].chunk;
     rc = ensure_ce_rows(s, (most > 0 ? most : 1) * T);
@@ -912,12 +900,16 @@ int bma_scorer_group_score(bma_scorer** group, int n, const long long* ids, int 
       if (rc != 0) return rc;
     }
     for (int r = 0; r < n; ++r) {
-      for (int q = 0; q < n; ++q) {           // the all-gather, as local copies
-        int rc = layer_unpack(group[r], l, pass[r], group[q]->xchg_send, q, P, st);
-        if (rc != 0) return rc;
-      }
-      int rc = layer_publish_base(group[r], l, pass[r], P, st);
-      if (rc != 0) return rc;
+      bma_scorer* s = group[r];
+      const size_t blk = 2 * (size_t)pass[r].pre_chunk * s->kv_dim;
+      for (int q = 0; q < n; ++q)             // the all-gather, as local copies into this rank's receive buffer
+        BMA_CHECK(cudaMemcpyAsync(s->xchg_recv + q * blk, group[q]->xchg_send, blk * sizeof(__nv_bfloat16),
+                                  cudaMemcpyDeviceToDevice, st), "group_score: gather copy");
+      BMA_LAUNCH(launch_unpack_prefix_kv(s->xchg_recv, static_cast<long long>(blk), pass[r].pre_chunk, n, P,
+                                         s->qk + s->q_dim, s->qk_dim, s->vt, s->ld_vt, pass[r].pre_n,
+                                         pass[r].n_share, layer_pre_qk(s, l) + s->q_dim, s->qk_dim,
+                                         layer_pre_vt(s, l), s->ld_vtp, s->kv_dim, st), "unpack_prefix_kv");
+      int rc = 0;
       rc = layer_back(group[r], l, pass[r], st);
       if (rc != 0) return rc;
     }

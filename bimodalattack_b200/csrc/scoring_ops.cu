@@ -159,6 +159,54 @@ cudaError_t launch_append_prefix_kv(const __nv_bfloat16* k_tail, long long ldk, 
   return cudaGetLastError();
 }
 
+// Split prefill: ONE launch scatters every rank's gathered block ([chunk x kv_dim K rows | kv_dim x chunk
+// V^T], `blk` elements apart in `recv`) into prefix keys [q chunk, min(P, (q+1) chunk)) and appends the
+// base suffix's n_base K/V rows (tail rows base_row0.. of this rank) at key index P.
+__global__ void __launch_bounds__(256)
+unpack_prefix_kv_kernel(const __nv_bfloat16* __restrict__ recv, long long blk, int chunk, int n_ranks, int P,
+                        const __nv_bfloat16* __restrict__ k_tail, long long ldk,
+                        const __nv_bfloat16* __restrict__ vt_tail, long long ldvt, int base_row0, int n_base,
+                        __nv_bfloat16* __restrict__ k_pre, long long ldkp,
+                        __nv_bfloat16* __restrict__ vt_pre, long long ldvtp, int kv_dim) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n_keys = (long long)P + n_base;
+  if (i >= n_keys * kv_dim) return;
+  {                                                   // K: consecutive threads -> consecutive columns
+    const int key = static_cast<int>(i / kv_dim), c = static_cast<int>(i - (long long)key * kv_dim);
+    __nv_bfloat16 v;
+    if (key < P) {
+      const int q = key / chunk, r = key - q * chunk;
+      v = recv[q * blk + (long long)r * kv_dim + c];
+    } else {
+      v = k_tail[(long long)(base_row0 + key - P) * ldk + c];
+    }
+    k_pre[(long long)key * ldkp + c] = v;
+  }
+  {                                                   // V^T: consecutive threads -> consecutive keys
+    const int dim = static_cast<int>(i / n_keys), key = static_cast<int>(i - (long long)dim * n_keys);
+    __nv_bfloat16 v;
+    if (key < P) {
+      const int q = key / chunk, r = key - q * chunk;
+      v = recv[q * blk + (long long)chunk * kv_dim + (long long)dim * chunk + r];
+    } else {
+      v = vt_tail[(long long)dim * ldvt + base_row0 + key - P];
+    }
+    vt_pre[(long long)dim * ldvtp + key] = v;
+  }
+  (void)n_ranks;
+}
+
+cudaError_t launch_unpack_prefix_kv(const __nv_bfloat16* recv, long long blk, int chunk, int n_ranks, int P,
+                                    const __nv_bfloat16* k_tail, long long ldk, const __nv_bfloat16* vt_tail,
+                                    long long ldvt, int base_row0, int n_base, __nv_bfloat16* k_pre, long long ldkp,
+                                    __nv_bfloat16* vt_pre, long long ldvtp, int kv_dim, cudaStream_t stream) {
+  const long long total = ((long long)P + n_base) * kv_dim;
+  if (total <= 0) return cudaSuccess;
+  unpack_prefix_kv_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, stream>>>(
+      recv, blk, chunk, n_ranks, P, k_tail, ldk, vt_tail, ldvt, base_row0, n_base, k_pre, ldkp, vt_pre, ldvtp, kv_dim);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------
 // out[row, :] = slot[s] >= 0 ? round_bf16(W[ids[b, slot[s]], :] * scale) : fixed[s, :]
 // Uniform layout (row_info == null): row = b*S + s. Ragged layout: (b, s) = row_info[row], b = -1
