@@ -328,7 +328,55 @@ class BimodalAttack:
                 return out
         return self._gradient_eager(optim_ids, image)
 
+    def _native_gradient(self):
+        """The native forward/backward (gradient.py) when this model is covered, else None (HF autograd)."""
+        if not hasattr(self, "_native_grad"):
+            self._native_grad = None
+            self._native_grad_why = "disabled (BMA_NATIVE_GRAD=0)"
+            if os.environ.get("BMA_NATIVE_GRAD", "1") != "0" and self.device.type == "cuda":
+                from .gradient import NativeGradient
+                self._native_grad_why = NativeGradient.supported(self.engine)
+                if self._native_grad_why is None and self.target_ids.numel() <= 128:
+                    self._native_grad = NativeGradient(self.engine)
+        return self._native_grad
+
+    def _gradient_native(self, ng, optim_ids: torch.Tensor, image: Optional[torch.Tensor]):
+        """compute_gradient on this package's kernels: decoder forward + input-gradient backward native
+        (gradient.py); the token gradient is the tcgen05 GEMM; the image gradient continues from the
+        image-feature gradient through the vision tower."""
+        cfg, model, W = self.config, self.model, self.embedding_layer.weight.detach()
+        e = self.segment_embeds
+        optim_embeds = W[optim_ids.reshape(-1)].unsqueeze(0)           # the one-hot product of :959-968 is a row gather
+        feats = None
+        if cfg.pgd_attack:
+            with torch.enable_grad():
+                feats = image_features(model, self._normalize_pixels(image), self.gemma_processor)
+            seq = [e["before_img"], feats.detach().to(W.dtype), e["before_suffix"], optim_embeds, e["after"], e["target"]]
+        else:
+            seq = [e["before"], optim_embeds, e["after"], e["target"]]
+        offs, at = {}, 0
+        for name, t in zip(("a", "img", "b", "optim") if cfg.pgd_attack else ("a", "optim"), seq):
+            offs[name] = (at, at + t.shape[1])
+            at += t.shape[1]
+        with torch.no_grad():
+            dx0 = ng.forward_backward(torch.cat(seq, dim=1)[0], self.target_ids)
+        onehot_grad = g_image = None
+        if cfg.gcg_attack:
+            lo, hi = offs["optim"]
+            onehot_grad = native.token_grad(dx0[lo:hi], W).unsqueeze(0)
+        if cfg.pgd_attack:
+            lo, hi = offs["img"]
+            g_image = torch.autograd.grad(feats, image, grad_outputs=dx0[lo:hi].reshape(feats.shape).to(feats.dtype))[0]
+        return onehot_grad, g_image
+
     def _gradient_eager(self, optim_ids: torch.Tensor, image: Optional[torch.Tensor]):
+        ng = self._native_gradient()
+        if ng is not None:
+            return self._gradient_native(ng, optim_ids, image)
+        return self._gradient_hf(optim_ids, image)
+
+    def _gradient_hf(self, optim_ids: torch.Tensor, image: Optional[torch.Tensor]):
+        """HF autograd at batch 1 (models the native step does not cover, and the A/B reference for it)."""
         cfg, model, emb = self.config, self.model, self.embedding_layer
         W = emb.weight
         # the reference multiplies a one-hot by W (:959-968): a row gather, and -- also for Gemma --

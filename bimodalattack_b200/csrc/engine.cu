@@ -408,7 +408,9 @@ int run_layers(bma_scorer* s, Pass& ps, cudaStream_t st) {
 
 extern "C" {
 
-int bma_version(void) { return 100; }
+int bma_version(void) { return 200; }
+void bma_set_last_error(const char* msg) { g_last_error = msg != nullptr ? msg : ""; }
+void bma_count_launches(unsigned long long n) { g_launches += n; }
 const char* bma_last_error(void) { return g_last_error.c_str(); }
 unsigned long long bma_launch_count(void) { return g_launches; }
 

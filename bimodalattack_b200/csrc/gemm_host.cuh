@@ -117,8 +117,12 @@ inline cudaError_t launch_gemm(const __nv_bfloat16* A, long long lda, const __nv
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) return cudaSuccess;
   watchdog_attach();
   CUtensorMap ta, tb;
-  if (!make_tmap_bf16(&ta, A, p.M, p.K, lda, GEMM_BM)) return cudaErrorInvalidValue;
-  if (!make_tmap_bf16(&tb, B, p.N, p.K, ldb, BN / CTAS)) return cudaErrorInvalidValue;
+  const int nb = p.batch > 1 ? p.batch : 1;
+  if (nb > 1 && ((p.a_col != 0 || p.b_col != 0) && p.K % GEMM_BK != 0)) return cudaErrorInvalidValue;
+  if (!make_tmap_bf16(&ta, A, p.M + (long long)(nb - 1) * p.a_row, p.K + (long long)(nb - 1) * p.a_col, lda, GEMM_BM))
+    return cudaErrorInvalidValue;
+  if (!make_tmap_bf16(&tb, B, p.N + (long long)(nb - 1) * p.b_row, p.K + (long long)(nb - 1) * p.b_col, ldb, BN / CTAS))
+    return cudaErrorInvalidValue;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tn_kernel<BN, EPI, HD, CTAS>,
@@ -129,7 +133,8 @@ inline cudaError_t launch_gemm(const __nv_bfloat16* A, long long lda, const __nv
   }
   const int m_tiles = ((p.M + GEMM_BM - 1) / GEMM_BM + CTAS - 1) / CTAS;
   const int n_tiles = (p.N + BN - 1) / BN;
-  int grid = m_tiles * n_tiles * CTAS;
+  long long grid_ll = (long long)m_tiles * n_tiles * CTAS * nb;
+  int grid = grid_ll > (1 << 30) ? (1 << 30) : static_cast<int>(grid_ll);
   const int cap = (max_ctas > 0 ? max_ctas : num_sms()) / CTAS * CTAS;
   if (grid > cap) grid = cap;
   if constexpr (CTAS == 1) {

@@ -25,6 +25,14 @@ struct GemmParams {
   int M, N, K;
   const int* M_dev;           // optional: the live row count on the device (<= M). M then only bounds
                               // the grid and the TMA maps, so a ragged pass needs no host round trip
+  // Batched mode (batch > 1): `batch` independent M x N x K problems inside the SAME A / B matrices.
+  // Problem b reads A at (row a_row * b, column a_col * b) and B at (b_row * b, b_col * b) -- heads
+  // laid side by side along the columns, or stacked along the rows -- and writes C + c_batch * b.
+  int batch;
+  int a_row, a_col, b_row, b_col;
+  long long c_batch;
+  float* C32;                 // EPI_STORE: raw fp32 accumulators instead of bf16 (attention scores)
+  const __nv_bfloat16* bias;  // EPI_STORE: [N] added in fp32 before the bf16 rounding (nn.Linear bias)
   int group_m;                // rasterisation: m-blocks per L2 supergroup
   // output
   __nv_bfloat16* C;           // EPI_STORE/ROPE/GLU/STORE_T
@@ -40,6 +48,7 @@ struct GemmParams {
   const int2* row_info;
   __nv_bfloat16* Vt;          // EPI_ROPE: columns >= rope_cols (the V heads) go here TRANSPOSED,
   long long ldvt;             //   Vt[(col - rope_cols) * ldvt + row], for the K-major PV operand
+  int v_rowmajor;             // EPI_ROPE: ALSO store the V heads row-major into C (ldc then spans Q|K|V)
   // optional per-head RMSNorm on Q and K before the rotation (Gemma-3 q_norm / k_norm):
   // y = bf16(x * rstd * (1 + w)), w is [head_dim]; columns < q_cols are Q heads
   const __nv_bfloat16* q_norm_w;
@@ -69,7 +78,7 @@ struct GemmCfg {
   static constexpr int kStageBytesA = GEMM_BM * GEMM_BK * 2;
   static constexpr int kStageBytesB = (BN / CTAS) * GEMM_BK * 2;
   static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
-  static constexpr int kStages = CTAS == 2 ? (BN >= 256 ? 7 : 9) : (BN >= 256) ? 4 : (BN >= 128 ? 6 : 10);
+  static constexpr int kStages = CTAS == 2 ? (BN >= 256 ? 7 : 9) : (BN >= 256) ? 4 : (BN >= 128 ? 6 : (BN >= 64 ? 8 : 10));
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
@@ -89,6 +98,12 @@ __device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const uint32_t
     if (v * 8 + 8 <= valid_cols) {
       uint4 q = make_uint4(p[v * 4 + 0], p[v * 4 + 1], p[v * 4 + 2], p[v * 4 + 3]);
       *reinterpret_cast<uint4*>(dst + v * 8) = q;
+    } else if (v * 8 < valid_cols) {              // ragged last vector (N not a multiple of 8)
+      uint16_t* d16 = reinterpret_cast<uint16_t*>(dst + v * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (v * 8 + j < valid_cols)
+          d16[j] = static_cast<uint16_t>((j & 1) ? (p[v * 4 + (j >> 1)] >> 16) : (p[v * 4 + (j >> 1)] & 0xffffu));
     }
   }
 }
@@ -123,11 +138,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const int M = p.M_dev != nullptr ? min(p.M, __ldg(p.M_dev)) : p.M;
   const int m_tiles = ((M + GEMM_BM - 1) / GEMM_BM + CTAS - 1) / CTAS;    // in units of CTAS*128 rows
   const int n_tiles = (p.N + BN - 1) / BN;
-  const int num_tiles = m_tiles * n_tiles;
+  const int tiles_per_batch = m_tiles * n_tiles;
+  const int num_tiles = tiles_per_batch * (p.batch > 1 ? p.batch : 1);
   const int k_blocks = (p.K + GEMM_BK - 1) / GEMM_BK;
   const int group_m = max(1, (p.group_m > 0 ? p.group_m : 16) / CTAS);
 
-  auto tile_coords = [&](int tile, int& m_blk, int& n_blk) {
+  auto tile_coords = [&](int tile, int& m_blk, int& n_blk) -> int {
+    const int b = tile / tiles_per_batch;
+    tile -= b * tiles_per_batch;
     const int per_group = group_m * n_tiles;
     const int g = tile / per_group;
     const int first_m = g * group_m;
@@ -135,6 +153,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const int r = tile - g * per_group;
     m_blk = (first_m + r % rows_in_group) * CTAS + static_cast<int>(cta_rank);   // this CTA's 128-row block
     n_blk = r / rows_in_group;
+    return b;
   };
 
   if (warp == 0 && lane == 0) {
@@ -173,22 +192,24 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
       uint32_t phase = 0;
       for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
         int m_blk, n_blk;
-        tile_coords(tile, m_blk, n_blk);
+        const int bi = tile_coords(tile, m_blk, n_blk);
+        const int a_r0 = bi * p.a_row + m_blk * GEMM_BM, a_c0 = bi * p.a_col;
+        const int b_r0 = bi * p.b_row + n_blk * BN, b_c0 = bi * p.b_col;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1, 0x100 + stage);
           if constexpr (CTAS == 2) {
             // both CTAs' bytes are credited to the LEADER's full barrier, which the MMA issuer waits on
             if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
             const uint32_t bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
-            tma_load_2d_pair(smem_a + stage * Cfg::kStageBytesA, &tmap_a, bar, kb * GEMM_BK, m_blk * GEMM_BM);
-            tma_load_2d_pair(smem_b + stage * Cfg::kStageBytesB, &tmap_b, bar, kb * GEMM_BK,
-                             n_blk * BN + static_cast<int>(cta_rank) * (BN / 2));
+            tma_load_2d_pair(smem_a + stage * Cfg::kStageBytesA, &tmap_a, bar, a_c0 + kb * GEMM_BK, a_r0);
+            tma_load_2d_pair(smem_b + stage * Cfg::kStageBytesB, &tmap_b, bar, b_c0 + kb * GEMM_BK,
+                             b_r0 + static_cast<int>(cta_rank) * (BN / 2));
           } else {
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
             tma_load_2d(smem_a + stage * Cfg::kStageBytesA, &tmap_a, &full_bar[stage],
-                        kb * GEMM_BK, m_blk * GEMM_BM);
+                        a_c0 + kb * GEMM_BK, a_r0);
             tma_load_2d(smem_b + stage * Cfg::kStageBytesB, &tmap_b, &full_bar[stage],
-                        kb * GEMM_BK, n_blk * BN);
+                        b_c0 + kb * GEMM_BK, b_r0);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -233,15 +254,17 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     uint32_t acc_phase = 0;
     for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
       int m_blk, n_blk;
-      tile_coords(tile, m_blk, n_blk);
+      const int bi = tile_coords(tile, m_blk, n_blk);
       mbar_wait(&tmem_full[acc], acc_phase, 0x400 + acc);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * BN;
       const int row = m_blk * GEMM_BM + sub * 32 + lane;
       const bool row_ok = row < M;
       const int n0 = n_blk * BN;
+      (void)bi;
 
       if constexpr (EPI == EPI_STORE) {
+        const long long c_off = (long long)bi * p.c_batch;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
           uint32_t r[32];
@@ -250,9 +273,28 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
           const int col = n0 + c0;
           const int valid = min(32, p.N - col);
           if (row_ok && valid > 0) {
+            if (p.C32 != nullptr) {                  // raw fp32 accumulators (16-byte aligned rows)
+              float* dst = p.C32 + c_off + (long long)row * p.ldc + col;
+#pragma unroll
+              for (int v = 0; v < 8; ++v) {
+                if (v * 4 + 4 <= valid) {
+                  *reinterpret_cast<uint4*>(dst + v * 4) = make_uint4(r[v * 4], r[v * 4 + 1], r[v * 4 + 2], r[v * 4 + 3]);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    if (v * 4 + j < valid) dst[v * 4 + j] = __uint_as_float(r[v * 4 + j]);
+                }
+              }
+              continue;
+            }
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < valid) r[j] = __float_as_uint(__uint_as_float(r[j]) + __bfloat162float(p.bias[col + j]));
+            }
             uint32_t o[16];
             if (p.R != nullptr) {
-              const uint4* rp = reinterpret_cast<const uint4*>(p.R + (long long)row * p.ldr + col);
+              const uint4* rp = reinterpret_cast<const uint4*>(p.R + c_off + (long long)row * p.ldr + col);
 #pragma unroll
               for (int v = 0; v < 4; ++v) {
                 uint4 q = make_uint4(0, 0, 0, 0);
@@ -272,7 +314,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
               for (int j = 0; j < 16; ++j)
                 o[j] = pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
             }
-            store_bf16x32(p.C + (long long)row * p.ldc + col, o, valid);
+            store_bf16x32(p.C + c_off + (long long)row * p.ldc + col, o, valid);
           }
         }
       } else if constexpr (EPI == EPI_ROPE) {
@@ -357,6 +399,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                   if (col_h + c0 + j < p.N) dst[(long long)j * p.ldvt] = __float2bfloat16_rn(__uint_as_float(r[j]));
+                }
+                if (p.v_rowmajor) {
+                  uint32_t o[16];
+#pragma unroll
+                  for (int j = 0; j < 16; ++j)
+                    o[j] = pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+                  store_bf16x32(p.C + (long long)row * p.ldc + col_h + c0, o, min(32, p.N - (col_h + c0)));
                 }
               }
             }

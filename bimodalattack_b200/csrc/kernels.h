@@ -77,4 +77,37 @@ cudaError_t launch_ce_finalize(const float2* part, const float* tgt_logit, const
                                int T, float* loss, unsigned long long* key, int* all_match_flag,
                                unsigned int idx_base, cudaStream_t stream);
 
+// ---- native gradient step (phase_a.cu) ---------------------------------------------------------
+cudaError_t launch_softmax_rows(const float* S, long long lds, __nv_bfloat16* P, long long ldp, int H, int L,
+                                float scale, int causal, cudaStream_t st);
+cudaError_t launch_softmax_bwd_rows(const __nv_bfloat16* P, long long ldp, const float* dP, long long ldd,
+                                    __nv_bfloat16* dS, long long lds, int H, int L, float scale, int causal,
+                                    cudaStream_t st);
+cudaError_t launch_transpose_bf16(const __nv_bfloat16* src, long long lds, long long src_batch, __nv_bfloat16* dst,
+                                  long long ldd, long long dst_batch, int rows, int cols, int batch, cudaStream_t st);
+cudaError_t launch_rmsnorm_bwd(const __nv_bfloat16* dy, long long lddy, const __nv_bfloat16* x, long long ldx,
+                               const __nv_bfloat16* w, const __nv_bfloat16* dres, long long ldr, __nv_bfloat16* dx,
+                               long long lddx, int rows, int d, float eps, int mode, cudaStream_t st);
+cudaError_t launch_layernorm(const __nv_bfloat16* x, long long ldx, const __nv_bfloat16* w, const __nv_bfloat16* b,
+                             __nv_bfloat16* y, long long ldy, int rows, int d, float eps, cudaStream_t st);
+cudaError_t launch_layernorm_bwd(const __nv_bfloat16* dy, long long lddy, const __nv_bfloat16* x, long long ldx,
+                                 const __nv_bfloat16* w, const __nv_bfloat16* dres, long long ldr, __nv_bfloat16* dx,
+                                 long long lddx, int rows, int d, float eps, cudaStream_t st);
+cudaError_t launch_rope_bwd(__nv_bfloat16* g, long long ld, const float* cosT, const float* sinT, int rows,
+                            int n_heads, int hd, int pos0, cudaStream_t st);
+cudaError_t launch_glu(const __nv_bfloat16* gu, long long ldg, __nv_bfloat16* out, long long ldo, int rows, int d_ff,
+                       int act, cudaStream_t st);
+cudaError_t launch_glu_bwd(const __nv_bfloat16* gu, long long ldg, const __nv_bfloat16* dact, long long lda,
+                           __nv_bfloat16* dgu, long long ldd, int rows, int d_ff, int act, cudaStream_t st);
+cudaError_t launch_act(const __nv_bfloat16* x, const __nv_bfloat16* dy, __nv_bfloat16* out, long long n, int kind,
+                       cudaStream_t st);
+cudaError_t launch_ce_grad(const __nv_bfloat16* logits, long long ldl, const long long* target, __nv_bfloat16* dlogits,
+                           long long ldd, float* loss_rows, int T, int V, cudaStream_t st);
+cudaError_t launch_patchify(const float* img, __nv_bfloat16* patches, long long ldp, int C, int H, int W, int p,
+                            const float* mean, const float* sd, cudaStream_t st);
+cudaError_t launch_unpatchify_grad(const __nv_bfloat16* dpatches, long long ldp, float* gimg, int C, int H, int W,
+                                   int p, const float* sd, cudaStream_t st);
+cudaError_t launch_add_rows(const __nv_bfloat16* a, long long lda, const __nv_bfloat16* b, long long ldb, int b_rows,
+                            __nv_bfloat16* out, long long ldo, int rows, int d, cudaStream_t st);
+
 }  // namespace bma

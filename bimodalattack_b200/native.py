@@ -39,6 +39,18 @@ class LayerWeights(C.Structure):
     ]
 
 
+class GemmDesc(C.Structure):
+    """``bma_gemm_desc`` (include/bimodal_b200.h)."""
+    _fields_ = [
+        ("A", C.c_void_p), ("lda", C.c_longlong), ("B", C.c_void_p), ("ldb", C.c_longlong),
+        ("C", C.c_void_p), ("C32", C.c_void_p), ("ldc", C.c_longlong),
+        ("R", C.c_void_p), ("ldr", C.c_longlong), ("bias", C.c_void_p),
+        ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("block_n", C.c_int), ("ctas", C.c_int),
+        ("batch", C.c_int), ("a_row", C.c_int), ("a_col", C.c_int), ("b_row", C.c_int), ("b_col", C.c_int),
+        ("c_batch", C.c_longlong), ("transpose_out", C.c_int),
+    ]
+
+
 # name -> (restype, argtypes); mirrors include/bimodal_b200.h one to one
 _P, _LL, _I, _F = C.c_void_p, C.c_longlong, C.c_int, C.c_float
 _ULL, _U32 = C.c_ulonglong, C.c_uint
@@ -76,6 +88,22 @@ SIGNATURES = {
     "bma_scorer_last_rows": (_LL, [_P]),
     "bma_scorer_set_dedupe": (_I, [_P, _I]),
     "bma_scorer_score_host": (_I, [_P, _P, _I, _I, _P, _P, _I, _P, _I, _I, _P, _P, _U32, _P, _I, _P]),
+    "bma_gemm_ex": (_I, [C.POINTER(GemmDesc), _P]),
+    "bma_qkv_rope": (_I, [_P, _LL, _P, _P, _LL, _P, _LL, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "bma_softmax_rows": (_I, [_P, _LL, _P, _LL, _I, _I, _F, _I, _P]),
+    "bma_softmax_bwd_rows": (_I, [_P, _LL, _P, _LL, _P, _LL, _I, _I, _F, _I, _P]),
+    "bma_transpose_bf16": (_I, [_P, _LL, _LL, _P, _LL, _LL, _I, _I, _I, _P]),
+    "bma_rmsnorm_bwd": (_I, [_P, _LL, _P, _LL, _P, _P, _LL, _P, _LL, _I, _I, _F, _I, _P]),
+    "bma_layernorm": (_I, [_P, _LL, _P, _P, _P, _LL, _I, _I, _F, _P]),
+    "bma_layernorm_bwd": (_I, [_P, _LL, _P, _LL, _P, _P, _LL, _P, _LL, _I, _I, _F, _P]),
+    "bma_rope_bwd": (_I, [_P, _LL, _P, _P, _I, _I, _I, _I, _P]),
+    "bma_glu": (_I, [_P, _LL, _P, _LL, _I, _I, _I, _P]),
+    "bma_glu_bwd": (_I, [_P, _LL, _P, _LL, _P, _LL, _I, _I, _I, _P]),
+    "bma_act": (_I, [_P, _P, _P, _LL, _I, _P]),
+    "bma_ce_grad": (_I, [_P, _LL, _P, _P, _LL, _P, _I, _I, _P]),
+    "bma_patchify": (_I, [_P, _P, _LL, _I, _I, _I, _I, C.POINTER(_F), C.POINTER(_F), _P]),
+    "bma_unpatchify_grad": (_I, [_P, _LL, _P, _I, _I, _I, _I, C.POINTER(_F), _P]),
+    "bma_add_rows": (_I, [_P, _LL, _P, _LL, _I, _P, _LL, _I, _I, _P]),
     "bma_gemm_bf16": (_I, [_P, _LL, _P, _LL, _P, _LL, _P, _LL, _I, _I, _I, _I, _P]),
     "bma_rmsnorm": (_I, [_P, _LL, _P, _P, _LL, _I, _I, _F, _I, _P]),
     "bma_add_norm": (_I, [_P, _LL, _P, _P, _LL, _P, _P, _LL, _I, _I, _F, _I, _P]),

@@ -208,6 +208,66 @@ int bma_attention(const void* q, long long ldq, const void* k_tail, long long ld
                   const void* vt_pre, long long ldvtp, void* out, long long ldo, int M, int S, int P,
                   int n_heads, int kv_group, int head_dim, float scale, void* stream);
 
+/* ---- gradient step (reference BimodalAttack.compute_gradient, :953-1028) ---------------------
+ * Batch-1 forward + INPUT-gradient backward through the decoder and the CLIP tower on this library's
+ * kernels. The host (bimodalattack_b200/gradient.py) strings the calls below together on one stream
+ * (the whole step is captured into a CUDA graph). Contractions: the tcgen05 GEMM with a selectable
+ * tile and epilogue; per-head attention products use its batched mode. Everything else: row kernels
+ * with the rounding points of the bf16 autograd graph the reference runs. */
+typedef struct {
+  const void* A; long long lda;     /* [M, K] bf16, K contiguous                                   */
+  const void* B; long long ldb;     /* [N, K] bf16, K contiguous:  C = A * B^T                      */
+  void* C; float* C32; long long ldc; /* bf16 output, or raw fp32 accumulators when C32 != NULL     */
+  const void* R; long long ldr;     /* optional bf16 residual added after the bf16 rounding (N % 8 == 0) */
+  const void* bias;                 /* optional [N] bf16, added in fp32 before the rounding         */
+  int M, N, K;
+  int block_n, ctas;                /* tile: 64/128/160/256 columns; ctas 2 = CTA pair (block_n 256) */
+  int batch;                        /* > 1: problem b reads A at (a_row b, a_col b), B at (b_row b,  */
+  int a_row, a_col, b_row, b_col;   /*      b_col b) inside the same matrices, writes C + c_batch b  */
+  long long c_batch;
+  int transpose_out;                /* out[n, m] (N <= 128): the big operand streams once as A       */
+} bma_gemm_desc;
+int bma_gemm_ex(const bma_gemm_desc* g, void* stream);
+/* Fused QKV projection of ONE sequence (rows at positions pos0..): Q|K rotated (HF rounding points),
+ * V stored row-major into qkv (ldc spans Q|K|V) AND transposed into vt[(kv_dim), ldvt]. */
+int bma_qkv_rope(const void* xn, long long ldx, const void* w_qkv, void* qkv, long long ldc, void* vt, long long ldvt,
+                 const float* rope_cos, const float* rope_sin, int rows, int d, int q_dim, int kv_dim, int head_dim,
+                 int pos0, void* stream);
+/* P = softmax(scale S) per (head, row) of one sequence, causal or full; pad columns zeroed. */
+int bma_softmax_rows(const float* S, long long lds, void* P, long long ldp, int H, int L, float scale, int causal,
+                     void* stream);
+/* dS = P (dP - sum(P dP)) scale */
+int bma_softmax_bwd_rows(const void* P, long long ldp, const float* dP, long long ldd, void* dS, long long lds, int H,
+                         int L, float scale, int causal, void* stream);
+int bma_transpose_bf16(const void* src, long long lds, long long src_batch, void* dst, long long ldd,
+                       long long dst_batch, int rows, int cols, int batch, void* stream);
+/* dx = dres + d(rmsnorm)/dx (mode as bma_model_desc.norm_mode); dres may be NULL */
+int bma_rmsnorm_bwd(const void* dy, long long lddy, const void* x, long long ldx, const void* w, const void* dres,
+                    long long ldr, void* dx, long long lddx, int rows, int d, float eps, int mode, void* stream);
+int bma_layernorm(const void* x, long long ldx, const void* w, const void* b, void* y, long long ldy, int rows, int d,
+                  float eps, void* stream);
+int bma_layernorm_bwd(const void* dy, long long lddy, const void* x, long long ldx, const void* w, const void* dres,
+                      long long ldr, void* dx, long long lddx, int rows, int d, float eps, void* stream);
+int bma_rope_bwd(void* g, long long ld, const float* rope_cos, const float* rope_sin, int rows, int n_heads,
+                 int head_dim, int pos0, void* stream);
+/* GLU on the packed gate|up layout of w_gate_up (per 256 columns: 128 gate, 128 up) and its backward */
+int bma_glu(const void* gu, long long ldg, void* out, long long ldo, int rows, int d_ff, int act, void* stream);
+int bma_glu_bwd(const void* gu, long long ldg, const void* dact, long long lda, void* dgu, long long ldd, int rows,
+                int d_ff, int act, void* stream);
+/* pointwise activation (kind 0 quick_gelu, 1 erf-GELU): out = f(x), or out = dy f'(x) when dy != NULL */
+int bma_act(const void* x, const void* dy, void* out, long long n, int kind, void* stream);
+/* dlogits = (softmax(logits) - onehot(target)) / T over T rows (F.cross_entropy mean, :1010-1012) */
+int bma_ce_grad(const void* logits, long long ldl, const long long* target, void* dlogits, long long ldd,
+                float* loss_rows, int T, int V, void* stream);
+/* patch embedding as a GEMM: im2col with the Normalize folded in, and its adjoint back to fp32 pixels */
+int bma_patchify(const float* img, void* patches, long long ldp, int C, int H, int W, int patch,
+                 const float* mean_host, const float* std_host, void* stream);
+int bma_unpatchify_grad(const void* dpatches, long long ldp, float* grad_img, int C, int H, int W, int patch,
+                        const float* std_host, void* stream);
+/* out[r] = a[r] + b[r % b_rows] */
+int bma_add_rows(const void* a, long long lda, const void* b, long long ldb, int b_rows, void* out, long long ldo,
+                 int rows, int d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

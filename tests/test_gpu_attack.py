@@ -112,6 +112,9 @@ def test_gradient_matches_oracle(cuda_device, mode):
     optim_ids = tok(INIT, add_special_tokens=False, return_tensors="pt")["input_ids"].to(cuda_device)
     img_a = image.clone().requires_grad_() if cfg.pgd_attack else None
     img_b = image.clone().requires_grad_() if cfg.pgd_attack else None
+    # this test pins the HF-autograd path (same backward graph as the reference) to the oracle; the
+    # native forward/backward has its own parity test against fp32 autograd (test_gpu_gradient.py)
+    atk._native_grad, atk._native_grad_why = None, "HF path under test"
     g_tok, g_img = atk.compute_gradient(optim_ids, img_a)
     w_tok, w_img = ora.gradient(optim_ids, img_b)
     assert g_tok.shape == w_tok.shape and g_tok.dtype == w_tok.dtype == torch.bfloat16
