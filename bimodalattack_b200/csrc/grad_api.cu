@@ -43,6 +43,12 @@ int bma_gemm_ex(const bma_gemm_desc* g, void* stream) {
   p.c_batch = g->c_batch;
   cudaStream_t st = as_stream(stream);
   const __nv_bfloat16 *A = bf(g->A), *B = bf(g->B);
+  // rows of the output are written with 16-byte stores
+  if (!g->transpose_out && (g->C32 != nullptr ? (g->ldc % 4 != 0 || (reinterpret_cast<uintptr_t>(g->C32) & 15))
+                                              : (g->ldc % 8 != 0 || (reinterpret_cast<uintptr_t>(g->C) & 15))))
+    return done(cudaErrorInvalidValue, "gemm_ex: output rows must be 16-byte aligned (ldc % 8 bf16, % 4 fp32)", 0);
+  if (g->R != nullptr && (g->ldr % 8 != 0 || g->N % 8 != 0))
+    return done(cudaErrorInvalidValue, "gemm_ex: residual needs N % 8 == 0 and ldr % 8 == 0", 0);
   if (g->transpose_out) {            // out[n, m]: the big operand streams once as A (M = its rows)
     if (g->batch > 1 || g->C32 != nullptr) return done(cudaErrorInvalidValue, "gemm_ex: transpose_out is plain bf16", 0);
     if (g->N <= 32) return done(launch_gemm<32, EPI_STORE_T>(A, g->lda, B, g->ldb, p, st), "gemm_ex(T,32)");

@@ -34,14 +34,17 @@ def test_gemm_ex_tiles_bias_residual_fp32(cuda_device, M, N, K, tile):
     B = (torch.randn(N, K, generator=g) * 0.5).to(cuda_device).bfloat16()
     bias = torch.randn(N, generator=g).to(cuda_device).bfloat16()
     want = A.float() @ B.float().T
-    out = torch.zeros(M, N, dtype=torch.bfloat16, device=cuda_device)
+    Np = (N + 7) // 8 * 8                   # output rows are written with 16-byte stores: padded leading dimension
+    out = torch.zeros(M, Np, dtype=torch.bfloat16, device=cuda_device)[:, :N]
     k.gemm(A, B, out=out, M=M, N=N, K=K, tile=tile)
     _close(out, want, what="plain")
     k.gemm(A, B, out=out, M=M, N=N, K=K, tile=tile, bias=bias)
     _close(out, want + bias.float(), what="bias")
-    o32 = torch.zeros(M, N, dtype=torch.float32, device=cuda_device)
+    o32 = torch.zeros(M, Np, dtype=torch.float32, device=cuda_device)[:, :N]
     k.gemm(A, B, out32=o32, M=M, N=N, K=K, tile=tile)
     assert float((o32 - want).abs().max()) <= 1e-3 * float(want.abs().max())
+    with pytest.raises(RuntimeError):       # an unaligned leading dimension is refused, not mis-stored
+        k.gemm(A, B, out=torch.zeros(M, N + 1, dtype=torch.bfloat16, device=cuda_device)[:, :N], M=M, N=N, K=K, tile=tile)
     if N % 8 == 0:
         R = torch.randn(M, N, generator=g).to(cuda_device).bfloat16()
         k.gemm(A, B, out=out, M=M, N=N, K=K, tile=tile, R=R, ldr=N)
