@@ -60,6 +60,17 @@ def image_features(model, pixel_values: torch.Tensor, gemma_processor: bool) -> 
     return torch.stack(list(pooled), 0) if isinstance(pooled, (list, tuple)) else pooled
 
 
+def find_vision_parts(model):
+    """(vision tower, multimodal projector) of a LLaVA-style HF object (transformers 4.50 and 5.x layouts),
+    or None."""
+    inner = getattr(model, "model", model)
+    tower = getattr(inner, "vision_tower", None) or getattr(model, "vision_tower", None)
+    proj = getattr(inner, "multi_modal_projector", None) or getattr(model, "multi_modal_projector", None)
+    if tower is None or proj is None or not hasattr(proj, "linear_1"):
+        return None
+    return tower, proj
+
+
 def _patch_conv_forward(conv: torch.nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
     """forward() for a patch-embedding Conv2d whose stride equals its kernel (CLIP / SigLIP): the
     non-overlapping patches are unfolded by pure reshapes and multiplied by the [out, C*p*p] view
@@ -340,6 +351,19 @@ class BimodalAttack:
                     self._native_grad = NativeGradient(self.engine)
         return self._native_grad
 
+    def _native_tower(self):
+        """The native CLIP tower + projector (gradient.NativeVisionTower) when covered, else None."""
+        if not hasattr(self, "_native_vt"):
+            self._native_vt = None
+            self._native_vt_why = "disabled (BMA_NATIVE_TOWER=0)"
+            if (self.config.pgd_attack and not self.gemma_processor and self.device.type == "cuda"
+                    and os.environ.get("BMA_NATIVE_TOWER", "1") != "0"):
+                from .gradient import NativeVisionTower
+                self._native_vt_why = NativeVisionTower.supported(self.model, self.normalize)
+                if self._native_vt_why is None:
+                    self._native_vt = NativeVisionTower(self.model, self.normalize)
+        return self._native_vt
+
     def _gradient_native(self, ng, optim_ids: torch.Tensor, image: Optional[torch.Tensor]):
         """compute_gradient on this package's kernels: decoder forward + input-gradient backward native
         (gradient.py); the token gradient is the tcgen05 GEMM; the image gradient continues from the
@@ -348,9 +372,14 @@ class BimodalAttack:
         e = self.segment_embeds
         optim_embeds = W[optim_ids.reshape(-1)].unsqueeze(0)           # the one-hot product of :959-968 is a row gather
         feats = None
+        tower = self._native_tower() if cfg.pgd_attack else None
         if cfg.pgd_attack:
-            with torch.enable_grad():
-                feats = image_features(model, self._normalize_pixels(image), self.gemma_processor)
+            if tower is not None:
+                with torch.no_grad():
+                    feats = tower.forward(image)             # raw pixels in: Normalize is folded into the im2col
+            else:
+                with torch.enable_grad():
+                    feats = image_features(model, self._normalize_pixels(image), self.gemma_processor)
             seq = [e["before_img"], feats.detach().to(W.dtype), e["before_suffix"], optim_embeds, e["after"], e["target"]]
         else:
             seq = [e["before"], optim_embeds, e["after"], e["target"]]
@@ -366,7 +395,11 @@ class BimodalAttack:
             onehot_grad = native.token_grad(dx0[lo:hi], W).unsqueeze(0)
         if cfg.pgd_attack:
             lo, hi = offs["img"]
-            g_image = torch.autograd.grad(feats, image, grad_outputs=dx0[lo:hi].reshape(feats.shape).to(feats.dtype))[0]
+            if tower is not None:
+                with torch.no_grad():
+                    g_image = tower.backward(dx0[lo:hi]).view_as(image)
+            else:
+                g_image = torch.autograd.grad(feats, image, grad_outputs=dx0[lo:hi].reshape(feats.shape).to(feats.dtype))[0]
         return onehot_grad, g_image
 
     def _gradient_eager(self, optim_ids: torch.Tensor, image: Optional[torch.Tensor]):
@@ -484,41 +517,48 @@ class BimodalAttack:
         return (image - cache[0]) / cache[1]
 
     def scoring_features(self, image: torch.Tensor) -> torch.Tensor:
-        """Image features for the scoring phase (no gradient): normalise (reusing the PGD kernel's fused
-        output when it is current), vision tower, projector. The tower at batch 1 is ~400 small launches,
-        so after two eager calls it is replayed from a CUDA graph on a static pixel buffer."""
-        pix = self._normalized(image)
+        """Image features for the scoring phase (no gradient): the native CLIP tower + projector on the raw
+        pixels when the model is covered, else normalise (reusing the PGD kernel's fused output when it is
+        current) + the HF tower. Either way ~100-400 small launches at batch 1, so after two eager calls the
+        pass is replayed from a CUDA graph on a static input buffer."""
+        tower = self._native_tower()
+        if tower is not None:
+            src = image.detach()
+            fn = lambda t: tower.forward(t).clone()                     # noqa: E731
+        else:
+            src = self._normalized(image)
+            fn = lambda t: image_features(self.model, t, self.gemma_processor)   # noqa: E731
         st = self._feat_graph
-        key = (tuple(pix.shape), pix.dtype)
+        key = (tuple(src.shape), src.dtype, tower is not None)
         if not self.graph_gradient or st is None or st.get("key") != key:
             st = self._feat_graph = {"key": key, "calls": 0, "graph": None, "failed": not self.graph_gradient}
         st["calls"] += 1
         if st["failed"] or st["calls"] <= 2:
             with torch.no_grad():
-                return image_features(self.model, pix, self.gemma_processor)
+                return fn(src)
         if st["graph"] is None:
             try:
                 with torch.no_grad():
-                    pix_s = pix.detach().clone()
+                    src_s = src.detach().clone()
                     side = torch.cuda.Stream(device=self.device)
                     side.wait_stream(torch.cuda.current_stream(self.device))
                     with torch.cuda.stream(side):
-                        image_features(self.model, pix_s, self.gemma_processor)
+                        fn(src_s)
                     torch.cuda.current_stream(self.device).wait_stream(side)
                     torch.cuda.synchronize(self.device)
                     graph = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(graph):
-                        out = image_features(self.model, pix_s, self.gemma_processor)
-                st.update(graph=graph, pix=pix_s, out=out)
+                        out = fn(src_s)
+                st.update(graph=graph, pix=src_s, out=out)
             except Exception as exc:                   # noqa: BLE001
                 logger.warning(f"CUDA-graph capture of the vision tower failed ({type(exc).__name__}: {exc}); "
                                "staying on the eager path")
                 st["failed"] = True
                 torch.cuda.synchronize(self.device)
                 with torch.no_grad():
-                    return image_features(self.model, pix, self.gemma_processor)
+                    return fn(src)
         with torch.no_grad():
-            st["pix"].copy_(pix)
+            st["pix"].copy_(src)
             st["graph"].replay()
             return st["out"].clone()
 

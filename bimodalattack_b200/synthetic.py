@@ -133,6 +133,8 @@ def make_llava(size: str = "tiny", dtype=torch.float32, device=None, seed: int =
         cfg = _llava_config(1024, 256, 2, 2, 2, 512, 128, 64, 3, 4, 128, 28, 14)
     elif size == "small128":
         cfg = _llava_config(4096, 512, 3, 4, 4, 1024, 128, 128, 3, 4, 256, 56, 14)
+    elif size == "small128v":      # small128 with a CLIP tower of head_dim 64 (what the native tower covers), 4 layers
+        cfg = _llava_config(4096, 512, 3, 4, 4, 1024, 128, 128, 4, 2, 256, 56, 14)
     elif size == "7b":
         cfg = _llava_config(32064, 4096, 32, 32, 32, 11008, 128, 1024, 24, 16, 4096, 336, 14)
     else:

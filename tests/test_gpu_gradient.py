@@ -207,7 +207,48 @@ def _grad_setup(device, size, px, mode):
     return atk, model, tok, proc, norm, image, cfg
 
 
-@pytest.mark.parametrize("size,px,mode", [("tiny128", 28, "joint"), ("tiny128", 28, "gcg_only"), ("small128", 56, "joint")])
+@pytest.mark.parametrize("rc_px", [0, 42])
+def test_native_vision_tower_forward_and_backward(cuda_device, rc_px):
+    """CLIP tower + projector on the native kernels (head_dim 64, quick_gelu, LayerNorm, biases, patch
+    conv as GEMM, Normalize folded in) against HF: features vs ``get_image_features`` and the pixel
+    gradient vs fp32 autograd, with HF's own bf16 autograd as the error yardstick. rc_px = 42: a second
+    tower swapped in at its own image size (LLaVA-RC, BASELINE config 3)."""
+    import copy
+    from bimodalattack_b200 import synthetic as syn
+    from bimodalattack_b200.attack import image_features
+    from bimodalattack_b200.gradient import NativeVisionTower
+    atk, model, tok, proc, norm, image, cfg = _grad_setup(cuda_device, "small128v", 56, "joint")
+    if rc_px:
+        syn.swap_in_robust_clip(model, image_size=rc_px)
+        image = torch.rand((1, 3, rc_px, rc_px), generator=torch.Generator().manual_seed(6)).to(cuda_device)
+    assert NativeVisionTower.supported(model, norm) is None
+    vt = NativeVisionTower(model, norm)
+    got = vt.forward(image).clone()
+    want_bf16 = image_features(model, norm(image), False)
+    twin = copy.deepcopy(model).float()
+    img32 = image.clone().requires_grad_()
+    want = image_features(twin, norm(img32), False)
+    assert got.shape == want.shape
+
+    def rel(a, b):
+        return float((a.float() - b.float()).norm() / (b.float().norm() + 1e-30))
+
+    e_n, e_h = rel(got, want), rel(want_bf16, want)
+    print(f"features rel err vs fp32: native {e_n:.4f}  hf-bf16 {e_h:.4f}")
+    assert e_n <= 1.5 * e_h + 2e-3
+    d_feats = (torch.randn(want.shape, generator=torch.Generator().manual_seed(1)).to(cuda_device) * 1e-2).bfloat16()
+    g_true = torch.autograd.grad(want, img32, d_feats.float())[0]
+    img16 = image.clone().requires_grad_()
+    g_hf = torch.autograd.grad(image_features(model, norm(img16), False), img16, d_feats)[0]
+    g_nat = vt.backward(d_feats)
+    e_n, e_h = rel(g_nat, g_true), rel(g_hf, g_true)
+    print(f"pixel grad rel err vs fp32: native {e_n:.4f}  hf-bf16 {e_h:.4f}")
+    assert e_n <= 1.5 * e_h + 5e-3
+    assert float((torch.sign(g_nat) == torch.sign(g_true)).float().mean()) >= float((torch.sign(g_hf) == torch.sign(g_true)).float().mean()) - 0.02
+
+
+@pytest.mark.parametrize("size,px,mode", [("tiny128", 28, "joint"), ("tiny128", 28, "gcg_only"), ("small128", 56, "joint"),
+                                          ("small128v", 56, "joint")])
 def test_native_gradient_matches_autograd(cuda_device, size, px, mode):
     """compute_gradient on the native kernels vs autograd: the fp32 gradient of the same model is the
     truth; the reference's bf16 autograd path (HF, sdpa) sets the error scale."""
@@ -215,6 +256,7 @@ def test_native_gradient_matches_autograd(cuda_device, size, px, mode):
     from bimodalattack_b200 import BimodalAttack
     atk, model, tok, proc, norm, image, cfg = _grad_setup(cuda_device, size, px, mode)
     assert atk._native_gradient() is not None, atk._native_grad_why
+    assert (atk._native_tower() is not None) == (size == "small128v"), atk._native_vt_why
     optim_ids = tok(cfg.optim_str_init, add_special_tokens=False, return_tensors="pt")["input_ids"].to(cuda_device)
     joint = cfg.pgd_attack
     atk.graph_gradient = False
