@@ -33,6 +33,27 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 }
 inline int warp_blocks(long long rows) { return static_cast<int>((rows * 32 + 255) / 256); }
 
+// Row reductions with TPR threads per row: 32 (one warp per row, 8 rows per block) for tall matrices,
+// 256 (one block per row) when there are too few rows to fill the machine with warps (the batch-1
+// gradient step: a few hundred rows).
+template <int TPR>
+__device__ __forceinline__ float row_sum(float v, float* red) {
+  v = warp_sum(v);
+  if constexpr (TPR == 32) {
+    return v;
+  } else {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();                       // `red` may still be read from the previous reduction
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float t = 0.0f;
+#pragma unroll
+    for (int i = 0; i < TPR / 32; ++i) t += red[i];
+    return t;
+  }
+}
+inline bool few_rows(int rows) { return rows < 4096; }
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -132,28 +153,30 @@ cudaError_t launch_transpose_bf16(const __nv_bfloat16* src, long long lds, long 
 //   forward   h = bf16(x * rstd);  y = w * h  (mode 0, Llama)    |   y = bf16(x * rstd * (1 + w))  (mode 1, Gemma)
 //   backward  dh = bf16(dy * w)  [mode 1: dy * (1 + w), fp32];  dx = bf16(rstd * (dh - xhat * mean(dh * xhat)))
 //   out       dx_out = bf16(dres + dx)   (the residual branch's gradient, when given)
+template <int TPR>
 __global__ void __launch_bounds__(256)
 rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const __nv_bfloat16* __restrict__ x,
                    long long ldx, const __nv_bfloat16* __restrict__ w, const __nv_bfloat16* dres, long long ldr,
                    __nv_bfloat16* dx, long long lddx, int rows, int d, float eps, int mode) {
-  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (r >= rows) return;
+  __shared__ float red[8];
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) / TPR;
+  const int lane = threadIdx.x % TPR;
+  if (r >= rows) return;      // whole rows (warps / blocks) leave together
   const uint4* xv = reinterpret_cast<const uint4*>(x + (long long)r * ldx);
   const uint4* gv = reinterpret_cast<const uint4*>(dy + (long long)r * lddy);
   const uint4* wv = reinterpret_cast<const uint4*>(w);
   const int nvec = d >> 3;
   float ss = 0.0f;
-  for (int v = lane; v < nvec; v += 32) {
+  for (int v = lane; v < nvec; v += TPR) {
     float a[8];
     unpack8(xv[v], a);
 #pragma unroll
     for (int j = 0; j < 8; ++j) ss = fmaf(a[j], a[j], ss);
   }
-  ss = warp_sum(ss);
+  ss = row_sum<TPR>(ss, red);
   const float rstd = rsqrtf(ss / static_cast<float>(d) + eps);
   float dot = 0.0f;                       // sum(dh * xhat)
-  for (int v = lane; v < nvec; v += 32) {
+  for (int v = lane; v < nvec; v += TPR) {
     float a[8], g[8], ww[8];
     unpack8(xv[v], a); unpack8(gv[v], g); unpack8(wv[v], ww);
 #pragma unroll
@@ -162,10 +185,10 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const _
       dot = fmaf(dh, a[j] * rstd, dot);
     }
   }
-  dot = warp_sum(dot) / static_cast<float>(d);
+  dot = row_sum<TPR>(dot, red) / static_cast<float>(d);
   const uint4* rv = dres != nullptr ? reinterpret_cast<const uint4*>(dres + (long long)r * ldr) : nullptr;
   uint4* ov = reinterpret_cast<uint4*>(dx + (long long)r * lddx);
-  for (int v = lane; v < nvec; v += 32) {
+  for (int v = lane; v < nvec; v += TPR) {
     float a[8], g[8], ww[8], o[8];
     unpack8(xv[v], a); unpack8(gv[v], g); unpack8(wv[v], ww);
     float rs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -185,41 +208,44 @@ cudaError_t launch_rmsnorm_bwd(const __nv_bfloat16* dy, long long lddy, const __
                                long long lddx, int rows, int d, float eps, int mode, cudaStream_t st) {
   if (rows <= 0) return cudaSuccess;
   if ((d & 7) || (lddy & 7) || (ldx & 7) || (lddx & 7) || (dres != nullptr && (ldr & 7))) return cudaErrorInvalidValue;
-  rmsnorm_bwd_kernel<<<warp_blocks(rows), 256, 0, st>>>(dy, lddy, x, ldx, w, dres, ldr, dx, lddx, rows, d, eps, mode);
+  if (few_rows(rows)) rmsnorm_bwd_kernel<256><<<rows, 256, 0, st>>>(dy, lddy, x, ldx, w, dres, ldr, dx, lddx, rows, d, eps, mode);
+  else rmsnorm_bwd_kernel<32><<<warp_blocks(rows), 256, 0, st>>>(dy, lddy, x, ldx, w, dres, ldr, dx, lddx, rows, d, eps, mode);
   return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------
 // LayerNorm (CLIP): y = bf16((x - mean) * rstd * w + b), statistics in fp32; optional residual-free.
+template <int TPR>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ w,
                  const __nv_bfloat16* __restrict__ b, __nv_bfloat16* __restrict__ y, long long ldy, int rows, int d,
                  float eps) {
-  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (r >= rows) return;
+  __shared__ float red[8];
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) / TPR;
+  const int lane = threadIdx.x % TPR;
+  if (r >= rows) return;      // whole rows (warps / blocks) leave together
   const uint4* xv = reinterpret_cast<const uint4*>(x + (long long)r * ldx);
   const int nvec = d >> 3;
   float s1 = 0.0f;
-  for (int v = lane; v < nvec; v += 32) {
+  for (int v = lane; v < nvec; v += TPR) {
     float a[8];
     unpack8(xv[v], a);
 #pragma unroll
     for (int j = 0; j < 8; ++j) s1 += a[j];
   }
-  const float mean = warp_sum(s1) / static_cast<float>(d);
+  const float mean = row_sum<TPR>(s1, red) / static_cast<float>(d);
   float s2 = 0.0f;
-  for (int v = lane; v < nvec; v += 32) {
+  for (int v = lane; v < nvec; v += TPR) {
     float a[8];
     unpack8(xv[v], a);
 #pragma unroll
     for (int j = 0; j < 8; ++j) { const float c = a[j] - mean; s2 = fmaf(c, c, s2); }
   }
-  const float rstd = rsqrtf(warp_sum(s2) / static_cast<float>(d) + eps);
+  const float rstd = rsqrtf(row_sum<TPR>(s2, red) / static_cast<float>(d) + eps);
   const uint4* wv = reinterpret_cast<const uint4*>(w);
   const uint4* bv = reinterpret_cast<const uint4*>(b);
   uint4* yv = reinterpret_cast<uint4*>(y + (long long)r * ldy);
-  for (int v = lane; v < nvec; v += 32) {
+  for (int v = lane; v < nvec; v += TPR) {
     float a[8], ww[8], bb[8], o[8];
     unpack8(xv[v], a); unpack8(wv[v], ww); unpack8(bv[v], bb);
 #pragma unroll
@@ -232,40 +258,43 @@ cudaError_t launch_layernorm(const __nv_bfloat16* x, long long ldx, const __nv_b
                              __nv_bfloat16* y, long long ldy, int rows, int d, float eps, cudaStream_t st) {
   if (rows <= 0) return cudaSuccess;
   if ((d & 7) || (ldx & 7) || (ldy & 7)) return cudaErrorInvalidValue;
-  layernorm_kernel<<<warp_blocks(rows), 256, 0, st>>>(x, ldx, w, b, y, ldy, rows, d, eps);
+  if (few_rows(rows)) layernorm_kernel<256><<<rows, 256, 0, st>>>(x, ldx, w, b, y, ldy, rows, d, eps);
+  else layernorm_kernel<32><<<warp_blocks(rows), 256, 0, st>>>(x, ldx, w, b, y, ldy, rows, d, eps);
   return cudaGetLastError();
 }
 
 // dx = bf16(dres + rstd * (g - mean(g) - xhat * mean(g * xhat))), g = dy * w
+template <int TPR>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const __nv_bfloat16* __restrict__ x,
                      long long ldx, const __nv_bfloat16* __restrict__ w, const __nv_bfloat16* dres, long long ldr,
                      __nv_bfloat16* dx, long long lddx, int rows, int d, float eps) {
-  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (r >= rows) return;
+  __shared__ float red[8];
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) / TPR;
+  const int lane = threadIdx.x % TPR;
+  if (r >= rows) return;      // whole rows (warps / blocks) leave together
   const uint4* xv = reinterpret_cast<const uint4*>(x + (long long)r * ldx);
   const uint4* gv = reinterpret_cast<const uint4*>(dy + (long long)r * lddy);
   const uint4* wv = reinterpret_cast<const uint4*>(w);
   const int nvec = d >> 3;
   float s1 = 0.0f;
-  for (int v = lane; v < nvec; v += 32) {
+  for (int v = lane; v < nvec; v += TPR) {
     float a[8];
     unpack8(xv[v], a);
 #pragma unroll
     for (int j = 0; j < 8; ++j) s1 += a[j];
   }
-  const float mean = warp_sum(s1) / static_cast<float>(d);
+  const float mean = row_sum<TPR>(s1, red) / static_cast<float>(d);
   float s2 = 0.0f;
-  for (int v = lane; v < nvec; v += 32) {
+  for (int v = lane; v < nvec; v += TPR) {
     float a[8];
     unpack8(xv[v], a);
 #pragma unroll
     for (int j = 0; j < 8; ++j) { const float c = a[j] - mean; s2 = fmaf(c, c, s2); }
   }
-  const float rstd = rsqrtf(warp_sum(s2) / static_cast<float>(d) + eps);
+  const float rstd = rsqrtf(row_sum<TPR>(s2, red) / static_cast<float>(d) + eps);
   float sg = 0.0f, sgx = 0.0f;
-  for (int v = lane; v < nvec; v += 32) {
+  for (int v = lane; v < nvec; v += TPR) {
     float a[8], g[8], ww[8];
     unpack8(xv[v], a); unpack8(gv[v], g); unpack8(wv[v], ww);
 #pragma unroll
@@ -275,11 +304,11 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long lddy, const
       sgx = fmaf(gg, (a[j] - mean) * rstd, sgx);
     }
   }
-  sg = warp_sum(sg) / static_cast<float>(d);
-  sgx = warp_sum(sgx) / static_cast<float>(d);
+  sg = row_sum<TPR>(sg, red) / static_cast<float>(d);
+  sgx = row_sum<TPR>(sgx, red) / static_cast<float>(d);
   const uint4* rv = dres != nullptr ? reinterpret_cast<const uint4*>(dres + (long long)r * ldr) : nullptr;
   uint4* ov = reinterpret_cast<uint4*>(dx + (long long)r * lddx);
-  for (int v = lane; v < nvec; v += 32) {
+  for (int v = lane; v < nvec; v += TPR) {
     float a[8], g[8], ww[8], o[8];
     unpack8(xv[v], a); unpack8(gv[v], g); unpack8(wv[v], ww);
     float rs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -298,7 +327,8 @@ cudaError_t launch_layernorm_bwd(const __nv_bfloat16* dy, long long lddy, const 
                                  long long lddx, int rows, int d, float eps, cudaStream_t st) {
   if (rows <= 0) return cudaSuccess;
   if ((d & 7) || (lddy & 7) || (ldx & 7) || (lddx & 7) || (dres != nullptr && (ldr & 7))) return cudaErrorInvalidValue;
-  layernorm_bwd_kernel<<<warp_blocks(rows), 256, 0, st>>>(dy, lddy, x, ldx, w, dres, ldr, dx, lddx, rows, d, eps);
+  if (few_rows(rows)) layernorm_bwd_kernel<256><<<rows, 256, 0, st>>>(dy, lddy, x, ldx, w, dres, ldr, dx, lddx, rows, d, eps);
+  else layernorm_bwd_kernel<32><<<warp_blocks(rows), 256, 0, st>>>(dy, lddy, x, ldx, w, dres, ldr, dx, lddx, rows, d, eps);
   return cudaGetLastError();
 }
 
