@@ -449,7 +449,7 @@ def main():
             atk.engine.prefill(pl.prefix)
             # multi-rank: the library reduces the winner key (one NCCL all-reduce) before it leaves the device
             atk.engine.score_host(ids_host[lo:hi], pl, atk.target_ids, loss_host[lo:hi], key_host, idx_base=lo,
-                                  base_ids_host=base_host)
+                                  base_ids_host=base_host, batch_hint=-(-sw // world))
         return int(key_host.item())
 
     for _ in range(max(1, args.warmup // 2)):
@@ -503,8 +503,7 @@ def main():
                 pl = atk._plan(build_batch(image))
                 eng.prefill(pl.prefix, deferred=False)
                 all_loss = eng.score(sampled, pl, atk.target_ids, base_ids=base_ids)
-                u_loss, u_idx = atk._winner()
-                eng.attach_comm(bdist.native_comm(dev, w))
+                u_loss, u_idx = atk._winner()        # (the communicator stays detached: this is the last scoring call)
             # tie-aware: bf16 activation noise (row offsets move the attention's key-block boundaries) is
             # 2 bf16 ulps of the loss; the sharded winner must be within that of the unsharded minimum
             import math

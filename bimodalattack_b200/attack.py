@@ -656,7 +656,9 @@ class BimodalAttack:
         base_ids = base[1] if base is not None and base[0] is ids else None
         # with a split prefill every rank takes part in the per-layer exchange, candidates or not
         if hi > lo or (self.world.size > 1 and base_ids is not None):
-            loss[lo:hi] = eng.score(ids[lo:hi], plan, self.target_ids, idx_base=lo, reset=False, base_ids=base_ids)
+            hint = -(-ids.shape[0] // self.world.size)          # the largest shard: every rank sizes its workspace alike
+            loss[lo:hi] = eng.score(ids[lo:hi], plan, self.target_ids, idx_base=lo, reset=False, base_ids=base_ids,
+                                    batch_hint=hint)
         bdist.reduce_winner(eng.key, eng.flag if self.config.early_stop else None, self.world)
         if self.world.size > 1 and (gather or self.gather_all_losses):
             bdist.gather_losses(loss, lo, hi, self.world)

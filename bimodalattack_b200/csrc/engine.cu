@@ -77,6 +77,16 @@ struct bma_scorer {
   int vrank = 0, vsize = 1;
   __nv_bfloat16 *xchg_send = nullptr, *xchg_recv = nullptr;
   size_t xchg_elems = 0;
+  // peer-memory exchange (NVLink): every rank's prefix buffers + flag words mapped into this process
+  // (cudaIpc handles between the ranks of a box, plain pointers between the scorers of a test group)
+  int peer_n = 0, peer_rank = 0;
+  bool peer_ipc = false;
+  void* peer_qk[8] = {};
+  void* peer_vt[8] = {};
+  void* peer_flags[8] = {};
+  unsigned long long* flags_dev = nullptr;     // [8] one word per sending rank
+  unsigned int* done_dev = nullptr;            // block counter of the scatter kernel
+  unsigned long long epoch = 0;                // exchanges issued so far (same on every rank)
   // workspace
   __nv_bfloat16 *x = nullptr, *xn = nullptr, *qk = nullptr, *vt = nullptr, *attn = nullptr, *act = nullptr;
   __nv_bfloat16* prefix_qk = nullptr;    // [layers][max_prefix][qk_dim]   Q|K rows of the prefix
@@ -112,6 +122,8 @@ struct bma_scorer {
 int comm_allgather_bytes(bma_comm* c, const void* send, void* recv, size_t bytes_per_rank, cudaStream_t st);
 int comm_rank(const bma_comm* c);
 int comm_size(const bma_comm* c);
+
+extern "C" int bma_scorer_clear_peers(bma_scorer* s);
 
 namespace {
 struct ProfScope {
@@ -271,6 +283,12 @@ int layer_pack(bma_scorer* s, int l, const Pass& ps, cudaStream_t st) {
   return copy_kv(s, s->qk + s->q_dim, s->qk_dim, s->vt, s->ld_vt, s->xchg_send, s->kv_dim,
                  s->xchg_send + (size_t)ps.pre_chunk * s->kv_dim, ps.pre_chunk, ps.pre_n, 0, st);
 }
+// The base suffix's first n_share rows (they follow the prefix rows) -> prefix keys [P, P + n_share).
+int layer_publish_base(bma_scorer* s, int l, const Pass& ps, int P, cudaStream_t st) {
+  ProfScope pr(s, PC_EMBED, 0, st);
+  return copy_kv(s, s->qk + (size_t)ps.pre_n * s->qk_dim + s->q_dim, s->qk_dim, s->vt + ps.pre_n, s->ld_vt,
+                 layer_pre_qk(s, l) + s->q_dim, s->qk_dim, layer_pre_vt(s, l), s->ld_vtp, ps.n_share, P, st);
+}
 // Everything a single rank publishes in one copy: prefix rows [0, pre_n) (pre0 == 0) + the base rows.
 int layer_publish_local(bma_scorer* s, int l, const Pass& ps, int P, cudaStream_t st) {
   ProfScope pr(s, PC_EMBED, 0, st);
@@ -367,6 +385,47 @@ int layer_back(bma_scorer* s, int l, Pass& ps, cudaStream_t st) {
   return 0;
 }
 
+// Peer-memory exchange of layer l, send side: this rank's prefix-position K/V go straight into every
+// rank's layer-l prefix buffers (its own too), then its flag is raised on every rank.
+int layer_scatter_peers(bma_scorer* s, int l, const Pass& ps, cudaStream_t st) {
+  void* pk[8]; void* pv[8];
+  const size_t qk_off = ((size_t)l * s->desc.max_prefix * s->qk_dim + s->q_dim) * sizeof(__nv_bfloat16);
+  const size_t vt_off = (size_t)l * s->kv_dim * s->ld_vtp * sizeof(__nv_bfloat16);
+  for (int q = 0; q < s->peer_n; ++q) {
+    pk[q] = static_cast<char*>(s->peer_qk[q]) + qk_off;
+    pv[q] = static_cast<char*>(s->peer_vt[q]) + vt_off;
+  }
+  ++s->epoch;
+  ProfScope pr(s, PC_EMBED, 0, st);
+  BMA_LAUNCH(launch_prefix_scatter(s->qk + s->q_dim, s->qk_dim, s->vt, s->ld_vt, pk, pv, s->peer_flags, s->peer_n,
+                                   s->peer_rank, s->qk_dim, s->ld_vtp, ps.pre_n, ps.pre0, s->kv_dim, s->done_dev,
+                                   s->epoch, st), "prefix_scatter");
+  return 0;
+}
+// ... receive side: wait until every rank's flag has reached this exchange, then append the base rows locally.
+int layer_wait_peers(bma_scorer* s, int l, const Pass& ps, int P, cudaStream_t st) {
+  {
+    ProfScope pr(s, PC_EMBED, 0, st);
+    BMA_LAUNCH(launch_prefix_wait(s->flags_dev, s->peer_n, s->epoch, st), "prefix_wait");
+  }
+  return layer_publish_base(s, l, ps, P, st);
+}
+int layer_exchange_peers(bma_scorer* s, int l, const Pass& ps, int P, cudaStream_t st) {
+  int rc = layer_scatter_peers(s, l, ps, st);
+  if (rc != 0) return rc;
+  return layer_wait_peers(s, l, ps, P, st);
+}
+// Barrier over the ranks (no data): nobody writes into a rank's prefix buffers while that rank may still
+// be reading them for an earlier pass.
+int peers_barrier(bma_scorer* s, cudaStream_t st) {
+  Pass none;
+  none.pre_n = 0; none.pre0 = 0;
+  int rc = layer_scatter_peers(s, 0, none, st);
+  if (rc != 0) return rc;
+  BMA_LAUNCH(launch_prefix_wait(s->flags_dev, s->peer_n, s->epoch, st), "prefix_wait");
+  return 0;
+}
+
 // A whole pass on ONE scorer (no other scorer takes part in the prefix exchange except through `comm`).
 int run_layers(bma_scorer* s, Pass& ps, cudaStream_t st) {
   const bma_model_desc& D = s->desc;
@@ -377,7 +436,9 @@ int run_layers(bma_scorer* s, Pass& ps, cudaStream_t st) {
     if (rc != 0) return rc;
     if (ps.prefill && l == D.n_layers - 1) break;   // only this layer's K/V are needed
     if (ps.publish) {
-      if (ps.pre_chunk > 0) {                        // prefix positions split over the ranks of comm
+      if (ps.pre_chunk > 0 && s->peer_n > 1) {       // split prefill over NVLink peer memory
+        rc = layer_exchange_peers(s, l, ps, P, st);
+      } else if (ps.pre_chunk > 0) {                 // split prefill through an NCCL all-gather
         rc = layer_pack(s, l, ps, st);
         if (rc != 0) return rc;
         const size_t blk = 2 * (size_t)ps.pre_chunk * s->kv_dim;
@@ -509,6 +570,8 @@ bma_scorer* bma_scorer_create(const bma_model_desc* desc) {
   ok = ok && dev_alloc(&s->cand_tmp, static_cast<size_t>(D.max_rows) + 1, &s->ws_bytes);
   ok = ok && dev_alloc(&s->total_rows_dev, 1, &s->ws_bytes);
   ok = ok && dev_alloc(&s->rows_accum_dev, 1, &s->ws_bytes);
+  ok = ok && dev_alloc(&s->flags_dev, 8, &s->ws_bytes);
+  ok = ok && dev_alloc(&s->done_dev, 1, &s->ws_bytes);
   ok = ok && dev_alloc(&s->base_dev, 4096, &s->ws_bytes);
   ok = ok && cudaHostAlloc(reinterpret_cast<void**>(&s->total_rows_host), sizeof(int), cudaHostAllocDefault) == cudaSuccess;
   ok = ok && dev_alloc(&s->ids_dev, static_cast<size_t>(D.max_rows), &s->ws_bytes);
@@ -525,6 +588,8 @@ bma_scorer* bma_scorer_create(const bma_model_desc* desc) {
 
 void bma_scorer_destroy(bma_scorer* s) {
   if (s == nullptr) return;
+  bma_scorer_clear_peers(s);
+  cudaFree(s->flags_dev); cudaFree(s->done_dev);
   cudaFree(s->x); cudaFree(s->xn); cudaFree(s->qk); cudaFree(s->vt); cudaFree(s->attn); cudaFree(s->act);
   cudaFree(s->prefix_qk); cudaFree(s->prefix_vt); cudaFree(s->ce_part); cudaFree(s->ce_arg); cudaFree(s->tgt_logit);
   cudaFree(s->xchg_send); cudaFree(s->xchg_recv); cudaFree(s->rows_accum_dev);
@@ -788,6 +853,8 @@ int score_one(bma_scorer* s, const ScoreArgs& a, cudaStream_t st, bool reset_cou
   if (rc != 0) return rc;
   const int size = s->comm != nullptr ? comm_size(s->comm) : 1;
   const int rank = s->comm != nullptr ? comm_rank(s->comm) : 0;
+  if (s->peer_n > 1 && (s->peer_n != size || s->peer_rank != rank))
+    return fail(cudaErrorInvalidValue, "score: peer set does not match the communicator");
   if (a.B <= 0 && !(size > 1 && s->pending_prefix != nullptr && a.base_ids != nullptr)) return 0;
   if (reset_counters) {
     s->last_rows = 0;
@@ -800,7 +867,10 @@ int score_one(bma_scorer* s, const ScoreArgs& a, cudaStream_t st, bool reset_cou
     rc = bma_scorer_prefill(s, s->pending_prefix, s->pending_P, st);
     if (rc != 0) return rc;
   }
-  if (sp.fused && sp.pre_chunk > 0) {
+  if (sp.fused && sp.pre_chunk > 0 && s->peer_n > 1) {
+    rc = peers_barrier(s, st);       // every rank is done reading its prefix buffers from earlier passes
+    if (rc != 0) return rc;
+  } else if (sp.fused && sp.pre_chunk > 0) {
     rc = ensure_xchg(s, sp.pre_chunk, size);
     if (rc != 0) return rc;
   }
@@ -846,7 +916,7 @@ int bma_scorer_score(bma_scorer* s, const long long* ids, int ids_stride, int B,
 int bma_scorer_group_score(bma_scorer** group, int n, const long long* ids, int ids_stride, int B,
                            const int* slot, const void* fixed, int S, const long long* target_ids, int T,
                            int ce_row0, float* loss, unsigned long long* key, int* all_match,
-                           const long long* base_ids, int n_id_rows, void* stream) {
+                           const long long* base_ids, int n_id_rows, int use_peers, void* stream) {
   if (group == nullptr || n <= 0) return fail(cudaErrorInvalidValue, "group_score: empty group");
   cudaStream_t st = as_stream(stream);
   std::vector<ScoreArgs> args(n);
@@ -881,10 +951,23 @@ int bma_scorer_group_score(bma_scorer** group, int n, const long long* ids, int 
     return 0;
   }
   const int P = group[0]->pending_P;
+  const bool via_peers = n <= 8 && use_peers;
   for (int r = 0; r < n; ++r) {
     bma_scorer* s = group[r];
-    int rc = ensure_xchg(s, plans[r].pre_chunk, n);
-    if (rc != 0) return rc;
+    int rc = 0;
+    if (via_peers) {                           // the scorers of the group are each other's "peers": plain pointers
+      bma_scorer_clear_peers(s);
+      BMA_CHECK(cudaMemsetAsync(s->flags_dev, 0, 8 * sizeof(unsigned long long), st), "group_score: reset flags");
+      BMA_CHECK(cudaMemsetAsync(s->done_dev, 0, sizeof(unsigned int), st), "group_score: reset counter");
+      s->epoch = 0;
+      s->peer_n = n; s->peer_rank = r; s->peer_ipc = false;
+      for (int q = 0; q < n; ++q) {
+        s->peer_qk[q] = group[q]->prefix_qk; s->peer_vt[q] = group[q]->prefix_vt; s->peer_flags[q] = group[q]->flags_dev;
+      }
+    } else {
+      rc = ensure_xchg(s, plans[r].pre_chunk, n);
+      if (rc != 0) return rc;
+    }
     const int most = args[r].B < plans[r].chunk ? args[r].B : plans[r].chunk;
     rc = ensure_ce_rows(s, (most > 0 ? most : 1) * T);
     if (rc != 0) return rc;
@@ -898,24 +981,31 @@ int bma_scorer_group_score(bma_scorer** group, int n, const long long* ids, int 
     for (int r = 0; r < n; ++r) {
       int rc = layer_front(group[r], l, pass[r], st);
       if (rc != 0) return rc;
-      rc = layer_pack(group[r], l, pass[r], st);
+      rc = via_peers ? layer_scatter_peers(group[r], l, pass[r], st) : layer_pack(group[r], l, pass[r], st);
       if (rc != 0) return rc;
     }
     for (int r = 0; r < n; ++r) {
       bma_scorer* s = group[r];
-      const size_t blk = 2 * (size_t)pass[r].pre_chunk * s->kv_dim;
-      for (int q = 0; q < n; ++q)             // the all-gather, as local copies into this rank's receive buffer
-        BMA_CHECK(cudaMemcpyAsync(s->xchg_recv + q * blk, group[q]->xchg_send, blk * sizeof(__nv_bfloat16),
-                                  cudaMemcpyDeviceToDevice, st), "group_score: gather copy");
-      BMA_LAUNCH(launch_unpack_prefix_kv(s->xchg_recv, static_cast<long long>(blk), pass[r].pre_chunk, n, P,
-                                         s->qk + s->q_dim, s->qk_dim, s->vt, s->ld_vt, pass[r].pre_n,
-                                         pass[r].n_share, layer_pre_qk(s, l) + s->q_dim, s->qk_dim,
-                                         layer_pre_vt(s, l), s->ld_vtp, s->kv_dim, st), "unpack_prefix_kv");
       int rc = 0;
+      if (via_peers) {
+        rc = layer_wait_peers(s, l, pass[r], P, st);
+        if (rc != 0) return rc;
+      } else {
+        const size_t blk = 2 * (size_t)pass[r].pre_chunk * s->kv_dim;
+        for (int q = 0; q < n; ++q)             // the all-gather, as local copies into this rank's receive buffer
+          BMA_CHECK(cudaMemcpyAsync(s->xchg_recv + q * blk, group[q]->xchg_send, blk * sizeof(__nv_bfloat16),
+                                    cudaMemcpyDeviceToDevice, st), "group_score: gather copy");
+        BMA_LAUNCH(launch_unpack_prefix_kv(s->xchg_recv, static_cast<long long>(blk), pass[r].pre_chunk, n, P,
+                                           s->qk + s->q_dim, s->qk_dim, s->vt, s->ld_vt, pass[r].pre_n,
+                                           pass[r].n_share, layer_pre_qk(s, l) + s->q_dim, s->qk_dim,
+                                           layer_pre_vt(s, l), s->ld_vtp, s->kv_dim, st), "unpack_prefix_kv");
+      }
       rc = layer_back(group[r], l, pass[r], st);
       if (rc != 0) return rc;
     }
   }
+  if (via_peers)
+    for (int r = 0; r < n; ++r) bma_scorer_clear_peers(group[r]);
   for (int r = 0; r < n; ++r) {
     bma_scorer* s = group[r];
     int rc = chunk_end(s, args[r], 0, nb0[r], st);
@@ -960,6 +1050,55 @@ int bma_scorer_score_host(bma_scorer* s, const long long* ids_host, int ids_stri
   BMA_CHECK(cudaMemcpyAsync(key_host, s->key_dev, sizeof(unsigned long long),
                             cudaMemcpyDeviceToHost, st), "score_host: D2H key");
   BMA_CHECK(cudaStreamSynchronize(st), "score_host: sync");
+  return 0;
+}
+
+// ---- peer memory (NVLink) ------------------------------------------------------------------------
+int bma_scorer_clear_peers(bma_scorer* s) {
+  if (s == nullptr) return 0;
+  if (s->peer_ipc) {
+    for (int q = 0; q < s->peer_n; ++q) {
+      if (q == s->peer_rank) continue;
+      if (s->peer_qk[q] != nullptr) cudaIpcCloseMemHandle(s->peer_qk[q]);
+      if (s->peer_vt[q] != nullptr) cudaIpcCloseMemHandle(s->peer_vt[q]);
+      if (s->peer_flags[q] != nullptr) cudaIpcCloseMemHandle(s->peer_flags[q]);
+    }
+  }
+  for (int q = 0; q < 8; ++q) { s->peer_qk[q] = s->peer_vt[q] = s->peer_flags[q] = nullptr; }
+  s->peer_n = 0; s->peer_ipc = false;
+  return 0;
+}
+
+int bma_scorer_export_ipc(bma_scorer* s, void* out192) {
+  if (s == nullptr || out192 == nullptr) return fail(cudaErrorInvalidValue, "export_ipc: bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  cudaIpcMemHandle_t h[3];
+  // flags and epoch restart here, BEFORE the handles travel: no peer can signal into this scorer earlier
+  bma_scorer_clear_peers(s);
+  BMA_CHECK(cudaMemset(s->flags_dev, 0, 8 * sizeof(unsigned long long)), "export_ipc: reset flags");
+  BMA_CHECK(cudaMemset(s->done_dev, 0, sizeof(unsigned int)), "export_ipc: reset counter");
+  s->epoch = 0;
+  BMA_CHECK(cudaIpcGetMemHandle(&h[0], s->prefix_qk), "export_ipc: prefix K");
+  BMA_CHECK(cudaIpcGetMemHandle(&h[1], s->prefix_vt), "export_ipc: prefix V^T");
+  BMA_CHECK(cudaIpcGetMemHandle(&h[2], s->flags_dev), "export_ipc: flags");
+  memcpy(out192, h, sizeof(h));
+  return 0;
+}
+
+int bma_scorer_import_ipc(bma_scorer* s, const void* handles, int size, int rank) {
+  if (s == nullptr || handles == nullptr || size < 2 || size > 8 || rank < 0 || rank >= size)
+    return fail(cudaErrorInvalidValue, "import_ipc: bad arguments (2..8 ranks)");
+  const cudaIpcMemHandle_t* h = static_cast<const cudaIpcMemHandle_t*>(handles);
+  s->peer_n = size; s->peer_rank = rank; s->peer_ipc = true;
+  for (int q = 0; q < size; ++q) {
+    if (q == rank) {
+      s->peer_qk[q] = s->prefix_qk; s->peer_vt[q] = s->prefix_vt; s->peer_flags[q] = s->flags_dev;
+      continue;
+    }
+    BMA_CHECK(cudaIpcOpenMemHandle(&s->peer_qk[q], h[3 * q + 0], cudaIpcMemLazyEnablePeerAccess), "import_ipc: open prefix K");
+    BMA_CHECK(cudaIpcOpenMemHandle(&s->peer_vt[q], h[3 * q + 1], cudaIpcMemLazyEnablePeerAccess), "import_ipc: open prefix V^T");
+    BMA_CHECK(cudaIpcOpenMemHandle(&s->peer_flags[q], h[3 * q + 2], cudaIpcMemLazyEnablePeerAccess), "import_ipc: open flags");
+  }
   return 0;
 }
 

@@ -60,6 +60,11 @@ cudaError_t launch_unpack_prefix_kv(const __nv_bfloat16* recv, long long blk, in
                                     const __nv_bfloat16* k_tail, long long ldk, const __nv_bfloat16* vt_tail,
                                     long long ldvt, int base_row0, int n_base, __nv_bfloat16* k_pre, long long ldkp,
                                     __nv_bfloat16* vt_pre, long long ldvtp, int kv_dim, cudaStream_t stream);
+cudaError_t launch_prefix_scatter(const __nv_bfloat16* k_tail, long long ldk, const __nv_bfloat16* vt_tail, long long ldvt,
+                                  void* const* peer_k, void* const* peer_vt, void* const* peer_flags, int n_ranks,
+                                  int my_rank, long long ldkp, long long ldvtp, int n, int key0, int kv_dim,
+                                  unsigned int* done_counter, unsigned long long epoch, cudaStream_t stream);
+cudaError_t launch_prefix_wait(unsigned long long* flags, int n_ranks, unsigned long long epoch, cudaStream_t stream);
 cudaError_t launch_rmsnorm(const __nv_bfloat16* x, long long ldx, const __nv_bfloat16* w,
                            __nv_bfloat16* y, long long ldy, int rows, int d, float eps, int mode,
                            int gather_T, int gather_S, int gather_off, const int* gather_vstart,

@@ -208,6 +208,85 @@ cudaError_t launch_unpack_prefix_kv(const __nv_bfloat16* recv, long long blk, in
 }
 
 // ------------------------------------------------------------------------------------------------
+// Split prefill over NVLink peer memory. Every rank owns the K / V^T of `n` prefix positions starting at
+// key `key0` (tail rows [0, n) of its pass) and STORES them straight into the per-layer prefix buffers
+// of every rank of the box -- its own included -- through peer-mapped pointers (st.global over
+// NVLink 5 / NVSwitch); no staging buffer, no collective. The last block to finish fences at system
+// scope and raises this rank's flag on every peer; prefix_wait_kernel then spins (bounded, then traps)
+// until all ranks' flags have reached the epoch of this exchange.
+struct PeerPtrs {
+  __nv_bfloat16* k[8];              // per rank: K columns of this layer's prefix buffer  ([key][ldkp])
+  __nv_bfloat16* vt[8];             // per rank: V^T of this layer's prefix buffer        ([dim][ldvtp])
+  unsigned long long* flags[8];     // per rank: its flag array, one word per sending rank
+};
+
+__global__ void __launch_bounds__(256)
+prefix_scatter_kernel(const __nv_bfloat16* __restrict__ k_tail, long long ldk, const __nv_bfloat16* __restrict__ vt_tail,
+                      long long ldvt, PeerPtrs peers, int n_ranks, int my_rank, long long ldkp, long long ldvtp,
+                      int n, int key0, int kv_dim, unsigned int* done_counter, unsigned long long epoch) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (long long)n * kv_dim) {
+    const int key = static_cast<int>(i / kv_dim), c = static_cast<int>(i - (long long)key * kv_dim);
+    const __nv_bfloat16 kv = k_tail[(long long)key * ldk + c];          // K: consecutive threads -> consecutive columns
+    const int dim = static_cast<int>(i / n), kk = static_cast<int>(i - (long long)dim * n);
+    const __nv_bfloat16 vv = vt_tail[(long long)dim * ldvt + kk];       // V^T: consecutive threads -> consecutive keys
+    for (int q = 0; q < n_ranks; ++q) {
+      peers.k[q][(long long)(key0 + key) * ldkp + c] = kv;
+      peers.vt[q][(long long)dim * ldvtp + key0 + kk] = vv;
+    }
+  }
+  // publish: every block's stores are fenced system-wide before it counts itself done; the last one signals
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(done_counter, 1u);
+    if (prev == gridDim.x - 1) {
+      *done_counter = 0;                                     // ready for the next exchange
+      __threadfence_system();
+      for (int q = 0; q < n_ranks; ++q)
+        atomicExch_system(peers.flags[q] + my_rank, epoch);
+    }
+  }
+}
+
+__global__ void prefix_wait_kernel(volatile unsigned long long* flags, int n_ranks, unsigned long long epoch) {
+  const int q = threadIdx.x;
+  if (q < n_ranks) {
+    unsigned int spins = 0;
+    while (flags[q] < epoch) {
+      if (++spins > (1u << 27)) {                            // ~seconds: a rank never arrived
+        if (g_watchdog_host != nullptr) { *g_watchdog_host = 0xE000u | q; __threadfence_system(); }
+        __trap();
+      }
+    }
+  }
+  __threadfence_system();
+}
+
+cudaError_t launch_prefix_scatter(const __nv_bfloat16* k_tail, long long ldk, const __nv_bfloat16* vt_tail, long long ldvt,
+                                  void* const* peer_k, void* const* peer_vt, void* const* peer_flags, int n_ranks,
+                                  int my_rank, long long ldkp, long long ldvtp, int n, int key0, int kv_dim,
+                                  unsigned int* done_counter, unsigned long long epoch, cudaStream_t stream) {
+  if (n_ranks < 1 || n_ranks > 8) return cudaErrorInvalidValue;
+  PeerPtrs pp{};
+  for (int q = 0; q < n_ranks; ++q) {
+    pp.k[q] = static_cast<__nv_bfloat16*>(peer_k[q]);
+    pp.vt[q] = static_cast<__nv_bfloat16*>(peer_vt[q]);
+    pp.flags[q] = static_cast<unsigned long long*>(peer_flags[q]);
+  }
+  const long long total = (long long)(n > 0 ? n : 0) * kv_dim;
+  const int blocks = total > 0 ? static_cast<int>((total + 255) / 256) : 1;   // a rank without positions still signals
+  prefix_scatter_kernel<<<blocks, 256, 0, stream>>>(k_tail, ldk, vt_tail, ldvt, pp, n_ranks, my_rank, ldkp, ldvtp,
+                                                    n > 0 ? n : 0, key0, kv_dim, done_counter, epoch);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_prefix_wait(unsigned long long* flags, int n_ranks, unsigned long long epoch, cudaStream_t stream) {
+  prefix_wait_kernel<<<1, 32, 0, stream>>>(flags, n_ranks, epoch);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 // out[row, :] = slot[s] >= 0 ? round_bf16(W[ids[b, slot[s]], :] * scale) : fixed[s, :]
 // Uniform layout (row_info == null): row = b*S + s. Ragged layout: (b, s) = row_info[row], b = -1
 // reads the base ids.

@@ -77,6 +77,26 @@ def native_comm(device, w: Optional[World] = None):
     return handle
 
 
+def exchange_peer_handles(lib, scorer, device) -> None:
+    """Collective: map every rank's prefix buffers + flag words into every other rank's scorer
+    (cudaIpc handles, 192 bytes per rank, carried by torch.distributed) -- the NVLink peer-memory
+    exchange of the split prefill (include/bimodal_b200.h, bma_scorer_export_ipc / import_ipc)."""
+    import ctypes as C
+    from . import native
+    w = world()
+    if w.size < 2 or w.size > 8:
+        return
+    buf = (C.c_ubyte * 192)()
+    with torch.cuda.device(device):
+        native.check(lib.bma_scorer_export_ipc(scorer, buf), "scorer_export_ipc")
+    mine = torch.tensor(list(buf), dtype=torch.uint8, device=device)
+    gathered = torch.empty(192 * w.size, dtype=torch.uint8, device=device)
+    td.all_gather_into_tensor(gathered, mine)        # also orders "flags reset" before anybody's first signal
+    raw = bytes(gathered.cpu().tolist())
+    with torch.cuda.device(device):
+        native.check(lib.bma_scorer_import_ipc(scorer, raw, w.size, w.rank), "scorer_import_ipc")
+
+
 def reduce_winner(key: torch.Tensor, flag: Optional[torch.Tensor], w: World) -> None:
     """In-place MIN all-reduce of the int64 key (and MAX of the early-stop flag when given): ONE NCCL
     launch on the scorer's stream through the library's communicator; torch.distributed (gloo in

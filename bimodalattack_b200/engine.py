@@ -110,6 +110,10 @@ class ScoringEngine:
         self.fused_prefill = True
         self.prefill_tag = None          # what the resident prefix K/V were computed from (set by the attack)
         self.comm = None                 # native NCCL communicator (dist.native_comm) for multi-rank runs
+        # multi-rank split prefill through NVLink peer memory (cudaIpc-mapped prefix buffers + flags)
+        # instead of an NCCL all-gather per layer; BMA_PEER_MEMORY=0 keeps the all-gather (A/B runs)
+        import os
+        self.peer_memory = os.environ.get("BMA_PEER_MEMORY", "1") != "0"
         self._last_prefix: Optional[torch.Tensor] = None
         self._prefix_stale = False
 
@@ -165,6 +169,11 @@ class ScoringEngine:
         native.check(self.lib.bma_scorer_set_dedupe(handle, int(self.dedupe_candidates)), "scorer_set_dedupe")
         if self.comm is not None:
             native.check(self.lib.bma_scorer_set_comm(handle, self.comm), "scorer_set_comm")
+            if self.peer_memory:
+                # collective: every rank re-creates its scorer at the same call (capacities depend only on
+                # quantities that are equal on all ranks), so the handle exchange lines up
+                from . import dist as bdist
+                bdist.exchange_peer_handles(self.lib, handle, self.device)
         self._cap_rows, self._cap_prefix = cap_rows, cap_prefix
         self._prefix_stale = True        # a new scorer has no prefix K/V yet
         for i, layer in enumerate(self.lm.layers):
@@ -225,10 +234,16 @@ class ScoringEngine:
         self._ensure(rows, prefix)
 
     def attach_comm(self, comm):
-        """Native communicator (``dist.native_comm``): the fused prefill is then split over its ranks."""
+        """Native communicator (``dist.native_comm``): the fused prefill is then split over its ranks.
+        Collective when a scorer already exists (peer handles are exchanged)."""
         self.comm = comm
         if self._scorer is not None:
             native.check(self.lib.bma_scorer_set_comm(self._scorer, comm), "scorer_set_comm")
+            if comm is None:
+                native.check(self.lib.bma_scorer_clear_peers(self._scorer), "scorer_clear_peers")
+            elif self.peer_memory:
+                from . import dist as bdist
+                bdist.exchange_peer_handles(self.lib, self._scorer, self.device)
 
     def prefill(self, prefix_embeds: Optional[torch.Tensor], deferred: Optional[bool] = None):
         """Compute and keep the K/V of the shared prefix ([P, d] bf16; None/empty = no prefix). With
@@ -261,7 +276,7 @@ class ScoringEngine:
                                                        native.stream_ptr(self.device)), "scorer_reset_key")
 
     def score(self, ids: torch.Tensor, plan: TailPlan, target_ids: torch.Tensor, idx_base: int = 0,
-              reset: bool = True, base_ids: Optional[torch.Tensor] = None) -> torch.Tensor:
+              reset: bool = True, base_ids: Optional[torch.Tensor] = None, batch_hint: int = 0) -> torch.Tensor:
         """Per-candidate mean CE (fp32, [B]). ``self.key`` receives the packed (loss, index) minimum
         and ``self.flag`` the early-stop indicator. ``base_ids`` ([n_optim] int64): the suffix the
         candidates were sampled from; rows a candidate shares with it are computed once."""
@@ -271,7 +286,8 @@ class ScoringEngine:
         S, row0 = self._tail_rows(plan, T)
         self._check_length(S)
         share = self._share_rows(ids, base_ids)
-        self._ensure(max(self._cap_rows, (min(B, 4096) + (1 if share else 0)) * S + self._fused_rows(share)),
+        # batch_hint: the largest shard of a multi-rank call, so every rank sizes (and re-creates) alike
+        self._ensure(max(self._cap_rows, (min(max(B, batch_hint), 4096) + (1 if share else 0)) * S + self._fused_rows(share)),
                      max(self._cap_prefix, self.prefix_len + share))
         if self._prefix_stale:           # the workspace was re-created after the last prefill
             self.prefill(self._last_prefix, deferred=getattr(self, "_last_deferred", None))
@@ -325,14 +341,15 @@ class ScoringEngine:
 
     def score_host(self, ids_host: torch.Tensor, plan: TailPlan, target_ids: torch.Tensor,
                    loss_host: torch.Tensor, key_host: torch.Tensor, idx_base: int = 0,
-                   base_ids_host: Optional[torch.Tensor] = None):
+                   base_ids_host: Optional[torch.Tensor] = None, batch_hint: int = 0):
         """End-to-end entry: pinned host ids in, pinned host losses + key out (synchronises)."""
         B, T = ids_host.shape[0], target_ids.numel()
         S, row0 = self._tail_rows(plan, T)
         self._check_length(S)
         share = self._share_rows(ids_host, base_ids_host)
-        self._ensure(max(self._cap_rows, (min(B, 4096) + (1 if share else 0)) * S + self._fused_rows(share),
-                         B * ids_host.shape[1]),
+        Bh = max(B, batch_hint)
+        self._ensure(max(self._cap_rows, (min(Bh, 4096) + (1 if share else 0)) * S + self._fused_rows(share),
+                         Bh * ids_host.shape[1]),
                      max(self._cap_prefix, self.prefix_len + share))
         if self._prefix_stale:
             self.prefill(self._last_prefix, deferred=getattr(self, "_last_deferred", None))
@@ -346,7 +363,7 @@ class ScoringEngine:
 
 
 def group_score(engines, ids: torch.Tensor, plan: TailPlan, target_ids: torch.Tensor,
-                base_ids: torch.Tensor) -> torch.Tensor:
+                base_ids: torch.Tensor, use_peers: bool = True) -> torch.Tensor:
     """Single-process form of the multi-rank scoring path (C ABI ``bma_scorer_group_score``): the
     engines act as the ranks of one box on one device -- contiguous candidate shards, the deferred
     prefix split over them, the per-layer K/V all-gather done as local copies. Every engine must have
@@ -371,7 +388,7 @@ def group_score(engines, ids: torch.Tensor, plan: TailPlan, target_ids: torch.Te
         native.check(e0.lib.bma_scorer_group_score(
             handles, len(engines), ids.data_ptr(), ids.stride(0), B, plan.slot.data_ptr(), plan.fixed.data_ptr(),
             S, tgt.data_ptr(), T, row0, loss.data_ptr(), e0.key.data_ptr(), e0.flag.data_ptr(),
-            base_ids.data_ptr(), plan.n_id_rows, native.stream_ptr(e0.device)), "scorer_group_score")
+            base_ids.data_ptr(), plan.n_id_rows, int(use_peers), native.stream_ptr(e0.device)), "scorer_group_score")
     for e in engines:
         e._pending_rows = 0
     return loss

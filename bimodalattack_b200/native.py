@@ -75,7 +75,10 @@ SIGNATURES = {
     "bma_scorer_prefill_deferred": (_I, [_P, _P, _I]),
     "bma_scorer_reset_key": (_I, [_P, _P, _P, _P]),
     "bma_scorer_score": (_I, [_P, _P, _I, _I, _P, _P, _I, _P, _I, _I, _P, _P, _P, _U32, _P, _I, _P]),
-    "bma_scorer_group_score": (_I, [C.POINTER(_P), _I, _P, _I, _I, _P, _P, _I, _P, _I, _I, _P, _P, _P, _P, _I, _P]),
+    "bma_scorer_group_score": (_I, [C.POINTER(_P), _I, _P, _I, _I, _P, _P, _I, _P, _I, _I, _P, _P, _P, _P, _I, _I, _P]),
+    "bma_scorer_export_ipc": (_I, [_P, _P]),
+    "bma_scorer_import_ipc": (_I, [_P, _P, _I, _I]),
+    "bma_scorer_clear_peers": (_I, [_P]),
     "bma_scorer_set_comm": (_I, [_P, _P]),
     "bma_comm_unique_id": (_I, [_P]),
     "bma_comm_create": (_P, [_P, _I, _I]),

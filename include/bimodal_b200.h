@@ -177,7 +177,17 @@ int bma_scorer_set_comm(bma_scorer* s, bma_comm* comm);
 int bma_scorer_group_score(bma_scorer** group, int n, const long long* ids, int ids_stride, int B,
                            const int* slot, const void* fixed, int S, const long long* target_ids, int T,
                            int ce_row0, float* loss, unsigned long long* key, int* all_match,
-                           const long long* base_ids, int n_id_rows, void* stream);
+                           const long long* base_ids, int n_id_rows, int use_peers, void* stream);
+/* Peer-memory form of the split prefill (NVLink 5 / NVSwitch): every rank maps the other ranks' per-layer
+ * prefix buffers and flag words (cudaIpc handles, exchanged by the host) and each layer's prefix K/V slice
+ * is STORED straight into all of them by one kernel that then raises this rank's flag everywhere; a
+ * bounded spin on the local flags replaces the collective. Without peers the exchange is an NCCL
+ * all-gather (bma_scorer_set_comm). export: 3 x 64 handle bytes of this scorer; import: the handles of all
+ * `size` ranks ([size][3][64], 2..8 ranks of one box) -- both collective over the ranks, repeated whenever a
+ * scorer is re-created. group_score's use_peers runs the same kernels between the scorers of one process. */
+int bma_scorer_export_ipc(bma_scorer* s, void* out192);
+int bma_scorer_import_ipc(bma_scorer* s, const void* handles, int size, int rank);
+int bma_scorer_clear_peers(bma_scorer* s);
 
 /* Optional per-class CUDA-event profile of the scoring pass (events on the launching stream).
  * Classes: 0 tail-embed, 1 rmsnorm, 2 gemm qkv+rope, 3 attention, 4 gemm o_proj, 5 gemm gate/up+GLU,

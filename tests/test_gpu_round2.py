@@ -91,11 +91,14 @@ def test_fused_prefill_matches_separate_prefill(cuda_device, size, px, n):
     assert bool(((fused[:64] - want).abs() <= 2e-2 * want.abs() + 1e-3).all()), (fused[:64] - want).abs().max()
 
 
+@pytest.mark.parametrize("peers", [True, False])
 @pytest.mark.parametrize("ranks,n", [(2, 48), (3, 50), (4, 3), (8, 130)])
-def test_split_prefill_over_emulated_ranks(cuda_device, ranks, n):
+def test_split_prefill_over_emulated_ranks(cuda_device, ranks, n, peers):
     """Multi-rank scoring on ONE device (bma_scorer_group_score): the candidates are sharded like
     dist.shard_bounds, the prefix positions are split over the ranks and every layer's K/V slices are
-    exchanged (local copies standing in for the NCCL all-gather). Every row is computed from the same
+    exchanged -- peers=True: the peer-memory kernels (scatter into every scorer's prefix buffers + flag
+    signal / wait, plain pointers standing in for the cudaIpc mappings); peers=False: the pack / unpack
+    kernels around local copies standing in for the NCCL all-gather. Every row is computed from the same
     K/V as on a single rank (only its offset inside the row space, hence the attention's key-block
     boundaries, differs), so losses agree with the single-rank fused pass to bf16 re-association noise,
     including ranks that own no candidate at all (n < ranks)."""
@@ -116,7 +119,7 @@ def test_split_prefill_over_emulated_ranks(cuda_device, ranks, n):
         group = [ScoringEngine(model) for _ in range(ranks)]
         for e in group:
             e.prefill(plan.prefix, deferred=True)
-        split = group_score(group, cand, plan, atk.target_ids, base).clone()
+        split = group_score(group, cand, plan, atk.target_ids, base, use_peers=peers).clone()
         key_split = int(group[0].key.item())
         # afterwards every emulated rank holds the complete prefix K/V: a plain score call on any of them agrees
         later = group[-1].score(cand, plan, atk.target_ids, base_ids=base).clone()
