@@ -5,6 +5,7 @@
 // the Python host).
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -51,6 +52,16 @@ inline const __nv_bfloat16* bf(const void* p) { return static_cast<const __nv_bf
 inline __nv_bfloat16* bf(void* p) { return static_cast<__nv_bfloat16*>(p); }
 
 constexpr int kCeBlockN = 256;
+
+// K-block stagger of the token-gradient GEMM (BMA_TOKGRAD_STAGGER overrides, 0 = off; A/B runs)
+inline int token_grad_stagger() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("BMA_TOKGRAD_STAGGER");
+    v = e != nullptr ? atoi(e) : 7;
+  }
+  return v;
+}
 
 }  // namespace
 
@@ -499,6 +510,7 @@ int bma_token_grad(const void* grad_embeds, long long ld_g, const void* W, long 
     const int nt = n_tok - t0 < 128 ? n_tok - t0 : 128;
     GemmParams p{};
     p.M = V; p.N = nt; p.K = d; p.group_m = 1 << 20;
+    p.k_stagger = token_grad_stagger();
     p.C = bf(out) + (long long)t0 * ld_out; p.ldc = ld_out;
     const __nv_bfloat16* g = bf(grad_embeds) + (long long)t0 * ld_g;
     if (nt <= 32) {
@@ -734,7 +746,7 @@ int plan_score(bma_scorer* s, const ScoreArgs& a, ScorePlan& sp, int rank, int s
   if (sp.fused) {
     const int P = s->pending_P;
     if (size > 1) {
-      sp.pre_chunk = (P + size - 1) / size;
+      sp.pre_chunk = ((P + size - 1) / size + 7) & ~7;    // 8-aligned key offsets: 16-byte stores into the V^T rows
       sp.pre0 = rank * sp.pre_chunk < P ? rank * sp.pre_chunk : P;
       sp.pre_n = P - sp.pre0 < sp.pre_chunk ? P - sp.pre0 : sp.pre_chunk;
     } else {

@@ -31,6 +31,9 @@ struct GemmParams {
   int batch;
   int a_row, a_col, b_row, b_col;
   long long c_batch;
+  int k_stagger;              // > 0: tile t walks its K blocks starting at (t * k_stagger) % k_blocks, so CTAs that
+                              // stream different rows of a power-of-two-pitch matrix do not all touch the same
+                              // HBM channels at the same time (token gradient: 8 KB pitch, tiles 1 MB apart)
   float* C32;                 // EPI_STORE: raw fp32 accumulators instead of bf16 (attention scores)
   const __nv_bfloat16* bias;  // EPI_STORE: [N] added in fp32 before the bf16 rounding (nn.Linear bias)
   int group_m;                // rasterisation: m-blocks per L2 supergroup
@@ -195,7 +198,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const int bi = tile_coords(tile, m_blk, n_blk);
         const int a_r0 = bi * p.a_row + m_blk * GEMM_BM, a_c0 = bi * p.a_col;
         const int b_r0 = bi * p.b_row + n_blk * BN, b_c0 = bi * p.b_col;
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        const int kb0 = p.k_stagger > 0 ? static_cast<int>(((long long)tile * p.k_stagger) % k_blocks) : 0;
+        for (int kk = 0; kk < k_blocks; ++kk) {
+          const int kb = kk + kb0 < k_blocks ? kk + kb0 : kk + kb0 - k_blocks;
           mbar_wait(&empty_bar[stage], phase ^ 1, 0x100 + stage);
           if constexpr (CTAS == 2) {
             // both CTAs' bytes are credited to the LEADER's full barrier, which the MMA issuer waits on

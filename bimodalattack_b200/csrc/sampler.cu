@@ -13,6 +13,8 @@
 // larger key means "earlier in torch.topk(-grad)" and equal gradients resolve to the lower token
 // id. The not-allowed mask (reference: grad[:, not_allowed_ids] = inf) is a V-bit set folded into
 // the read; the caller's gradient is not modified.
+#include <cstdlib>
+
 #include <cuda_fp16.h>
 #include <curand_kernel.h>
 
@@ -195,6 +197,119 @@ topk_merge_kernel(const uint64_t* __restrict__ cand, int n_cand, int k, int k_po
         static_cast<long long>(0xFFFFFFFFu - static_cast<uint32_t>(sel[i] & 0xFFFFFFFFull));
 }
 
+// ------------------------------------------------------------------------------------------------
+// One-launch top-k for 16-bit gradients (what the product feeds: the bf16 token gradient) over
+// vocabularies of at most 65 536 tokens: value and index both fit 16 bits, so a row's keys are 32-bit
+//   (orderable16(-g) << 16) | (0xFFFF - index)
+// and the whole row (V * 4 B <= 256 KB... 128 KB at V = 32 064) sits in ONE CTA's shared memory: read the
+// row once with 16-byte loads, 8-bit radix select (<= 4 passes), bitonic sort of the k winners, int64
+// ids out in torch.topk order. Same ordering as the 64-bit two-level path (bf16/fp16 -> fp32 is an
+// order-preserving injection; ties resolve to the lower token id).
+__device__ __forceinline__ uint32_t orderable16_neg(uint16_t bits, bool is_nan) {
+  if (is_nan) return 0xFFFFu;
+  const uint16_t u = bits ^ 0x8000u;                       // -g
+  return (u & 0x8000u) ? static_cast<uint16_t>(~u) : static_cast<uint16_t>(u | 0x8000u);
+}
+template <typename T>
+__device__ __forceinline__ uint32_t make_key16(uint16_t bits, uint32_t idx, const uint32_t* mask);
+template <>
+__device__ __forceinline__ uint32_t make_key16<__nv_bfloat16>(uint16_t bits, uint32_t idx, const uint32_t* mask) {
+  if (mask != nullptr && ((mask[idx >> 5] >> (idx & 31)) & 1u)) bits = 0x7F80u;        // +inf
+  const bool nan = (bits & 0x7FFFu) > 0x7F80u;
+  return (orderable16_neg(bits, nan) << 16) | (0xFFFFu - idx);
+}
+template <>
+__device__ __forceinline__ uint32_t make_key16<__half>(uint16_t bits, uint32_t idx, const uint32_t* mask) {
+  if (mask != nullptr && ((mask[idx >> 5] >> (idx & 31)) & 1u)) bits = 0x7C00u;        // +inf
+  const bool nan = (bits & 0x7FFFu) > 0x7C00u;
+  return (orderable16_neg(bits, nan) << 16) | (0xFFFFu - idx);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024)
+topk_row16_kernel(const T* __restrict__ grad, long long row_stride, int V, int k, int k_pow2,
+                  const uint32_t* __restrict__ mask, long long* __restrict__ topk_ids) {
+  extern __shared__ uint32_t sm32[];              // [V] keys, then [k_pow2] winners
+  uint32_t* keys = sm32;
+  uint32_t* sel = sm32 + V;
+  __shared__ uint32_t hist[256];
+  __shared__ uint32_t ctl[4];                     // prefix, mask, remaining, done
+  __shared__ uint32_t out_count;
+  const int row = blockIdx.x;
+  const uint16_t* src = reinterpret_cast<const uint16_t*>(grad + static_cast<long long>(row) * row_stride);
+  if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    const int nv = V >> 3;
+    for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+      const uint4 q = reinterpret_cast<const uint4*>(src)[v];
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t i = static_cast<uint32_t>(v * 8 + 2 * j);
+        keys[i] = make_key16<T>(static_cast<uint16_t>(w[j] & 0xFFFFu), i, mask);
+        keys[i + 1] = make_key16<T>(static_cast<uint16_t>(w[j] >> 16), i + 1, mask);
+      }
+    }
+    for (int i = (nv << 3) + threadIdx.x; i < V; i += blockDim.x) keys[i] = make_key16<T>(src[i], i, mask);
+  } else {
+    for (int i = threadIdx.x; i < V; i += blockDim.x) keys[i] = make_key16<T>(src[i], i, mask);
+  }
+  for (int i = threadIdx.x; i < k_pow2; i += blockDim.x) sel[i] = 0u;
+  if (threadIdx.x == 0) { ctl[0] = 0; ctl[1] = 0; ctl[2] = static_cast<uint32_t>(k); ctl[3] = 0; out_count = 0; }
+  __syncthreads();
+  if (V > k) {
+    for (int pass = 0; pass < 4; ++pass) {
+      const int shift = 24 - 8 * pass;
+      for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+      __syncthreads();
+      const uint32_t prefix = ctl[0], pmask = ctl[1];
+      for (int i = threadIdx.x; i < V; i += blockDim.x) {
+        const uint32_t key = keys[i];
+        if ((key & pmask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        uint32_t remaining = ctl[2], above = 0;
+        int d = 255;
+        for (; d > 0; --d) {
+          if (above + hist[d] >= remaining) break;
+          above += hist[d];
+        }
+        remaining -= above;
+        ctl[0] = prefix | (static_cast<uint32_t>(d) << shift);
+        ctl[1] = pmask | (255u << shift);
+        ctl[2] = remaining;
+        if (hist[d] == remaining) ctl[3] = 1;     // the whole bucket is wanted: prefix (low bits 0) is the threshold
+      }
+      __syncthreads();
+      if (ctl[3] != 0) break;
+    }
+  }
+  const uint32_t kth = V > k ? ctl[0] : 0u;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+    const uint32_t key = keys[i];
+    if (key >= kth) {
+      const uint32_t pos = atomicAdd(&out_count, 1u);
+      if (pos < static_cast<uint32_t>(k)) sel[pos] = key;
+    }
+  }
+  __syncthreads();
+  for (int size = 2; size <= k_pow2; size <<= 1) {            // bitonic sort, descending
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = threadIdx.x; i < k_pow2; i += blockDim.x) {
+        const int j = i ^ stride;
+        if (j > i) {
+          const uint32_t a = sel[i], b = sel[j];
+          const bool desc = ((i & size) == 0);
+          if (desc ? (a < b) : (a > b)) { sel[i] = b; sel[j] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < k; i += blockDim.x)
+    topk_ids[static_cast<long long>(row) * k + i] = static_cast<long long>(0xFFFFu - (sel[i] & 0xFFFFu));
+}
+
 // torch's grid for an n-element distribution kernel: min(sms * (max_threads_per_sm / 256),
 // ceil(n / 256)) blocks of 256 threads; element e is produced by thread e % T on its
 // (e / T)-th value, values coming four at a time from one Philox counter step.
@@ -283,6 +398,16 @@ static int topk_chunk_len(int V) {
   return len < 4096 ? 4096 : len;
 }
 
+// BMA_TOPK_ONE_LAUNCH=0 keeps the two-level path for 16-bit gradients too (A/B runs)
+static bool topk_one_launch_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("BMA_TOPK_ONE_LAUNCH");
+    v = (e != nullptr && atoi(e) == 0) ? 0 : 1;
+  }
+  return v != 0;
+}
+
 size_t sampler_workspace_bytes(int n_tok, int V, int topk) {
   const int chunk_len = topk_chunk_len(V);
   const int chunks = (V + chunk_len - 1) / chunk_len;
@@ -300,10 +425,15 @@ cudaError_t launch_sample_ids(const long long* ids, const void* grad, int grad_d
   if (n_tok <= 0 || V <= 0 || search_width <= 0) return cudaErrorInvalidValue;
   if (topk <= 0 || topk > V || topk > 4096) return cudaErrorInvalidValue;
   if (n_replace <= 0 || n_replace > n_tok) return cudaErrorInvalidValue;
-  int dev = 0, sms = 148, mtps = 2048;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaDeviceGetAttribute(&mtps, cudaDevAttrMaxThreadsPerMultiProcessor, dev);
+  static int sms = 0, mtps = 0;                     // one device per process
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&mtps, cudaDevAttrMaxThreadsPerMultiProcessor, dev);
+    if (sms <= 0) sms = 148;
+    if (mtps <= 0) mtps = 2048;
+  }
 
   const int chunk_len = topk_chunk_len(V);
   const int chunks = (V + chunk_len - 1) / chunk_len;
@@ -312,9 +442,32 @@ cudaError_t launch_sample_ids(const long long* ids, const void* grad, int grad_d
                             ? topk_ids_out
                             : reinterpret_cast<long long*>(cand + static_cast<size_t>(n_tok) * chunks * topk);
 
+  cudaError_t e;
+  int k_pow2 = 1;
+  while (k_pow2 < topk) k_pow2 <<= 1;
+  // 16-bit gradients over <= 65 536 tokens: the whole row fits one CTA's shared memory as 32-bit keys
+  const size_t smem16 = (static_cast<size_t>(V) + k_pow2) * sizeof(uint32_t);
+  const bool one_launch = (grad_dtype == 0 || grad_dtype == 1) && V <= 65536 && smem16 <= 220 * 1024 &&
+                          topk_one_launch_enabled();
+  if (one_launch) {
+    static size_t attr16[2] = {0, 0};
+    if (attr16[grad_dtype] < smem16) {
+      e = grad_dtype == 0 ? cudaFuncSetAttribute(topk_row16_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem16))
+                          : cudaFuncSetAttribute(topk_row16_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem16));
+      if (e != cudaSuccess) return e;
+      attr16[grad_dtype] = smem16;
+    }
+    if (grad_dtype == 0)
+      topk_row16_kernel<__nv_bfloat16><<<n_tok, 1024, smem16, stream>>>(static_cast<const __nv_bfloat16*>(grad), row_stride, V,
+                                                                         topk, k_pow2, mask_bits, topk_ids);
+    else
+      topk_row16_kernel<__half><<<n_tok, 1024, smem16, stream>>>(static_cast<const __half*>(grad), row_stride, V, topk, k_pow2,
+                                                                  mask_bits, topk_ids);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  } else {
   const size_t smem1 = static_cast<size_t>(chunk_len) * sizeof(uint64_t);
   dim3 grid1(chunks, n_tok);
-  cudaError_t e;
 #define BMA_LAUNCH_CHUNK(T)                                                                       \
   do {                                                                                            \
     e = cudaFuncSetAttribute(topk_chunk_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
@@ -331,8 +484,6 @@ cudaError_t launch_sample_ids(const long long* ids, const void* grad, int grad_d
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
 
-  int k_pow2 = 1;
-  while (k_pow2 < topk) k_pow2 <<= 1;
   const int n_cand = chunks * topk;
   const size_t smem2 = static_cast<size_t>(n_cand + k_pow2) * sizeof(uint64_t);
   e = cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -341,6 +492,7 @@ cudaError_t launch_sample_ids(const long long* ids, const void* grad, int grad_d
   topk_merge_kernel<<<n_tok, TOPK_THREADS, smem2, stream>>>(cand, n_cand, topk, k_pow2, topk_ids);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
+  }
 
   const long long n1 = static_cast<long long>(search_width) * n_tok;
   const long long n2 = static_cast<long long>(search_width) * n_replace;

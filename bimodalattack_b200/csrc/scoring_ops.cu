@@ -224,15 +224,29 @@ __global__ void __launch_bounds__(256)
 prefix_scatter_kernel(const __nv_bfloat16* __restrict__ k_tail, long long ldk, const __nv_bfloat16* __restrict__ vt_tail,
                       long long ldvt, PeerPtrs peers, int n_ranks, int my_rank, long long ldkp, long long ldvtp,
                       int n, int key0, int kv_dim, unsigned int* done_counter, unsigned long long epoch) {
+  // 16-byte units: K rows are contiguous along the columns; V^T rows along the keys (8 keys per unit,
+  // vector stores when the destination key index is 8-aligned -- the host rounds the per-rank slice to 8)
+  const int kvec = kv_dim >> 3, nvec = (n + 7) >> 3;
+  const long long k_units = (long long)n * kvec, v_units = (long long)kv_dim * nvec;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < (long long)n * kv_dim) {
-    const int key = static_cast<int>(i / kv_dim), c = static_cast<int>(i - (long long)key * kv_dim);
-    const __nv_bfloat16 kv = k_tail[(long long)key * ldk + c];          // K: consecutive threads -> consecutive columns
-    const int dim = static_cast<int>(i / n), kk = static_cast<int>(i - (long long)dim * n);
-    const __nv_bfloat16 vv = vt_tail[(long long)dim * ldvt + kk];       // V^T: consecutive threads -> consecutive keys
-    for (int q = 0; q < n_ranks; ++q) {
-      peers.k[q][(long long)(key0 + key) * ldkp + c] = kv;
-      peers.vt[q][(long long)dim * ldvtp + key0 + kk] = vv;
+  if (i < k_units) {
+    const int key = static_cast<int>(i / kvec), c = static_cast<int>(i - (long long)key * kvec) * 8;
+    const uint4 v = *reinterpret_cast<const uint4*>(k_tail + (long long)key * ldk + c);
+    for (int q = 0; q < n_ranks; ++q)
+      *reinterpret_cast<uint4*>(peers.k[q] + (long long)(key0 + key) * ldkp + c) = v;
+  } else if (i < k_units + v_units) {
+    const long long j = i - k_units;
+    const int dim = static_cast<int>(j / nvec), kk = static_cast<int>(j - (long long)dim * nvec) * 8;
+    const __nv_bfloat16* src = vt_tail + (long long)dim * ldvt + kk;
+    if (kk + 8 <= n && ((key0 | ldvtp | ldvt) & 7) == 0) {
+      const uint4 v = *reinterpret_cast<const uint4*>(src);
+      for (int q = 0; q < n_ranks; ++q)
+        *reinterpret_cast<uint4*>(peers.vt[q] + (long long)dim * ldvtp + key0 + kk) = v;
+    } else {
+      for (int e = 0; e < 8 && kk + e < n; ++e) {
+        const __nv_bfloat16 v = src[e];
+        for (int q = 0; q < n_ranks; ++q) peers.vt[q][(long long)dim * ldvtp + key0 + kk + e] = v;
+      }
     }
   }
   // publish: every block's stores are fenced system-wide before it counts itself done; the last one signals
@@ -274,7 +288,9 @@ cudaError_t launch_prefix_scatter(const __nv_bfloat16* k_tail, long long ldk, co
     pp.vt[q] = static_cast<__nv_bfloat16*>(peer_vt[q]);
     pp.flags[q] = static_cast<unsigned long long*>(peer_flags[q]);
   }
-  const long long total = (long long)(n > 0 ? n : 0) * kv_dim;
+  if ((kv_dim & 7) || (ldk & 7) || (ldkp & 7)) return cudaErrorInvalidValue;
+  const int nn = n > 0 ? n : 0;
+  const long long total = (long long)nn * (kv_dim >> 3) + (long long)kv_dim * ((nn + 7) >> 3);
   const int blocks = total > 0 ? static_cast<int>((total + 255) / 256) : 1;   // a rank without positions still signals
   prefix_scatter_kernel<<<blocks, 256, 0, stream>>>(k_tail, ldk, vt_tail, ldvt, pp, n_ranks, my_rank, ldkp, ldvtp,
                                                     n > 0 ? n : 0, key0, kv_dim, done_counter, epoch);
