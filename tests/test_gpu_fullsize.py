@@ -164,3 +164,56 @@ def test_gemma4b_losses_match_oracle_sample(cuda_device):
     assert bool((diff <= 3 * ulp + 1e-3).all()), (diff / ulp).max()      # see the LLaVA test for the 3
     assert float((diff / ulp).mean()) <= 1.0
     atk.engine.close()
+
+
+def test_headline_native_gradient_vs_hf_autograd(llava7b):
+    """compute_gradient at the headline size (LLaVA-1.5-7B architecture, L = 638): the native
+    forward + input-gradient backward (decoder and CLIP tower on this library's kernels) and HF's
+    bf16 autograd on the same model, both against an fp32 autograd run of the same (bf16-valued)
+    weights. Two bf16 evaluations differ from the truth by re-association noise through 32 + 23
+    layers; the native path must be no farther from the fp32 truth than 1.5x the reference's own bf16
+    path, for the token gradient (GCG consumes its top-k per position) and the image gradient (PGD
+    consumes its sign pattern)."""
+    import copy
+    from bimodalattack_b200.attack import image_features
+    h = llava7b
+    atk, model = h["atk"], h["model"]
+    optim_ids = h["base"].view(1, -1)
+    assert atk._native_gradient() is not None, atk._native_grad_why
+    assert atk._native_tower() is not None, atk._native_vt_why
+    atk.graph_gradient = False
+    n_tok, n_img = atk._gradient_eager(optim_ids, h["image"].clone().requires_grad_())
+    w_tok, w_img = atk._gradient_hf(optim_ids, h["image"].clone().requires_grad_())
+    atk.graph_gradient = True
+    native_loss = float(atk._native_grad.loss)
+    # fp32 truth
+    twin = copy.deepcopy(model).float()
+    emb32 = twin.get_input_embeddings()
+    img = h["image"].clone().requires_grad_()
+    e = {k: emb32(v) for k, v in atk.segment_ids.items()}
+    oe = emb32.weight.detach()[optim_ids].clone().requires_grad_()
+    feats = image_features(twin, atk._normalize_pixels(img), False)
+    x = torch.cat([e["before_img"], feats, e["before_suffix"], oe, e["after"], e["target"]], 1)
+    T = atk.target_ids.shape[1]
+    logits = twin(inputs_embeds=x, logits_to_keep=T + 1).logits[:, :-1]
+    loss = torch.nn.functional.cross_entropy(logits.reshape(-1, logits.shape[-1]), atk.target_ids.view(-1))
+    g_e, t_img = torch.autograd.grad(loss, (oe, img))
+    t_tok = (g_e[0] @ emb32.weight.detach().T).unsqueeze(0)
+    del twin
+
+    def rel(a, b):
+        return float((a.float() - b.float()).norm() / (b.float().norm() + 1e-30))
+
+    k = 256
+    top = lambda t: (-t.float()[0]).topk(k, dim=1).indices                  # noqa: E731
+    ov = lambda a, b: sum(len(set(x.tolist()) & set(y.tolist())) for x, y in zip(top(a), top(b))) / (k * a.shape[1])   # noqa: E731
+    sg = lambda a, b: float((torch.sign(a) == torch.sign(b)).float().mean())                                           # noqa: E731
+    print(f"7B gradient vs fp32 autograd -- token rel L2: native {rel(n_tok, t_tok):.4f} hf-bf16 {rel(w_tok, t_tok):.4f}; "
+          f"image rel L2: native {rel(n_img, t_img):.4f} hf-bf16 {rel(w_img, t_img):.4f}; "
+          f"sign agreement: native {sg(n_img, t_img):.4f} hf-bf16 {sg(w_img, t_img):.4f}; "
+          f"top-{k} overlap: native {ov(n_tok, t_tok):.4f} hf-bf16 {ov(w_tok, t_tok):.4f}")
+    assert rel(n_tok, t_tok) <= 1.5 * rel(w_tok, t_tok) + 5e-3
+    assert rel(n_img, t_img) <= 1.5 * rel(w_img, t_img) + 5e-3
+    assert sg(n_img, t_img) >= sg(w_img, t_img) - 0.02
+    assert ov(n_tok, t_tok) >= ov(w_tok, t_tok) - 0.03
+    assert abs(native_loss - float(loss)) <= 2e-2 * abs(float(loss))
