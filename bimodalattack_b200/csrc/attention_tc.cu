@@ -514,13 +514,15 @@ cudaError_t launch_prefix_tail_attention(const AttnParams& a, int n_heads, cudaS
   if (a.M <= 0) return cudaSuccess;
   if (a.S <= 0 || a.P < 0 || a.kv_group <= 0) return cudaErrorInvalidValue;
   if (a.head_dim == 128) {
-    // default: split-key kernel (attention_split.cu); BMA_ATTN_SPLIT=0 keeps this file's kernel (A/B runs)
-    static int use_split = -1;
-    if (use_split < 0) {
-      const char* e = getenv("BMA_ATTN_SPLIT");
-      use_split = (e != nullptr && atoi(e) == 0) ? 0 : 1;
+    // default: two-CTAs-per-SM kernel (attention_occ.cu). BMA_ATTN=split selects the split-key kernel
+    // (attention_split.cu), BMA_ATTN=tc this file's kernel (A/B runs).
+    static int which = -1;
+    if (which < 0) {
+      const char* e = getenv("BMA_ATTN");
+      which = e == nullptr ? 0 : (e[0] == 's' ? 1 : (e[0] == 't' ? 2 : 0));
     }
-    return use_split ? launch_attention_split(a, n_heads, stream) : launch_atc<128, 128>(a, n_heads, stream);
+    if (which == 0) return launch_attention_occ(a, n_heads, stream);
+    return which == 1 ? launch_attention_split(a, n_heads, stream) : launch_atc<128, 128>(a, n_heads, stream);
   }
   if (a.head_dim == 256) return launch_atc<256, 64>(a, n_heads, stream);
   if (a.head_dim == 64) return launch_atc<64, 128>(a, n_heads, stream);

@@ -8,10 +8,10 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompil
 if [[ "${1:-}" == "-v" ]]; then FLAGS+=(-Xptxas -v); fi
 mkdir -p "$HERE/_obj"
 pids=()
-for f in pgd_step sampler scoring_ops attention_tc attention_split engine comm phase_a grad_api; do
+for f in pgd_step sampler scoring_ops attention_tc attention_split attention_occ engine comm phase_a grad_api; do
   "$NVCC" "${FLAGS[@]}" -c "$HERE/$f.cu" -o "$HERE/_obj/$f.o" &
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait "$p"; done
-"$NVCC" -shared -o "$OUT" "$HERE"/_obj/{pgd_step,sampler,scoring_ops,attention_tc,attention_split,engine,comm,phase_a,grad_api}.o -ldl
+"$NVCC" -shared -o "$OUT" "$HERE"/_obj/{pgd_step,sampler,scoring_ops,attention_tc,attention_split,attention_occ,engine,comm,phase_a,grad_api}.o -ldl
 echo "built $OUT"

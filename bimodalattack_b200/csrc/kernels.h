@@ -29,6 +29,8 @@ struct AttnParams {
 cudaError_t launch_prefix_tail_attention(const AttnParams& p, int n_heads, cudaStream_t stream);
 // head_dim 128: split-key kernel, the two softmax threads of a row never synchronise inside an item
 cudaError_t launch_attention_split(const AttnParams& p, int n_heads, cudaStream_t stream);
+// head_dim 128: 64-key blocks, small enough for TWO resident CTAs per SM (the default)
+cudaError_t launch_attention_occ(const AttnParams& p, int n_heads, cudaStream_t stream);
 
 cudaError_t launch_pgd_step(float* x, const float* g, const float* x0, float* norm_out,
                             long long n, float step, float eps, const float* mean,

@@ -37,6 +37,14 @@ __device__ __forceinline__ uint64_t make_key(float g, uint32_t idx, const uint32
   return (static_cast<uint64_t>(orderable_neg(g)) << 32) | static_cast<uint64_t>(0xFFFFFFFFu - idx);
 }
 
+// Histogram increment with warp aggregation: gradient rows put almost every key into two or three
+// exponent buckets, so plain shared-memory atomics serialise; lanes that hit the same bin elect one
+// leader that adds their count.
+__device__ __forceinline__ void hist_add(uint32_t* hist, uint32_t bin) {
+  const uint32_t peers = __match_any_sync(__activemask(), bin);
+  if ((threadIdx.x & 31) == static_cast<uint32_t>(__ffs(peers) - 1)) atomicAdd(&hist[bin], __popc(peers));
+}
+
 // Select the k largest of n unique keys held in shared memory. On return *kth_out is a threshold
 // such that exactly k keys are >= it. hist/ctl are shared scratch (256 + 4 words).
 __device__ void radix_select_topk(const uint64_t* keys, int n, int k, uint32_t* hist,
@@ -55,7 +63,7 @@ __device__ void radix_select_topk(const uint64_t* keys, int n, int k, uint32_t* 
     const uint64_t prefix = ctl[0], pmask = ctl[1];
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
       const uint64_t key = keys[i];
-      if ((key & pmask) == prefix) atomicAdd(&hist[static_cast<uint32_t>(key >> shift) & 255u], 1u);
+      if ((key & pmask) == prefix) hist_add(hist, static_cast<uint32_t>(key >> shift) & 255u);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -264,7 +272,7 @@ topk_row16_kernel(const T* __restrict__ grad, long long row_stride, int V, int k
       const uint32_t prefix = ctl[0], pmask = ctl[1];
       for (int i = threadIdx.x; i < V; i += blockDim.x) {
         const uint32_t key = keys[i];
-        if ((key & pmask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        if ((key & pmask) == prefix) hist_add(hist, (key >> shift) & 255u);
       }
       __syncthreads();
       if (threadIdx.x == 0) {
