@@ -73,6 +73,66 @@ __device__ __forceinline__ Block block_of(int j, int n_pre, int P, int kt0, int 
   return b;
 }
 
+// One query row's pass over a 64-key block of S (tensor memory, 32 columns at a time). MASKED = false is
+// the hot path (every key of the block is visible to every row of the warp: most prefix blocks) and does
+// no per-element tests at all; MASKED = true keeps the row's visible column range [vlo, vhi).
+template <bool MASKED>
+__device__ __forceinline__ float block_row_max_impl(uint32_t ts, int n_mma, int vlo, int vhi) {
+  float raw = -INFINITY;
+#pragma unroll
+  for (int c0 = 0; c0 < BN; c0 += 32) {
+    if (!MASKED || c0 < n_mma) {
+      uint32_t r[32];
+      tmem_ld_32x32(ts + c0, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float v = __uint_as_float(r[i]);
+        if (MASKED && !(c0 + i >= vlo && c0 + i < vhi)) v = -INFINITY;
+        raw = fmaxf(raw, v);
+      }
+    }
+  }
+  return raw;
+}
+// P = exp2(s * scale - m) as packed bf16 pairs over the S columns just read (P_g occupies columns [0, 32)
+// of S_st: chunk 0 -> columns 0..15, chunk 1 -> 16..31); returns the row sum.
+template <bool MASKED>
+__device__ __forceinline__ float block_row_exp_impl(uint32_t ts, int n_mma, int vlo, int vhi, float scale_log2, float m_use) {
+  float rs = 0.0f;
+#pragma unroll
+  for (int c0 = 0; c0 < BN; c0 += 32) {
+    if (!MASKED || c0 < n_mma) {
+      uint32_t r[32], pk[16];
+      tmem_ld_32x32(ts + c0, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        float v0 = __uint_as_float(r[i]), v1 = __uint_as_float(r[i + 1]);
+        if (MASKED) {
+          if (!(c0 + i >= vlo && c0 + i < vhi)) v0 = -INFINITY;
+          if (!(c0 + i + 1 >= vlo && c0 + i + 1 < vhi)) v1 = -INFINITY;
+        }
+        const float p0 = ex2(fmaf(v0, scale_log2, -m_use));         // -inf -> 0
+        const float p1 = ex2(fmaf(v1, scale_log2, -m_use));
+        rs += p0 + p1;
+        pk[i >> 1] = pack_bf16x2(p0, p1);
+      }
+      tmem_st_32x16(ts + (c0 >> 1), pk);
+    }
+  }
+  return rs;
+}
+
+// The masked variants are real calls (rare path): inlined next to the hot path the compiler merges the
+// two bodies into one predicated loop and every block pays for the per-element tests again.
+__device__ __noinline__ float block_row_max_masked(uint32_t ts, int n_mma, int vlo, int vhi) {
+  return block_row_max_impl<true>(ts, n_mma, vlo, vhi);
+}
+__device__ __noinline__ float block_row_exp_masked(uint32_t ts, int n_mma, int vlo, int vhi, float scale_log2, float m_use) {
+  return block_row_exp_impl<true>(ts, n_mma, vlo, vhi, scale_log2, m_use);
+}
+
 __global__ void __launch_bounds__(THREADS, 2)
 attention_occ_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kt,
                      const __grid_constant__ CUtensorMap tm_kp, const __grid_constant__ CUtensorMap tm_vt,
@@ -90,10 +150,10 @@ attention_occ_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   uint64_t* v_full = bars + 6;        // [2]
   uint64_t* v_empty = bars + 8;       // [2]
   uint64_t* s_full = bars + 10;       // [2]
-  uint64_t* p_full = bars + 12;       // [1]  the 4 softmax warps have written P_g
-  uint64_t* p_empty = bars + 13;      // [1]  PV_g has retired
-  uint64_t* o_empty = bars + 14;      // [1]  4 warps: the item's output has left TMEM
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* p_full = bars + 12;       // [2]  per S/P buffer: the 4 softmax warps have written P_g
+  uint64_t* p_empty = bars + 14;      // [2]  per S/P buffer: PV_g has retired
+  uint64_t* o_empty = bars + 16;      // [1]  4 warps: the item's output has left TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int M = p.M_dev != nullptr ? min(p.M, __ldg(p.M_dev)) : p.M;   // live row count (ragged pass)
@@ -107,9 +167,9 @@ attention_occ_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   }
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);  mbar_init(q_empty, 1);
-    mbar_init(p_full, 4);  mbar_init(p_empty, 1);
     mbar_init(o_empty, 4);
     for (int i = 0; i < 2; ++i) {
+      mbar_init(&p_full[i], 4);  mbar_init(&p_empty[i], 1);
       mbar_init(&k_full[i], 1);  mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1);  mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
@@ -175,7 +235,7 @@ attention_occ_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       auto issue_pv = [&](uint32_t g, int n_mma, bool first, uint32_t item_par) {
         const int st = g & 1;
         mbar_wait(&v_full[st], (g >> 1) & 1, 0x860 + st);
-        mbar_wait(p_full, g & 1, 0x862);
+        mbar_wait(&p_full[st], (g >> 1) & 1, 0x862);
         if (first) mbar_wait(o_empty, item_par ^ 1, 0x863);      // the previous item's output was read out
         tc_fence_after();
         constexpr uint32_t idesc = umma_idesc_bf16(BM, HD);
@@ -183,7 +243,7 @@ attention_occ_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         const uint32_t vb = smem_u32(sV + st * VTILE);
         for (int kk = 0; kk < n_mma / 16; ++kk)
           umma_bf16_ts(tmem_o, pa + kk * 8, umma_desc_k_sw128(vb + kk * 32), idesc, !(first && kk == 0));
-        umma_commit(p_empty);
+        umma_commit(&p_empty[st]);
         umma_commit(&v_empty[st]);
       };
       bool have_pending = false;
@@ -243,41 +303,32 @@ attention_occ_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         const Block b = block_of(j, n_pre, p.P, kt0, r1);
         const int st = it & 1;
         const uint32_t ts = tmem_s + lane_off + st * BN;
-        const bool masked = !b.pre || b.key0 + BN > p_shared;
+        // this row's visible columns of the block: prefix keys below its limit, or its own candidate's
+        // tail keys up to itself
+        int vlo = 0, vhi = BN;
+        if (b.pre) {
+          if (b.key0 + BN > p_shared) vhi = min(max(plim - b.key0, 0), BN);
+        } else {
+          vlo = max(cs - b.key0, 0);
+          vhi = min(max(min(rq + 1, r1) - b.key0, 0), BN);
+        }
+        const bool all_visible = __all_sync(0xffffffffu, vlo == 0 && vhi == BN);
         mbar_wait(&s_full[st], (it >> 1) & 1, 0x910 + st);
         tc_fence_after();
-        // pass 1: row maximum over the block's visible keys (32 columns at a time)
-        float raw = -INFINITY;
-#pragma unroll
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          if (c0 < b.n_mma) {
-            uint32_t r[32];
-            tmem_ld_32x32(ts + c0, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float v = __uint_as_float(r[i]);
-              if (masked) {
-                const int key = b.key0 + c0 + i;
-                const bool vis = b.pre ? (key < plim) : (key >= cs && key <= rq && key < r1);
-                if (!vis) v = -INFINITY;
-              } else if (c0 + i >= b.n_mma) {
-                v = -INFINITY;
-              }
-              raw = fmaxf(raw, v);
-            }
-          }
-        }
+        // pass 1: row maximum over the visible keys
+        const float raw = all_visible ? block_row_max_impl<false>(ts, b.n_mma, vlo, vhi)
+                                      : block_row_max_masked(ts, b.n_mma, vlo, vhi);
         const float bm = raw * p.scale_log2;
         const bool raise = bm > m_ref + kRaise;
         const float m_new = raise ? bm : m_ref;
         const float m_use = (m_new == -INFINITY) ? 0.0f : m_new;
         const float factor = raise ? ex2(m_ref - m_use) : 1.0f;
-        // PV_{g-1} has retired: all four warps delivered P_{g-1} (keeps the p_full phases in step) and O is
-        // quiescent for the rescale below. Usually satisfied long before.
-        mbar_wait(p_empty, (it & 1) ^ 1, 0x920);
+        // No wait on the previous PV here: P_g has its own buffer and barrier (s_full of block g implies that
+        // PV_{g-2}, the last reader of this buffer, has retired -- the tensor pipe completes in order), so the
+        // softmax of block g overlaps PV_{g-1}. Only the rare rescale needs O quiescent.
         const bool fix = raise && (m_ref != -INFINITY) && (j > 0);
         if (__any_sync(0xffffffffu, fix)) {                // rare: rescale this row of O in TMEM
+          mbar_wait(&p_empty[(it - 1) & 1], ((it - 1) >> 1) & 1, 0x920);    // PV_{g-1} has retired
           tc_fence_after();
           const float f = fix ? factor : 1.0f;
 #pragma unroll
@@ -291,49 +342,20 @@ attention_occ_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
           }
           tmem_st_wait();
         }
-        // pass 2: P = exp2(s * scale - m) as packed bf16 pairs over the S columns just read
-        float rs = 0.0f;
-#pragma unroll
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t pk[16];
-          if (c0 < b.n_mma) {
-            uint32_t r[32];
-            tmem_ld_32x32(ts + c0, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              float v0 = __uint_as_float(r[i]), v1 = __uint_as_float(r[i + 1]);
-              if (masked) {
-                const int key = b.key0 + c0 + i;
-                const bool vis0 = b.pre ? (key < plim) : (key >= cs && key <= rq && key < r1);
-                const bool vis1 = b.pre ? (key + 1 < plim) : (key + 1 >= cs && key + 1 <= rq && key + 1 < r1);
-                if (!vis0) v0 = -INFINITY;
-                if (!vis1) v1 = -INFINITY;
-              } else {
-                if (c0 + i >= b.n_mma) v0 = -INFINITY;
-                if (c0 + i + 1 >= b.n_mma) v1 = -INFINITY;
-              }
-              const float p0 = ex2(fmaf(v0, p.scale_log2, -m_use));         // -inf -> 0
-              const float p1 = ex2(fmaf(v1, p.scale_log2, -m_use));
-              rs += p0 + p1;
-              pk[i >> 1] = pack_bf16x2(p0, p1);
-            }
-            // all of this 32-column chunk of S is in registers: its first 16 columns take the packed P
-            // (chunk 0 -> columns 0..15, chunk 1 -> columns 16..31: P_g occupies columns [0, 32) of S_st)
-            tmem_st_32x16(ts + (c0 >> 1), pk);
-          }
-        }
+        // pass 2: exponentials, P back into tensor memory
+        const float rs = all_visible ? block_row_exp_impl<false>(ts, b.n_mma, vlo, vhi, p.scale_log2, m_use)
+                                     : block_row_exp_masked(ts, b.n_mma, vlo, vhi, p.scale_log2, m_use);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(p_full);
+        if (lane == 0) mbar_arrive(&p_full[st]);
         l_run = l_run * factor + rs;
         m_ref = m_new;
       }
 
       // ---- end of the item: normalise and store this thread's output row
       {
-        mbar_wait(p_empty, (it & 1) ^ 1, 0x940);              // the item's last PV has retired
+        mbar_wait(&p_empty[(it - 1) & 1], ((it - 1) >> 1) & 1, 0x940);   // the item's last PV has retired
         tc_fence_after();
         const float inv = l_run > 0.0f ? 1.0f / l_run : 0.0f;
         __nv_bfloat16* dst = p.out + (long long)rq * p.ldo + head * HD;
