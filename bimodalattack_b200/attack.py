@@ -34,7 +34,7 @@ from . import native
 from .config import BimodalAttackConfig, BimodalAttackResult
 from .engine import ScoringEngine, unpack_key
 from .segments import TailPlan, plan_tail, segment_order
-from .utils import INIT_CHARS, AttackBuffer, find_executable_batch_size, get_nonascii_toks
+from .utils import INIT_CHARS, AttackBuffer, get_nonascii_toks
 
 logger = logging.getLogger("gcg")          # same logger name and format as the reference (:26-36)
 if not logger.hasHandlers():
@@ -636,8 +636,9 @@ class BimodalAttack:
                 self._plans[key] = plan
         return plan
 
-    # scoring (:1278-1310). search_batch_size is accepted for interface compatibility; the native
-    # workspace is sized up front, so no OOM-driven chunk search is needed.
+    # scoring (:1278-1310). search_batch_size is accepted for interface compatibility only: the native
+    # workspace is sized up front and the scorer chunks internally, so the reference's OOM-driven
+    # halving wrapper (utils.py:57-115, find_executable_batch_size) has nothing to do here and is not ported.
     def _compute_candidates_loss_original(self, search_batch_size: int, batch: CandidateBatch,
                                           gather: bool = False) -> torch.Tensor:
         plan = self._plan(batch)
@@ -820,12 +821,12 @@ class BimodalAttack:
                     if cfg.joint_eval:
                         build = self._build_input_embeds_gcg_pgd if cfg.pgd_after_gcg else self._build_input_embeds_pgd
                         batch = build(sampled, feats, search_width=width, single=True)
-                        find_executable_batch_size(self._compute_candidates_loss_original, chunk)(batch)
+                        self._compute_candidates_loss_original(chunk, batch)
                         cand_min, best_idx = self._winner()
                         scored_with_image = True
                     elif cfg.gcg_attack:
                         batch = self._build_input_embeds_gcg(sampled, search_width=width, single=True)
-                        find_executable_batch_size(self._compute_candidates_loss_original, chunk)(batch)
+                        self._compute_candidates_loss_original(chunk, batch)
                         cand_min, best_idx = self._winner()
                     chosen = sampled[best_idx].unsqueeze(0)
                     if not cfg.pgd_after_gcg:
@@ -841,7 +842,7 @@ class BimodalAttack:
                         record(current, optim_ids, image)
                 else:
                     batch = self._build_input_embeds_gcg(sampled, search_width=width, no_joint_eval=True)
-                    find_executable_batch_size(self._compute_candidates_loss_original, chunk)(batch)
+                    self._compute_candidates_loss_original(chunk, batch)
                     current, best_idx = self._winner()
                     optim_ids = sampled[best_idx].unsqueeze(0)
                     record(current, optim_ids, None)

@@ -34,6 +34,10 @@ struct GemmParams {
   int k_stagger;              // > 0: tile t walks its K blocks starting at (t * k_stagger) % k_blocks, so CTAs that
                               // stream different rows of a power-of-two-pitch matrix do not all touch the same
                               // HBM channels at the same time (token gradient: 8 KB pitch, tiles 1 MB apart)
+  int causal;                 // (single-CTA tiles) products of ONE causal sequence, rows = cols = positions:
+                              //   1: skip tiles that lie entirely above the diagonal   (S = Q K^T, dP = dO V^T)
+                              //   2: K runs over keys <= the tile's last row           (O = P V,  dQ = dS K)
+                              //   3: K runs over queries >= the tile's first row       (dK = dS^T Q, dV = P^T dO)
   float* C32;                 // EPI_STORE: raw fp32 accumulators instead of bf16 (attention scores)
   const __nv_bfloat16* bias;  // EPI_STORE: [N] added in fp32 before the bf16 rounding (nn.Linear bias)
   int group_m;                // rasterisation: m-blocks per L2 supergroup
@@ -159,6 +163,13 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     return b;
   };
 
+  // causal products: which tiles exist and which K blocks they need (same answer in every warp role)
+  auto tile_active = [&](int m_blk, int n_blk) { return p.causal != 1 || n_blk * BN <= m_blk * GEMM_BM + GEMM_BM - 1; };
+  auto k_first = [&](int m_blk) { return p.causal == 3 ? min(k_blocks, (m_blk * GEMM_BM) / GEMM_BK) : 0; };
+  auto k_last = [&](int m_blk) {
+    return p.causal == 2 ? min(k_blocks, ((m_blk + 1) * GEMM_BM + GEMM_BK - 1) / GEMM_BK) : k_blocks;
+  };
+
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
@@ -198,8 +209,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const int bi = tile_coords(tile, m_blk, n_blk);
         const int a_r0 = bi * p.a_row + m_blk * GEMM_BM, a_c0 = bi * p.a_col;
         const int b_r0 = bi * p.b_row + n_blk * BN, b_c0 = bi * p.b_col;
+        if (!tile_active(m_blk, n_blk)) continue;
+        const int kf = k_first(m_blk), kl = k_last(m_blk);
         const int kb0 = p.k_stagger > 0 ? static_cast<int>(((long long)tile * p.k_stagger) % k_blocks) : 0;
-        for (int kk = 0; kk < k_blocks; ++kk) {
+        for (int kk = kf; kk < kl; ++kk) {
           const int kb = kk + kb0 < k_blocks ? kk + kb0 : kk + kb0 - k_blocks;
           mbar_wait(&empty_bar[stage], phase ^ 1, 0x100 + stage);
           if constexpr (CTAS == 2) {
@@ -229,10 +242,14 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
+        int m_blk, n_blk;
+        tile_coords(tile, m_blk, n_blk);
+        if (!tile_active(m_blk, n_blk)) continue;
+        const int kf = k_first(m_blk), kl = k_last(m_blk);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 0x200 + acc);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        for (int kb = kf; kb < kl; ++kb) {
           mbar_wait(&full_bar[stage], phase, 0x300 + stage);
           tc_fence_after();
           const uint64_t da = umma_desc_k_sw128(smem_u32(smem_a + stage * Cfg::kStageBytesA));
@@ -240,8 +257,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             // advance 16 elements (32 B) along K inside the 128-B swizzle atom: +2 in 16-B units
-            if constexpr (CTAS == 2) umma_bf16_ss_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-            else umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            if constexpr (CTAS == 2) umma_bf16_ss_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb != kf) || k != 0);
+            else umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb != kf) || k != 0);
           }
           // frees the smem slot (in both CTAs of a pair) once these MMAs retire
           if constexpr (CTAS == 2) umma_commit_pair(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
@@ -260,6 +277,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
       int m_blk, n_blk;
       const int bi = tile_coords(tile, m_blk, n_blk);
+      if (!tile_active(m_blk, n_blk)) continue;
       mbar_wait(&tmem_full[acc], acc_phase, 0x400 + acc);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * BN;

@@ -41,6 +41,9 @@ int bma_gemm_ex(const bma_gemm_desc* g, void* stream) {
   p.bias = bf(g->bias);
   p.batch = g->batch; p.a_row = g->a_row; p.a_col = g->a_col; p.b_row = g->b_row; p.b_col = g->b_col;
   p.c_batch = g->c_batch;
+  if (g->causal != 0 && (g->ctas == 2 || g->transpose_out || g->causal < 0 || g->causal > 3))
+    return done(cudaErrorInvalidValue, "gemm_ex: causal modes 1..3 need single-CTA tiles", 0);
+  p.causal = g->causal;
   cudaStream_t st = as_stream(stream);
   const __nv_bfloat16 *A = bf(g->A), *B = bf(g->B);
   // rows of the output are written with 16-byte stores

@@ -52,7 +52,7 @@ class _Lib:
 
     def gemm(self, A, B, out=None, out32=None, M=None, N=None, K=None, lda=None, ldb=None, ldc=None, R=None, ldr=0,
              bias=None, tile=None, batch=1, a_row=0, a_col=0, b_row=0, b_col=0, c_batch=0, transpose_out=False,
-             a_off=0, b_off=0, c_off=0):
+             a_off=0, b_off=0, c_off=0, causal=0):
         """C = A . B^T with raw strides; ``*_off`` are element offsets into the tensors."""
         g = native.GemmDesc()
         g.A = A.data_ptr() + 2 * a_off
@@ -73,6 +73,7 @@ class _Lib:
         g.block_n, g.ctas = bn, ctas
         g.batch, g.a_row, g.a_col, g.b_row, g.b_col, g.c_batch = batch, a_row, a_col, b_row, b_col, c_batch
         g.transpose_out = int(transpose_out)
+        g.causal = causal
         native.check(self.lib.bma_gemm_ex(C.byref(g), self.st), "gemm_ex")
 
 
@@ -84,19 +85,20 @@ class _AttentionProducts:
     def _attn_forward(self, QKV, P, L, scale, causal):
         k, lib, H, hd, qd, Lp = self.k, self.k.lib, self.H, self.hd, self.q_dim, self.Lp
         # S_h = Q_h K_h^T (fp32), heads side by side along the columns of QKV
+        # (causal sequences: tiles above the diagonal are never computed, K ranges stop / start at the diagonal)
         k.gemm(QKV, QKV, out32=self.S32, M=L, N=L, K=hd, lda=self.qkv_dim, ldb=self.qkv_dim, ldc=Lp, tile=(128, 1),
-               batch=H, a_col=hd, b_col=hd, b_off=qd, c_batch=L * Lp)
+               batch=H, a_col=hd, b_col=hd, b_off=qd, c_batch=L * Lp, causal=1 if causal else 0)
         native.check(lib.bma_softmax_rows(self.S32.data_ptr(), Lp, P.data_ptr(), Lp, H, L, scale, causal, k.st), "softmax")
         # O_h = P_h V_h: P stacked along the rows, V^T stacked along the rows
         k.gemm(P, self.VT, out=self.ATT, M=L, N=hd, K=L, lda=Lp, ldb=Lp, ldc=qd, tile=(128, 1),
-               batch=H, a_row=L, b_row=hd, c_batch=hd)
+               batch=H, a_row=L, b_row=hd, c_batch=hd, causal=2 if causal else 0)
 
     def _attn_backward(self, QKV, P, L, scale, causal):
         """DATT (gradient of the attention output) -> DQKV (gradients of Q | K | V, before any rotary)."""
         k, lib, H, hd, qd, Lp = self.k, self.k.lib, self.H, self.hd, self.q_dim, self.Lp
         # dP_h = dO_h V_h^T (fp32)
         k.gemm(self.DATT, QKV, out32=self.S32, M=L, N=L, K=hd, lda=qd, ldb=self.qkv_dim, ldc=Lp, tile=(128, 1),
-               batch=H, a_col=hd, b_col=hd, b_off=2 * qd, c_batch=L * Lp)
+               batch=H, a_col=hd, b_col=hd, b_off=2 * qd, c_batch=L * Lp, causal=1 if causal else 0)
         native.check(lib.bma_softmax_bwd_rows(P.data_ptr(), Lp, self.S32.data_ptr(), Lp, self.DS.data_ptr(), Lp,
                                               H, L, scale, causal, k.st), "softmax_bwd")
         # K-major operands of the three products: Q^T | K^T, dO^T, dS^T, P^T
@@ -106,11 +108,11 @@ class _AttentionProducts:
         self._transpose(P, Lp, L * Lp, self.P_T, Lp, L * Lp, L, L, H)
         # dQ_h = dS_h K_h ; dK_h = dS_h^T Q_h ; dV_h = P_h^T dO_h  -> the Q | K | V columns of DQKV
         k.gemm(self.DS, self.QK_T, out=self.DQKV, M=L, N=hd, K=L, lda=Lp, ldb=Lp, ldc=self.qkv_dim, tile=(128, 1),
-               batch=H, a_row=L, b_row=hd, b_off=qd * Lp, c_batch=hd)
+               batch=H, a_row=L, b_row=hd, b_off=qd * Lp, c_batch=hd, causal=2 if causal else 0)
         k.gemm(self.DS_T, self.QK_T, out=self.DQKV, M=L, N=hd, K=L, lda=Lp, ldb=Lp, ldc=self.qkv_dim, tile=(128, 1),
-               batch=H, a_row=L, b_row=hd, c_batch=hd, c_off=qd)
+               batch=H, a_row=L, b_row=hd, c_batch=hd, c_off=qd, causal=3 if causal else 0)
         k.gemm(self.P_T, self.DATT_T, out=self.DQKV, M=L, N=hd, K=L, lda=Lp, ldb=Lp, ldc=self.qkv_dim, tile=(128, 1),
-               batch=H, a_row=L, b_row=hd, c_batch=hd, c_off=2 * qd)
+               batch=H, a_row=L, b_row=hd, c_batch=hd, c_off=2 * qd, causal=3 if causal else 0)
 
     def _transpose(self, src, lds, src_batch, dst, ldd, dst_batch, rows, cols, batch, src_off=0):
         native.check(self.k.lib.bma_transpose_bf16(src.data_ptr() + 2 * src_off, lds, src_batch, dst.data_ptr(), ldd,

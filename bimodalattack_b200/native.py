@@ -47,7 +47,7 @@ class GemmDesc(C.Structure):
         ("R", C.c_void_p), ("ldr", C.c_longlong), ("bias", C.c_void_p),
         ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("block_n", C.c_int), ("ctas", C.c_int),
         ("batch", C.c_int), ("a_row", C.c_int), ("a_col", C.c_int), ("b_row", C.c_int), ("b_col", C.c_int),
-        ("c_batch", C.c_longlong), ("transpose_out", C.c_int),
+        ("c_batch", C.c_longlong), ("transpose_out", C.c_int), ("causal", C.c_int),
     ]
 
 

@@ -236,6 +236,10 @@ typedef struct {
   int a_row, a_col, b_row, b_col;   /*      b_col b) inside the same matrices, writes C + c_batch b  */
   long long c_batch;
   int transpose_out;                /* out[n, m] (N <= 128): the big operand streams once as A       */
+  int causal;                       /* products of ONE causal sequence (single-CTA tiles): 1 skip tiles above the
+                                       diagonal (S = Q K^T, dP = dO V^T), 2 K over keys <= the tile's last row
+                                       (O = P V, dQ = dS K), 3 K over queries >= the tile's first row
+                                       (dK = dS^T Q, dV = P^T dO); 0 = plain                                  */
 } bma_gemm_desc;
 int bma_gemm_ex(const bma_gemm_desc* g, void* stream);
 /* Fused QKV projection of ONE sequence (rows at positions pos0..): Q|K rotated (HF rounding points),

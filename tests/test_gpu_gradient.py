@@ -306,3 +306,38 @@ def test_native_gradient_matches_autograd(cuda_device, size, px, mode):
         agree = float((torch.sign(n_img) == torch.sign(t_img)).float().mean())
         agree_hf = float((torch.sign(h_img) == torch.sign(t_img)).float().mean())
         assert agree >= agree_hf - 0.02
+
+
+def test_gemm_ex_causal_modes(cuda_device):
+    """Products of one causal sequence: tiles above the diagonal skipped (mode 1), K ranges cut at the
+    diagonal (modes 2 and 3). Same numbers as the dense products on causally masked operands."""
+    k = _k(cuda_device)
+    H, L, hd = 3, 300, 128
+    Lp = (L + 7) // 8 * 8
+    g = torch.Generator().manual_seed(5)
+    Q = (torch.randn(L, H * hd, generator=g) * 0.3).to(cuda_device).bfloat16()
+    Kk = (torch.randn(L, H * hd, generator=g) * 0.3).to(cuda_device).bfloat16()
+    tril = torch.ones(L, L, dtype=torch.bool, device=cuda_device).tril()
+    S = torch.full((H, L, Lp), float("nan"), dtype=torch.float32, device=cuda_device)
+    k.gemm(Q, Kk, out32=S, M=L, N=L, K=hd, ldc=Lp, tile=(128, 1), batch=H, a_col=hd, b_col=hd, c_batch=L * Lp, causal=1)
+    want = torch.einsum("qhd,khd->hqk", Q.float().view(L, H, hd), Kk.float().view(L, H, hd))
+    got = S[:, :, :L]
+    assert float((got - want)[:, tril].abs().max()) <= 1e-3 * float(want.abs().max())     # the lower triangle is all there
+    assert bool(torch.isnan(got[:, :128, 128:]).all())                                    # tiles above the diagonal: untouched
+    # mode 2: O = P V with a lower-triangular P
+    P = torch.zeros(H, L, Lp, dtype=torch.bfloat16, device=cuda_device)
+    P[:, :, :L] = (torch.rand(H, L, L, generator=g).to(cuda_device) * tril).bfloat16()
+    V = (torch.randn(L, H * hd, generator=g) * 0.3).to(cuda_device).bfloat16()
+    Vt = torch.zeros(H * hd, Lp, dtype=torch.bfloat16, device=cuda_device)
+    Vt[:, :L] = V.T
+    O = torch.zeros(L, H * hd, dtype=torch.bfloat16, device=cuda_device)
+    k.gemm(P, Vt, out=O, M=L, N=hd, K=L, lda=Lp, ldb=Lp, ldc=H * hd, tile=(128, 1), batch=H, a_row=L, b_row=hd, c_batch=hd, causal=2)
+    _close(O, torch.einsum("hqk,khd->qhd", P[:, :, :L].float(), V.float().view(L, H, hd)).reshape(L, H * hd), what="causal PV")
+    # mode 3: dK = dS^T Q with dS^T upper-triangular in (key, query)
+    dSt = torch.zeros(H, L, Lp, dtype=torch.bfloat16, device=cuda_device)
+    dSt[:, :, :L] = (torch.randn(H, L, L, generator=g).to(cuda_device) * tril.T).bfloat16()
+    Qt = torch.zeros(H * hd, Lp, dtype=torch.bfloat16, device=cuda_device)
+    Qt[:, :L] = Q.T
+    dK = torch.zeros(L, H * hd, dtype=torch.bfloat16, device=cuda_device)
+    k.gemm(dSt, Qt, out=dK, M=L, N=hd, K=L, lda=Lp, ldb=Lp, ldc=H * hd, tile=(128, 1), batch=H, a_row=L, b_row=hd, c_batch=hd, causal=3)
+    _close(dK, torch.einsum("hkq,qhd->khd", dSt[:, :, :L].float(), Q.float().view(L, H, hd)).reshape(L, H * hd), what="causal dK")
