@@ -308,8 +308,18 @@ def hbm_bound_kernels(atk, model, sampled, optim_ids, image, original, cfg, peak
     grad = native.token_grad(g, W)
     ids = optim_ids.reshape(-1)
     secs = timeit(lambda: native.sample_ids(ids, grad, cfg.search_width, cfg.topk, cfg.n_replace, None, 1, 0))
-    out["sampler"] = entry("sampler", "topk_chunk + topk_merge + sample_replace", secs,
-                           n_tok * V * 2 + n_tok * cfg.topk * 8 + cfg.search_width * n_tok * 8, launches=3)
+    two = grad.shape[1] > 65536
+    out["sampler"] = entry("sampler", ("topk_chunk + topk_merge" if two else "topk_row16 (one launch)") + " + sample_replace", secs,
+                           n_tok * V * 2 + n_tok * cfg.topk * 8 + cfg.search_width * n_tok * 8, launches=3 if two else 2)
+    # BASELINE config 2, second variant: a random 30 % of the vocabulary not allowed (the mask is a V-bit set folded
+    # into the top-k read; the scoring phase does not depend on it)
+    gm = torch.Generator().manual_seed(30)
+    banned = torch.randperm(V, generator=gm)[: int(0.3 * V)].to(dev)
+    mask = native.pack_mask_bits(banned, V, dev)
+    secs = timeit(lambda: native.sample_ids(ids, grad, cfg.search_width, cfg.topk, cfg.n_replace, mask, 1, 0))
+    out["sampler_masked_30pct"] = entry("sampler", "same, 30 % of the vocabulary masked out", secs,
+                                        n_tok * V * 2 + V // 8 + n_tok * cfg.topk * 8 + cfg.search_width * n_tok * 8,
+                                        launches=3 if two else 2)
     if image is not None:
         x = image.clone()
         gi = torch.randn_like(x)

@@ -139,13 +139,27 @@ __global__ void __launch_bounds__(256)
 append_prefix_kv_kernel(const __nv_bfloat16* __restrict__ k_tail, long long ldk,
                         const __nv_bfloat16* __restrict__ vt_tail, long long ldvt,
                         __nv_bfloat16* __restrict__ k_pre, long long ldkp,
-                        __nv_bfloat16* __restrict__ vt_pre, long long ldvtp, int n, int kv_dim, int P) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n * kv_dim) return;
-  const int key = i / kv_dim, c = i - key * kv_dim;     // K: consecutive threads -> consecutive columns
-  k_pre[(long long)(P + key) * ldkp + c] = k_tail[(long long)key * ldk + c];
-  const int dim = i / n, kk = i - dim * n;              // V^T: consecutive threads -> consecutive keys
-  vt_pre[(long long)dim * ldvtp + P + kk] = vt_tail[(long long)dim * ldvt + kk];
+                        __nv_bfloat16* __restrict__ vt_pre, long long ldvtp, int n, int kv_dim, int P, int vec_v) {
+  // 16-byte units: K rows are contiguous along the columns, V^T rows along the keys (vector stores when
+  // the destination key index, both leading dimensions and both base pointers are 8-aligned: vec_v)
+  const int kvec = kv_dim >> 3, nvec = (n + 7) >> 3;
+  const long long k_units = (long long)n * kvec;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < k_units) {
+    const int key = static_cast<int>(i / kvec), c = static_cast<int>(i - (long long)key * kvec) * 8;
+    *reinterpret_cast<uint4*>(k_pre + (long long)(P + key) * ldkp + c) =
+        *reinterpret_cast<const uint4*>(k_tail + (long long)key * ldk + c);
+  } else if (i < k_units + (long long)kv_dim * nvec) {
+    const long long j = i - k_units;
+    const int dim = static_cast<int>(j / nvec), kk = static_cast<int>(j - (long long)dim * nvec) * 8;
+    const __nv_bfloat16* src = vt_tail + (long long)dim * ldvt + kk;
+    __nv_bfloat16* dst = vt_pre + (long long)dim * ldvtp + P + kk;
+    if (vec_v && kk + 8 <= n) {
+      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+    } else {
+      for (int e = 0; e < 8 && kk + e < n; ++e) dst[e] = src[e];
+    }
+  }
 }
 
 cudaError_t launch_append_prefix_kv(const __nv_bfloat16* k_tail, long long ldk, const __nv_bfloat16* vt_tail,
@@ -153,9 +167,14 @@ cudaError_t launch_append_prefix_kv(const __nv_bfloat16* k_tail, long long ldk, 
                                     __nv_bfloat16* vt_pre, long long ldvtp, int n, int kv_dim, int P,
                                     cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
-  const int total = n * kv_dim;
-  append_prefix_kv_kernel<<<(total + 255) / 256, 256, 0, stream>>>(k_tail, ldk, vt_tail, ldvt, k_pre, ldkp,
-                                                                   vt_pre, ldvtp, n, kv_dim, P);
+  if ((kv_dim & 7) || (ldk & 7) || (ldkp & 7) || (reinterpret_cast<uintptr_t>(k_tail) & 15) ||
+      (reinterpret_cast<uintptr_t>(k_pre) & 15))
+    return cudaErrorInvalidValue;
+  const int vec_v = ((P & 7) == 0 && (ldvt & 7) == 0 && (ldvtp & 7) == 0 && (reinterpret_cast<uintptr_t>(vt_tail) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(vt_pre) & 15) == 0) ? 1 : 0;
+  const long long total = (long long)n * (kv_dim >> 3) + (long long)kv_dim * ((n + 7) >> 3);
+  append_prefix_kv_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, stream>>>(k_tail, ldk, vt_tail, ldvt, k_pre, ldkp,
+                                                                                      vt_pre, ldvtp, n, kv_dim, P, vec_v);
   return cudaGetLastError();
 }
 

@@ -51,6 +51,9 @@ class TailPlan:
     n_id_rows: int = 0               # one past the last tail row that depends on the candidate's ids
 
 
+_SLOT_CACHE: Dict[tuple, torch.Tensor] = {}     # (device, slot tuple) -> int32 device tensor: no H2D copy per step
+
+
 def plan_tail(order: Sequence[str], parts: Dict[str, torch.Tensor], n_optim: int) -> TailPlan:
     """``parts[name]`` is the [1, L, d] embedding of every fixed segment in ``order``."""
     if "optim" not in order:
@@ -72,5 +75,11 @@ def plan_tail(order: Sequence[str], parts: Dict[str, torch.Tensor], n_optim: int
             rows.append(t)
     fixed = torch.cat(rows, 0).contiguous()
     n_id_rows = max(i for i, v in enumerate(slot) if v >= 0) + 1
-    return TailPlan(prefix=prefix, slot=torch.tensor(slot, dtype=torch.int32, device=dev), fixed=fixed,
+    key = (str(dev), tuple(slot))
+    slot_t = _SLOT_CACHE.get(key)
+    if slot_t is None:
+        if len(_SLOT_CACHE) > 64:
+            _SLOT_CACHE.clear()
+        slot_t = _SLOT_CACHE[key] = torch.tensor(slot, dtype=torch.int32, device=dev)
+    return TailPlan(prefix=prefix, slot=slot_t, fixed=fixed,
                     n_prefix=0 if prefix is None else prefix.shape[0], n_tail=len(slot), n_id_rows=n_id_rows)
