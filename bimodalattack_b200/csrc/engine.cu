@@ -111,6 +111,7 @@ struct bma_scorer {
   int* cand_vstart = nullptr;
   int2* cand_tmp = nullptr;
   int dedupe = 1;                        // identical candidates share one set of rows (bma_scorer_set_dedupe)
+  int fused_publish = 1;                 // prefix / base K/V leave through the QKV GEMM's epilogue (bma_scorer_set_fused_publish)
   int* total_rows_dev = nullptr;         // live row count of the current chunk (read by every kernel of the pass)
   int* total_rows_host = nullptr;        // pinned
   unsigned long long* rows_accum_dev = nullptr;   // rows run by the ragged chunks of the last score call
@@ -239,6 +240,20 @@ inline __nv_bfloat16* layer_pre_vt(bma_scorer* s, int l) {
   return s->prefix_vt + (size_t)l * s->kv_dim * s->ld_vtp;
 }
 
+// Fused publish (default): the QKV GEMM's epilogue stores the K/V of the prefix rows and of the base rows
+// straight into the per-layer prefix buffers (of every rank when the prefix is split over NVLink peers),
+// so the per-layer exchange is part of the GEMM. BMA_FUSED_PUBLISH=0 selects the separate copy / scatter
+// kernels (A/B runs); the NCCL all-gather exchange always uses pack + unpack.
+inline int fused_publish_default() {
+  const char* e = getenv("BMA_FUSED_PUBLISH");
+  return (e != nullptr && atoi(e) == 0) ? 0 : 1;
+}
+inline bool publish_in_epilogue(const bma_scorer* s, const Pass& ps) {
+  if (!ps.publish || ps.prefill || !s->fused_publish) return false;
+  if (ps.pre_chunk > 0 && s->peer_n <= 1) return false;      // split prefill through NCCL: pack / all-gather / unpack
+  return true;
+}
+
 // pre-norm + fused QKV projection (+ q/k-norm + rotary, V transposed)
 int layer_front(bma_scorer* s, int l, Pass& ps, cudaStream_t st) {
   const bma_model_desc& D = s->desc;
@@ -264,6 +279,21 @@ int layer_front(bma_scorer* s, int l, Pass& ps, cudaStream_t st) {
   if (D.qk_norm) {
     p.q_norm_w = bf(W.q_norm); p.k_norm_w = bf(W.k_norm);
     p.q_cols = s->q_dim; p.qk_norm_eps = D.rms_eps;
+  }
+  if (publish_in_epilogue(s, ps)) {
+    // the prefix rows' and the base rows' K/V leave through this GEMM's epilogue: into this rank's per-layer
+    // prefix buffers and, when the prefix positions are split over the ranks of the box, into every peer's
+    const bool peers = ps.pre_chunk > 0 && s->peer_n > 1;
+    p.pub_rows = ps.pre_n + ps.n_share; p.pub_pre_n = ps.pre_n;
+    p.pub_key0 = ps.pre0; p.pub_base_key = s->prefix_len;
+    p.pub_n = peers ? s->peer_n : 1; p.pub_self = peers ? s->peer_rank : 0;
+    p.pub_kcol0 = s->q_dim; p.pub_ldk = s->qk_dim; p.pub_ldvt = s->ld_vtp;
+    const size_t qk_off = (size_t)l * D.max_prefix * s->qk_dim + s->q_dim;
+    const size_t vt_off = (size_t)l * s->kv_dim * s->ld_vtp;
+    for (int q = 0; q < p.pub_n; ++q) {
+      p.pub_k[q] = (peers ? static_cast<__nv_bfloat16*>(s->peer_qk[q]) : s->prefix_qk) + qk_off;
+      p.pub_vt[q] = (peers ? static_cast<__nv_bfloat16*>(s->peer_vt[q]) : s->prefix_vt) + vt_off;
+    }
   }
   ProfScope pr(s, PC_GEMM_QKV, gemm_flops(p), st);
   if (D.head_dim == 128) {
@@ -419,9 +449,21 @@ int layer_wait_peers(bma_scorer* s, int l, const Pass& ps, int P, cudaStream_t s
     ProfScope pr(s, PC_EMBED, 0, st);
     BMA_LAUNCH(launch_prefix_wait(s->flags_dev, s->peer_n, s->epoch, st), "prefix_wait");
   }
+  if (publish_in_epilogue(s, ps)) return 0;          // the base rows went out with the GEMM
   return layer_publish_base(s, l, ps, P, st);
 }
+// Fused publish: the QKV GEMM has already stored this rank's slice into every rank's buffers; what is left
+// of the exchange is ONE launch that raises this rank's flag on every peer (stream order + a system-scope
+// fence put the GEMM's peer stores before it) and waits for the other ranks' flags.
+int layer_signal_peers(bma_scorer* s, bool wait, cudaStream_t st) {
+  ++s->epoch;
+  ProfScope pr(s, PC_EMBED, 0, st);
+  BMA_LAUNCH(launch_prefix_signal_wait(s->peer_flags, s->flags_dev, s->peer_n, s->peer_rank, s->epoch, 1, wait ? 1 : 0,
+                                       st), "prefix_signal_wait");
+  return 0;
+}
 int layer_exchange_peers(bma_scorer* s, int l, const Pass& ps, int P, cudaStream_t st) {
+  if (publish_in_epilogue(s, ps)) return layer_signal_peers(s, true, st);
   int rc = layer_scatter_peers(s, l, ps, st);
   if (rc != 0) return rc;
   return layer_wait_peers(s, l, ps, P, st);
@@ -429,6 +471,7 @@ int layer_exchange_peers(bma_scorer* s, int l, const Pass& ps, int P, cudaStream
 // Barrier over the ranks (no data): nobody writes into a rank's prefix buffers while that rank may still
 // be reading them for an earlier pass.
 int peers_barrier(bma_scorer* s, cudaStream_t st) {
+  if (s->fused_publish) return layer_signal_peers(s, true, st);
   Pass none;
   none.pre_n = 0; none.pre0 = 0;
   int rc = layer_scatter_peers(s, 0, none, st);
@@ -465,7 +508,7 @@ int run_layers(bma_scorer* s, Pass& ps, cudaStream_t st) {
                                              ps.pre_n, ps.n_share, layer_pre_qk(s, l) + s->q_dim, s->qk_dim,
                                              layer_pre_vt(s, l), s->ld_vtp, s->kv_dim, st), "unpack_prefix_kv");
         }
-      } else {
+      } else if (!publish_in_epilogue(s, ps)) {
         rc = layer_publish_local(s, l, ps, P, st);
       }
       if (rc != 0) return rc;
@@ -555,6 +598,7 @@ bma_scorer* bma_scorer_create(const bma_model_desc* desc) {
   }
   bma_scorer* s = new bma_scorer();
   s->desc = D;
+  s->fused_publish = fused_publish_default();
   s->layers.resize(D.n_layers);
   s->q_dim = D.n_heads * D.head_dim;
   s->kv_dim = D.n_kv_heads * D.head_dim;
@@ -703,6 +747,12 @@ long long bma_scorer_last_rows(const bma_scorer* s) {
   unsigned long long ragged = 0;     // synchronising read: the ragged chunks counted their rows on the device
   if (cudaMemcpy(&ragged, s->rows_accum_dev, sizeof(ragged), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
   return s->last_rows + static_cast<long long>(ragged);
+}
+
+int bma_scorer_set_fused_publish(bma_scorer* s, int enable) {
+  if (s == nullptr) return fail(cudaErrorInvalidValue, "set_fused_publish: null scorer");
+  s->fused_publish = enable != 0;
+  return 0;
 }
 
 int bma_scorer_set_dedupe(bma_scorer* s, int enable) {
@@ -993,7 +1043,9 @@ int bma_scorer_group_score(bma_scorer** group, int n, const long long* ids, int 
     for (int r = 0; r < n; ++r) {
       int rc = layer_front(group[r], l, pass[r], st);
       if (rc != 0) return rc;
-      rc = via_peers ? layer_scatter_peers(group[r], l, pass[r], st) : layer_pack(group[r], l, pass[r], st);
+      if (!via_peers) rc = layer_pack(group[r], l, pass[r], st);
+      else if (publish_in_epilogue(group[r], pass[r])) rc = layer_signal_peers(group[r], false, st);
+      else rc = layer_scatter_peers(group[r], l, pass[r], st);
       if (rc != 0) return rc;
     }
     for (int r = 0; r < n; ++r) {

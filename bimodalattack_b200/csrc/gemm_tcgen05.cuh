@@ -70,6 +70,16 @@ struct GemmParams {
   float2* ce_part;            // [n_tiles][M] (running max, sum of exp)
   float* tgt_logit;           // [M]
   int* ce_arg;                // [n_tiles][M] first column attaining the tile maximum (torch.argmax order)
+  // EPI_ROPE, fused K/V publish (pub_rows > 0): the leading rows of the pass ALSO store their K heads and V
+  // heads into per-layer prefix buffers -- rows [0, pub_pre_n) are prefix positions pub_key0 + r and go to
+  // all pub_n targets (the ranks of the box incl. this one: peer-mapped pointers, st.global over NVLink, so
+  // the per-layer all-gather of the split prefill rides in this GEMM's epilogue tile by tile); rows
+  // [pub_pre_n, pub_rows) are the base suffix's rows and go to target pub_self only, at key pub_base_key + ...
+  int pub_rows, pub_pre_n, pub_key0, pub_base_key, pub_n, pub_self;
+  int pub_kcol0;              // first K-head column of the projection (= q_dim)
+  long long pub_ldk, pub_ldvt;
+  __nv_bfloat16* pub_k[8];    // [key][pub_ldk], column 0 = first K-head column
+  __nv_bfloat16* pub_vt[8];   // [dim][pub_ldvt]
 };
 
 constexpr int GEMM_BM = 128;
@@ -407,6 +417,16 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 __nv_bfloat16* dst = p.C + (long long)row * p.ldc + col_h + c0;
                 store_bf16x32(dst, o1, 32);
                 store_bf16x32(dst + HALF, o2, 32);
+                if (row < p.pub_rows && col_h >= p.pub_kcol0) {       // K head of a prefix / base row
+                  const bool pre = row < p.pub_pre_n;
+                  const long long off = (long long)(pre ? p.pub_key0 + row : p.pub_base_key + row - p.pub_pre_n) *
+                                            p.pub_ldk + (col_h - p.pub_kcol0) + c0;
+#pragma unroll 1
+                  for (int q = pre ? 0 : p.pub_self; q < (pre ? p.pub_n : p.pub_self + 1); ++q) {
+                    store_bf16x32(p.pub_k[q] + off, o1, 32);
+                    store_bf16x32(p.pub_k[q] + off + HALF, o2, 32);
+                  }
+                }
               }
             }
           } else {
@@ -422,6 +442,18 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                   if (col_h + c0 + j < p.N) dst[(long long)j * p.ldvt] = __float2bfloat16_rn(__uint_as_float(r[j]));
+                }
+                if (row < p.pub_rows) {                               // V head of a prefix / base row
+                  const bool pre = row < p.pub_pre_n;
+                  const long long off = (long long)(col_h + c0 - p.rope_cols) * p.pub_ldvt +
+                                        (pre ? p.pub_key0 + row : p.pub_base_key + row - p.pub_pre_n);
+#pragma unroll 1
+                  for (int q = pre ? 0 : p.pub_self; q < (pre ? p.pub_n : p.pub_self + 1); ++q) {
+                    __nv_bfloat16* pd = p.pub_vt[q] + off;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                      if (col_h + c0 + j < p.N) pd[(long long)j * p.pub_ldvt] = __float2bfloat16_rn(__uint_as_float(r[j]));
+                  }
                 }
                 if (p.v_rowmajor) {
                   uint32_t o[16];

@@ -296,6 +296,40 @@ __global__ void prefix_wait_kernel(volatile unsigned long long* flags, int n_ran
   __threadfence_system();
 }
 
+// Fused publish (the QKV GEMM's epilogue has stored this rank's K/V slice into every rank's buffers): raise
+// this rank's flag on every peer, then wait for all ranks' flags. The GEMM precedes this launch in stream
+// order, so its peer stores are performed before the system-scope fence below, and the flag after it.
+struct PeerFlags { unsigned long long* f[8]; };
+__global__ void prefix_signal_wait_kernel(PeerFlags peers, volatile unsigned long long* flags, int n_ranks, int my_rank,
+                                          unsigned long long epoch, int signal, int wait) {
+  const int q = threadIdx.x;
+  if (q < n_ranks) {
+    if (signal) {
+      __threadfence_system();
+      atomicExch_system(peers.f[q] + my_rank, epoch);
+    }
+    if (wait) {
+      unsigned int spins = 0;
+      while (flags[q] < epoch) {
+        if (++spins > (1u << 27)) {                          // ~seconds: a rank never arrived
+          if (g_watchdog_host != nullptr) { *g_watchdog_host = 0xE100u | q; __threadfence_system(); }
+          __trap();
+        }
+      }
+    }
+  }
+  __threadfence_system();
+}
+
+cudaError_t launch_prefix_signal_wait(void* const* peer_flags, unsigned long long* my_flags, int n_ranks, int my_rank,
+                                      unsigned long long epoch, int signal, int wait, cudaStream_t stream) {
+  if (n_ranks < 1 || n_ranks > 8) return cudaErrorInvalidValue;
+  PeerFlags pf{};
+  for (int q = 0; q < n_ranks; ++q) pf.f[q] = static_cast<unsigned long long*>(peer_flags[q]);
+  prefix_signal_wait_kernel<<<1, 32, 0, stream>>>(pf, my_flags, n_ranks, my_rank, epoch, signal, wait);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_prefix_scatter(const __nv_bfloat16* k_tail, long long ldk, const __nv_bfloat16* vt_tail, long long ldvt,
                                   void* const* peer_k, void* const* peer_vt, void* const* peer_flags, int n_ranks,
                                   int my_rank, long long ldkp, long long ldvtp, int n, int key0, int kv_dim,

@@ -105,6 +105,8 @@ class ScoringEngine:
         self.prefix_len = 0
         self.share_suffix_head = True    # compute tail rows shared with the base suffix once (see score())
         self.dedupe_candidates = True    # ... and the rows of identical candidates once
+        self.fused_publish = None        # None: library default (on; BMA_FUSED_PUBLISH=0 turns it off). Set BEFORE the
+                                         # first score call: prefix / base K/V leave through the QKV GEMM's epilogue
         # fused prefill: the prefix positions ride in the first chunk of the next score() call as extra
         # rows (one [prefix | base | candidates] row space per layer) instead of a separate pass
         self.fused_prefill = True
@@ -167,6 +169,8 @@ class ScoringEngine:
                                self.lib.bma_last_error().decode("utf-8", "replace"))
         self._scorer = handle
         native.check(self.lib.bma_scorer_set_dedupe(handle, int(self.dedupe_candidates)), "scorer_set_dedupe")
+        if self.fused_publish is not None:
+            native.check(self.lib.bma_scorer_set_fused_publish(handle, int(self.fused_publish)), "scorer_set_fused_publish")
         if self.comm is not None:
             native.check(self.lib.bma_scorer_set_comm(handle, self.comm), "scorer_set_comm")
             if self.peer_memory:

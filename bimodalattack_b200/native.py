@@ -90,6 +90,7 @@ SIGNATURES = {
     "bma_comm_reduce_winner": (_I, [_P, _P, _P, _P]),
     "bma_scorer_last_rows": (_LL, [_P]),
     "bma_scorer_set_dedupe": (_I, [_P, _I]),
+    "bma_scorer_set_fused_publish": (_I, [_P, _I]),
     "bma_scorer_score_host": (_I, [_P, _P, _I, _I, _P, _P, _I, _P, _I, _I, _P, _P, _U32, _P, _I, _P]),
     "bma_gemm_ex": (_I, [C.POINTER(GemmDesc), _P]),
     "bma_qkv_rope": (_I, [_P, _LL, _P, _P, _LL, _P, _LL, _P, _P, _I, _I, _I, _I, _I, _I, _P]),

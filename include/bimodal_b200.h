@@ -141,6 +141,11 @@ long long bma_scorer_last_rows(const bma_scorer* s);
 /* With base_ids: candidates identical to an earlier candidate of the chunk (or to the base) reuse its
  * rows instead of recomputing them (default on); their loss is the representative's. */
 int bma_scorer_set_dedupe(bma_scorer* s, int enable);
+/* With base_ids / a deferred prefix: the K/V of the prefix rows and of the base rows are stored into the
+ * per-layer prefix buffers by the QKV projection's epilogue -- and, when the prefix is split over the
+ * ranks of a box, into every peer's buffers over NVLink, so the per-layer all-gather is part of the
+ * GEMM (default on; BMA_FUSED_PUBLISH=0 or enable = 0 selects the separate copy / scatter kernels). */
+int bma_scorer_set_fused_publish(bma_scorer* s, int enable);
 
 /* Same call with HOST buffers for ids / loss / key (pinned recommended): copies in, scores,
  * copies out and synchronises the stream. This is the end-to-end entry the benchmark times. */

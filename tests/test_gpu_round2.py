@@ -133,6 +133,43 @@ def test_split_prefill_over_emulated_ranks(cuda_device, ranks, n, peers):
         e.close()
 
 
+@pytest.mark.parametrize("ranks,n,size,px", [(1, 70, "tiny128", 28), (2, 48, "tiny128", 28), (8, 130, "tiny128", 28),
+                                             (3, 200, "small128", 56)])
+def test_fused_publish_is_bit_identical_to_separate_kernels(cuda_device, ranks, n, size, px):
+    """The QKV GEMM's epilogue stores the prefix rows' and the base rows' K/V into the per-layer prefix
+    buffers of every (emulated) rank itself; the separate append / scatter kernels it replaces copy the
+    same bf16 values afterwards. Same row space, same values: losses and winner keys are bit-identical."""
+    from bimodalattack_b200 import BimodalAttack
+    from bimodalattack_b200.attack import image_features
+    from bimodalattack_b200.engine import ScoringEngine, group_score
+    model, tok, proc, norm, image, cfg = _setup(cuda_device, size=size, image_px=px, search_width=n, **JOINT)
+    atk = BimodalAttack(model, tok, proc, cfg, normalize=norm)
+    atk._prepare([{"role": "user", "content": PROMPT}], TARGET)
+    base = tok(INIT, add_special_tokens=False, return_tensors="pt")["input_ids"].to(cuda_device).reshape(-1).contiguous()
+    cand = _related(base, n, 8, 1000, seed=ranks, device=cuda_device)
+    out = {}
+    with torch.no_grad():
+        feats = image_features(model, norm(image), False)
+        plan = atk._plan(atk._build_input_embeds_pgd(cand, feats, search_width=n, single=True))
+        for fused in (True, False):
+            group = [ScoringEngine(model) for _ in range(ranks)]
+            for e in group:
+                e.fused_publish = fused
+                e.prefill(plan.prefix, deferred=True)
+            if ranks == 1:
+                loss = group[0].score(cand, plan, atk.target_ids, base_ids=base).clone()
+                again = group[0].score(cand, plan, atk.target_ids, base_ids=base).clone()   # base rows only
+            else:
+                loss = group_score(group, cand, plan, atk.target_ids, base, use_peers=True).clone()
+                again = group[-1].score(cand, plan, atk.target_ids, base_ids=base).clone()
+            out[fused] = (loss, again, int(group[0].key.item()))
+            for e in group:
+                e.close()
+    assert torch.equal(out[True][0], out[False][0])
+    assert torch.equal(out[True][1], out[False][1])
+    assert out[True][2] == out[False][2]
+
+
 # ------------------------------------------------------------------------------------------------
 def _greedy_target(model, atk, cand_row, feats, n_tokens):
     """Target ids the model itself predicts greedily after [prefix, cand_row, after]: with them as the
