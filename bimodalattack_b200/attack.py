@@ -524,7 +524,7 @@ class BimodalAttack:
         tower = self._native_tower()
         if tower is not None:
             src = image.detach()
-            fn = lambda t: tower.forward(t).clone()                     # noqa: E731
+            fn = lambda t: tower.forward(t, keep=False).clone()                     # noqa: E731
         else:
             src = self._normalized(image)
             fn = lambda t: image_features(self.model, t, self.gemma_processor)   # noqa: E731

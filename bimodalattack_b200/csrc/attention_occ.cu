@@ -41,6 +41,7 @@ struct Params {
   const int2* row_meta;
   int P_shared;
   int pre_rows;
+  int no_tail;                // rows attend to the prefix keys only
   int n_heads, kv_group;
   float scale_log2;
 };
@@ -196,7 +197,7 @@ attention_occ_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         const int kvh = head / p.kv_group;
         const int r0 = tile * BM, r1 = min(M, r0 + BM);
         const int kt0 = tail_start(r0, p.S, p.row_meta);
-        const int nb = n_pre + (r1 - kt0 + BN - 1) / BN;
+        const int nb = n_pre + (p.no_tail ? 0 : (r1 - kt0 + BN - 1) / BN);
         mbar_wait(q_empty, (item_n & 1) ^ 1, 0x800);
         mbar_arrive_expect_tx(q_full, QTILE);
         tma_load_2d(sQ, &tm_q, q_full, head * HD, r0);
@@ -254,7 +255,7 @@ attention_occ_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         const int head = item / m_tiles, tile = item - head * m_tiles;
         const int r0 = tile * BM, r1 = min(M, r0 + BM);
         const int kt0 = tail_start(r0, p.S, p.row_meta);
-        const int nb = n_pre + (r1 - kt0 + BN - 1) / BN;
+        const int nb = n_pre + (p.no_tail ? 0 : (r1 - kt0 + BN - 1) / BN);
         (void)head;
         mbar_wait(q_full, item_n & 1, 0x840);
         for (int j = 0; j < nb; ++j, ++it) {
@@ -289,7 +290,7 @@ attention_occ_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       const int head = item / m_tiles, tile = item - head * m_tiles;
       const int r0 = tile * BM, r1 = min(M, r0 + BM);
       const int kt0 = tail_start(r0, p.S, p.row_meta);
-      const int nb = n_pre + (r1 - kt0 + BN - 1) / BN;
+      const int nb = n_pre + (p.no_tail ? 0 : (r1 - kt0 + BN - 1) / BN);
       const int rq = r0 + row_in_tile;
       int cs = (rq / p.S) * p.S, plim = p.P;
       if (p.row_meta != nullptr && rq < M) {
@@ -414,7 +415,8 @@ cudaError_t launch_attention_occ(const AttnParams& a, int n_heads, cudaStream_t 
   }
   Params p{};
   p.out = a.out; p.ldo = a.ldo;
-  p.M = a.M; p.S = a.S; p.P = a.P; p.M_dev = a.M_dev;
+  p.M = a.M; p.S = a.S > 0 ? a.S : 1; p.P = a.P; p.M_dev = a.M_dev;
+  p.no_tail = a.no_tail;
   p.row_meta = a.row_meta;
   p.P_shared = a.row_meta != nullptr ? a.P_shared : a.P;
   p.pre_rows = a.row_meta != nullptr ? a.pre_rows : 0;

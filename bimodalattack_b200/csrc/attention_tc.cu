@@ -70,6 +70,7 @@ struct AtcParams {
   const int2* row_meta;      // ragged rows: (first row of the row's candidate, visible prefix keys)
   int P_shared;              // prefix keys every row sees (== P without row_meta)
   int pre_rows;              // leading rows that are shared-prefix positions (fused prefill): they see fewer keys
+  int no_tail;               // rows attend to the prefix keys only
   int n_heads, kv_group;
   int q_col0, k_col0;        // column of head 0 inside the Q / K tensor maps
   float scale_log2;
@@ -180,7 +181,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         const int kvh = head / p.kv_group;
         const int r0 = tile * ATC_BM, r1 = min(M, r0 + ATC_BM);
         const int kt0 = tail_key_start(r0, p.S, p.row_meta);
-        const int nb = n_pre + (r1 - kt0 + BN - 1) / BN;
+        const int nb = n_pre + (p.no_tail ? 0 : (r1 - kt0 + BN - 1) / BN);
         {
           const int qb = item_n % QB;
           const uint32_t qpar = (item_n / QB) & 1;
@@ -257,7 +258,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         const int head = item / m_tiles, tile = item - head * m_tiles;
         const int r0 = tile * ATC_BM, r1 = min(M, r0 + ATC_BM);
         const int kt0 = tail_key_start(r0, p.S, p.row_meta);
-        const int nb = n_pre + (r1 - kt0 + BN - 1) / BN;
+        const int nb = n_pre + (p.no_tail ? 0 : (r1 - kt0 + BN - 1) / BN);
         const int qb = item_n % QB;
         if (QB == 1 && have_pending) {                  // a single Q tile cannot be prefetched: do not hold
           issue_pv(pend_g, pend_n, pend_first, pend_item_par);   // the last PV back behind the Q reload
@@ -309,7 +310,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       const int head = item / m_tiles, tile = item - head * m_tiles;
       const int r0 = tile * ATC_BM, r1 = min(M, r0 + ATC_BM);
       const int kt0 = tail_key_start(r0, p.S, p.row_meta);
-      const int nb = n_pre + (r1 - kt0 + BN - 1) / BN;
+      const int nb = n_pre + (p.no_tail ? 0 : (r1 - kt0 + BN - 1) / BN);
       const int rq = r0 + row_in_tile;
       int cs = (rq / p.S) * p.S, plim = p.P;
       if (p.row_meta != nullptr && rq < M) {
@@ -493,7 +494,8 @@ static cudaError_t launch_atc(const AttnParams& a, int n_heads, cudaStream_t str
   }
   AtcParams p{};
   p.out = a.out; p.ldo = a.ldo;
-  p.M = a.M; p.S = a.S; p.P = a.P; p.M_dev = a.M_dev;
+  p.M = a.M; p.S = a.S > 0 ? a.S : 1; p.P = a.P; p.M_dev = a.M_dev;
+  p.no_tail = a.no_tail;
   p.row_meta = a.row_meta;
   p.P_shared = a.row_meta != nullptr ? a.P_shared : a.P;
   p.pre_rows = a.row_meta != nullptr ? a.pre_rows : 0;
@@ -512,7 +514,8 @@ static cudaError_t launch_atc(const AttnParams& a, int n_heads, cudaStream_t str
 
 cudaError_t launch_prefix_tail_attention(const AttnParams& a, int n_heads, cudaStream_t stream) {
   if (a.M <= 0) return cudaSuccess;
-  if (a.S <= 0 || a.P < 0 || a.kv_group <= 0) return cudaErrorInvalidValue;
+  if (a.P < 0 || a.kv_group <= 0) return cudaErrorInvalidValue;
+  if (a.no_tail ? (a.P <= 0 || a.row_meta != nullptr) : a.S <= 0) return cudaErrorInvalidValue;
   if (a.head_dim == 128) {
     // default: two-CTAs-per-SM kernel (attention_occ.cu). BMA_ATTN=split selects the split-key kernel
     // (attention_split.cu), BMA_ATTN=tc this file's kernel (A/B runs).
@@ -521,7 +524,7 @@ cudaError_t launch_prefix_tail_attention(const AttnParams& a, int n_heads, cudaS
       const char* e = getenv("BMA_ATTN");
       which = e == nullptr ? 0 : (e[0] == 's' ? 1 : (e[0] == 't' ? 2 : 0));
     }
-    if (which == 0) return launch_attention_occ(a, n_heads, stream);
+    if (which == 0 || a.no_tail) return launch_attention_occ(a, n_heads, stream);
     return which == 1 ? launch_attention_split(a, n_heads, stream) : launch_atc<128, 128>(a, n_heads, stream);
   }
   if (a.head_dim == 256) return launch_atc<256, 64>(a, n_heads, stream);

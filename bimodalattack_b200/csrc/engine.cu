@@ -1216,6 +1216,7 @@ int bma_attention(const void* q, long long ldq, const void* k_tail, long long ld
   a.vt_pre = bf(vt_pre); a.ldvtp = ldvtp;
   a.out = bf(out); a.ldo = ldo;
   a.M = M; a.S = S; a.P = P; a.kv_group = kv_group;
+  a.no_tail = S == 0 ? 1 : 0;          // S = 0: the rows attend to the P prefix keys only
   a.scale_log2 = scale * 1.4426950408889634f;
   BMA_LAUNCH(launch_prefix_tail_attention(a, n_heads, as_stream(stream)), "attention");
   return 0;

@@ -21,6 +21,9 @@ struct AttnParams {
   const int2* row_meta;
   int P_shared;
   int pre_rows;                 // leading rows that are prefix positions themselves (fused prefill)
+  int no_tail;                  // 1: rows attend to the P prefix keys only (no causal tail at all): plain
+                                // non-causal attention of one sequence over itself (vision tower) when K/V^T
+                                // of all its rows are handed in as the "prefix"
   int kv_group;                 // query heads per kv head
   int head_dim;                 // 128 or 256
   float scale_log2;             // softmax scale * log2(e)

@@ -402,9 +402,11 @@ class NativeVisionTower(_AttentionProducts):
         native.check(self.k.lib.bma_act(x.data_ptr(), None if dy is None else dy.data_ptr(), out.data_ptr(),
                                         x.numel(), kind, self.k.st), "act")
 
-    def forward(self, image: torch.Tensor) -> torch.Tensor:
+    def forward(self, image: torch.Tensor, keep: bool = True) -> torch.Tensor:
         """image: [1, 3, px, px] fp32 raw pixels in [0, 1] -> image features [1, n_feat, d_llm] bf16 (a view of
-        an internal buffer, valid until the next call)."""
+        an internal buffer, valid until the next call). ``keep=False`` (scoring phase, no backward follows): the
+        per-head products S = QK^T -> softmax -> PV, whose probabilities the backward needs, are replaced by ONE
+        launch of the library's tcgen05 flash-attention kernel in its no-tail mode (bma_attention, S = 0)."""
         k, lib, st = self.k, self.k.lib, self.k.st
         L, Lp, D, F = self.L, self.Lp, self.D, self.F
         if tuple(image.shape[-3:]) != (3, self.px, self.px) or image.dtype != torch.float32:
@@ -423,7 +425,13 @@ class NativeVisionTower(_AttentionProducts):
             self._ln(X, lyr.layer_norm1, self.XN, L)
             k.gemm(self.XN, self.w_qkv[l], out=QKV, M=L, N=self.qkv_dim, K=D, bias=self.b_qkv[l])
             self._transpose(QKV, self.qkv_dim, 0, self.VT, Lp, 0, L, D, 1, src_off=2 * D)
-            self._attn_forward(QKV, P, L, self.scale, causal=0)
+            if keep:
+                self._attn_forward(QKV, P, L, self.scale, causal=0)
+            else:
+                kp = QKV.data_ptr() + 2 * D
+                native.check(lib.bma_attention(QKV.data_ptr(), self.qkv_dim, kp, self.qkv_dim, self.VT.data_ptr(), Lp,
+                                               kp, self.qkv_dim, self.VT.data_ptr(), Lp, self.ATT.data_ptr(), D,
+                                               L, 0, L, self.H, 1, self.hd, self.scale, st), "attention(no tail)")
             k.gemm(self.ATT, a.out_proj.weight, out=XMID, M=L, N=D, K=D, bias=a.out_proj.bias, R=X, ldr=D)
             self._ln(XMID, lyr.layer_norm2, self.XN, L)
             k.gemm(self.XN, lyr.mlp.fc1.weight, out=H1, M=L, N=F, K=D, bias=lyr.mlp.fc1.bias)

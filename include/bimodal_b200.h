@@ -217,7 +217,10 @@ int bma_add_norm(const void* y, long long ldy, const void* w_post, void* x, long
                  void* stream);
 /* Shared-prefix + causal-tail attention, head_dim 64, 128 or 256. q/k_* are row-major
  * [rows, heads*head_dim]; the value operands are TRANSPOSED: vt_tail is [kv_heads*head_dim, M]
- * (row stride ldvt), vt_pre [kv_heads*head_dim, P]. */
+ * (row stride ldvt), vt_pre [kv_heads*head_dim, P]. S = 0: no causal tail at all -- every row attends to
+ * the P prefix keys only (plain non-causal attention of one sequence over itself when its own K / V^T are
+ * handed in as the prefix: the vision tower of the scoring phase); k_tail / vt_tail must still be valid
+ * pointers (they are mapped, never read). */
 int bma_attention(const void* q, long long ldq, const void* k_tail, long long ldk,
                   const void* vt_tail, long long ldvt, const void* k_pre, long long ldkp,
                   const void* vt_pre, long long ldvtp, void* out, long long ldo, int M, int S, int P,

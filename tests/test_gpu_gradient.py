@@ -236,6 +236,12 @@ def test_native_vision_tower_forward_and_backward(cuda_device, rc_px):
     e_n, e_h = rel(got, want), rel(want_bf16, want)
     print(f"features rel err vs fp32: native {e_n:.4f}  hf-bf16 {e_h:.4f}")
     assert e_n <= 1.5 * e_h + 2e-3
+    # scoring-phase forward (no backward follows): one flash-attention launch per layer instead of the products
+    got_flash = vt.forward(image, keep=False).clone()
+    e_f = rel(got_flash, want)
+    print(f"features rel err vs fp32: native flash {e_f:.4f}")
+    assert e_f <= 1.5 * e_h + 2e-3
+    assert bool(torch.equal(vt.forward(image).clone(), got))      # ... and leaves the keep=True state usable
     d_feats = (torch.randn(want.shape, generator=torch.Generator().manual_seed(1)).to(cuda_device) * 1e-2).bfloat16()
     g_true = torch.autograd.grad(want, img32, d_feats.float())[0]
     img16 = image.clone().requires_grad_()

@@ -254,3 +254,28 @@ def test_prefix_tail_attention(lib, cuda_device, B, S, P, H, G, D):
     assert not bool(torch.isnan(out.float()).any())
     # bf16 P and bf16 output: 2^-7 relative to the output scale (|out| <~ 1 for unit-variance V)
     assert (out.float() - want).abs().max().item() <= 2.5e-2
+
+
+@pytest.mark.parametrize("L,H,D", [(577, 16, 64), (257, 4, 64), (50, 2, 64), (577, 4, 128), (130, 2, 128), (64, 1, 128)])
+def test_attention_no_tail_is_plain_self_attention(lib, cuda_device, L, H, D):
+    """S = 0: every row attends to the P "prefix" keys only. With the sequence's own K / V^T handed in as
+    the prefix (inside a row-major Q | K | V buffer, the way the vision tower calls it) that is plain
+    non-causal self-attention (reference modeling_clip eager attention: softmax(Q K^T / sqrt(d)) V)."""
+    from bimodalattack_b200 import native
+    g = torch.Generator(device="cpu").manual_seed(L * H + D)
+    qkv = torch.randn((L, 3 * H * D), generator=g).to(cuda_device).to(torch.bfloat16)
+    Lp = (L + 7) // 8 * 8
+    vT = torch.full((H * D, Lp), float("nan"), dtype=torch.bfloat16, device=cuda_device)   # padding must not leak
+    vT[:, :L] = qkv[:, 2 * H * D:].T
+    out = torch.zeros((L, H * D), dtype=torch.bfloat16, device=cuda_device)
+    kp = qkv.data_ptr() + 2 * H * D
+    scale = D ** -0.5
+    native.check(lib.bma_attention(qkv.data_ptr(), qkv.stride(0), kp, qkv.stride(0), vT.data_ptr(), Lp,
+                                   kp, qkv.stride(0), vT.data_ptr(), Lp, out.data_ptr(), out.stride(0),
+                                   L, 0, L, H, 1, D, scale, _stream()), "attention(no tail)")
+    torch.cuda.synchronize()
+    q, k, v = (qkv[:, i * H * D:(i + 1) * H * D].float().view(L, H, D) for i in range(3))
+    p_ = torch.softmax(torch.einsum("qhd,khd->hqk", q, k) * scale, dim=-1)
+    want = torch.einsum("hqk,khd->qhd", p_, v).reshape(L, H * D)
+    assert not bool(torch.isnan(out.float()).any())
+    assert (out.float() - want).abs().max().item() <= 2.5e-2
