@@ -383,10 +383,10 @@ def main():
     sampled = bdist.broadcast_candidates(sampled, n_tok, dev, w)
     if joint:
         image = bdist.broadcast_tensor(image.contiguous(), w)
-    lo, hi = bdist.shard_bounds(sw, w)
     base_ids = optim_ids.reshape(-1).to(torch.int64).contiguous()
     atk.engine.share_suffix_head = not args.no_suffix_sharing
     atk._base = (sampled, base_ids)          # the suffix the candidates were sampled from (all ranks)
+    lo, hi = bdist.shard_bounds(sw, w)       # (replaced below by the row-balanced slice the scorer itself uses)
 
     def build_batch(img):
         if joint:
@@ -412,6 +412,7 @@ def main():
     with torch.no_grad():
         plan = atk._plan(build_batch(image))
     S, T = plan.n_tail, atk.target_ids.numel()
+    lo, hi, shard_hint = atk.shard(sampled, base_ids, plan)   # this rank's slice (row-balanced when N > 1)
     clocks = ClockSampler(local)
     barrier()
     launches0 = lib.bma_launch_count()
@@ -459,7 +460,7 @@ def main():
             atk.engine.prefill(pl.prefix)
             # multi-rank: the library reduces the winner key (one NCCL all-reduce) before it leaves the device
             atk.engine.score_host(ids_host[lo:hi], pl, atk.target_ids, loss_host[lo:hi], key_host, idx_base=lo,
-                                  base_ids_host=base_host, batch_hint=-(-sw // world))
+                                  base_ids_host=base_host, batch_hint=shard_hint)
         return int(key_host.item())
 
     for _ in range(max(1, args.warmup // 2)):

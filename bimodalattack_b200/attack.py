@@ -257,6 +257,7 @@ class BimodalAttack:
             # the library's own NCCL communicator: split prefill + the winner all-reduce on the scorer's stream
             self.engine.attach_comm(bdist.native_comm(self.device, self.world))
         self.gather_all_losses = False    # multi-rank: also all-reduce the per-candidate loss vector
+        self.balance_shards = os.environ.get("BMA_BALANCE_SHARDS", "1") != "0"   # multi-rank: shards of equal ROWS (shard())
         self.step_hook = None             # optional callable(step_index) run at the end of every step
         self.graph_gradient = os.environ.get("BMA_GRAPH_GRADIENT", "1") != "0"
         # patch-embedding convolutions run as unfold + GEMM while run() is active (see _patch_conv_forward);
@@ -444,7 +445,8 @@ class BimodalAttack:
         onehot_grad = None
         if g_embeds is not None:
             # (1) token gradient: G_embeds . W^T on the tcgen05 GEMM, W streamed once
-            onehot_grad = native.token_grad(g_embeds[0], W.detach()).unsqueeze(0)
+            # (an fp16 model: bf16 copies of both operands -- wider exponent range, 3 mantissa bits fewer)
+            onehot_grad = native.token_grad(g_embeds[0].to(torch.bfloat16), self.engine._w(emb.weight)).unsqueeze(0)
         return onehot_grad, g_image
 
     def _gradient_graphed(self, optim_ids: torch.Tensor, image: Optional[torch.Tensor]):
@@ -649,15 +651,14 @@ class BimodalAttack:
             eng.prefill(plan.prefix)      # deferred: rides in the first chunk of the score call below
             eng.prefill_tag = tag
         ids = batch.sampled_ids
-        lo, hi = bdist.shard_bounds(ids.shape[0], self.world)
         eng.want_all_match = bool(self.config.early_stop)
         eng.reset_key()
         loss = torch.full((ids.shape[0],), float("inf"), dtype=torch.float32, device=self.device)
         base = getattr(self, "_base", None)
         base_ids = base[1] if base is not None and base[0] is ids else None
+        lo, hi, hint = self.shard(ids, base_ids, plan)       # hint = the largest shard: every rank sizes its workspace alike
         # with a split prefill every rank takes part in the per-layer exchange, candidates or not
         if hi > lo or (self.world.size > 1 and base_ids is not None):
-            hint = -(-ids.shape[0] // self.world.size)          # the largest shard: every rank sizes its workspace alike
             loss[lo:hi] = eng.score(ids[lo:hi], plan, self.target_ids, idx_base=lo, reset=False, base_ids=base_ids,
                                     batch_hint=hint)
         bdist.reduce_winner(eng.key, eng.flag if self.config.early_stop else None, self.world)
@@ -666,6 +667,25 @@ class BimodalAttack:
         if self.config.early_stop and int(eng.flag.item()) != 0:
             self.stop_flag = True
         return loss
+
+    def shard(self, ids: torch.Tensor, base_ids: Optional[torch.Tensor], plan: TailPlan) -> Tuple[int, int, int]:
+        """(lo, hi, largest shard) of this rank's contiguous slice of the candidates. With a base suffix the
+        shards are balanced by decoder ROWS, not by count: a candidate first replaced at position j owns the
+        tail rows from j on (suffix-head sharing), so equal counts would leave the ranks with unequal work.
+        Every rank derives the same cuts from the (broadcast) ids."""
+        w, n = self.world, int(ids.shape[0])
+        if w.size == 1:
+            return 0, n, n
+        even = -(-n // w.size)
+        if base_ids is None or not self.balance_shards or n < 2 * w.size or not self.engine.share_suffix_head:
+            lo, hi = bdist.shard_bounds(n, w)
+            return lo, hi, even
+        diff = ids != base_ids.view(1, -1)
+        first = torch.where(diff.any(1), diff.int().argmax(1), ids.shape[1] + plan.n_tail)   # == base: no rows at all
+        cuts = bdist.balanced_cuts((plan.n_tail - first).clamp_(min=0) + 1, w.size)
+        widest = max(b - a for a, b in zip(cuts, cuts[1:]))
+        # a stable capacity hint (the workspace is re-created, collectively, only when it grows)
+        return cuts[w.rank], cuts[w.rank + 1], max(widest, even + even // 4 + 1)
 
     def _winner(self) -> Tuple[float, int]:
         """(min loss, argmin) from the packed key the scorer (and the all-reduce) left on device."""

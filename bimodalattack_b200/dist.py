@@ -34,6 +34,26 @@ def shard_bounds(n: int, w: World) -> Tuple[int, int]:
     return lo, lo + base + (1 if w.rank < extra else 0)
 
 
+def balanced_cuts(cost: torch.Tensor, size: int) -> list:
+    """``size + 1`` cut points of ``range(len(cost))`` into CONTIGUOUS shards of near-equal total cost
+    (``cost[i]`` = decoder rows candidate i will run: with suffix-head sharing a candidate replaced at
+    position j owns only the tail rows from j on, so equal COUNTS give the ranks unequal work and the
+    slowest rank sets the step time). Deterministic in ``cost``: every rank computes the same cuts from the
+    broadcast ids. One small D2H copy when ``cost`` lives on a device."""
+    n = int(cost.shape[0])
+    if size <= 1 or n == 0:
+        return [0] + [n] * max(size, 1)
+    cum = torch.cumsum(cost.to(torch.int64), 0)
+    k = torch.arange(1, size, device=cost.device, dtype=torch.int64)
+    # shard r ends at the first candidate whose running cost reaches r/size of the total
+    target = (cum[-1] * k + size - 1) // size
+    cuts = (torch.searchsorted(cum, target, right=False) + 1).clamp_(max=n)
+    out = [0] + [int(c) for c in cuts.tolist()] + [n]
+    for i in range(1, len(out)):           # monotone (zero-cost runs can make searchsorted tie)
+        out[i] = max(out[i], out[i - 1])
+    return out
+
+
 def pack_key(loss: float, index: int) -> int:
     """Host mirror of the device packing (csrc/scoring_ops.cu:pack_loss_key)."""
     import struct

@@ -52,9 +52,15 @@ class ScoringEngine:
         self.lm, self.head, self.cfg = lm, head, cfg
         self.device = next(lm.parameters()).device
         native.require_cuda(next(lm.parameters()), "model")
-        self.dtype = next(lm.parameters()).dtype
-        if self.dtype != torch.bfloat16:
-            raise RuntimeError(f"bimodal_b200 scorer computes in bf16; model is {self.dtype}")
+        # The kernels compute in bf16 (north_star). An fp16 model -- the reference loads LLaVA / LLaVA-RC in
+        # float16, utils/experiments_utils.py:91-100 -- is ACCEPTED: the scorer works on bf16 copies of the decoder
+        # weights (``_w``), its inputs are cast on entry and the per-candidate losses then agree with the fp16
+        # reference to bf16 tolerance, not to fp16's. The model object itself is not touched.
+        self.model_dtype = next(lm.parameters()).dtype
+        if self.model_dtype not in (torch.bfloat16, torch.float16):
+            raise RuntimeError(f"bimodal_b200 scorer computes in bf16 and accepts bf16 / fp16 models; model is {self.model_dtype}")
+        self.dtype = torch.bfloat16
+        self._shadow = {}
         mt = getattr(cfg, "model_type", "")
         if mt not in ("llama", "gemma3_text"):
             raise RuntimeError(f"bimodal_b200 scorer: decoder type '{mt}' is not supported (llama, gemma3_text)")
@@ -120,13 +126,23 @@ class ScoringEngine:
         self._prefix_stale = False
 
     # -------------------------------------------------------------------------------------------
+    def _w(self, t: torch.Tensor) -> torch.Tensor:
+        """The tensor the kernels read for parameter ``t``: ``t`` itself for a bf16 model (borrowed, never
+        copied), a cached bf16 copy for an fp16 model."""
+        if t.dtype == torch.bfloat16:
+            return t
+        c = self._shadow.get(id(t))
+        if c is None:
+            c = self._shadow[id(t)] = t.detach().to(torch.bfloat16).contiguous()
+        return c
+
     def _pack_weights(self):
         self.w_qkv, self.w_gate_up = [], []
         with torch.no_grad():
             for layer in self.lm.layers:
                 a, m = layer.self_attn, layer.mlp
-                self.w_qkv.append(torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], 0).contiguous())
-                g, u = m.gate_proj.weight, m.up_proj.weight
+                self.w_qkv.append(torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], 0).to(self.dtype).contiguous())
+                g, u = m.gate_proj.weight.to(self.dtype), m.up_proj.weight.to(self.dtype)
                 if self.d_ff % 128 != 0:
                     raise RuntimeError("bimodal_b200 scorer: intermediate_size must be a multiple of 128")
                 gu = torch.stack([g.view(self.d_ff // 128, 128, self.d), u.view(self.d_ff // 128, 128, self.d)], 1)
@@ -183,24 +199,24 @@ class ScoringEngine:
         for i, layer in enumerate(self.lm.layers):
             cos, sin = self._layer_rope(i)
             w = native.LayerWeights(
-                w_qkv=self.w_qkv[i].data_ptr(), w_o=layer.self_attn.o_proj.weight.data_ptr(),
-                w_gate_up=self.w_gate_up[i].data_ptr(), w_down=layer.mlp.down_proj.weight.data_ptr(),
-                norm_attn=layer.input_layernorm.weight.data_ptr(),
+                w_qkv=self.w_qkv[i].data_ptr(), w_o=self._w(layer.self_attn.o_proj.weight).data_ptr(),
+                w_gate_up=self.w_gate_up[i].data_ptr(), w_down=self._w(layer.mlp.down_proj.weight).data_ptr(),
+                norm_attn=self._w(layer.input_layernorm.weight).data_ptr(),
                 rope_cos=cos.data_ptr(), rope_sin=sin.data_ptr())
             if self.gemma:       # HF names: post_attention_layernorm is the POST-attention norm here
-                w.norm_mlp = layer.pre_feedforward_layernorm.weight.data_ptr()
-                w.norm_post_attn = layer.post_attention_layernorm.weight.data_ptr()
-                w.norm_post_mlp = layer.post_feedforward_layernorm.weight.data_ptr()
-                w.q_norm = layer.self_attn.q_norm.weight.data_ptr()
-                w.k_norm = layer.self_attn.k_norm.weight.data_ptr()
+                w.norm_mlp = self._w(layer.pre_feedforward_layernorm.weight).data_ptr()
+                w.norm_post_attn = self._w(layer.post_attention_layernorm.weight).data_ptr()
+                w.norm_post_mlp = self._w(layer.post_feedforward_layernorm.weight).data_ptr()
+                w.q_norm = self._w(layer.self_attn.q_norm.weight).data_ptr()
+                w.k_norm = self._w(layer.self_attn.k_norm.weight).data_ptr()
             else:                # Llama: post_attention_layernorm is the pre-MLP norm
-                w.norm_mlp = layer.post_attention_layernorm.weight.data_ptr()
+                w.norm_mlp = self._w(layer.post_attention_layernorm.weight).data_ptr()
             if not (layer.self_attn.o_proj.weight.is_contiguous() and layer.mlp.down_proj.weight.is_contiguous()):
                 raise RuntimeError("bimodal_b200 scorer: non-contiguous projection weight")
             native.check(self.lib.bma_scorer_set_layer(handle, i, C.byref(w)), "scorer_set_layer")
-        ew = self.embed.weight
-        native.check(self.lib.bma_scorer_set_head(handle, self.lm.norm.weight.data_ptr(),
-                                                  self.head.weight.data_ptr(), ew.data_ptr(), ew.stride(0)),
+        ew = self._w(self.embed.weight)
+        native.check(self.lib.bma_scorer_set_head(handle, self._w(self.lm.norm.weight).data_ptr(),
+                                                  self._w(self.head.weight).data_ptr(), ew.data_ptr(), ew.stride(0)),
                      "scorer_set_head")
 
     def close(self):
@@ -274,6 +290,11 @@ class ScoringEngine:
         self._last_prefix = None if P == 0 else pe
         self._prefix_stale = False
 
+    def _fixed(self, plan: TailPlan) -> torch.Tensor:
+        """``plan.fixed`` in the compute dtype (a cast copy for an fp16 model; alive until the call is enqueued)."""
+        f = plan.fixed
+        return f if f.dtype == self.dtype else f.to(self.dtype)
+
     def reset_key(self):
         with torch.cuda.device(self.device):
             native.check(self.lib.bma_scorer_reset_key(self._scorer, self.key.data_ptr(), self.flag.data_ptr(),
@@ -298,11 +319,12 @@ class ScoringEngine:
         ids = ids.to(torch.int64).contiguous()
         tgt = target_ids.reshape(-1).to(torch.int64).contiguous()   # validated by the caller
         loss = torch.empty(B, dtype=torch.float32, device=self.device)
+        fixed = self._fixed(plan)
         if reset:
             self.reset_key()
         with torch.cuda.device(self.device):
             native.check(self.lib.bma_scorer_score(
-                self._scorer, ids.data_ptr(), ids.stride(0), B, plan.slot.data_ptr(), plan.fixed.data_ptr(),
+                self._scorer, ids.data_ptr(), ids.stride(0), B, plan.slot.data_ptr(), fixed.data_ptr(),
                 S, tgt.data_ptr(), T, row0, loss.data_ptr(), self.key.data_ptr(),
                 self.flag.data_ptr() if self.want_all_match else None,
                 idx_base, None if not share else base_ids.data_ptr(), plan.n_id_rows,
@@ -357,10 +379,11 @@ class ScoringEngine:
                      max(self._cap_prefix, self.prefix_len + share))
         if self._prefix_stale:
             self.prefill(self._last_prefix, deferred=getattr(self, "_last_deferred", None))
+        fixed = self._fixed(plan)
         with torch.cuda.device(self.device):
             native.check(self.lib.bma_scorer_score_host(
                 self._scorer, ids_host.data_ptr(), ids_host.stride(0), B, plan.slot.data_ptr(),
-                plan.fixed.data_ptr(), S, target_ids.data_ptr(), T, row0, loss_host.data_ptr(),
+                fixed.data_ptr(), S, target_ids.data_ptr(), T, row0, loss_host.data_ptr(),
                 key_host.data_ptr(), idx_base, None if not share else base_ids_host.data_ptr(), plan.n_id_rows,
                 native.stream_ptr(self.device)), "scorer_score_host")
         self._pending_rows = 0
@@ -388,9 +411,10 @@ def group_score(engines, ids: torch.Tensor, plan: TailPlan, target_ids: torch.Te
     loss = torch.empty(B, dtype=torch.float32, device=e0.device)
     e0.reset_key()
     handles = (C.c_void_p * len(engines))(*[e._scorer for e in engines])
+    fixed = e0._fixed(plan)
     with torch.cuda.device(e0.device):
         native.check(e0.lib.bma_scorer_group_score(
-            handles, len(engines), ids.data_ptr(), ids.stride(0), B, plan.slot.data_ptr(), plan.fixed.data_ptr(),
+            handles, len(engines), ids.data_ptr(), ids.stride(0), B, plan.slot.data_ptr(), fixed.data_ptr(),
             S, tgt.data_ptr(), T, row0, loss.data_ptr(), e0.key.data_ptr(), e0.flag.data_ptr(),
             base_ids.data_ptr(), plan.n_id_rows, int(use_peers), native.stream_ptr(e0.device)), "scorer_group_score")
     for e in engines:

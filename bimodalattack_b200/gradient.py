@@ -138,6 +138,8 @@ class NativeGradient(_AttentionProducts):
     @staticmethod
     def supported(engine: ScoringEngine) -> Optional[str]:
         """None when the decoder is covered, else the reason it is not."""
+        if getattr(engine, "model_dtype", torch.bfloat16) != torch.bfloat16:
+            return f"{engine.model_dtype} model (the native gradient step reads the bf16 parameters in place)"
         if engine.gemma:
             return "Gemma-3 decoder (sandwich norms, q/k-norm)"
         if engine.n_kv != engine.n_heads:

@@ -65,3 +65,27 @@ def test_two_rank_winner_reduce(tmp_path):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, 37, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+def test_balanced_cuts_cover_everything_and_even_out_the_cost():
+    """Row-balanced sharding (dist.balanced_cuts): contiguous, complete, monotone, and the most expensive
+    shard is close to total / size (within one candidate's cost) -- versus equal counts, which can be far off."""
+    import torch
+    from bimodalattack_b200.dist import World, balanced_cuts, shard_bounds
+    g = torch.Generator().manual_seed(0)
+    for n in (0, 1, 5, 64, 512, 513):
+        for size in (1, 2, 3, 8):
+            cost = torch.randint(1, 42, (n,), generator=g)
+            cuts = balanced_cuts(cost, size)
+            assert len(cuts) == size + 1 and cuts[0] == 0 and cuts[-1] == n
+            assert all(a <= b for a, b in zip(cuts, cuts[1:]))
+            if n >= 2 * size:
+                worst = max(int(cost[a:b].sum()) for a, b in zip(cuts, cuts[1:]))
+                assert worst <= int(cost.sum()) / size + int(cost.max())
+    # a skewed batch: the first half of the candidates costs 4x the second half
+    cost = torch.cat([torch.full((256,), 40), torch.full((256,), 10)])
+    cuts = balanced_cuts(cost, 8)
+    bal = max(int(cost[a:b].sum()) for a, b in zip(cuts, cuts[1:]))
+    even = max(int(cost[slice(*shard_bounds(512, World(r, 8)))].sum()) for r in range(8))
+    assert bal < 0.7 * even
+    assert balanced_cuts(torch.ones(7, dtype=torch.int64), 1) == [0, 7]

@@ -398,3 +398,53 @@ def test_sample_ids_on_tied_bf16_rows_agree_outside_tie_groups(cuda_device, V):
     # wherever the ids differ, it is inside a tie group, at the position the reference replaced
     bad = diff.any(1)
     assert bool((n_equal[bad] > 1).all())
+
+
+# ------------------------------------------------------------------------------------------------
+def test_fp16_model_is_accepted_and_scored_to_bf16_tolerance(cuda_device):
+    """The reference loads LLaVA / LLaVA-RC in float16 (utils/experiments_utils.py:91-100). The library
+    computes in bf16: an fp16 model object is accepted as it is (bf16 copies of the decoder weights, HF
+    autograd + HF tower for the gradient step), per-candidate losses agree with the reference dataflow run
+    on the fp16 model itself and with an fp32 twin to bf16 tolerance, the winner is the fp32 argmin up to
+    that tolerance, and run() completes with finite, non-increasing best losses."""
+    import copy
+    import torchvision.transforms as T
+    from bimodalattack_b200 import BimodalAttack, BimodalAttackConfig, synthetic as syn
+    from bimodalattack_b200.attack import image_features
+    from oracle import hotpath
+    tok = syn.make_tokenizer(1024)
+    proc = syn.make_llava_processor(tok, 28)
+    model = syn.make_llava("tiny128", dtype=torch.float16, device=cuda_device, head_gain=20.0, attn_implementation="sdpa")
+    assert next(model.parameters()).dtype == torch.float16
+    norm = T.Normalize(syn.CLIP_MEAN, syn.CLIP_STD)
+    image = torch.rand((1, 3, 28, 28), generator=torch.Generator().manual_seed(5)).to(cuda_device)
+    cfg = BimodalAttackConfig(num_steps=3, search_width=48, topk=32, seed=1, allow_non_ascii=True, alpha=4 / 255,
+                              eps=64 / 255, optim_str_init=INIT, verbosity="ERROR", images_folder=None, **JOINT)
+    atk = BimodalAttack(model, tok, proc, cfg, normalize=norm)
+    atk._prepare([{"role": "user", "content": PROMPT}], TARGET)
+    assert atk.engine.model_dtype == torch.float16 and atk.engine.dtype == torch.bfloat16
+    assert atk._native_gradient() is None and atk._native_tower() is None       # HF paths for the fp16 object
+    base = tok(INIT, add_special_tokens=False, return_tensors="pt")["input_ids"].to(cuda_device).reshape(-1).contiguous()
+    cand = _related(base, 48, 8, 1000, seed=3, device=cuda_device)
+    with torch.no_grad():
+        feats = image_features(model, norm(image), False)
+        assert feats.dtype == torch.float16
+        batch = atk._build_input_embeds_pgd(cand, feats, search_width=48, single=True)
+        got = atk._compute_candidates_loss_original(48, batch).clone()
+        key_loss, key_idx = atk._winner()
+        order = hotpath.segment_order("pgd", "llava", single=True)
+        ora16 = hotpath.OracleAttack(model, tok, proc, cfg, normalize=norm)
+        ora16.target_ids = atk.target_ids
+        ora16.seg_embeds = {k: ora16.emb(v) for k, v in atk.segment_ids.items()}
+        want16, _ = hotpath.candidates_loss(model, hotpath.assemble(ora16._parts(cand, feats), order, 48), atk.target_ids, 16)
+        want32 = _oracle32_losses(model, tok, proc, cfg, norm, atk, cand, feats, order)
+    want16 = want16.float()
+    assert bool(torch.isfinite(got).all())
+    assert bool(((got - want32).abs() <= 2e-2 * want32.abs() + 1e-3).all()), (got - want32).abs().max()
+    assert bool(((got - want16).abs() <= 2e-2 * want16.abs() + 2e-3).all()), (got - want16).abs().max()
+    assert key_idx == int(got.argmin())
+    assert float(want32[key_idx]) <= float(want32.min()) + 2e-2 * abs(float(want32.min())) + 1e-3
+    res = BimodalAttack(model, tok, proc, cfg, normalize=norm).run([{"role": "user", "content": PROMPT}], "goal", TARGET,
+                                                                   image.clone())
+    assert len(res.losses) == 3 and all(l == l and abs(l) != float("inf") for l in res.losses)
+    assert next(model.parameters()).dtype == torch.float16                      # the caller's object is untouched
