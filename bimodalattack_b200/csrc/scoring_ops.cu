@@ -423,11 +423,13 @@ cudaError_t launch_build_tail_embeds(const long long* ids, int ids_stride, const
 }
 
 // ------------------------------------------------------------------------------------------------
+constexpr int kNormRegVecs = 16;     // 16-byte vectors a lane keeps in registers: rows of up to 4096 elements
+
 // RMSNorm, one warp per output row. mode 0 (Llama): y = bf16(w * bf16(x * rstd));
 // mode 1 (Gemma): y = bf16(x * rstd * (1 + w)). Row gather: when gather_T > 0 output row r reads
 // input row start(r / gather_T) + gather_off + (r % gather_T), where start(c) = c * gather_S for
 // the uniform layout and gather_vstart[c] for the ragged one.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
                const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ y, long long ldy,
                int rows, int d, float eps, int mode, int gather_T, int gather_S, int gather_off,
@@ -445,6 +447,51 @@ rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
   const uint4* wv = reinterpret_cast<const uint4*>(w);
   uint4* dst = reinterpret_cast<uint4*>(y + (long long)r * ldy);
   const int nvec = d >> 3;
+  if (nvec <= 32 * kNormRegVecs) {
+    // Row in registers (d <= 4096): x is read ONCE, all of a lane's 16-byte loads are in flight together.
+    uint4 q[kNormRegVecs];
+#pragma unroll
+    for (int i = 0; i < kNormRegVecs; ++i) {
+      const int v = lane + 32 * i;
+      q[i] = v < nvec ? src[v] : make_uint4(0u, 0u, 0u, 0u);
+    }
+    float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kNormRegVecs; ++i) {
+      const uint32_t in[4] = {q[i].x, q[i].y, q[i].z, q[i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float a = bf16_lo(in[j]), b = bf16_hi(in[j]);
+        s0 = fmaf(a, a, s0);
+        s1 = fmaf(b, b, s1);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(s0 + s1) / static_cast<float>(d) + eps);
+#pragma unroll
+    for (int i = 0; i < kNormRegVecs; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+        const uint4 ww = wv[v];
+        const uint32_t in[4] = {q[i].x, q[i].y, q[i].z, q[i].w};
+        const uint32_t wi[4] = {ww.x, ww.y, ww.z, ww.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float a = bf16_lo(in[j]) * rstd, b = bf16_hi(in[j]) * rstd;
+          if (mode == 0) {
+            a = bf16_round(a) * bf16_lo(wi[j]);
+            b = bf16_round(b) * bf16_hi(wi[j]);
+          } else {
+            a = a * (1.0f + bf16_lo(wi[j]));
+            b = b * (1.0f + bf16_hi(wi[j]));
+          }
+          o[j] = pack_bf16x2(a, b);
+        }
+        dst[v] = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+    return;
+  }
   float ss = 0.0f;
   for (int v = lane; v < nvec; v += 32) {
     const uint4 q = src[v];
@@ -485,8 +532,8 @@ cudaError_t launch_rmsnorm(const __nv_bfloat16* x, long long ldx, const __nv_bfl
                            cudaStream_t stream, const int* rows_dev) {
   if (rows <= 0) return cudaSuccess;
   if ((d & 7) != 0 || (ldx & 7) != 0 || (ldy & 7) != 0) return cudaErrorInvalidValue;
-  const int blocks = static_cast<int>(((long long)rows * 32 + 255) / 256);
-  rmsnorm_kernel<<<blocks, 256, 0, stream>>>(x, ldx, w, y, ldy, rows, d, eps, mode, gather_T,
+  const int blocks = static_cast<int>(((long long)rows * 32 + 127) / 128);      // 4 rows per block (~150 registers)
+  rmsnorm_kernel<<<blocks, 128, 0, stream>>>(x, ldx, w, y, ldy, rows, d, eps, mode, gather_T,
                                              gather_S, gather_off, gather_vstart, rows_dev);
   return cudaGetLastError();
 }
