@@ -1,20 +1,33 @@
-// Shared-prefix + causal-tail attention for head_dim 128, "two CTAs per SM" variant.
+// Shared-prefix + causal-tail attention for head_dim 128, "two CTAs per SM" variant (the default).
 //
 // Same problem, masks and TMA layouts as attention_split.cu / attention_tc.cu. ncu showed the
 // one-CTA-per-SM kernels latency-bound (tensor pipe 25 %, no unit saturated): per key block the chain
 // S = Q K^T -> tcgen05.ld -> softmax -> tcgen05.st P -> O += P V is long and a single CTA has only one
 // or two blocks in flight. Instead of a deeper hand-built pipeline this kernel is made SMALL enough
 // for two CTAs to be resident per SM, so the hardware interleaves two independent chains:
-//   * 64-key blocks (BN = 64): K tile 16 KB, V^T tile 16 KB, two stages each; ONE Q tile (32 KB)
-//     -> 97 KB of shared memory per CTA;
+//   * 64-key blocks (BN = 64): K tile 16 KB, V^T tile 16 KB, two stages each; ONE Q tile (32 KB); a
+//     16 KB staging tile for the output's TMA store -> 113 KB of shared memory per CTA;
 //   * tensor memory: S_0 S_1 (64 columns each) + O (128 columns) = 256 of the 512 columns;
-//   * 256 threads, <= 128 registers: ONE softmax thread per query row (4 warps); the row's 64 scores
-//     are read from tensor memory twice (maximum, then exponentials) 32 columns at a time instead of
-//     being held in registers; no exchange between threads at all;
+//   * 256 threads, <= 128 registers: ONE softmax thread per query row (4 warps), nothing is exchanged
+//     between threads. A block whose 64 keys are visible to all 32 rows of the warp (most prefix
+//     blocks) keeps its 64 scores in registers between the maximum and the exponentials; the other
+//     blocks (partial last prefix block, base-suffix boundary, causal tail: ~4 of 13 per item) test a
+//     64-bit visibility mask of the row with predicates (ptxas: R2P + predicated FMNMX / FSEL), 32
+//     columns at a time, as real calls so the hot path carries no mask code;
 //   * P never touches shared memory: bf16 pairs go back over the S columns with tcgen05.st and the
-//     P V MMAs read their A operand from tensor memory (as in attention_split.cu).
+//     P V MMAs read their A operand from tensor memory (as in attention_split.cu);
+//   * an item's output rows are written AFTER the first key block of the next item (its last PV and
+//     the slowest warp of its last masked block get a block of slack), through a swizzled staging
+//     tile and one TMA store per [32 rows][64 columns] box.
 //   warp 0  TMA producer   warp 1  MMA issuer (flat stream over work items; S_g is issued before the
 //   PV of block g-1)   warp 2  TMEM allocator   warps 4-7  softmax + output
+//
+// Measured (tools/ab_attention.py, same process, sustained clocks, 15 872 rows x 616 prefix keys x 32
+// heads): 324 us for the round-2 two-pass version -> 262 us. Tried on the way and dropped (numbers in
+// DESIGN.md 3.2): Q as the TMEM A operand with a single S buffer (366 us: the S -> softmax -> PV chain
+// of a CTA becomes strictly serial), two threads per row / eight softmax warps (347 us), back-off in
+// the control warps' barrier polls (no change). BMA_OCC_TIMING=1 prints per-phase cycle counts of the
+// softmax warps of CTA 0, BMA_OCC_KNOCK removes one cost at a time (timing only, wrong results).
 #include <cstdio>
 #include <cstdlib>
 
@@ -27,7 +40,6 @@ namespace bma {
 namespace occ {
 
 constexpr int BM = 128, BN = 64, HD = 128, THREADS = 256;
-constexpr int THREADS3 = 384;                 // MODE 3: eight softmax warps (two threads per query row)
 constexpr int QPANEL = BM * 128;              // [128 rows][64 dims] bf16, 128-byte swizzle
 constexpr int QTILE = 2 * QPANEL;             // 32 KB
 constexpr int KPANEL = BN * 128;              // [64 keys][64 dims]
@@ -51,8 +63,9 @@ struct Params {
   int no_tail;                // rows attend to the prefix keys only
   int n_heads, kv_group;
   float scale_log2;
+  int pv_first;               // MMA issuer: last PV of an item before the wait for the next Q tile (A/B switch)
+  int defer;                  // write an item's output after the first block of the next item (A/B switch)
   unsigned long long* dbg;    // TIMING instantiation only
-  int sleep_tma, sleep_mma;   // back-off (ns) inside the control warps' barrier polls
   int knock;                  // TIMING only: knock-out experiments (wrong results, timing only), BMA_OCC_KNOCK bits:
                               // 1 no ex2, 2 no maximum, 4 no QK MMAs, 8 no PV MMAs, 16 no K/V loads, 32 no output
 };
@@ -71,20 +84,6 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r
       : "memory");
 }
 
-__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)[8]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
 // TMA store of one [rows][64 columns] bf16 box (128-byte swizzle) from shared memory; bulk-group completion.
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -93,24 +92,6 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-
-// Barrier wait of a control warp (TMA producer, MMA issuer): its poll loop shares a scheduler with a softmax
-// warp, so it backs off between polls instead of competing for issue slots.
-__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t code, int ns) {
-  if (mbar_try_wait(bar, parity)) return;
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (ns > 0) __nanosleep(ns);
-    if (++spins > (1u << 26)) {
-      atomicExch(&g_watchdog_code, code);
-      if (g_watchdog_host != nullptr) {
-        *g_watchdog_host = code | (blockIdx.x << 16);
-        __threadfence_system();
-      }
-      __trap();
-    }
-  }
-}
 
 struct Block { int pre; int key0; int n_mma; };
 
@@ -126,131 +107,6 @@ __device__ __forceinline__ Block block_of(int j, int n_pre, int P, int kt0, int 
   return b;
 }
 
-// One query row's pass over a 64-key block of S (tensor memory, 32 columns at a time). MASKED = false is
-// the hot path (every key of the block is visible to every row of the warp: most prefix blocks) and does
-// no per-element tests at all; MASKED = true keeps the row's visible column range [vlo, vhi).
-template <bool MASKED>
-__device__ __forceinline__ float block_row_max_impl(uint32_t ts, int n_mma, int vlo, int vhi) {
-  float raw = -INFINITY;
-#pragma unroll
-  for (int c0 = 0; c0 < BN; c0 += 32) {
-    if (!MASKED || c0 < n_mma) {
-      uint32_t r[32];
-      tmem_ld_32x32(ts + c0, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float v = __uint_as_float(r[i]);
-        if (MASKED && !(c0 + i >= vlo && c0 + i < vhi)) v = -INFINITY;
-        raw = fmaxf(raw, v);
-      }
-    }
-  }
-  return raw;
-}
-// P = exp2(s * scale - m) as packed bf16 pairs over the S columns just read (P_g occupies columns [0, 32)
-// of S_st: chunk 0 -> columns 0..15, chunk 1 -> 16..31); returns the row sum.
-template <bool MASKED>
-__device__ __forceinline__ float block_row_exp_impl(uint32_t ts, int n_mma, int vlo, int vhi, float scale_log2, float m_use) {
-  float rs = 0.0f;
-#pragma unroll
-  for (int c0 = 0; c0 < BN; c0 += 32) {
-    if (!MASKED || c0 < n_mma) {
-      uint32_t r[32], pk[16];
-      tmem_ld_32x32(ts + c0, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        float v0 = __uint_as_float(r[i]), v1 = __uint_as_float(r[i + 1]);
-        if (MASKED) {
-          if (!(c0 + i >= vlo && c0 + i < vhi)) v0 = -INFINITY;
-          if (!(c0 + i + 1 >= vlo && c0 + i + 1 < vhi)) v1 = -INFINITY;
-        }
-        const float p0 = ex2(fmaf(v0, scale_log2, -m_use));         // -inf -> 0
-        const float p1 = ex2(fmaf(v1, scale_log2, -m_use));
-        rs += p0 + p1;
-        pk[i >> 1] = pack_bf16x2(p0, p1);
-      }
-      tmem_st_32x16(ts + (c0 >> 1), pk);
-    }
-  }
-  return rs;
-}
-
-// Blocks that are not entirely visible to all 32 rows of the warp (the partial last prefix block, the
-// base-suffix boundary, the causal tail: ~4 of 13 blocks per item) are real calls, so the hot path's code
-// stays free of mask tests. They run in four groups of 16 key columns: a group no row of the warp sees is
-// skipped (P = 0), a group every row sees entirely runs unmasked code, only mixed groups test per element.
-__device__ __forceinline__ int group_class(int g0, int vlo, int vhi) {       // 0 none, 1 all, 2 mixed (warp-uniform)
-  if (__all_sync(0xffffffffu, vhi <= g0 || vlo >= g0 + 16)) return 0;
-  return __all_sync(0xffffffffu, vlo <= g0 && vhi >= g0 + 16) ? 1 : 2;
-}
-__device__ __noinline__ float block_row_max_masked(uint32_t ts, int n_mma, int vlo, int vhi) {
-  float raw = -INFINITY;
-#pragma unroll
-  for (int g0 = 0; g0 < BN; g0 += 16) {
-    if (g0 >= n_mma) break;
-    const int cls = group_class(g0, vlo, vhi);
-    if (cls == 0) continue;
-    uint32_t r[16];
-    tmem_ld_32x16(ts + g0, r);
-    tmem_ld_wait();
-    if (cls == 1) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) raw = fmaxf(raw, __uint_as_float(r[i]));
-    } else {
-#pragma unroll
-      for (int i = 0; i < 16; ++i)
-        raw = fmaxf(raw, (g0 + i >= vlo && g0 + i < vhi) ? __uint_as_float(r[i]) : -INFINITY);
-    }
-  }
-  return raw;
-}
-// P_g occupies columns [0, 32) of the S buffer as bf16 pairs: group g0 writes columns [g0/2, g0/2 + 8), which
-// only overlap S columns of groups that have been read already.
-__device__ __noinline__ float block_row_exp_masked(uint32_t ts, int n_mma, int vlo, int vhi, float scale_log2, float m_use) {
-  float rs = 0.0f;
-#pragma unroll
-  for (int g0 = 0; g0 < BN; g0 += 16) {
-    if (g0 >= n_mma) break;
-    const int cls = group_class(g0, vlo, vhi);
-    uint32_t pk[8];
-    if (cls == 0) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) pk[i] = 0u;
-    } else {
-      uint32_t r[16];
-      tmem_ld_32x16(ts + g0, r);
-      tmem_ld_wait();
-      if (cls == 1) {
-#pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          const float p0 = ex2(fmaf(__uint_as_float(r[i]), scale_log2, -m_use));
-          const float p1 = ex2(fmaf(__uint_as_float(r[i + 1]), scale_log2, -m_use));
-          rs += p0 + p1;
-          pk[i >> 1] = pack_bf16x2(p0, p1);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          const float v0 = (g0 + i >= vlo && g0 + i < vhi) ? __uint_as_float(r[i]) : -INFINITY;
-          const float v1 = (g0 + i + 1 >= vlo && g0 + i + 1 < vhi) ? __uint_as_float(r[i + 1]) : -INFINITY;
-          const float p0 = ex2(fmaf(v0, scale_log2, -m_use));         // -inf -> 0
-          const float p1 = ex2(fmaf(v1, scale_log2, -m_use));
-          rs += p0 + p1;
-          pk[i >> 1] = pack_bf16x2(p0, p1);
-        }
-      }
-    }
-    tmem_st_32x8(ts + (g0 >> 1), pk);
-  }
-  return rs;
-}
-
-// ---- MODE 3 (two threads per query row): helpers
-__device__ __forceinline__ void bar_pair(int quad) {          // the two warps that share a TMEM lane quadrant
-  asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
-}
 // bit c set <=> key column c of the block is visible to this row (columns [vlo, vhi))
 __device__ __forceinline__ uint64_t window_mask(int vlo, int vhi) {
   if (vhi <= vlo) return 0ull;
@@ -268,10 +124,9 @@ __device__ __noinline__ float masked_max32(uint32_t taddr, uint32_t bits) {
     if ((bits >> i) & 1u) raw = fmaxf(raw, __uint_as_float(r[i]));
   return raw;
 }
-// P over 32 score columns with the visibility bits applied, stored as 16 packed columns at tp once both warps of
-// the quadrant have finished reading S (the store overlaps the partner's score columns); returns the row sum
-template <bool PAIR>
-__device__ __noinline__ float masked_exp32_store(uint32_t ts, uint32_t tp, uint32_t bits, float scale_log2, float m_use, int quad) {
+// P over 32 score columns with the visibility bits applied, stored as 16 packed columns at tp (which only overlaps
+// score columns that have been read already); returns the row sum
+__device__ __noinline__ float masked_exp32_store(uint32_t ts, uint32_t tp, uint32_t bits, float scale_log2, float m_use) {
   uint32_t pk[16];
   float rs = 0.0f;
   if (__all_sync(0xffffffffu, bits == 0u)) {
@@ -290,24 +145,9 @@ __device__ __noinline__ float masked_exp32_store(uint32_t ts, uint32_t tp, uint3
       pk[i >> 1] = pack_bf16x2(p0, p1);
     }
   }
-  if (PAIR) bar_pair(quad);
   tmem_st_32x16(tp, pk);
   return rs;
 }
-// Rare path: multiply 64 columns of one row of the O accumulator by f.
-__device__ __noinline__ void rescale_o_half(uint32_t to, float f) {
-#pragma unroll
-  for (int c0 = 0; c0 < 64; c0 += 32) {
-    uint32_t r[32];
-    tmem_ld_32x32(to + c0, r);
-    tmem_ld_wait();
-#pragma unroll
-    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
-    tmem_st_32x32(to + c0, r);
-  }
-  tmem_st_wait();
-}
-
 // Rare path: multiply one row of the O accumulator (128 fp32 columns in tensor memory) by f.
 __device__ __noinline__ void rescale_o_row(uint32_t to, float f) {
 #pragma unroll
@@ -322,12 +162,10 @@ __device__ __noinline__ void rescale_o_row(uint32_t to, float f) {
   tmem_st_wait();
 }
 
-// MODE 0: two passes over S in tensor memory (maximum, then exponentials). MODE 1: ONE pass, the row's 64
-// scores stay in registers between the maximum and the exponentials (half the tensor-memory reads, one
-// load round trip per block instead of four). TIMING: warp 4 / lane 0 of CTA 0 accumulates clock64() deltas
-// per phase into p.dbg (tools/bench_attention.py, BMA_OCC_TIMING=1).
-template <int MODE, bool TIMING>
-__global__ void __launch_bounds__(MODE == 3 ? THREADS3 : THREADS, 2)
+// TIMING: the softmax warps of CTA 0 accumulate clock64() deltas per phase in registers and write them to
+// p.dbg at the end (tools/bench_attention.py, BMA_OCC_TIMING=1); p.knock then also applies.
+template <bool TIMING>
+__global__ void __launch_bounds__(THREADS, 2)
 attention_occ_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kt,
                      const __grid_constant__ CUtensorMap tm_kp, const __grid_constant__ CUtensorMap tm_vt,
                      const __grid_constant__ CUtensorMap tm_vp, const __grid_constant__ CUtensorMap tm_o,
@@ -350,7 +188,6 @@ attention_occ_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   uint64_t* p_full = bars + 12;       // [2]  per S/P buffer: the 4 softmax warps have written P_g
   uint64_t* p_empty = bars + 14;      // [2]  per S/P buffer: PV_g has retired
   uint64_t* o_empty = bars + 16;      // [1]  4 warps: the item's output has left TMEM
-  uint64_t* qt_full = bars + 17;      // [1]  MODE 2: 4 warps have copied the item's Q tile into tensor memory
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -364,10 +201,10 @@ attention_occ_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     tma_prefetch_desc(&tm_vt); tma_prefetch_desc(&tm_vp); tma_prefetch_desc(&tm_o);
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(q_full, 1);  mbar_init(q_empty, MODE == 2 ? 4 : 1);
-    mbar_init(o_empty, MODE == 3 ? 8 : 4); mbar_init(qt_full, 4);
+    mbar_init(q_full, 1);  mbar_init(q_empty, 1);
+    mbar_init(o_empty, 4);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&p_full[i], MODE == 3 ? 8 : 4);  mbar_init(&p_empty[i], 1);
+      mbar_init(&p_full[i], 4);  mbar_init(&p_empty[i], 1);
       mbar_init(&k_full[i], 1);  mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1);  mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
@@ -382,8 +219,7 @@ attention_occ_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_s = tmem_base;             // S_st at + 64 st (MODE 2: one S buffer, Q at + 64)
-  const uint32_t tmem_q = tmem_base + 64;        // MODE 2: Q as packed bf16 pairs, 64 columns
+  const uint32_t tmem_s = tmem_base;             // S_st at + 64 st
   const uint32_t tmem_o = tmem_base + 128;       // O: 128 columns
 
   if (warp == 0) {
@@ -396,7 +232,7 @@ attention_occ_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         const int r0 = tile * BM, r1 = min(M, r0 + BM);
         const int kt0 = tail_start(r0, p.S, p.row_meta);
         const int nb = n_pre + (p.no_tail ? 0 : (r1 - kt0 + BN - 1) / BN);
-        mbar_wait_backoff(q_empty, (item_n & 1) ^ 1, 0x800, p.sleep_tma);
+        mbar_wait(q_empty, (item_n & 1) ^ 1, 0x800);
         mbar_arrive_expect_tx(q_full, QTILE);
         tma_load_2d(sQ, &tm_q, q_full, head * HD, r0);
         tma_load_2d(sQ + QPANEL, &tm_q, q_full, head * HD + 64, r0);
@@ -404,7 +240,7 @@ attention_occ_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
           const Block b = block_of(j, n_pre, p.P, kt0, r1);
           const uint32_t g = it + j;
           const int st = g & 1;
-          mbar_wait_backoff(&k_empty[st], ((g >> 1) & 1) ^ 1, 0x810 + st, p.sleep_tma);
+          mbar_wait(&k_empty[st], ((g >> 1) & 1) ^ 1, 0x810 + st);
           if (TIMING && (p.knock & 16)) { mbar_arrive(&k_full[st]); return; }
           mbar_arrive_expect_tx(&k_full[st], KTILE);
           const CUtensorMap* mk = b.pre ? &tm_kp : &tm_kt;
@@ -415,7 +251,7 @@ attention_occ_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
           const Block b = block_of(j, n_pre, p.P, kt0, r1);
           const uint32_t g = it + j;
           const int st = g & 1;
-          mbar_wait_backoff(&v_empty[st], ((g >> 1) & 1) ^ 1, 0x820 + st, p.sleep_tma);
+          mbar_wait(&v_empty[st], ((g >> 1) & 1) ^ 1, 0x820 + st);
           if (TIMING && (p.knock & 16)) { mbar_arrive(&v_full[st]); return; }
           mbar_arrive_expect_tx(&v_full[st], VTILE);
           tma_load_2d(sV + st * VTILE, b.pre ? &tm_vp : &tm_vt, &v_full[st], b.key0, kvh * HD);
@@ -428,43 +264,6 @@ attention_occ_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         it += nb;
       }
     }
-  } else if (warp == 1 && MODE == 2) {
-    if (lane == 0) {
-      // ------------------------------------------------------------------ MMA issuer, Q in tensor memory
-      // One S buffer (P in place): S_g, PV_g, S_{g+1}, ... strictly in order; the other resident CTA fills
-      // the tensor pipe while this one's softmax runs.
-      uint32_t it = 0, item_n = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
-        const int tile = item % m_tiles;
-        const int r0 = tile * BM, r1 = min(M, r0 + BM);
-        const int kt0 = tail_start(r0, p.S, p.row_meta);
-        const int nb = n_pre + (p.no_tail ? 0 : (r1 - kt0 + BN - 1) / BN);
-        mbar_wait_backoff(qt_full, item_n & 1, 0x840, p.sleep_mma);
-        for (int j = 0; j < nb; ++j, ++it) {
-          const Block b = block_of(j, n_pre, p.P, kt0, r1);
-          const int st = it & 1;
-          mbar_wait_backoff(&k_full[st], (it >> 1) & 1, 0x850 + st, p.sleep_mma);
-          tc_fence_after();
-          const uint32_t idesc = umma_idesc_bf16(BM, b.n_mma);
-          const uint32_t kb = smem_u32(sK + st * KTILE);
-#pragma unroll
-          for (int ks = 0; ks < HD / 16; ++ks)
-            umma_bf16_ts(tmem_s, tmem_q + ks * 8, umma_desc_k_sw128(kb + (ks >> 2) * KPANEL + (ks & 3) * 32), idesc, ks != 0);
-          umma_commit(&s_full[0]);
-          umma_commit(&k_empty[st]);
-          mbar_wait_backoff(&v_full[st], (it >> 1) & 1, 0x860 + st, p.sleep_mma);
-          mbar_wait_backoff(&p_full[0], it & 1, 0x862, p.sleep_mma);
-          if (j == 0) mbar_wait_backoff(o_empty, (item_n & 1) ^ 1, 0x863, p.sleep_mma);   // the previous item's output was read out
-          tc_fence_after();
-          constexpr uint32_t idesc_pv = umma_idesc_bf16(BM, HD);
-          const uint32_t vb = smem_u32(sV + st * VTILE);
-          for (int kk = 0; kk < b.n_mma / 16; ++kk)
-            umma_bf16_ts(tmem_o, tmem_s + kk * 8, umma_desc_k_sw128(vb + kk * 32), idesc_pv, !(j == 0 && kk == 0));
-          umma_commit(&p_empty[0]);
-          umma_commit(&v_empty[st]);
-        }
-      }
-    }
   } else if (warp == 1) {
     if (lane == 0) {
       // ------------------------------------------------------------------ MMA issuer
@@ -472,16 +271,16 @@ attention_occ_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       // O (+)= P_g V_g; `first`: this PV overwrites O (first block of its item)
       auto issue_pv = [&](uint32_t g, int n_mma, bool first, uint32_t item_par) {
         const int st = g & 1;
-        mbar_wait_backoff(&v_full[st], (g >> 1) & 1, 0x860 + st, p.sleep_mma);
-        mbar_wait_backoff(&p_full[st], (g >> 1) & 1, 0x862, p.sleep_mma);
-        if (first) mbar_wait_backoff(o_empty, item_par ^ 1, 0x863, p.sleep_mma);      // the previous item's output was read out
+        mbar_wait(&v_full[st], (g >> 1) & 1, 0x860 + st);
+        mbar_wait(&p_full[st], (g >> 1) & 1, 0x862);
+        if (first) mbar_wait(o_empty, item_par ^ 1, 0x863);      // the previous item's output was read out
         tc_fence_after();
         constexpr uint32_t idesc = umma_idesc_bf16(BM, HD);
         const uint32_t pa = tmem_s + st * BN;                    // P_g: bf16 pairs, 8 columns per 16 keys
         const uint32_t vb = smem_u32(sV + st * VTILE);
         if (!(TIMING && (p.knock & 8)))
-        for (int kk = 0; kk < n_mma / 16; ++kk)
-          umma_bf16_ts(tmem_o, pa + kk * 8, umma_desc_k_sw128(vb + kk * 32), idesc, !(first && kk == 0));
+          for (int kk = 0; kk < n_mma / 16; ++kk)
+            umma_bf16_ts(tmem_o, pa + kk * 8, umma_desc_k_sw128(vb + kk * 32), idesc, !(first && kk == 0));
         umma_commit(&p_empty[st]);
         umma_commit(&v_empty[st]);
       };
@@ -490,24 +289,30 @@ attention_occ_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       int pend_n = 0;
       bool pend_first = false;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
-        const int head = item / m_tiles, tile = item - head * m_tiles;
+        const int tile = item % m_tiles;
         const int r0 = tile * BM, r1 = min(M, r0 + BM);
         const int kt0 = tail_start(r0, p.S, p.row_meta);
         const int nb = n_pre + (p.no_tail ? 0 : (r1 - kt0 + BN - 1) / BN);
-        (void)head;
-        mbar_wait_backoff(q_full, item_n & 1, 0x840, p.sleep_mma);
+        // the Q tile is single-buffered: its load only starts when the previous item's last S has completed, so
+        // the previous item's last PV is issued before waiting for it, not behind it
+        if (have_pending && p.pv_first && !mbar_try_wait(q_full, item_n & 1)) {
+          issue_pv(pend_g, pend_n, pend_first, pend_item_par);
+          have_pending = false;
+        }
+        mbar_wait(q_full, item_n & 1, 0x840);
         for (int j = 0; j < nb; ++j, ++it) {
           const Block b = block_of(j, n_pre, p.P, kt0, r1);
           const int st = it & 1;
-          mbar_wait_backoff(&k_full[st], (it >> 1) & 1, 0x850 + st, p.sleep_mma);     // (S_st is free: the PV of block it-2 precedes this MMA)
+          mbar_wait(&k_full[st], (it >> 1) & 1, 0x850 + st);     // (S_st is free: the PV of block it-2 precedes this MMA)
           tc_fence_after();
           const uint32_t idesc = umma_idesc_bf16(BM, b.n_mma);
           const uint32_t qa = smem_u32(sQ), kb = smem_u32(sK + st * KTILE);
-          if (!(TIMING && (p.knock & 4)))
+          if (!(TIMING && (p.knock & 4))) {
 #pragma unroll
-          for (int ks = 0; ks < HD / 16; ++ks)
-            umma_bf16_ss(tmem_s + st * BN, umma_desc_k_sw128(qa + (ks >> 2) * QPANEL + (ks & 3) * 32),
-                         umma_desc_k_sw128(kb + (ks >> 2) * KPANEL + (ks & 3) * 32), idesc, ks != 0);
+            for (int ks = 0; ks < HD / 16; ++ks)
+              umma_bf16_ss(tmem_s + st * BN, umma_desc_k_sw128(qa + (ks >> 2) * QPANEL + (ks & 3) * 32),
+                           umma_desc_k_sw128(kb + (ks >> 2) * KPANEL + (ks & 3) * 32), idesc, ks != 0);
+          }
           umma_commit(&s_full[st]);
           umma_commit(&k_empty[st]);
           if (j == nb - 1) umma_commit(q_empty);
@@ -518,20 +323,71 @@ attention_occ_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       }
       if (have_pending) issue_pv(pend_g, pend_n, pend_first, pend_item_par);
     }
-  } else if (warp >= 4 && MODE == 3) {
-    // -------------------------------------------------------------------- softmax, TWO threads per query row
-    // Warps w and w + 4 share a TMEM lane quadrant (the same 32 rows): both read all 64 scores of a block for the
-    // row maximum (identical decisions, nothing to exchange), each computes the exponentials of ITS 32 key
-    // columns and owns 64 columns of the O row. One named barrier per block keeps a P store from overwriting
-    // score columns the partner has not read yet. Four softmax warps per scheduler instead of two.
-    const int quad = warp & 3, half = (warp >> 2) - 1;
-    const int row_in_tile = quad * 32 + lane;
-    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-    const int own = half * 32, oth = 32 - own;
-    float* l_x = reinterpret_cast<float*>(sO);     // [2 (item parity)][128 rows][2 halves] partial row sums
-    constexpr float kRaise = 8.0f;
-    uint32_t it = 0, item_n = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
+  } else if (warp >= 4) {
+    // -------------------------------------------------------------------- softmax: one thread per query row
+    const int sub = warp & 3;
+    const int row_in_tile = sub * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(sub * 32) << 16;
+    constexpr float kRaise = 8.0f;               // raise the reference max only beyond 2^8: P stays <= 256
+    uint32_t it = 0;
+    uint32_t acc[14];                            // TIMING: cycle counts per phase, kept in registers
+#pragma unroll
+    for (int i = 0; i < 14; ++i) acc[i] = 0;
+
+    // ---- end of an item: normalise and store this thread's output row (e_it = the item's last block + 1).
+    // The warp's 32 rows go out as two [32 rows][64 columns] boxes: each thread writes its row's 128 bytes into the
+    // staging buffer (16-byte chunk c of row r at chunk position c ^ (r & 7): the 128-byte swizzle of the tensor
+    // map, bank-conflict free), one TMA store per box. Rows >= M of the tensor map are clipped by the TMA unit;
+    // rows between the live count and M receive finite values nobody reads.
+    auto write_output = [&](float e_l, int e_head, int e_r0, uint32_t e_it) {
+      long long t0 = 0, t1 = 0;
+      if (TIMING) t0 = clock64();
+      mbar_wait(&p_empty[(e_it - 1) & 1], ((e_it - 1) >> 1) & 1, 0x940);   // the item's last PV has retired
+      tc_fence_after();
+      if (TIMING) t1 = clock64();
+      const float inv = e_l > 0.0f ? 1.0f / e_l : 0.0f;
+      uint8_t* so = sO + sub * OSTAGE;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (lane == 0) tma_store_wait_read();            // the previous box has been read out of the buffer
+        __syncwarp();
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          uint32_t a[32];
+          tmem_ld_32x32(tmem_o + lane_off + h * 64 + c0, a);
+          tmem_ld_wait();
+#pragma unroll
+          for (int v4 = 0; v4 < 4; ++v4) {
+            const int chunk = (c0 >> 3) + v4;
+            *reinterpret_cast<uint4*>(so + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = make_uint4(
+                pack_bf16x2(__uint_as_float(a[v4 * 8 + 0]) * inv, __uint_as_float(a[v4 * 8 + 1]) * inv),
+                pack_bf16x2(__uint_as_float(a[v4 * 8 + 2]) * inv, __uint_as_float(a[v4 * 8 + 3]) * inv),
+                pack_bf16x2(__uint_as_float(a[v4 * 8 + 4]) * inv, __uint_as_float(a[v4 * 8 + 5]) * inv),
+                pack_bf16x2(__uint_as_float(a[v4 * 8 + 6]) * inv, __uint_as_float(a[v4 * 8 + 7]) * inv));
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && !(TIMING && (p.knock & 32))) {
+          tma_store_2d(&tm_o, so, e_head * HD + h * 64, e_r0 + sub * 32);
+          tma_store_commit();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty);
+      if (TIMING) {
+        acc[6] += 1;                                                        // items
+        acc[7] += static_cast<uint32_t>(t1 - t0);                           // wait for the last PV
+        acc[8] += static_cast<uint32_t>(clock64() - t1);                    // output rows
+      }
+    };
+    float prev_l = 0.0f;
+    int prev_head = 0, prev_r0 = 0;
+    uint32_t prev_it = 0;
+    bool have_prev = false;
+
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int head = item / m_tiles, tile = item - head * m_tiles;
       const int r0 = tile * BM, r1 = min(M, r0 + BM);
       const int kt0 = tail_start(r0, p.S, p.row_meta);
@@ -549,220 +405,6 @@ attention_occ_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         const Block b = block_of(j, n_pre, p.P, kt0, r1);
         const int st = it & 1;
         const uint32_t ts = tmem_s + lane_off + st * BN;
-        int vlo = 0, vhi = BN;
-        if (b.pre) {
-          if (b.key0 + BN > p_shared) vhi = min(max(plim - b.key0, 0), BN);
-        } else {
-          vlo = max(cs - b.key0, 0);
-          vhi = min(max(min(rq + 1, r1) - b.key0, 0), BN);
-        }
-        const bool all_visible = __all_sync(0xffffffffu, vlo == 0 && vhi == BN);
-        mbar_wait(&s_full[st], (it >> 1) & 1, 0x910 + st);
-        tc_fence_after();
-
-        float m_new, m_use, factor;
-        auto update_max = [&](float raw) -> bool {
-          const float bm = raw * p.scale_log2;
-          const bool raise = bm > m_ref + kRaise;
-          m_new = raise ? bm : m_ref;
-          m_use = (m_new == -INFINITY) ? 0.0f : m_new;
-          factor = raise ? ex2(m_ref - m_use) : 1.0f;
-          const bool fix = raise && (m_ref != -INFINITY) && (j > 0);
-          const bool any_fix = __any_sync(0xffffffffu, fix);
-          if (any_fix) {                                   // rare: rescale this thread's half of the O row
-            mbar_wait(&p_empty[(it - 1) & 1], ((it - 1) >> 1) & 1, 0x920);
-            tc_fence_after();
-            rescale_o_half(tmem_o + lane_off + half * 64, fix ? factor : 1.0f);
-          }
-          return any_fix;
-        };
-
-        float rs;
-        if (all_visible) {
-          uint32_t r[32];
-          tmem_ld_32x32(ts + oth, r);
-          tmem_ld_wait();
-          float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            mx0 = fmaxf(mx0, __uint_as_float(r[i]));
-            mx1 = fmaxf(mx1, __uint_as_float(r[i + 1]));
-          }
-          tmem_ld_32x32(ts + own, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            mx0 = fmaxf(mx0, __uint_as_float(r[i]));
-            mx1 = fmaxf(mx1, __uint_as_float(r[i + 1]));
-          }
-          if (update_max(fmaxf(mx0, mx1))) {               // the rescale used the registers: read S again
-            tmem_ld_32x32(ts + own, r);
-            tmem_ld_wait();
-          }
-          float s0 = 0.0f, s1 = 0.0f;
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float p0 = ex2(fmaf(__uint_as_float(r[i]), p.scale_log2, -m_use));
-            const float p1 = ex2(fmaf(__uint_as_float(r[i + 1]), p.scale_log2, -m_use));
-            s0 += p0; s1 += p1;
-            pk[i >> 1] = pack_bf16x2(p0, p1);
-          }
-          bar_pair(quad);                                   // the partner has read these score columns
-          tmem_st_32x16(ts + (own >> 1), pk);
-          rs = s0 + s1;
-        } else {
-          const uint64_t vis = window_mask(vlo, vhi);
-          const uint32_t v_own = static_cast<uint32_t>(vis >> own), v_oth = static_cast<uint32_t>(vis >> oth);
-          const float raw = fmaxf(masked_max32(ts + oth, v_oth), masked_max32(ts + own, v_own));
-          update_max(raw);
-          rs = masked_exp32_store<true>(ts + own, ts + (own >> 1), v_own, p.scale_log2, m_use, quad);
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[st]);
-        l_run = l_run * factor + rs;
-        m_ref = m_new;
-      }
-
-      // ---- end of the item: the two partial row sums meet, each thread writes 64 output columns
-      {
-        float* lx = l_x + (item_n & 1) * (BM * 2);
-        lx[row_in_tile * 2 + half] = l_run;
-        mbar_wait(&p_empty[(it - 1) & 1], ((it - 1) >> 1) & 1, 0x940);   // the item's last PV has retired
-        tc_fence_after();
-        bar_pair(quad);
-        const float l_tot = lx[row_in_tile * 2] + lx[row_in_tile * 2 + 1];
-        const float inv = l_tot > 0.0f ? 1.0f / l_tot : 0.0f;
-        __nv_bfloat16* dst = p.out + (long long)rq * p.ldo + head * HD + half * 64;
-#pragma unroll
-        for (int c0 = 0; c0 < 64; c0 += 32) {
-          uint32_t a[32];
-          tmem_ld_32x32(tmem_o + lane_off + half * 64 + c0, a);
-          tmem_ld_wait();
-          if (rq < M) {
-#pragma unroll
-            for (int v4 = 0; v4 < 4; ++v4) {
-              reinterpret_cast<uint4*>(dst + c0)[v4] = make_uint4(
-                  pack_bf16x2(__uint_as_float(a[v4 * 8 + 0]) * inv, __uint_as_float(a[v4 * 8 + 1]) * inv),
-                  pack_bf16x2(__uint_as_float(a[v4 * 8 + 2]) * inv, __uint_as_float(a[v4 * 8 + 3]) * inv),
-                  pack_bf16x2(__uint_as_float(a[v4 * 8 + 4]) * inv, __uint_as_float(a[v4 * 8 + 5]) * inv),
-                  pack_bf16x2(__uint_as_float(a[v4 * 8 + 6]) * inv, __uint_as_float(a[v4 * 8 + 7]) * inv));
-            }
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(o_empty);
-      }
-    }
-  } else if (warp >= 4) {
-    // -------------------------------------------------------------------- softmax: one thread per query row
-    const int sub = warp & 3;
-    const int row_in_tile = sub * 32 + lane;
-    const uint32_t lane_off = static_cast<uint32_t>(sub * 32) << 16;
-    constexpr float kRaise = 8.0f;               // raise the reference max only beyond 2^8: P stays <= 256
-    uint32_t it = 0, item_n = 0;
-    uint32_t acc[14];                            // TIMING: cycle counts per phase, kept in registers
-#pragma unroll
-    for (int i = 0; i < 14; ++i) acc[i] = 0;
-    // MODE 2: this thread's row of the Q tile (shared memory, 128-byte swizzle) -> 64 columns of tensor memory
-    // as the A operand of S = Q K^T (two bf16 per column, the layout P uses for P V)
-    auto copy_q = [&](uint32_t n) {
-      mbar_wait(q_full, n & 1, 0x900);
-#pragma unroll
-      for (int pn = 0; pn < 2; ++pn) {
-        uint32_t r[32];
-        const uint8_t* src = sQ + pn * QPANEL + row_in_tile * 128;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint4 v = *reinterpret_cast<const uint4*>(src + ((c ^ (row_in_tile & 7)) << 4));
-          r[c * 4 + 0] = v.x; r[c * 4 + 1] = v.y; r[c * 4 + 2] = v.z; r[c * 4 + 3] = v.w;
-        }
-        tmem_st_32x32(tmem_q + lane_off + pn * 32, r);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) { mbar_arrive(q_empty); mbar_arrive(qt_full); }
-    };
-    // ---- end of an item: normalise and store this thread's output row (e_it = the item's last block + 1)
-    auto write_output = [&](float e_l, int e_head, int e_r0, uint32_t e_it) {
-        long long t0 = 0, t1 = 0;
-        if (TIMING) t0 = clock64();
-        if (MODE == 2) mbar_wait(&p_empty[0], (e_it - 1) & 1, 0x940);
-        else mbar_wait(&p_empty[(e_it - 1) & 1], ((e_it - 1) >> 1) & 1, 0x940);   // the item's last PV has retired
-        tc_fence_after();
-        if (TIMING) t1 = clock64();
-        const float inv = e_l > 0.0f ? 1.0f / e_l : 0.0f;
-        // The warp's 32 rows go out as two [32 rows][64 columns] boxes: each thread writes its row's 128 bytes
-        // into the staging buffer (16-byte chunk c of row r at chunk position c ^ (r & 7): the 128-byte swizzle
-        // of the tensor map, bank-conflict free), one TMA store per box. Rows >= M of the tensor map are clipped
-        // by the TMA unit; rows between the live count and M receive finite values nobody reads.
-        uint8_t* so = sO + sub * OSTAGE;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          if (lane == 0) tma_store_wait_read();            // the previous box has been read out of the buffer
-          __syncwarp();
-#pragma unroll
-          for (int c0 = 0; c0 < 64; c0 += 32) {
-            uint32_t a[32];
-            long long tl = 0;
-            if (TIMING) tl = clock64();
-            tmem_ld_32x32(tmem_o + lane_off + h * 64 + c0, a);
-            tmem_ld_wait();
-            if (TIMING) acc[11] += static_cast<uint32_t>(clock64() - tl);  // O load round trips
-#pragma unroll
-            for (int v4 = 0; v4 < 4; ++v4) {
-              const int chunk = (c0 >> 3) + v4;
-              *reinterpret_cast<uint4*>(so + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = make_uint4(
-                  pack_bf16x2(__uint_as_float(a[v4 * 8 + 0]) * inv, __uint_as_float(a[v4 * 8 + 1]) * inv),
-                  pack_bf16x2(__uint_as_float(a[v4 * 8 + 2]) * inv, __uint_as_float(a[v4 * 8 + 3]) * inv),
-                  pack_bf16x2(__uint_as_float(a[v4 * 8 + 4]) * inv, __uint_as_float(a[v4 * 8 + 5]) * inv),
-                  pack_bf16x2(__uint_as_float(a[v4 * 8 + 6]) * inv, __uint_as_float(a[v4 * 8 + 7]) * inv));
-            }
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0 && !(TIMING && (p.knock & 32))) {
-            tma_store_2d(&tm_o, so, e_head * HD + h * 64, e_r0 + sub * 32);
-            tma_store_commit();
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(o_empty);
-        if (TIMING) {
-          acc[6] += 1;                                                      // items
-          acc[7] += static_cast<uint32_t>(t1 - t0);                         // wait for the last PV
-          acc[8] += static_cast<uint32_t>(clock64() - t1);                  // output rows
-        }
-    };
-    float prev_l = 0.0f;
-    int prev_head = 0, prev_r0 = 0;
-    uint32_t prev_it = 0;
-    bool have_prev = false;
-    if (MODE == 2 && static_cast<int>(blockIdx.x) < n_items) copy_q(0);
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_n) {
-      const int head = item / m_tiles, tile = item - head * m_tiles;
-      const int r0 = tile * BM, r1 = min(M, r0 + BM);
-      const int kt0 = tail_start(r0, p.S, p.row_meta);
-      const int nb = n_pre + (p.no_tail ? 0 : (r1 - kt0 + BN - 1) / BN);
-      const int rq = r0 + row_in_tile;
-      int cs = (rq / p.S) * p.S, plim = p.P;
-      if (p.row_meta != nullptr && rq < M) {
-        const int2 rm = p.row_meta[rq];
-        cs = rm.x; plim = rm.y;
-      }
-      const int p_shared = r0 < p.pre_rows ? 0 : p.P_shared;
-      float m_ref = -INFINITY, l_run = 0.0f;
-
-      for (int j = 0; j < nb; ++j, ++it) {
-        const Block b = block_of(j, n_pre, p.P, kt0, r1);
-        const int st = MODE == 2 ? 0 : (it & 1);                       // S / P buffer and its barrier parity
-        const uint32_t spar = MODE == 2 ? (it & 1) : ((it >> 1) & 1);
-        const uint32_t ts = tmem_s + lane_off + st * BN;
         // this row's visible columns of the block: prefix keys below its limit, or its own candidate's
         // tail keys up to itself
         int vlo = 0, vhi = BN;
@@ -775,7 +417,7 @@ attention_occ_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         const bool all_visible = __all_sync(0xffffffffu, vlo == 0 && vhi == BN);
         long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
         if (TIMING) t0 = clock64();
-        mbar_wait(&s_full[st], spar, 0x910 + st);
+        mbar_wait(&s_full[st], (it >> 1) & 1, 0x910 + st);
         tc_fence_after();
         if (TIMING) t1 = clock64();
 
@@ -793,8 +435,7 @@ attention_occ_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
           const bool fix = raise && (m_ref != -INFINITY) && (j > 0);
           const bool any_fix = __any_sync(0xffffffffu, fix);
           if (any_fix) {                                   // rare: rescale this row of O in TMEM
-            if (MODE == 2) mbar_wait(&p_empty[0], (it - 1) & 1, 0x920);
-            else mbar_wait(&p_empty[(it - 1) & 1], ((it - 1) >> 1) & 1, 0x920);    // PV_{g-1} has retired
+            mbar_wait(&p_empty[(it - 1) & 1], ((it - 1) >> 1) & 1, 0x920);    // PV_{g-1} has retired
             tc_fence_after();
             rescale_o_row(tmem_o + lane_off, fix ? factor : 1.0f);
           }
@@ -802,24 +443,25 @@ attention_occ_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         };
 
         float rs;
-        if (MODE >= 1 && all_visible) {
-          // ---- one pass: the 64 scores stay in registers
+        if (all_visible) {
+          // ---- every key of the block is visible to every row of the warp: the 64 scores stay in registers
           uint32_t ra[32], rb[32];
           tmem_ld_32x32(ts, ra);
           tmem_ld_32x32(ts + 32, rb);
           tmem_ld_wait();
-          if (TIMING) acc[9] += static_cast<uint32_t>(clock64() - t1);   // S load round trip
-          float mx0 = -INFINITY, mx1 = -INFINITY;
+          float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
           if (TIMING && (p.knock & 2)) {
-            mx0 = mx1 = 0.0f;
+            mx0 = 0.0f;
           } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              mx0 = fmaxf(mx0, __uint_as_float(ra[i]));
-              mx1 = fmaxf(mx1, __uint_as_float(rb[i]));
+            for (int i = 0; i < 32; i += 4) {              // four independent chains (FMNMX3: two new values each)
+              mx0 = fmaxf(mx0, fmaxf(__uint_as_float(ra[i]), __uint_as_float(ra[i + 1])));
+              mx1 = fmaxf(mx1, fmaxf(__uint_as_float(ra[i + 2]), __uint_as_float(ra[i + 3])));
+              mx2 = fmaxf(mx2, fmaxf(__uint_as_float(rb[i]), __uint_as_float(rb[i + 1])));
+              mx3 = fmaxf(mx3, fmaxf(__uint_as_float(rb[i + 2]), __uint_as_float(rb[i + 3])));
             }
           }
-          if (update_max(fmaxf(mx0, mx1))) {               // the rescale used the registers: read S again
+          if (update_max(fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)))) {   // the rescale used the registers: read S again
             tmem_ld_32x32(ts, ra);
             tmem_ld_32x32(ts + 32, rb);
             tmem_ld_wait();
@@ -827,59 +469,35 @@ attention_occ_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
           if (TIMING) t2 = clock64();
           float s0 = 0.0f, s1 = 0.0f;
           uint32_t pk[16];
-          if (TIMING && (p.knock & 1)) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const float p0 = fmaf(__uint_as_float(ra[i]), p.scale_log2, -m_use), p1 = fmaf(__uint_as_float(ra[i + 1]), p.scale_log2, -m_use);
-              s0 += p0; s1 += p1;
-              pk[i >> 1] = pack_bf16x2(p0, p1);
-            }
-            tmem_st_32x16(ts, pk);
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const float p0 = fmaf(__uint_as_float(rb[i]), p.scale_log2, -m_use), p1 = fmaf(__uint_as_float(rb[i + 1]), p.scale_log2, -m_use);
-              s0 += p0; s1 += p1;
-              pk[i >> 1] = pack_bf16x2(p0, p1);
-            }
-            tmem_st_32x16(ts + 16, pk);
-          } else {
-
+          const bool no_ex2 = TIMING && (p.knock & 1);
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            const float p0 = ex2(fmaf(__uint_as_float(ra[i]), p.scale_log2, -m_use));
-            const float p1 = ex2(fmaf(__uint_as_float(ra[i + 1]), p.scale_log2, -m_use));
+            const float x0 = fmaf(__uint_as_float(ra[i]), p.scale_log2, -m_use);
+            const float x1 = fmaf(__uint_as_float(ra[i + 1]), p.scale_log2, -m_use);
+            const float p0 = no_ex2 ? x0 : ex2(x0), p1 = no_ex2 ? x1 : ex2(x1);
             s0 += p0; s1 += p1;
             pk[i >> 1] = pack_bf16x2(p0, p1);
           }
-          tmem_st_32x16(ts, pk);
+          tmem_st_32x16(ts, pk);                           // P_g: columns [0, 32) of S_st, bf16 pairs
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            const float p0 = ex2(fmaf(__uint_as_float(rb[i]), p.scale_log2, -m_use));
-            const float p1 = ex2(fmaf(__uint_as_float(rb[i + 1]), p.scale_log2, -m_use));
+            const float x0 = fmaf(__uint_as_float(rb[i]), p.scale_log2, -m_use);
+            const float x1 = fmaf(__uint_as_float(rb[i + 1]), p.scale_log2, -m_use);
+            const float p0 = no_ex2 ? x0 : ex2(x0), p1 = no_ex2 ? x1 : ex2(x1);
             s0 += p0; s1 += p1;
             pk[i >> 1] = pack_bf16x2(p0, p1);
           }
           tmem_st_32x16(ts + 16, pk);
-          }
           rs = s0 + s1;
-        } else if (MODE >= 1) {
-          // ---- blocks with hidden keys (the partial last prefix block, the base-suffix boundary, the causal
-          // tail): the row's visible columns as a 64-bit mask, tested per element with predicates (R2P +
-          // predicated max / select), 32 columns at a time; a half no row of the warp sees is skipped
+        } else {
+          // ---- blocks with hidden keys: the row's visible columns as a 64-bit mask, 32 columns at a time; a half
+          // no row of the warp sees is skipped (P = 0). Columns the MMA did not cover (>= n_mma) are never visible.
           const uint64_t vis = window_mask(vlo, vhi);
           const uint32_t v_lo = static_cast<uint32_t>(vis), v_hi = static_cast<uint32_t>(vis >> 32);
           update_max(fmaxf(masked_max32(ts, v_lo), masked_max32(ts + 32, v_hi)));
           if (TIMING) t2 = clock64();
-          rs = masked_exp32_store<false>(ts, ts, v_lo, p.scale_log2, m_use, 0);
-          rs += masked_exp32_store<false>(ts + 32, ts + 16, v_hi, p.scale_log2, m_use, 0);
-        } else {
-          // ---- two passes over tensor memory: row maximum over the visible keys, then exponentials
-          const float raw = all_visible ? block_row_max_impl<false>(ts, b.n_mma, vlo, vhi)
-                                        : block_row_max_masked(ts, b.n_mma, vlo, vhi);
-          update_max(raw);
-          if (TIMING) t2 = clock64();
-          rs = all_visible ? block_row_exp_impl<false>(ts, b.n_mma, vlo, vhi, p.scale_log2, m_use)
-                           : block_row_exp_masked(ts, b.n_mma, vlo, vhi, p.scale_log2, m_use);
+          rs = masked_exp32_store(ts, ts, v_lo, p.scale_log2, m_use);
+          rs += masked_exp32_store(ts + 32, ts + 16, v_hi, p.scale_log2, m_use);
         }
         if (TIMING) t3 = clock64();
         tmem_st_wait();
@@ -888,16 +506,17 @@ attention_occ_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         if (lane == 0) mbar_arrive(&p_full[st]);
         l_run = l_run * factor + rs;
         m_ref = m_new;
-        if (MODE == 1 && j == 0 && have_prev) {
+        long long t4 = 0;
+        if (TIMING) t4 = clock64();
+        if (j == 0 && have_prev) {                         // the previous item's output, one block late
           write_output(prev_l, prev_head, prev_r0, prev_it);
           have_prev = false;
         }
         if (TIMING) {
-          const long long t4 = clock64();
           acc[0] += 1;                                                      // blocks
           if (j == 0) acc[10] += static_cast<uint32_t>(t1 - t0);            // wait for S, first block of an item
           acc[1] += static_cast<uint32_t>(t1 - t0);                         // wait for S
-          acc[2] += static_cast<uint32_t>(t2 - t1);                         // maximum (MODE >= 1: load + maximum)
+          acc[2] += static_cast<uint32_t>(t2 - t1);                         // S load + maximum
           acc[3] += static_cast<uint32_t>(t3 - t2);                         // exponentials + P store issue
           acc[4] += static_cast<uint32_t>(t4 - t3);                         // store wait + arrive
           acc[5] += all_visible ? 0 : 1;
@@ -905,10 +524,7 @@ attention_occ_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         }
       }
 
-      // MODE 1 writes an item's output AFTER the first block of the next item (its last PV, and the slowest warp
-      // of its last masked block, get a whole block of slack; the tensor pipe has the next item's S_0 / S_1 to do)
-      if (MODE == 2 && item + static_cast<int>(gridDim.x) < n_items) copy_q(item_n + 1);   // next Q -> tensor memory
-      if (MODE == 1) {
+      if (p.defer) {
         prev_l = l_run; prev_head = head; prev_r0 = r0; prev_it = it; have_prev = true;
       } else {
         write_output(l_run, head, r0, it);
@@ -919,9 +535,9 @@ attention_occ_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 #pragma unroll
       for (int i = 0; i < 14; ++i) p.dbg[sub * 16 + i] = acc[i];
     }
+    if (lane == 0) tma_store_wait_read();                  // shared memory stays valid until the stores have read it
   }
 
-  if (warp >= 4 && lane == 0) tma_store_wait_read();       // shared memory stays valid until the stores have read it
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -947,27 +563,30 @@ cudaError_t launch_attention_occ(const AttnParams& a, int n_heads, cudaStream_t 
     tkp = tkt;
     tvp = tvt;
   }
-  // BMA_OCC_MODE = 0 | 1 (A/B runs); BMA_OCC_TIMING=1: per-phase cycle counts of one softmax warp on stderr
-  static int mode = -1, timing = 0;
+  // A/B switches (tools/ab_attention.py): BMA_OCC_DEFER, BMA_OCC_PVFIRST (default 1), BMA_OCC_TIMING = 1 (per-phase
+  // cycle counts of the softmax warps of CTA 0 on stderr; BMA_OCC_KNOCK then removes costs). Read once;
+  // BMA_OCC_RELOAD = 1 re-reads them at every launch (in-process A/B).
+  static int inited = 0, timing = 0, defer = 1, pv_first = 1, knock = 0, reload = 0;
   static unsigned long long* dbg = nullptr;
-  if (mode < 0) {
-    const char* e = getenv("BMA_OCC_MODE");
-    mode = e == nullptr ? 3 : (e[0] >= '0' && e[0] <= '3' ? e[0] - '0' : 3);
-    const char* t = getenv("BMA_OCC_TIMING");
-    timing = (t != nullptr && t[0] == '1');
-    {
-      cudaError_t e3 = cudaFuncSetAttribute(attention_occ_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-      if (e3 != cudaSuccess) { mode = -1; return e3; }
+  if (!inited || reload) {
+    const char* e = getenv("BMA_OCC_TIMING");
+    timing = (e != nullptr && e[0] == '1');
+    e = getenv("BMA_OCC_DEFER");
+    defer = (e != nullptr && e[0] == '0') ? 0 : 1;
+    e = getenv("BMA_OCC_PVFIRST");
+    pv_first = (e != nullptr && e[0] == '0') ? 0 : 1;
+    e = getenv("BMA_OCC_KNOCK");
+    knock = e != nullptr ? atoi(e) : 0;
+    e = getenv("BMA_OCC_RELOAD");
+    reload = (e != nullptr && e[0] == '1');
+    if (!inited) {
+      cudaError_t e1 = cudaFuncSetAttribute(attention_occ_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+      if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(attention_occ_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+      if (e1 != cudaSuccess) return e1;
+      inited = 1;
     }
-    const void* fns[6] = {(const void*)attention_occ_kernel<0, false>, (const void*)attention_occ_kernel<1, false>,
-                          (const void*)attention_occ_kernel<2, false>, (const void*)attention_occ_kernel<0, true>,
-                          (const void*)attention_occ_kernel<1, true>, (const void*)attention_occ_kernel<2, true>};
-    for (const void* f : fns) {
-      cudaError_t e2 = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-      if (e2 != cudaSuccess) { mode = -1; return e2; }
-    }
-    if (timing && cudaMalloc(&dbg, 64 * sizeof(unsigned long long)) != cudaSuccess) { mode = -1; return cudaErrorMemoryAllocation; }
   }
+  if (timing && dbg == nullptr && cudaMalloc(&dbg, 64 * sizeof(unsigned long long)) != cudaSuccess) return cudaErrorMemoryAllocation;
   Params p{};
   p.out = a.out; p.ldo = a.ldo;
   p.M = a.M; p.S = a.S > 0 ? a.S : 1; p.P = a.P; p.M_dev = a.M_dev;
@@ -977,55 +596,39 @@ cudaError_t launch_attention_occ(const AttnParams& a, int n_heads, cudaStream_t 
   p.pre_rows = a.row_meta != nullptr ? a.pre_rows : 0;
   p.n_heads = n_heads; p.kv_group = a.kv_group;
   p.scale_log2 = a.scale_log2;
-  static int sleep_tma = -1, sleep_mma = 0;
-  if (sleep_tma < 0) {
-    const char* e = getenv("BMA_OCC_SLEEP");               // "tma_ns,mma_ns"
-    sleep_tma = 0;
-    if (e != nullptr) sscanf(e, "%d,%d", &sleep_tma, &sleep_mma);
-  }
-  p.sleep_tma = sleep_tma; p.sleep_mma = sleep_mma;
+  p.defer = defer; p.pv_first = pv_first;
   watchdog_attach();
   const int m_tiles = (a.M + BM - 1) / BM;
   long long grid = (long long)m_tiles * n_heads;
   if (grid > 2ll * num_sms()) grid = 2ll * num_sms();
   const int g = static_cast<int>(grid);
-  if (timing) {
-    p.dbg = dbg;
-    const char* kn = getenv("BMA_OCC_KNOCK");
-    p.knock = kn != nullptr ? atoi(kn) : 0;
-    cudaMemsetAsync(dbg, 0, 64 * sizeof(unsigned long long), stream);
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0); cudaEventCreate(&e1);
-    cudaEventRecord(e0, stream);
-    if (mode == 0) attention_occ_kernel<0, true><<<g, THREADS, SMEM, stream>>>(tq, tkt, tkp, tvt, tvp, to, p);
-    else if (mode == 1) attention_occ_kernel<1, true><<<g, THREADS, SMEM, stream>>>(tq, tkt, tkp, tvt, tvp, to, p);
-    else attention_occ_kernel<2, true><<<g, THREADS, SMEM, stream>>>(tq, tkt, tkp, tvt, tvp, to, p);
-    cudaEventRecord(e1, stream);
-    unsigned long long hh[64];
-    float ms = 0.0f;
-    if (cudaStreamSynchronize(stream) == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
-    if (cudaMemcpy(hh, dbg, sizeof(hh), cudaMemcpyDeviceToHost) == cudaSuccess) {
-      fprintf(stderr, "occ timing mode %d knock %d: %.1f us\n", mode, p.knock, ms * 1e3);
-      for (int w = 0; w < 4; ++w) {
-        const unsigned long long* h = hh + w * 16;
-        if (h[0] == 0 || h[6] == 0) continue;
-        const double nb = (double)h[0], ni = (double)h[6], nm = (double)(h[5] ? h[5] : 1);
-        fprintf(stderr, "  warp %d: %llu blocks (%llu masked), %llu items; cycles/block: wait_s %.0f max %.0f exp %.0f "
-                "st_wait+arrive %.0f (S load %.0f); cycles/item: wait_s(first block) %.0f wait_pv %.0f output %.0f "
-                "(O loads %.0f); masked blocks: max %.0f exp %.0f\n", 4 + w, h[0], h[5], h[6],
-                h[1] / nb, h[2] / nb, h[3] / nb, h[4] / nb, h[9] / nb, h[10] / ni, h[7] / ni, h[8] / ni, h[11] / ni,
-                h[12] / nm, h[13] / nm);
-      }
+  if (!timing) {
+    attention_occ_kernel<false><<<g, THREADS, SMEM, stream>>>(tq, tkt, tkp, tvt, tvp, to, p);
+    return cudaGetLastError();
+  }
+  p.dbg = dbg;
+  p.knock = knock;
+  cudaMemsetAsync(dbg, 0, 64 * sizeof(unsigned long long), stream);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, stream);
+  attention_occ_kernel<true><<<g, THREADS, SMEM, stream>>>(tq, tkt, tkp, tvt, tvp, to, p);
+  cudaEventRecord(e1, stream);
+  unsigned long long hh[64];
+  float ms = 0.0f;
+  if (cudaStreamSynchronize(stream) == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (cudaMemcpy(hh, dbg, sizeof(hh), cudaMemcpyDeviceToHost) == cudaSuccess) {
+    fprintf(stderr, "occ timing, knock %d: %.1f us\n", p.knock, ms * 1e3);
+    for (int w = 0; w < 4; ++w) {
+      const unsigned long long* h = hh + w * 16;
+      if (h[0] == 0 || h[6] == 0) continue;
+      const double nb = (double)h[0], ni = (double)h[6], nm = (double)(h[5] ? h[5] : 1);
+      fprintf(stderr, "  warp %d: %llu blocks (%llu masked), %llu items; cycles/block: wait_s %.0f load+max %.0f exp %.0f "
+              "st_wait+arrive %.0f; cycles/item: wait_s(first block) %.0f wait_pv %.0f output %.0f; masked blocks: "
+              "max %.0f exp %.0f\n", 4 + w, h[0], h[5], h[6], h[1] / nb, h[2] / nb, h[3] / nb, h[4] / nb,
+              h[10] / ni, h[7] / ni, h[8] / ni, h[12] / nm, h[13] / nm);
     }
-  } else if (mode == 0) {
-    attention_occ_kernel<0, false><<<g, THREADS, SMEM, stream>>>(tq, tkt, tkp, tvt, tvp, to, p);
-  } else if (mode == 1) {
-    attention_occ_kernel<1, false><<<g, THREADS, SMEM, stream>>>(tq, tkt, tkp, tvt, tvp, to, p);
-  } else if (mode == 3) {
-    attention_occ_kernel<3, false><<<g, THREADS3, SMEM, stream>>>(tq, tkt, tkp, tvt, tvp, to, p);
-  } else {
-    attention_occ_kernel<2, false><<<g, THREADS, SMEM, stream>>>(tq, tkt, tkp, tvt, tvp, to, p);
   }
   return cudaGetLastError();
 }
