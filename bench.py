@@ -414,6 +414,7 @@ def main():
     S, T = plan.n_tail, atk.target_ids.numel()
     lo, hi, shard_hint = atk.shard(sampled, base_ids, plan)   # this rank's slice (row-balanced when N > 1)
     clocks = ClockSampler(local)
+    atk.engine.exchange_wait_ms(reset=True)
     barrier()
     launches0 = lib.bma_launch_count()
     clocks.start()
@@ -432,6 +433,23 @@ def main():
         td.all_reduce(ms, op=td.ReduceOp.MAX)
     ms_per_step = float(ms.item()) / args.steps
     value = sw / (ms_per_step * 1e-3)
+    # per rank: time spent waiting for other ranks in the per-layer prefix exchange (the straggler shows ~0)
+    exchange_wait, exchange_floor_us = None, None
+    if world > 1:
+        wt = torch.zeros(world, device=dev)
+        wt[rank] = atk.engine.exchange_wait_ms(reset=True) / args.steps
+        td.all_reduce(wt)
+        exchange_wait = [round(float(x), 3) for x in wt.tolist()]
+        # latency floor of one exchange: 200 data-free exchanges back to back, nothing else on the GPUs
+        atk.engine.peers_barrier(20)
+        barrier()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        atk.engine.peers_barrier(200)
+        b1.record()
+        b1.synchronize()
+        exchange_floor_us = round(b0.elapsed_time(b1) / 200 * 1e3, 2)
+        atk.engine.exchange_wait_ms(reset=True)
     rows_run = atk.engine.last_rows          # tail (+ fused prefix) rows of this rank's shard that went through the decoder
 
     # ---- per-class profile: a SEPARATE pass with an event pair around every launch -----------------
@@ -611,7 +629,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu,
         "roofline_hbm": hbm,
-        "full_step": full, "winner": {"loss": win_loss, "index": win_idx, "e2e_key": e2e_key, "unsharded_rank0": unsharded},
+        "exchange_wait_ms_per_step": exchange_wait, "exchange_floor_us": exchange_floor_us, "full_step": full, "winner": {"loss": win_loss, "index": win_idx, "e2e_key": e2e_key, "unsharded_rank0": unsharded},
         "a100_reference_published": (
             {"cand_per_s": 12.1, "s_per_iter": 43.9353,
              "note": "BASELINE.md: Gemma-3-4b-it joint_eval sw 512, A100-80GB, bf16"} if gemma and joint else

@@ -447,7 +447,7 @@ int layer_scatter_peers(bma_scorer* s, int l, const Pass& ps, cudaStream_t st) {
 int layer_wait_peers(bma_scorer* s, int l, const Pass& ps, int P, cudaStream_t st) {
   {
     ProfScope pr(s, PC_EMBED, 0, st);
-    BMA_LAUNCH(launch_prefix_wait(s->flags_dev, s->peer_n, s->epoch, st), "prefix_wait");
+    BMA_LAUNCH(launch_prefix_wait(s->flags_dev, s->peer_n, s->epoch, st, s->flags_dev + 8), "prefix_wait");
   }
   if (publish_in_epilogue(s, ps)) return 0;          // the base rows went out with the GEMM
   return layer_publish_base(s, l, ps, P, st);
@@ -459,7 +459,7 @@ int layer_signal_peers(bma_scorer* s, bool wait, cudaStream_t st) {
   ++s->epoch;
   ProfScope pr(s, PC_EMBED, 0, st);
   BMA_LAUNCH(launch_prefix_signal_wait(s->peer_flags, s->flags_dev, s->peer_n, s->peer_rank, s->epoch, 1, wait ? 1 : 0,
-                                       st), "prefix_signal_wait");
+                                       st, s->flags_dev + 8), "prefix_signal_wait");
   return 0;
 }
 int layer_exchange_peers(bma_scorer* s, int l, const Pass& ps, int P, cudaStream_t st) {
@@ -476,7 +476,7 @@ int peers_barrier(bma_scorer* s, cudaStream_t st) {
   none.pre_n = 0; none.pre0 = 0;
   int rc = layer_scatter_peers(s, 0, none, st);
   if (rc != 0) return rc;
-  BMA_LAUNCH(launch_prefix_wait(s->flags_dev, s->peer_n, s->epoch, st), "prefix_wait");
+  BMA_LAUNCH(launch_prefix_wait(s->flags_dev, s->peer_n, s->epoch, st, s->flags_dev + 8), "prefix_wait");
   return 0;
 }
 
@@ -626,7 +626,7 @@ bma_scorer* bma_scorer_create(const bma_model_desc* desc) {
   ok = ok && dev_alloc(&s->cand_tmp, static_cast<size_t>(D.max_rows) + 1, &s->ws_bytes);
   ok = ok && dev_alloc(&s->total_rows_dev, 1, &s->ws_bytes);
   ok = ok && dev_alloc(&s->rows_accum_dev, 1, &s->ws_bytes);
-  ok = ok && dev_alloc(&s->flags_dev, 8, &s->ws_bytes);
+  ok = ok && dev_alloc(&s->flags_dev, 16, &s->ws_bytes);   // [0, 8) flags, [8] accumulated exchange wait (ns)
   ok = ok && dev_alloc(&s->done_dev, 1, &s->ws_bytes);
   ok = ok && dev_alloc(&s->base_dev, 4096, &s->ws_bytes);
   ok = ok && cudaHostAlloc(reinterpret_cast<void**>(&s->total_rows_host), sizeof(int), cudaHostAllocDefault) == cudaSuccess;
@@ -1118,6 +1118,27 @@ int bma_scorer_score_host(bma_scorer* s, const long long* ids_host, int ids_stri
 }
 
 // ---- peer memory (NVLink) ------------------------------------------------------------------------
+// `count` data-free exchanges back to back on `stream` (collective over the ranks): the latency floor of one
+// per-layer exchange, measured by the caller with events around the call.
+int bma_scorer_peers_barrier(bma_scorer* s, int count, void* stream) {
+  if (s == nullptr || count < 0) return fail(cudaErrorInvalidValue, "peers_barrier: bad arguments");
+  if (s->peer_n <= 1) return 0;
+  for (int i = 0; i < count; ++i) {
+    const int rc = peers_barrier(s, static_cast<cudaStream_t>(stream));
+    if (rc != 0) return rc;
+  }
+  return 0;
+}
+
+// Nanoseconds this scorer's stream has spent in the per-layer prefix exchange waiting for other ranks' flags
+// since the last reset (synchronises the device: call it between steps).
+int bma_scorer_exchange_wait_ns(bma_scorer* s, unsigned long long* out, int reset) {
+  if (s == nullptr || out == nullptr) return fail(cudaErrorInvalidValue, "exchange_wait_ns: null argument");
+  BMA_CHECK(cudaMemcpy(out, s->flags_dev + 8, sizeof(unsigned long long), cudaMemcpyDeviceToHost), "exchange_wait_ns: read");
+  if (reset) BMA_CHECK(cudaMemset(s->flags_dev + 8, 0, sizeof(unsigned long long)), "exchange_wait_ns: reset");
+  return 0;
+}
+
 int bma_scorer_clear_peers(bma_scorer* s) {
   if (s == nullptr) return 0;
   if (s->peer_ipc) {

@@ -69,9 +69,11 @@ cudaError_t launch_prefix_scatter(const __nv_bfloat16* k_tail, long long ldk, co
                                   void* const* peer_k, void* const* peer_vt, void* const* peer_flags, int n_ranks,
                                   int my_rank, long long ldkp, long long ldvtp, int n, int key0, int kv_dim,
                                   unsigned int* done_counter, unsigned long long epoch, cudaStream_t stream);
-cudaError_t launch_prefix_wait(unsigned long long* flags, int n_ranks, unsigned long long epoch, cudaStream_t stream);
+cudaError_t launch_prefix_wait(unsigned long long* flags, int n_ranks, unsigned long long epoch, cudaStream_t stream,
+                               unsigned long long* wait_ns = nullptr);
 cudaError_t launch_prefix_signal_wait(void* const* peer_flags, unsigned long long* my_flags, int n_ranks, int my_rank,
-                                      unsigned long long epoch, int signal, int wait, cudaStream_t stream);
+                                      unsigned long long epoch, int signal, int wait, cudaStream_t stream,
+                                      unsigned long long* wait_ns = nullptr);
 cudaError_t launch_rmsnorm(const __nv_bfloat16* x, long long ldx, const __nv_bfloat16* w,
                            __nv_bfloat16* y, long long ldy, int rows, int d, float eps, int mode,
                            int gather_T, int gather_S, int gather_off, const int* gather_vstart,

@@ -282,8 +282,17 @@ prefix_scatter_kernel(const __nv_bfloat16* __restrict__ k_tail, long long ldk, c
   }
 }
 
-__global__ void prefix_wait_kernel(volatile unsigned long long* flags, int n_ranks, unsigned long long epoch) {
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// wait_ns (optional): nanoseconds this rank spent waiting for the other ranks' flags, accumulated over the
+// exchanges (bma_scorer_exchange_wait_ns): a rank that never waits is the one the others wait for.
+__global__ void prefix_wait_kernel(volatile unsigned long long* flags, int n_ranks, unsigned long long epoch,
+                                   unsigned long long* wait_ns) {
   const int q = threadIdx.x;
+  const unsigned long long t0 = (wait_ns != nullptr && q == 0) ? global_ns() : 0ull;
   if (q < n_ranks) {
     unsigned int spins = 0;
     while (flags[q] < epoch) {
@@ -293,6 +302,8 @@ __global__ void prefix_wait_kernel(volatile unsigned long long* flags, int n_ran
       }
     }
   }
+  __syncwarp();
+  if (wait_ns != nullptr && q == 0) atomicAdd(wait_ns, global_ns() - t0);
   __threadfence_system();
 }
 
@@ -301,13 +312,15 @@ __global__ void prefix_wait_kernel(volatile unsigned long long* flags, int n_ran
 // order, so its peer stores are performed before the system-scope fence below, and the flag after it.
 struct PeerFlags { unsigned long long* f[8]; };
 __global__ void prefix_signal_wait_kernel(PeerFlags peers, volatile unsigned long long* flags, int n_ranks, int my_rank,
-                                          unsigned long long epoch, int signal, int wait) {
+                                          unsigned long long epoch, int signal, int wait, unsigned long long* wait_ns) {
   const int q = threadIdx.x;
+  unsigned long long t0 = 0ull;
   if (q < n_ranks) {
     if (signal) {
       __threadfence_system();
       atomicExch_system(peers.f[q] + my_rank, epoch);
     }
+    if (wait_ns != nullptr && q == 0) t0 = global_ns();
     if (wait) {
       unsigned int spins = 0;
       while (flags[q] < epoch) {
@@ -318,15 +331,18 @@ __global__ void prefix_signal_wait_kernel(PeerFlags peers, volatile unsigned lon
       }
     }
   }
+  __syncwarp();
+  if (wait && wait_ns != nullptr && q == 0) atomicAdd(wait_ns, global_ns() - t0);
   __threadfence_system();
 }
 
 cudaError_t launch_prefix_signal_wait(void* const* peer_flags, unsigned long long* my_flags, int n_ranks, int my_rank,
-                                      unsigned long long epoch, int signal, int wait, cudaStream_t stream) {
+                                      unsigned long long epoch, int signal, int wait, cudaStream_t stream,
+                                      unsigned long long* wait_ns) {
   if (n_ranks < 1 || n_ranks > 8) return cudaErrorInvalidValue;
   PeerFlags pf{};
   for (int q = 0; q < n_ranks; ++q) pf.f[q] = static_cast<unsigned long long*>(peer_flags[q]);
-  prefix_signal_wait_kernel<<<1, 32, 0, stream>>>(pf, my_flags, n_ranks, my_rank, epoch, signal, wait);
+  prefix_signal_wait_kernel<<<1, 32, 0, stream>>>(pf, my_flags, n_ranks, my_rank, epoch, signal, wait, wait_ns);
   return cudaGetLastError();
 }
 
@@ -350,8 +366,9 @@ cudaError_t launch_prefix_scatter(const __nv_bfloat16* k_tail, long long ldk, co
   return cudaGetLastError();
 }
 
-cudaError_t launch_prefix_wait(unsigned long long* flags, int n_ranks, unsigned long long epoch, cudaStream_t stream) {
-  prefix_wait_kernel<<<1, 32, 0, stream>>>(flags, n_ranks, epoch);
+cudaError_t launch_prefix_wait(unsigned long long* flags, int n_ranks, unsigned long long epoch, cudaStream_t stream,
+                               unsigned long long* wait_ns) {
+  prefix_wait_kernel<<<1, 32, 0, stream>>>(flags, n_ranks, epoch, wait_ns);
   return cudaGetLastError();
 }
 

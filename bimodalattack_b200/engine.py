@@ -265,6 +265,23 @@ class ScoringEngine:
                 from . import dist as bdist
                 bdist.exchange_peer_handles(self.lib, self._scorer, self.device)
 
+    def peers_barrier(self, count: int = 1) -> None:
+        """``count`` data-free prefix exchanges on the current stream (collective over the ranks; no-op without peers)."""
+        if self._scorer is not None:
+            native.check(self.lib.bma_scorer_peers_barrier(self._scorer, count, torch.cuda.current_stream().cuda_stream),
+                         "peers_barrier")
+
+    def exchange_wait_ms(self, reset: bool = True) -> float:
+        """Milliseconds this rank's scorer stream spent waiting for the other ranks inside the per-layer prefix
+        exchange since the last reset (0 without peers). Synchronises the device. The rank whose figure stays near
+        zero is the one the others wait for (``BimodalAttack.rebalance``)."""
+        if self._scorer is None:
+            return 0.0
+        import ctypes as C
+        ns = C.c_ulonglong(0)
+        native.check(self.lib.bma_scorer_exchange_wait_ns(self._scorer, C.byref(ns), 1 if reset else 0), "exchange_wait_ns")
+        return ns.value * 1e-6
+
     def prefill(self, prefix_embeds: Optional[torch.Tensor], deferred: Optional[bool] = None):
         """Compute and keep the K/V of the shared prefix ([P, d] bf16; None/empty = no prefix). With
         ``fused_prefill`` (default) the work is deferred into the next ``score`` call that carries

@@ -193,6 +193,12 @@ int bma_scorer_group_score(bma_scorer** group, int n, const long long* ids, int 
 int bma_scorer_export_ipc(bma_scorer* s, void* out192);
 int bma_scorer_import_ipc(bma_scorer* s, const void* handles, int size, int rank);
 int bma_scorer_clear_peers(bma_scorer* s);
+/* `count` data-free exchanges (flag raise on every peer + wait for all flags) back to back on `stream`; collective
+ * over the ranks, no-op without peers. Timed by the caller: the latency floor of one per-layer exchange. */
+int bma_scorer_peers_barrier(bma_scorer* s, int count, void* stream);
+/* Nanoseconds spent in the per-layer prefix exchange waiting for other ranks' flags since the last reset
+ * (device-synchronising read). The rank whose figure stays near zero is the one the others wait for. */
+int bma_scorer_exchange_wait_ns(bma_scorer* s, unsigned long long* out_ns, int reset);
 
 /* Optional per-class CUDA-event profile of the scoring pass (events on the launching stream).
  * Classes: 0 tail-embed, 1 rmsnorm, 2 gemm qkv+rope, 3 attention, 4 gemm o_proj, 5 gemm gate/up+GLU,
