@@ -434,7 +434,7 @@ def main():
     ms_per_step = float(ms.item()) / args.steps
     value = sw / (ms_per_step * 1e-3)
     # per rank: time spent waiting for other ranks in the per-layer prefix exchange (the straggler shows ~0)
-    exchange_wait, exchange_floor_us = None, None
+    exchange_wait, exchange_floor_us, early_signal_ab, adaptive_ab = None, None, None, None
     if world > 1:
         wt = torch.zeros(world, device=dev)
         wt[rank] = atk.engine.exchange_wait_ms(reset=True) / args.steps
@@ -450,6 +450,53 @@ def main():
         b1.synchronize()
         exchange_floor_us = round(b0.elapsed_time(b1) / 200 * 1e3, 2)
         atk.engine.exchange_wait_ms(reset=True)
+
+        # A/B of the early signal (the QKV GEMM publishes first and raises the flags itself) in the same process
+        def timed_ms(n):
+            barrier()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for _ in range(n):
+                scoring_step()
+            t1.record()
+            barrier()
+            t = torch.tensor([t0.elapsed_time(t1)], device=dev)
+            td.all_reduce(t, op=td.ReduceOp.MAX)
+            return float(t.item()) / n
+        ab = {}
+        for name, flag in (("off", False), ("on", True), ("off2", False), ("on2", True)):
+            atk.engine.set_early_signal(flag)
+            scoring_step()
+            ms_ab = timed_ms(args.steps)
+            wt = torch.zeros(world, device=dev)
+            wt[rank] = atk.engine.exchange_wait_ms(reset=True) / (args.steps + 1)
+            td.all_reduce(wt)
+            ab[name] = {"candidates_per_s": round(sw / (ms_ab * 1e-3), 1), "ms_per_step": round(ms_ab, 3),
+                        "exchange_wait_ms_per_step": [round(float(x), 3) for x in wt.tolist()]}
+        early_signal_ab = ab
+        atk.engine.set_early_signal(False)
+
+        # straggler-aware shares (BimodalAttack.rebalance): 10 untimed steps move the candidate shares towards the
+        # ranks' measured speeds, then the same timed loop
+        atk.adapt_shares = True
+        atk._rebalance_calls = 2
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        atk.engine.exchange_wait_ms(reset=True)
+        for _ in range(10):
+            w0.record()
+            scoring_step()
+            w1.record()
+            w1.synchronize()
+            atk.rebalance(w0.elapsed_time(w1))
+        atk.adapt_shares = False             # frozen cuts for the timed steps (and everything after)
+        ms_ad = timed_ms(args.steps)
+        wt = torch.zeros(world, device=dev)
+        wt[rank] = atk.engine.exchange_wait_ms(reset=True) / args.steps
+        td.all_reduce(wt)
+        adaptive_ab = {"candidates_per_s": round(sw / (ms_ad * 1e-3), 1), "ms_per_step": round(ms_ad, 3),
+                       "rank_share": [round(x, 4) for x in (atk.rank_share or [])],
+                       "exchange_wait_ms_per_step": [round(float(x), 3) for x in wt.tolist()]}
+        atk.rank_share = None
     rows_run = atk.engine.last_rows          # tail (+ fused prefix) rows of this rank's shard that went through the decoder
 
     # ---- per-class profile: a SEPARATE pass with an event pair around every launch -----------------
@@ -629,7 +676,8 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu,
         "roofline_hbm": hbm,
-        "exchange_wait_ms_per_step": exchange_wait, "exchange_floor_us": exchange_floor_us, "full_step": full, "winner": {"loss": win_loss, "index": win_idx, "e2e_key": e2e_key, "unsharded_rank0": unsharded},
+        "exchange_wait_ms_per_step": exchange_wait, "exchange_floor_us": exchange_floor_us,
+        "early_signal_ab": early_signal_ab, "adaptive_shares_ab": adaptive_ab, "full_step": full, "winner": {"loss": win_loss, "index": win_idx, "e2e_key": e2e_key, "unsharded_rank0": unsharded},
         "a100_reference_published": (
             {"cand_per_s": 12.1, "s_per_iter": 43.9353,
              "note": "BASELINE.md: Gemma-3-4b-it joint_eval sw 512, A100-80GB, bf16"} if gemma and joint else

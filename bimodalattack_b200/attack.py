@@ -258,6 +258,11 @@ class BimodalAttack:
             self.engine.attach_comm(bdist.native_comm(self.device, self.world))
         self.gather_all_losses = False    # multi-rank: also all-reduce the per-candidate loss vector
         self.balance_shards = os.environ.get("BMA_BALANCE_SHARDS", "1") != "0"   # multi-rank: shards of equal ROWS (shard())
+        # ... weighted by the ranks' measured speeds (rebalance()): GPUs of one box run at different clocks under
+        # the power cap, and every layer's prefix exchange makes all ranks wait for the slowest
+        # (opt-in, BMA_ADAPT_SHARES=1: at N = 2 the persistent skew is ~1 % of a step, inside the run-to-run noise)
+        self.adapt_shares = os.environ.get("BMA_ADAPT_SHARES", "0") == "1"
+        self.rank_share: Optional[List[float]] = None
         self.step_hook = None             # optional callable(step_index) run at the end of every step
         self.graph_gradient = os.environ.get("BMA_GRAPH_GRADIENT", "1") != "0"
         # patch-embedding convolutions run as unfold + GEMM while run() is active (see _patch_conv_forward);
@@ -682,10 +687,34 @@ class BimodalAttack:
             return lo, hi, even
         diff = ids != base_ids.view(1, -1)
         first = torch.where(diff.any(1), diff.int().argmax(1), ids.shape[1] + plan.n_tail)   # == base: no rows at all
-        cuts = bdist.balanced_cuts((plan.n_tail - first).clamp_(min=0) + 1, w.size)
+        cuts = bdist.balanced_cuts((plan.n_tail - first).clamp_(min=0) + 1, w.size, self.rank_share)
         widest = max(b - a for a, b in zip(cuts, cuts[1:]))
         # a stable capacity hint (the workspace is re-created, collectively, only when it grows)
         return cuts[w.rank], cuts[w.rank + 1], max(widest, even + even // 4 + 1)
+
+    def rebalance(self, step_ms: float) -> Optional[List[float]]:
+        """Collective, after a scoring step (every rank, same call order): all-gathers (this rank's scoring time,
+        the time it spent waiting for other ranks in the prefix exchange) and moves the candidate shares towards
+        the ranks' measured speeds (``dist.updated_shares``); the next ``shard()`` uses them. Results do not depend
+        on the cuts (rows are computed independently). No-op on one rank, when disabled, or when nothing was
+        exchanged (no split prefill)."""
+        w = self.world
+        if w.size == 1 or not self.adapt_shares or not self.balance_shards:
+            return None
+        self._rebalance_calls = getattr(self, "_rebalance_calls", 0) + 1
+        if self._rebalance_calls <= 2:       # the first steps carry one-time costs (workspace, graph capture) that differ per rank
+            self.engine.exchange_wait_ms(reset=True)
+            return self.rank_share
+        mine = torch.tensor([float(step_ms), self.engine.exchange_wait_ms(reset=True)], dtype=torch.float32, device=self.device)
+        allr = torch.empty(2 * w.size, dtype=torch.float32, device=self.device)
+        torch.distributed.all_gather_into_tensor(allr, mine)
+        vals = allr.view(w.size, 2).tolist()
+        steps, waits = [v[0] for v in vals], [v[1] for v in vals]
+        if max(waits) <= 0.0 or min(steps) <= 0.0:
+            return self.rank_share
+        share = self.rank_share if self.rank_share is not None else [1.0 / w.size] * w.size
+        self.rank_share = bdist.updated_shares(share, steps, waits)
+        return self.rank_share
 
     def _winner(self) -> Tuple[float, int]:
         """(min loss, argmin) from the packed key the scorer (and the all-reduce) left on device."""
@@ -890,6 +919,8 @@ class BimodalAttack:
             phases = clock.read()
             for name, dst in (("gradient", g_times), ("pgd", p_times), ("sampling", s_times), ("loss", l_times)):
                 dst.extend(phases.get(name, []))
+            if self.world.size > 1 and phases.get("loss"):
+                self.rebalance(1e3 * sum(phases["loss"]))
             grad_time = phases["gradient"][-1] if phases.get("gradient") else 0.0
             pgd_time = phases["pgd"][-1] if phases.get("pgd") else 0.0
             sampling_time = sum(phases.get("sampling", []))

@@ -111,6 +111,7 @@ struct bma_scorer {
   int* cand_vstart = nullptr;
   int2* cand_tmp = nullptr;
   int dedupe = 1;                        // identical candidates share one set of rows (bma_scorer_set_dedupe)
+  int early_signal = 0;                  // split prefill over peers: the QKV GEMM raises the flags itself, publishing tiles first
   int fused_publish = 1;                 // prefix / base K/V leave through the QKV GEMM's epilogue (bma_scorer_set_fused_publish)
   int* total_rows_dev = nullptr;         // live row count of the current chunk (read by every kernel of the pass)
   int* total_rows_host = nullptr;        // pinned
@@ -254,6 +255,12 @@ inline bool publish_in_epilogue(const bma_scorer* s, const Pass& ps) {
   return true;
 }
 
+// Early signal (GemmParams::pub_flag): only with the fused publish, over peer memory, K/V column tiles aligned.
+inline bool early_signal(const bma_scorer* s, const Pass& ps) {
+  return publish_in_epilogue(s, ps) && ps.pre_chunk > 0 && s->peer_n > 1 && s->early_signal != 0 &&
+         s->q_dim % 256 == 0 && ps.pre_n + ps.n_share > 0;      // (a rank that publishes nothing signals by kernel)
+}
+
 // pre-norm + fused QKV projection (+ q/k-norm + rotary, V transposed)
 int layer_front(bma_scorer* s, int l, Pass& ps, cudaStream_t st) {
   const bma_model_desc& D = s->desc;
@@ -293,6 +300,12 @@ int layer_front(bma_scorer* s, int l, Pass& ps, cudaStream_t st) {
     for (int q = 0; q < p.pub_n; ++q) {
       p.pub_k[q] = (peers ? static_cast<__nv_bfloat16*>(s->peer_qk[q]) : s->prefix_qk) + qk_off;
       p.pub_vt[q] = (peers ? static_cast<__nv_bfloat16*>(s->peer_vt[q]) : s->prefix_vt) + vt_off;
+    }
+    if (early_signal(s, ps)) {         // this exchange's flag is raised by the GEMM itself (its publishing tiles run first)
+      ++s->epoch;
+      for (int q = 0; q < p.pub_n; ++q) p.pub_flag[q] = static_cast<unsigned long long*>(s->peer_flags[q]);
+      p.pub_epoch = s->epoch;
+      p.pub_done = s->done_dev;
     }
   }
   ProfScope pr(s, PC_GEMM_QKV, gemm_flops(p), st);
@@ -455,14 +468,20 @@ int layer_wait_peers(bma_scorer* s, int l, const Pass& ps, int P, cudaStream_t s
 // Fused publish: the QKV GEMM has already stored this rank's slice into every rank's buffers; what is left
 // of the exchange is ONE launch that raises this rank's flag on every peer (stream order + a system-scope
 // fence put the GEMM's peer stores before it) and waits for the other ranks' flags.
-int layer_signal_peers(bma_scorer* s, bool wait, cudaStream_t st) {
+int layer_signal_peers(bma_scorer* s, bool wait, cudaStream_t st, bool count_wait = true) {
   ++s->epoch;
   ProfScope pr(s, PC_EMBED, 0, st);
   BMA_LAUNCH(launch_prefix_signal_wait(s->peer_flags, s->flags_dev, s->peer_n, s->peer_rank, s->epoch, 1, wait ? 1 : 0,
-                                       st, s->flags_dev + 8), "prefix_signal_wait");
+                                       st, count_wait ? s->flags_dev + 8 : nullptr), "prefix_signal_wait");
   return 0;
 }
 int layer_exchange_peers(bma_scorer* s, int l, const Pass& ps, int P, cudaStream_t st) {
+  if (early_signal(s, ps)) {           // signalled from inside the QKV GEMM: only the wait is left
+    ProfScope pr(s, PC_EMBED, 0, st);
+    BMA_LAUNCH(launch_prefix_signal_wait(s->peer_flags, s->flags_dev, s->peer_n, s->peer_rank, s->epoch, 0, 1, st,
+                                         s->flags_dev + 8), "prefix_wait(early signal)");
+    return 0;
+  }
   if (publish_in_epilogue(s, ps)) return layer_signal_peers(s, true, st);
   int rc = layer_scatter_peers(s, l, ps, st);
   if (rc != 0) return rc;
@@ -471,12 +490,14 @@ int layer_exchange_peers(bma_scorer* s, int l, const Pass& ps, int P, cudaStream
 // Barrier over the ranks (no data): nobody writes into a rank's prefix buffers while that rank may still
 // be reading them for an earlier pass.
 int peers_barrier(bma_scorer* s, cudaStream_t st) {
-  if (s->fused_publish) return layer_signal_peers(s, true, st);
+  // (not counted as exchange wait: this one absorbs the ranks' START skew -- host jitter, the previous step's tail --
+  // which says nothing about their speed)
+  if (s->fused_publish) return layer_signal_peers(s, true, st, false);
   Pass none;
   none.pre_n = 0; none.pre0 = 0;
   int rc = layer_scatter_peers(s, 0, none, st);
   if (rc != 0) return rc;
-  BMA_LAUNCH(launch_prefix_wait(s->flags_dev, s->peer_n, s->epoch, st, s->flags_dev + 8), "prefix_wait");
+  BMA_LAUNCH(launch_prefix_wait(s->flags_dev, s->peer_n, s->epoch, st, nullptr), "prefix_wait");
   return 0;
 }
 
@@ -599,6 +620,10 @@ bma_scorer* bma_scorer_create(const bma_model_desc* desc) {
   bma_scorer* s = new bma_scorer();
   s->desc = D;
   s->fused_publish = fused_publish_default();
+  {
+    const char* e = getenv("BMA_EARLY_SIGNAL");       // off by default: no gain measured at N = 2 (bench.py: early_signal_ab)
+    s->early_signal = (e != nullptr && atoi(e) != 0) ? 1 : 0;
+  }
   s->layers.resize(D.n_layers);
   s->q_dim = D.n_heads * D.head_dim;
   s->kv_dim = D.n_kv_heads * D.head_dim;
@@ -747,6 +772,12 @@ long long bma_scorer_last_rows(const bma_scorer* s) {
   unsigned long long ragged = 0;     // synchronising read: the ragged chunks counted their rows on the device
   if (cudaMemcpy(&ragged, s->rows_accum_dev, sizeof(ragged), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
   return s->last_rows + static_cast<long long>(ragged);
+}
+
+int bma_scorer_set_early_signal(bma_scorer* s, int enable) {
+  if (s == nullptr) return fail(cudaErrorInvalidValue, "set_early_signal: null scorer");
+  s->early_signal = enable != 0;
+  return 0;
 }
 
 int bma_scorer_set_fused_publish(bma_scorer* s, int enable) {
@@ -1044,6 +1075,7 @@ int bma_scorer_group_score(bma_scorer** group, int n, const long long* ids, int 
       int rc = layer_front(group[r], l, pass[r], st);
       if (rc != 0) return rc;
       if (!via_peers) rc = layer_pack(group[r], l, pass[r], st);
+      else if (early_signal(group[r], pass[r])) rc = 0;       // the GEMM raised the flags
       else if (publish_in_epilogue(group[r], pass[r])) rc = layer_signal_peers(group[r], false, st);
       else rc = layer_scatter_peers(group[r], l, pass[r], st);
       if (rc != 0) return rc;

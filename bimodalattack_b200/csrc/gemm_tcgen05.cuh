@@ -80,6 +80,13 @@ struct GemmParams {
   long long pub_ldk, pub_ldvt;
   __nv_bfloat16* pub_k[8];    // [key][pub_ldk], column 0 = first K-head column
   __nv_bfloat16* pub_vt[8];   // [dim][pub_ldvt]
+  // Early signal (pub_flag[0] != nullptr; pub_kcol0 a multiple of BN): the tiles that publish -- the row blocks with
+  // prefix / base rows x the K and V column tiles -- are walked FIRST, and the epilogue warp that stores the last of
+  // them raises this rank's flag (word pub_self := pub_epoch) on all pub_n ranks from inside the GEMM. The other
+  // ranks' wait, launched after this GEMM, then has the rest of the GEMM as slack against rank-to-rank jitter.
+  unsigned long long* pub_flag[8];
+  unsigned long long pub_epoch;
+  unsigned int* pub_done;     // device counter, 0 between launches
 };
 
 constexpr int GEMM_BM = 128;
@@ -160,7 +167,22 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const int k_blocks = (p.K + GEMM_BK - 1) / GEMM_BK;
   const int group_m = max(1, (p.group_m > 0 ? p.group_m : 16) / CTAS);
 
+  // publish-first order (see GemmParams::pub_flag): virtual tiles [0, n_first) are the publishing tiles, the rest is
+  // the normal order with those tiles skipped (tile_active)
+  const bool pub_first = EPI == EPI_ROPE && p.pub_flag[0] != nullptr && p.pub_rows > 0 && p.batch <= 1;
+  const int pub_mu = pub_first ? (p.pub_rows + GEMM_BM * CTAS - 1) / (GEMM_BM * CTAS) : 0;   // row units that publish
+  const int pub_n0 = pub_first ? p.pub_kcol0 / BN : 0;                                        // first K/V column tile
+  const int n_first = pub_first ? pub_mu * (n_tiles - pub_n0) : 0;
+  const int num_virtual = num_tiles + n_first;
   auto tile_coords = [&](int tile, int& m_blk, int& n_blk) -> int {
+    if constexpr (EPI == EPI_ROPE) {
+      if (tile < n_first) {
+        m_blk = (tile % pub_mu) * CTAS + static_cast<int>(cta_rank);
+        n_blk = pub_n0 + tile / pub_mu;
+        return 0;
+      }
+      tile -= n_first;
+    }
     const int b = tile / tiles_per_batch;
     tile -= b * tiles_per_batch;
     const int per_group = group_m * n_tiles;
@@ -174,7 +196,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
   };
 
   // causal products: which tiles exist and which K blocks they need (same answer in every warp role)
-  auto tile_active = [&](int m_blk, int n_blk) { return p.causal != 1 || n_blk * BN <= m_blk * GEMM_BM + GEMM_BM - 1; };
+  auto tile_active = [&](int tile, int m_blk, int n_blk) {
+    if (pub_first && tile >= n_first && m_blk / CTAS < pub_mu && n_blk >= pub_n0) return false;   // done in the first segment
+    return p.causal != 1 || n_blk * BN <= m_blk * GEMM_BM + GEMM_BM - 1;
+  };
   auto k_first = [&](int m_blk) { return p.causal == 3 ? min(k_blocks, (m_blk * GEMM_BM) / GEMM_BK) : 0; };
   auto k_last = [&](int m_blk) {
     return p.causal == 2 ? min(k_blocks, ((m_blk + 1) * GEMM_BM + GEMM_BK - 1) / GEMM_BK) : k_blocks;
@@ -214,12 +239,12 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
+      for (int tile = unit0; tile < num_virtual; tile += unit_stride) {
         int m_blk, n_blk;
         const int bi = tile_coords(tile, m_blk, n_blk);
         const int a_r0 = bi * p.a_row + m_blk * GEMM_BM, a_c0 = bi * p.a_col;
         const int b_r0 = bi * p.b_row + n_blk * BN, b_c0 = bi * p.b_col;
-        if (!tile_active(m_blk, n_blk)) continue;
+        if (!tile_active(tile, m_blk, n_blk)) continue;
         const int kf = k_first(m_blk), kl = k_last(m_blk);
         const int kb0 = p.k_stagger > 0 ? static_cast<int>(((long long)tile * p.k_stagger) % k_blocks) : 0;
         for (int kk = kf; kk < kl; ++kk) {
@@ -251,10 +276,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
+      for (int tile = unit0; tile < num_virtual; tile += unit_stride) {
         int m_blk, n_blk;
         tile_coords(tile, m_blk, n_blk);
-        if (!tile_active(m_blk, n_blk)) continue;
+        if (!tile_active(tile, m_blk, n_blk)) continue;
         const int kf = k_first(m_blk), kl = k_last(m_blk);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 0x200 + acc);
         tc_fence_after();
@@ -284,10 +309,10 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const int sub = warp & 3;                 // TMEM sub-partition owned by this warp
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = unit0; tile < num_tiles; tile += unit_stride) {
+    for (int tile = unit0; tile < num_virtual; tile += unit_stride) {
       int m_blk, n_blk;
       const int bi = tile_coords(tile, m_blk, n_blk);
-      if (!tile_active(m_blk, n_blk)) continue;
+      if (!tile_active(tile, m_blk, n_blk)) continue;
       mbar_wait(&tmem_full[acc], acc_phase, 0x400 + acc);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * BN;
@@ -556,6 +581,23 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
       }
 
+      if constexpr (EPI == EPI_ROPE) {
+        if (pub_first && tile < n_first) {
+          // every epilogue warp of every publishing tile counts in; the last one raises the flags. Each lane fences
+          // its own stores (into the peers' memory) at system scope before its warp's increment.
+          __threadfence_system();
+          __syncwarp();
+          if (lane == 0) {
+            const unsigned int expect = static_cast<unsigned int>(n_first) * 4u * CTAS;
+            if (atomicAdd(p.pub_done, 1u) + 1u == expect) {
+              atomicExch(p.pub_done, 0u);
+              __threadfence_system();
+              for (int q = 0; q < p.pub_n; ++q)
+                atomicExch_system(p.pub_flag[q] + p.pub_self, p.pub_epoch);
+            }
+          }
+        }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {

@@ -8,8 +8,9 @@ lowest index exactly like ``torch.argmin``. Gradient, PGD and sampling run on ra
 """
 from __future__ import annotations
 
+import math
 from dataclasses import dataclass
-from typing import Optional, Tuple
+from typing import Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as td
@@ -34,8 +35,9 @@ def shard_bounds(n: int, w: World) -> Tuple[int, int]:
     return lo, lo + base + (1 if w.rank < extra else 0)
 
 
-def balanced_cuts(cost: torch.Tensor, size: int) -> list:
-    """``size + 1`` cut points of ``range(len(cost))`` into CONTIGUOUS shards of near-equal total cost
+def balanced_cuts(cost: torch.Tensor, size: int, share: Optional[Sequence[float]] = None) -> list:
+    """``size + 1`` cut points of ``range(len(cost))`` into CONTIGUOUS shards of near-equal total cost -- or, with
+    ``share`` (one positive weight per rank, e.g. the ranks' measured speeds), of total cost proportional to it
     (``cost[i]`` = decoder rows candidate i will run: with suffix-head sharing a candidate replaced at
     position j owns only the tail rows from j on, so equal COUNTS give the ranks unequal work and the
     slowest rank sets the step time). Deterministic in ``cost``: every rank computes the same cuts from the
@@ -45,13 +47,39 @@ def balanced_cuts(cost: torch.Tensor, size: int) -> list:
         return [0] + [n] * max(size, 1)
     cum = torch.cumsum(cost.to(torch.int64), 0)
     k = torch.arange(1, size, device=cost.device, dtype=torch.int64)
-    # shard r ends at the first candidate whose running cost reaches r/size of the total
-    target = (cum[-1] * k + size - 1) // size
+    # shard r ends at the first candidate whose running cost reaches r/size (or the ranks' cumulative share) of the total
+    if share is None:
+        target = (cum[-1] * k + size - 1) // size
+    else:
+        tot, acc, frac = float(sum(share)), 0.0, []
+        for x in list(share)[:-1]:
+            acc += float(x)
+            frac.append(acc / tot)
+        total = int(cum[-1].item())
+        target = torch.tensor([min(total, max(0, math.ceil(f * total))) for f in frac], device=cost.device, dtype=torch.int64)
     cuts = (torch.searchsorted(cum, target, right=False) + 1).clamp_(max=n)
     out = [0] + [int(c) for c in cuts.tolist()] + [n]
     for i in range(1, len(out)):           # monotone (zero-cost runs can make searchsorted tie)
         out[i] = max(out[i], out[i - 1])
     return out
+
+
+def updated_shares(share: Sequence[float], step_ms: Sequence[float], wait_ms: Sequence[float],
+                   damping: float = 0.5, spread: float = 1.25) -> list:
+    """Straggler-aware shares for the next step. Rank r did ``share[r]`` of the candidate rows in ``step_ms[r] -
+    wait_ms[r]`` of its own time (the rest it spent waiting for other ranks in the per-layer prefix exchange), so its
+    speed is ``share / busy`` and the shares that would let all ranks finish together are proportional to the speeds.
+    Damped (the replicated part of a rank's work -- its prefix slice, the vision tower -- does not move with the
+    share) and clamped to ``[1/spread, spread]`` times the equal share. Pure function of its arguments: every rank
+    computes the same list from the all-gathered inputs."""
+    n = len(share)
+    busy = [max(float(t) - float(w), 1e-3) for t, w in zip(step_ms, wait_ms)]
+    speed = [float(s) / b for s, b in zip(share, busy)]
+    tot = sum(speed)
+    new = [(1.0 - damping) * float(s) + damping * v / tot for s, v in zip(share, speed)]
+    new = [min(max(x, 1.0 / (spread * n)), spread / n) for x in new]
+    tot = sum(new)
+    return [x / tot for x in new]
 
 
 def pack_key(loss: float, index: int) -> int:

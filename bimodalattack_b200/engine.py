@@ -113,6 +113,7 @@ class ScoringEngine:
         self.dedupe_candidates = True    # ... and the rows of identical candidates once
         self.fused_publish = None        # None: library default (on; BMA_FUSED_PUBLISH=0 turns it off). Set BEFORE the
                                          # first score call: prefix / base K/V leave through the QKV GEMM's epilogue
+        self.early_signal = None         # None: library default (off; BMA_EARLY_SIGNAL=1). See set_early_signal()
         # fused prefill: the prefix positions ride in the first chunk of the next score() call as extra
         # rows (one [prefix | base | candidates] row space per layer) instead of a separate pass
         self.fused_prefill = True
@@ -187,6 +188,8 @@ class ScoringEngine:
         native.check(self.lib.bma_scorer_set_dedupe(handle, int(self.dedupe_candidates)), "scorer_set_dedupe")
         if self.fused_publish is not None:
             native.check(self.lib.bma_scorer_set_fused_publish(handle, int(self.fused_publish)), "scorer_set_fused_publish")
+        if self.early_signal is not None:
+            native.check(self.lib.bma_scorer_set_early_signal(handle, int(self.early_signal)), "scorer_set_early_signal")
         if self.comm is not None:
             native.check(self.lib.bma_scorer_set_comm(handle, self.comm), "scorer_set_comm")
             if self.peer_memory:
@@ -264,6 +267,13 @@ class ScoringEngine:
             elif self.peer_memory:
                 from . import dist as bdist
                 bdist.exchange_peer_handles(self.lib, self._scorer, self.device)
+
+    def set_early_signal(self, enable: bool) -> None:
+        """Split prefill over peer memory: the QKV GEMM publishes first and raises this rank's flag itself (True)
+        or one signal + wait launch follows it (False, default). Collective in effect: set it on every rank alike."""
+        self.early_signal = bool(enable)
+        if self._scorer is not None:
+            native.check(self.lib.bma_scorer_set_early_signal(self._scorer, int(self.early_signal)), "scorer_set_early_signal")
 
     def peers_barrier(self, count: int = 1) -> None:
         """``count`` data-free prefix exchanges on the current stream (collective over the ranks; no-op without peers)."""

@@ -81,6 +81,7 @@ SIGNATURES = {
     "bma_scorer_clear_peers": (_I, [_P]),
     "bma_scorer_exchange_wait_ns": (_I, [_P, C.POINTER(_ULL), _I]),
     "bma_scorer_peers_barrier": (_I, [_P, _I, _P]),
+    "bma_scorer_set_early_signal": (_I, [_P, _I]),
     "bma_scorer_set_comm": (_I, [_P, _P]),
     "bma_comm_unique_id": (_I, [_P]),
     "bma_comm_create": (_P, [_P, _I, _I]),

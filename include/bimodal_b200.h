@@ -190,6 +190,10 @@ int bma_scorer_group_score(bma_scorer** group, int n, const long long* ids, int 
  * all-gather (bma_scorer_set_comm). export: 3 x 64 handle bytes of this scorer; import: the handles of all
  * `size` ranks ([size][3][64], 2..8 ranks of one box) -- both collective over the ranks, repeated whenever a
  * scorer is re-created. group_score's use_peers runs the same kernels between the scorers of one process. */
+/* Split prefill over peer memory: 1 (BMA_EARLY_SIGNAL=1) = the QKV GEMM walks its publishing tiles first and raises
+ * this rank's flag itself, so the other ranks' wait has the rest of that GEMM as slack against rank-to-rank jitter;
+ * 0 (default) = one signal + wait launch after the GEMM. Same results either way. */
+int bma_scorer_set_early_signal(bma_scorer* s, int enable);
 int bma_scorer_export_ipc(bma_scorer* s, void* out192);
 int bma_scorer_import_ipc(bma_scorer* s, const void* handles, int size, int rank);
 int bma_scorer_clear_peers(bma_scorer* s);

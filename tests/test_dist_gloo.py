@@ -89,3 +89,26 @@ def test_balanced_cuts_cover_everything_and_even_out_the_cost():
     even = max(int(cost[slice(*shard_bounds(512, World(r, 8)))].sum()) for r in range(8))
     assert bal < 0.7 * even
     assert balanced_cuts(torch.ones(7, dtype=torch.int64), 1) == [0, 7]
+
+
+def test_weighted_cuts_and_share_update():
+    """dist.balanced_cuts with per-rank shares, and the straggler-aware share update: a rank that waits (it is
+    faster) gains work, the iteration equalises the ranks' busy times, shares stay normalised and clamped."""
+    import torch
+    from bimodalattack_b200 import dist as d
+    cost = torch.randint(1, 40, (512,), generator=torch.Generator().manual_seed(0))
+    assert d.balanced_cuts(cost, 4, [0.25] * 4) == d.balanced_cuts(cost, 4)
+    cuts = d.balanced_cuts(cost, 4, [0.1, 0.3, 0.3, 0.3])
+    tot = int(cost.sum())
+    part = [int(cost[a:b].sum()) for a, b in zip(cuts, cuts[1:])]
+    assert cuts[0] == 0 and cuts[-1] == 512 and cuts == sorted(cuts)
+    assert abs(part[0] / tot - 0.1) < 0.02 and all(abs(x / tot - 0.3) < 0.03 for x in part[1:])
+    share, speed = [0.5, 0.5], [0.95, 1.0]
+    for _ in range(12):
+        busy = [share[i] / speed[i] * 200.0 for i in range(2)]
+        t = max(busy)
+        share = d.updated_shares(share, [t, t], [t - b for b in busy])
+        assert abs(sum(share) - 1.0) < 1e-9
+    assert abs(share[0] / share[1] - 0.95) < 2e-3            # busy times equal <=> shares proportional to speeds
+    clamped = d.updated_shares([0.5, 0.5], [100.0, 100.0], [0.0, 90.0], damping=1.0)
+    assert max(clamped) <= 1.25 / 2 + 1e-9 and min(clamped) >= 1 / (1.25 * 2) - 0.02      # (renormalised after clamping)
