@@ -26,7 +26,8 @@
 // heads): 324 us for the round-2 two-pass version -> 262 us. Tried on the way and dropped (numbers in
 // DESIGN.md 3.2): Q as the TMEM A operand with a single S buffer (366 us: the S -> softmax -> PV chain
 // of a CTA becomes strictly serial), two threads per row / eight softmax warps (347 us), back-off in
-// the control warps' barrier polls (no change). BMA_OCC_TIMING=1 prints per-phase cycle counts of the
+// the control warps' barrier polls (no change). Scale-and-subtract / row sums use packed fp32 pairs (FFMA2 /
+// FADD2, bit-identical, ~3 %; BMA_OCC_PACKED=0 = scalar). BMA_OCC_TIMING=1 prints per-phase cycle counts of the
 // softmax warps of CTA 0, BMA_OCC_KNOCK removes one cost at a time (timing only, wrong results).
 #include <cstdio>
 #include <cstdlib>
@@ -74,6 +75,23 @@ __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// Packed fp32 pairs (Blackwell FFMA2 / FADD2): {d0, d1} = {a0, a1} * b + c and {d0, d1} += {a0, a1}; per lane the same
+// IEEE result as the scalar instructions, half the issue slots.
+__device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, float b, float c) {
+  uint64_t d, a, bb, cc;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(bb) : "f"(b));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(cc) : "f"(c));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(bb), "l"(cc));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
+__device__ __forceinline__ void add2(float& d0, float& d1, float a0, float a1) {
+  uint64_t d, a;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(d0), "f"(d1));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(d), "l"(a));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
 }
 __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
@@ -136,14 +154,18 @@ __device__ __noinline__ float masked_exp32_store(uint32_t ts, uint32_t tp, uint3
     uint32_t r[32];
     tmem_ld_32x32(ts, r);
     tmem_ld_wait();
+    float s0 = 0.0f, s1 = 0.0f;
 #pragma unroll
     for (int i = 0; i < 32; i += 2) {
-      const float x0 = ((bits >> i) & 1u) ? fmaf(__uint_as_float(r[i]), scale_log2, -m_use) : -INFINITY;
-      const float x1 = ((bits >> (i + 1)) & 1u) ? fmaf(__uint_as_float(r[i + 1]), scale_log2, -m_use) : -INFINITY;
+      float x0, x1;
+      fma2(x0, x1, __uint_as_float(r[i]), __uint_as_float(r[i + 1]), scale_log2, -m_use);
+      x0 = ((bits >> i) & 1u) ? x0 : -INFINITY;
+      x1 = ((bits >> (i + 1)) & 1u) ? x1 : -INFINITY;
       const float p0 = ex2(x0), p1 = ex2(x1);               // -inf -> 0
-      rs += p0 + p1;
+      add2(s0, s1, p0, p1);
       pk[i >> 1] = pack_bf16x2(p0, p1);
     }
+    rs = s0 + s1;
   }
   tmem_st_32x16(tp, pk);
   return rs;
@@ -164,7 +186,7 @@ __device__ __noinline__ void rescale_o_row(uint32_t to, float f) {
 
 // TIMING: the softmax warps of CTA 0 accumulate clock64() deltas per phase in registers and write them to
 // p.dbg at the end (tools/bench_attention.py, BMA_OCC_TIMING=1); p.knock then also applies.
-template <bool TIMING>
+template <bool TIMING, bool PACKED>
 __global__ void __launch_bounds__(THREADS, 2)
 attention_occ_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kt,
                      const __grid_constant__ CUtensorMap tm_kp, const __grid_constant__ CUtensorMap tm_vt,
@@ -472,19 +494,29 @@ attention_occ_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
           const bool no_ex2 = TIMING && (p.knock & 1);
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            const float x0 = fmaf(__uint_as_float(ra[i]), p.scale_log2, -m_use);
-            const float x1 = fmaf(__uint_as_float(ra[i + 1]), p.scale_log2, -m_use);
+            float x0, x1;
+            if (PACKED) {
+              fma2(x0, x1, __uint_as_float(ra[i]), __uint_as_float(ra[i + 1]), p.scale_log2, -m_use);
+            } else {
+              x0 = fmaf(__uint_as_float(ra[i]), p.scale_log2, -m_use);
+              x1 = fmaf(__uint_as_float(ra[i + 1]), p.scale_log2, -m_use);
+            }
             const float p0 = no_ex2 ? x0 : ex2(x0), p1 = no_ex2 ? x1 : ex2(x1);
-            s0 += p0; s1 += p1;
+            if (PACKED) add2(s0, s1, p0, p1); else { s0 += p0; s1 += p1; }
             pk[i >> 1] = pack_bf16x2(p0, p1);
           }
           tmem_st_32x16(ts, pk);                           // P_g: columns [0, 32) of S_st, bf16 pairs
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            const float x0 = fmaf(__uint_as_float(rb[i]), p.scale_log2, -m_use);
-            const float x1 = fmaf(__uint_as_float(rb[i + 1]), p.scale_log2, -m_use);
+            float x0, x1;
+            if (PACKED) {
+              fma2(x0, x1, __uint_as_float(rb[i]), __uint_as_float(rb[i + 1]), p.scale_log2, -m_use);
+            } else {
+              x0 = fmaf(__uint_as_float(rb[i]), p.scale_log2, -m_use);
+              x1 = fmaf(__uint_as_float(rb[i + 1]), p.scale_log2, -m_use);
+            }
             const float p0 = no_ex2 ? x0 : ex2(x0), p1 = no_ex2 ? x1 : ex2(x1);
-            s0 += p0; s1 += p1;
+            if (PACKED) add2(s0, s1, p0, p1); else { s0 += p0; s1 += p1; }
             pk[i >> 1] = pack_bf16x2(p0, p1);
           }
           tmem_st_32x16(ts + 16, pk);
@@ -563,10 +595,10 @@ cudaError_t launch_attention_occ(const AttnParams& a, int n_heads, cudaStream_t 
     tkp = tkt;
     tvp = tvt;
   }
-  // A/B switches (tools/ab_attention.py): BMA_OCC_DEFER, BMA_OCC_PVFIRST (default 1), BMA_OCC_TIMING = 1 (per-phase
+  // A/B switches (tools/ab_attention.py): BMA_OCC_DEFER, BMA_OCC_PVFIRST, BMA_OCC_PACKED (default 1), BMA_OCC_TIMING = 1 (per-phase
   // cycle counts of the softmax warps of CTA 0 on stderr; BMA_OCC_KNOCK then removes costs). Read once;
   // BMA_OCC_RELOAD = 1 re-reads them at every launch (in-process A/B).
-  static int inited = 0, timing = 0, defer = 1, pv_first = 1, knock = 0, reload = 0;
+  static int inited = 0, timing = 0, defer = 1, pv_first = 1, knock = 0, reload = 0, packed = 1;
   static unsigned long long* dbg = nullptr;
   if (!inited || reload) {
     const char* e = getenv("BMA_OCC_TIMING");
@@ -575,13 +607,16 @@ cudaError_t launch_attention_occ(const AttnParams& a, int n_heads, cudaStream_t 
     defer = (e != nullptr && e[0] == '0') ? 0 : 1;
     e = getenv("BMA_OCC_PVFIRST");
     pv_first = (e != nullptr && e[0] == '0') ? 0 : 1;
+    e = getenv("BMA_OCC_PACKED");
+    packed = (e != nullptr && e[0] == '0') ? 0 : 1;
     e = getenv("BMA_OCC_KNOCK");
     knock = e != nullptr ? atoi(e) : 0;
     e = getenv("BMA_OCC_RELOAD");
     reload = (e != nullptr && e[0] == '1');
     if (!inited) {
-      cudaError_t e1 = cudaFuncSetAttribute(attention_occ_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-      if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(attention_occ_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+      cudaError_t e1 = cudaFuncSetAttribute(attention_occ_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+      if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(attention_occ_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+      if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(attention_occ_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
       if (e1 != cudaSuccess) return e1;
       inited = 1;
     }
@@ -603,7 +638,8 @@ cudaError_t launch_attention_occ(const AttnParams& a, int n_heads, cudaStream_t 
   if (grid > 2ll * num_sms()) grid = 2ll * num_sms();
   const int g = static_cast<int>(grid);
   if (!timing) {
-    attention_occ_kernel<false><<<g, THREADS, SMEM, stream>>>(tq, tkt, tkp, tvt, tvp, to, p);
+    if (packed) attention_occ_kernel<false, true><<<g, THREADS, SMEM, stream>>>(tq, tkt, tkp, tvt, tvp, to, p);
+    else attention_occ_kernel<false, false><<<g, THREADS, SMEM, stream>>>(tq, tkt, tkp, tvt, tvp, to, p);
     return cudaGetLastError();
   }
   p.dbg = dbg;
@@ -612,7 +648,7 @@ cudaError_t launch_attention_occ(const AttnParams& a, int n_heads, cudaStream_t 
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0, stream);
-  attention_occ_kernel<true><<<g, THREADS, SMEM, stream>>>(tq, tkt, tkp, tvt, tvp, to, p);
+  attention_occ_kernel<true, true><<<g, THREADS, SMEM, stream>>>(tq, tkt, tkp, tvt, tvp, to, p);
   cudaEventRecord(e1, stream);
   unsigned long long hh[64];
   float ms = 0.0f;

@@ -9,7 +9,7 @@
 // With P = 0 and S = P_len the same kernel computes the prefix itself (plain causal attention).
 //
 // This file is the kernel for head_dim 256 (Gemma-3; 64-key blocks) and the A/B fallback for
-// head_dim 128 (BMA_ATTN_SPLIT=0); head_dim 128 normally runs attention_split.cu (per-half
+// head_dim 128 (BMA_ATTN=tc); head_dim 128 normally runs attention_occ.cu, BMA_ATTN=split attention_split.cu (per-half
 // accumulators, P in tensor memory).
 //
 //   warp 0      TMA producer: Q tile per item (double-buffered for head_dim 128: the next item's Q is

@@ -21,7 +21,7 @@ ldt, ldp = (M + 7) // 8 * 8, (P + 7) // 8 * 8
 vT, vpT = mk(H * D, ldt), mk(H * D, ldp)
 out = torch.zeros((M, H * D), dtype=torch.bfloat16, device=dev)
 st = torch.cuda.current_stream().cuda_stream
-KEYS = ["DEFER", "PVFIRST"]
+KEYS = ["DEFER", "PVFIRST", "PACKED"]
 def apply(cfg):
     for key in KEYS:
         os.environ.pop("BMA_OCC_" + key, None)
