@@ -54,6 +54,9 @@ def parse_args():
                          "GPUs scores search_width/N of them; weak: search_width candidates PER GPU")
     ap.add_argument("--full-steps", type=int, default=3, help="full attack steps timed for steps/s (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--multi-gpu-ab", action="store_true",
+                    help="N > 1: also time the two opt-in multi-GPU features in this process (early signal from inside the "
+                         "QKV GEMM, straggler-aware candidate shares) and report early_signal_ab / adaptive_shares_ab")
     ap.add_argument("--no-hbm-kernels", action="store_true", help="skip the HBM-bound kernel rooflines (roofline_hbm)")
     ap.add_argument("--no-suffix-sharing", action="store_true",
                     help="score every candidate's full tail (the north-star dataflow) instead of computing the "
@@ -451,52 +454,53 @@ def main():
         exchange_floor_us = round(b0.elapsed_time(b1) / 200 * 1e3, 2)
         atk.engine.exchange_wait_ms(reset=True)
 
-        # A/B of the early signal (the QKV GEMM publishes first and raises the flags itself) in the same process
-        def timed_ms(n):
-            barrier()
-            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            t0.record()
-            for _ in range(n):
+        if args.multi_gpu_ab:
+            # A/B of the early signal (the QKV GEMM publishes first and raises the flags itself) in the same process
+            def timed_ms(n):
+                barrier()
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0.record()
+                for _ in range(n):
+                    scoring_step()
+                t1.record()
+                barrier()
+                t = torch.tensor([t0.elapsed_time(t1)], device=dev)
+                td.all_reduce(t, op=td.ReduceOp.MAX)
+                return float(t.item()) / n
+            ab = {}
+            for name, flag in (("off", False), ("on", True), ("off2", False), ("on2", True)):
+                atk.engine.set_early_signal(flag)
                 scoring_step()
-            t1.record()
-            barrier()
-            t = torch.tensor([t0.elapsed_time(t1)], device=dev)
-            td.all_reduce(t, op=td.ReduceOp.MAX)
-            return float(t.item()) / n
-        ab = {}
-        for name, flag in (("off", False), ("on", True), ("off2", False), ("on2", True)):
-            atk.engine.set_early_signal(flag)
-            scoring_step()
-            ms_ab = timed_ms(args.steps)
-            wt = torch.zeros(world, device=dev)
-            wt[rank] = atk.engine.exchange_wait_ms(reset=True) / (args.steps + 1)
-            td.all_reduce(wt)
-            ab[name] = {"candidates_per_s": round(sw / (ms_ab * 1e-3), 1), "ms_per_step": round(ms_ab, 3),
-                        "exchange_wait_ms_per_step": [round(float(x), 3) for x in wt.tolist()]}
-        early_signal_ab = ab
-        atk.engine.set_early_signal(False)
+                ms_ab = timed_ms(args.steps)
+                wt = torch.zeros(world, device=dev)
+                wt[rank] = atk.engine.exchange_wait_ms(reset=True) / (args.steps + 1)
+                td.all_reduce(wt)
+                ab[name] = {"candidates_per_s": round(sw / (ms_ab * 1e-3), 1), "ms_per_step": round(ms_ab, 3),
+                            "exchange_wait_ms_per_step": [round(float(x), 3) for x in wt.tolist()]}
+            early_signal_ab = ab
+            atk.engine.set_early_signal(False)
 
-        # straggler-aware shares (BimodalAttack.rebalance): 10 untimed steps move the candidate shares towards the
-        # ranks' measured speeds, then the same timed loop
-        atk.adapt_shares = True
-        atk._rebalance_calls = 2
-        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        atk.engine.exchange_wait_ms(reset=True)
-        for _ in range(10):
-            w0.record()
-            scoring_step()
-            w1.record()
-            w1.synchronize()
-            atk.rebalance(w0.elapsed_time(w1))
-        atk.adapt_shares = False             # frozen cuts for the timed steps (and everything after)
-        ms_ad = timed_ms(args.steps)
-        wt = torch.zeros(world, device=dev)
-        wt[rank] = atk.engine.exchange_wait_ms(reset=True) / args.steps
-        td.all_reduce(wt)
-        adaptive_ab = {"candidates_per_s": round(sw / (ms_ad * 1e-3), 1), "ms_per_step": round(ms_ad, 3),
-                       "rank_share": [round(x, 4) for x in (atk.rank_share or [])],
-                       "exchange_wait_ms_per_step": [round(float(x), 3) for x in wt.tolist()]}
-        atk.rank_share = None
+            # straggler-aware shares (BimodalAttack.rebalance): 10 untimed steps move the candidate shares towards the
+            # ranks' measured speeds, then the same timed loop
+            atk.adapt_shares = True
+            atk._rebalance_calls = 2
+            w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            atk.engine.exchange_wait_ms(reset=True)
+            for _ in range(10):
+                w0.record()
+                scoring_step()
+                w1.record()
+                w1.synchronize()
+                atk.rebalance(w0.elapsed_time(w1))
+            atk.adapt_shares = False             # frozen cuts for the timed steps (and everything after)
+            ms_ad = timed_ms(args.steps)
+            wt = torch.zeros(world, device=dev)
+            wt[rank] = atk.engine.exchange_wait_ms(reset=True) / args.steps
+            td.all_reduce(wt)
+            adaptive_ab = {"candidates_per_s": round(sw / (ms_ad * 1e-3), 1), "ms_per_step": round(ms_ad, 3),
+                           "rank_share": [round(x, 4) for x in (atk.rank_share or [])],
+                           "exchange_wait_ms_per_step": [round(float(x), 3) for x in wt.tolist()]}
+            atk.rank_share = None
     rows_run = atk.engine.last_rows          # tail (+ fused prefix) rows of this rank's shard that went through the decoder
 
     # ---- per-class profile: a SEPARATE pass with an event pair around every launch -----------------
