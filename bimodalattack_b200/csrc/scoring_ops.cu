@@ -5,6 +5,8 @@
 //   rmsnorm             RMSNorm with HF's rounding points, optional row gather (target rows only)
 //   ce_finalize         combine the LM-head GEMM's per-tile (max, sum-exp) partials into per-token
 //                       CE, mean per candidate (bimodal_attack.py:1293-1298), packed argmin key
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -446,7 +448,8 @@ constexpr int kNormRegVecs = 16;     // 16-byte vectors a lane keeps in register
 // mode 1 (Gemma): y = bf16(x * rstd * (1 + w)). Row gather: when gather_T > 0 output row r reads
 // input row start(r / gather_T) + gather_off + (r % gather_T), where start(c) = c * gather_S for
 // the uniform layout and gather_vstart[c] for the ragged one.
-__global__ void __launch_bounds__(128)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB)
 rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
                const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ y, long long ldy,
                int rows, int d, float eps, int mode, int gather_T, int gather_S, int gather_off,
@@ -496,8 +499,11 @@ rmsnorm_kernel(const __nv_bfloat16* __restrict__ x, long long ldx,
         for (int j = 0; j < 4; ++j) {
           float a = bf16_lo(in[j]) * rstd, b = bf16_hi(in[j]) * rstd;
           if (mode == 0) {
-            a = bf16_round(a) * bf16_lo(wi[j]);
-            b = bf16_round(b) * bf16_hi(wi[j]);
+            // HF rounds x * rstd to bf16 before the weight multiply: both values through ONE packed conversion
+            // (F2FP, ALU pipe) instead of two scalar F2F round trips (XU pipe, quarter rate)
+            const uint32_t pr = pack_bf16x2(a, b);
+            a = bf16_lo(pr) * bf16_lo(wi[j]);
+            b = bf16_hi(pr) * bf16_hi(wi[j]);
           } else {
             a = a * (1.0f + bf16_lo(wi[j]));
             b = b * (1.0f + bf16_hi(wi[j]));
@@ -549,9 +555,22 @@ cudaError_t launch_rmsnorm(const __nv_bfloat16* x, long long ldx, const __nv_bfl
                            cudaStream_t stream, const int* rows_dev) {
   if (rows <= 0) return cudaSuccess;
   if ((d & 7) != 0 || (ldx & 7) != 0 || (ldy & 7) != 0) return cudaErrorInvalidValue;
-  const int blocks = static_cast<int>(((long long)rows * 32 + 127) / 128);      // 4 rows per block (~150 registers)
-  rmsnorm_kernel<<<blocks, 128, 0, stream>>>(x, ldx, w, y, ldy, rows, d, eps, mode, gather_T,
-                                             gather_S, gather_off, gather_vstart, rows_dev);
+  const int blocks = static_cast<int>(((long long)rows * 32 + 127) / 128);      // 4 rows per block
+  // BMA_NORM_MINB = 3 (150 registers, 12 resident warps per SM) | 4 (128 registers, 16 warps); A/B switch,
+  // re-read per launch when BMA_NORM_RELOAD = 1
+  static int minb = 0, reload = 0;
+  if (minb == 0 || reload) {
+    const char* e = getenv("BMA_NORM_MINB");
+    minb = (e != nullptr && e[0] == '3') ? 3 : 4;
+    e = getenv("BMA_NORM_RELOAD");
+    reload = (e != nullptr && e[0] == '1');
+  }
+  if (minb == 3)
+    rmsnorm_kernel<3><<<blocks, 128, 0, stream>>>(x, ldx, w, y, ldy, rows, d, eps, mode, gather_T,
+                                                  gather_S, gather_off, gather_vstart, rows_dev);
+  else
+    rmsnorm_kernel<4><<<blocks, 128, 0, stream>>>(x, ldx, w, y, ldy, rows, d, eps, mode, gather_T,
+                                                  gather_S, gather_off, gather_vstart, rows_dev);
   return cudaGetLastError();
 }
 
