@@ -170,6 +170,41 @@ def test_fused_publish_is_bit_identical_to_separate_kernels(cuda_device, ranks, 
     assert out[True][2] == out[False][2]
 
 
+@pytest.mark.parametrize("ranks,n,size,px", [(2, 48, "tiny128", 28), (8, 130, "tiny128", 28), (3, 200, "small128", 56)])
+def test_early_signal_is_bit_identical(cuda_device, ranks, n, size, px):
+    """Opt-in early signal (bma_scorer_set_early_signal): the QKV GEMM walks its publishing tiles first and raises the
+    rank's flag from its own epilogue, the exchange launch only waits. Tile ORDER changes, values do not: losses and
+    the winner key equal the default path's bit for bit; the wait accumulator and the bare barrier are callable on a
+    scorer without peers (0 ms, no-op)."""
+    from bimodalattack_b200 import BimodalAttack
+    from bimodalattack_b200.attack import image_features
+    from bimodalattack_b200.engine import ScoringEngine, group_score
+    model, tok, proc, norm, image, cfg = _setup(cuda_device, size=size, image_px=px, search_width=n, **JOINT)
+    atk = BimodalAttack(model, tok, proc, cfg, normalize=norm)
+    atk._prepare([{"role": "user", "content": PROMPT}], TARGET)
+    base = tok(INIT, add_special_tokens=False, return_tensors="pt")["input_ids"].to(cuda_device).reshape(-1).contiguous()
+    cand = _related(base, n, 8, 1000, seed=ranks, device=cuda_device)
+    out = {}
+    with torch.no_grad():
+        feats = image_features(model, norm(image), False)
+        plan = atk._plan(atk._build_input_embeds_pgd(cand, feats, search_width=n, single=True))
+        for early in (True, False):
+            group = [ScoringEngine(model) for _ in range(ranks)]
+            for e in group:
+                e.early_signal = early
+                e.prefill(plan.prefix, deferred=True)
+            loss = group_score(group, cand, plan, atk.target_ids, base, use_peers=True).clone()
+            again = group[-1].score(cand, plan, atk.target_ids, base_ids=base).clone()
+            out[early] = (loss, again, int(group[0].key.item()))
+            assert group[0].exchange_wait_ms(reset=True) >= 0.0
+            group[0].peers_barrier(3)            # no peers attached any more: a no-op
+            for e in group:
+                e.close()
+    assert torch.equal(out[True][0], out[False][0])
+    assert torch.equal(out[True][1], out[False][1])
+    assert out[True][2] == out[False][2]
+
+
 # ------------------------------------------------------------------------------------------------
 def _greedy_target(model, atk, cand_row, feats, n_tokens):
     """Target ids the model itself predicts greedily after [prefix, cand_row, after]: with them as the
