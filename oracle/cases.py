@@ -17,6 +17,13 @@ MODES = {
     # (bimodal_attack.py:661 formats current_loss while it is still None in that branch).
     "joint_masked_dynamic": dict(pgd_attack=True, gcg_attack=True, joint_eval=True, allow_non_ascii=False,
                                  dynamic_search=True, min_search_width=4, n_replace=2),
+    # round 2: the option paths the product implements beyond the five mode combinations
+    "joint_buffer3": dict(pgd_attack=True, gcg_attack=True, joint_eval=True, buffer_size=3),
+    "gcg_buffer2": dict(pgd_attack=False, gcg_attack=True, joint_eval=False, buffer_size=2),
+    "joint_early_stop": dict(pgd_attack=True, gcg_attack=True, joint_eval=True, early_stop=True),
+    "joint_batch8": dict(pgd_attack=True, gcg_attack=True, joint_eval=True, batch_size=8),
+    "gcg_nofilter_space": dict(pgd_attack=False, gcg_attack=True, joint_eval=False, filter_ids=False,
+                               add_space_before_target=True),
 }
 BASE = dict(num_steps=3, search_width=16, topk=32, seed=1, allow_non_ascii=True, alpha=4 / 255,
             eps=64 / 255, optim_str_init=INIT, verbosity="ERROR")

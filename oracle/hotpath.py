@@ -27,6 +27,10 @@ import torch
 import torch.nn.functional as F
 
 
+# initial characters for the extra buffer entries (reference bimodalattack/utils.py:8-12)
+INIT_CHARS = [".", ",", "!", "?", ";", ":", "(", ")", "[", "]", "{", "}", "@", "#", "$", "%", "&", "*", "w", "x", "y", "z"]
+
+
 # ------------------------------------------------------------------------------------------------
 # (4) PGD step -- bimodal_attack.py:1030-1037
 def pgd_step(image: torch.Tensor, eps: float, alpha: float, image_grad: torch.Tensor,
@@ -311,15 +315,37 @@ class OracleAttack:
         self.seg_ids = seg_ids
         self.seg_embeds = {k: self.emb(v) for k, v in seg_ids.items()}
 
-        # init buffer (:826-906) -- buffer_size 0/1 only: one scoring call on the initial suffix
+        # init buffer (:826-906): the initial suffix plus buffer_size - 1 random rows of INIT_CHARS tokens (one
+        # torch.randint on the default generator -- it moves the RNG stream of every later draw), all scored in the
+        # gcg_pgd / gcg order; the run starts from the entry with the lowest loss (:396-397). Inside the loop the
+        # buffer only collects (loss, suffix) pairs for logging (:618-619, :643-644), it never feeds back.
         optim_ids = tok(cfg.optim_str_init, add_special_tokens=False, return_tensors="pt")["input_ids"].to(model.device)
+        if isinstance(cfg.optim_str_init, str) and cfg.buffer_size > 1:
+            pool = tok(INIT_CHARS, add_special_tokens=False, return_tensors="pt")["input_ids"].squeeze().to(model.device)
+            pick = torch.randint(0, pool.shape[0], (cfg.buffer_size - 1, optim_ids.shape[1]))
+            optim_ids = torch.cat([optim_ids, pool[pick]], dim=0)
+        n_init = max(1, cfg.buffer_size)
         if cfg.pgd_attack:
             feats = self._features(image)
             order = segment_order("gcg_pgd", self.model_type, single=True)
-            init = assemble(self._parts(optim_ids, feats), order, 1)
+            init = assemble(self._parts(optim_ids, feats), order, n_init)
         else:
-            init = assemble(self._parts(optim_ids), segment_order("gcg", self.model_type, no_joint_eval=True), 1)
-        self.init_loss = self._loss(init, 1)[0]
+            init = assemble(self._parts(optim_ids), segment_order("gcg", self.model_type, no_joint_eval=True), n_init)
+        init_losses = self._loss(init, n_init)
+        entries: list = []                                                      # AttackBuffer.add (:96-106)
+        for i in range(n_init):
+            item = (init_losses[i], optim_ids[[i]])
+            if cfg.buffer_size == 0:
+                entries = [item]
+                continue
+            if len(entries) < cfg.buffer_size:
+                entries.append(item)
+            else:
+                entries[-1] = item
+            entries.sort(key=lambda x: x[0])
+        self.init_loss = entries[0][0]
+        self.init_buffer = entries
+        optim_ids = entries[0][1]
 
         log = StepLog()
         if cfg.pgd_attack:

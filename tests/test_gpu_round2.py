@@ -360,6 +360,38 @@ def test_run_option_combinations(cuda_device, case, tmp_path):
     assert not any(hasattr(m, "_bma_orig_forward") for m in model.modules())
 
 
+@pytest.mark.parametrize("case", ["buffer4", "gcg_buffer3_nofilter"])
+def test_initial_buffer_matches_oracle(cuda_device, case):
+    """buffer_size > 1 (:826-906): the extra entries are drawn with ONE torch.randint on the default generator (which
+    shifts every later draw), all entries are scored and the run starts from the best one. The oracle's buffer path
+    is pinned to the unmodified reference by the golden cases joint_buffer3 / gcg_buffer2; here the product must
+    draw the same entries, score them to bf16 tolerance and start from the (tie-aware) best."""
+    import bimodalattack_b200 as bma
+    from oracle import hotpath
+    model, tok, proc, norm, image, cfg = _setup(cuda_device, **RUN_CASES[case])
+    cfg.num_steps = 1
+    atk = bma.BimodalAttack(model, tok, proc, cfg, normalize=norm)
+    seen = {}
+    real = atk.init_buffer
+
+    def spy(img):
+        buf = real(img)
+        seen["entries"] = [(float(l), ids.reshape(-1).tolist()) for l, ids in buf.buffer]
+        return buf
+    atk.init_buffer = spy
+    res = atk.run([{"role": "user", "content": PROMPT}], "goal", TARGET, image.clone() if cfg.pgd_attack else None)
+    ora = hotpath.OracleAttack(model, tok, proc, cfg, normalize=norm)
+    log = ora.run([{"role": "user", "content": PROMPT}], TARGET, image.clone() if cfg.pgd_attack else None)
+    want_rows = sorted(tuple(ids.reshape(-1).tolist()) for _, ids in ora.init_buffer)
+    got_rows = sorted(tuple(ids) for _, ids in seen["entries"])
+    assert got_rows == want_rows and len(want_rows) == cfg.buffer_size       # the same random rows (repeats included)
+    want = {tuple(ids.reshape(-1).tolist()): float(l) for l, ids in ora.init_buffer}
+    for l, ids in seen["entries"]:
+        assert abs(l - want[tuple(ids)]) <= 0.0625 * 2 + 2e-2 * abs(want[tuple(ids)])
+    assert want[tuple(seen["entries"][0][1])] <= min(want.values()) + 0.0625 * 2     # starts from the best entry
+    assert abs(res.losses[0] - log.losses[0]) <= 0.0625 * 2 + 2e-2 * abs(log.losses[0])
+
+
 def test_run_restores_process_state(cuda_device):
     import bimodalattack_b200 as bma
     model, tok, proc, norm, image, cfg = _setup(cuda_device, **JOINT)
