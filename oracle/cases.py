@@ -24,6 +24,8 @@ MODES = {
     "joint_batch8": dict(pgd_attack=True, gcg_attack=True, joint_eval=True, batch_size=8),
     "gcg_nofilter_space": dict(pgd_attack=False, gcg_attack=True, joint_eval=False, filter_ids=False,
                                add_space_before_target=True),
+    "joint_listinit2": dict(pgd_attack=True, gcg_attack=True, joint_eval=True, buffer_size=2, n_replace=3,
+                            optim_str_init=["x x x x x x x x", "y y y z z y y y"]),
 }
 BASE = dict(num_steps=3, search_width=16, topk=32, seed=1, allow_non_ascii=True, alpha=4 / 255,
             eps=64 / 255, optim_str_init=INIT, verbosity="ERROR")
