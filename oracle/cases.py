@@ -60,3 +60,36 @@ def config_kwargs(mode: str) -> dict:
     kw = dict(BASE)
     kw.update(MODES[mode])
     return kw
+
+
+class MergingTokenizer:
+    """Tokenizer whose decode -> encode round trip FAILS for ids in ``bad`` (they decode to the text of the next id),
+    like BPE merges do for real vocabularies: what the reference's filter_ids (:166-186) exists for."""
+
+    def __init__(self, tok, bad):
+        self._tok, self._bad = tok, set(bad)
+
+    def __getattr__(self, name):
+        return getattr(self._tok, name)
+
+    def __call__(self, *a, **k):
+        return self._tok(*a, **k)
+
+    def _fix(self, ids):
+        return [int(i) + 1 if int(i) in self._bad else int(i) for i in ids]
+
+    def decode(self, ids, **k):
+        return self._tok.decode(self._fix(ids.tolist() if hasattr(ids, "tolist") else ids), **k)
+
+    def batch_decode(self, seqs, **k):
+        seqs = seqs.tolist() if hasattr(seqs, "tolist") else seqs
+        return [self._tok.decode(self._fix(s), **k) for s in seqs]
+
+
+def filter_case():
+    """(ids [40, 8], tokenizer) of the filter_ids vector: every 17th id from 100 on breaks the round trip."""
+    from bimodalattack_b200 import synthetic as syn
+    tok = MergingTokenizer(syn.make_tokenizer(1000), bad=range(100, 1000, 17))
+    g = torch.Generator().manual_seed(21)
+    ids = torch.randint(16, 990, (40, 8), generator=g)
+    return ids, tok

@@ -61,6 +61,9 @@ def function_vectors(ref) -> dict:
     stepped = ref.BimodalAttack.perform_pgd_step(_Self(), img.clone(), 64 / 255, 4 / 255, gr, orig)
     out["pgd"] = {"seed": 12, "shape": [1, 3, 9, 7], "eps": 64 / 255, "alpha": 4 / 255,
                   "out_hex": [float(v).hex() for v in stepped.detach().view(-1).tolist()]}
+    ids, tok = cases.filter_case()
+    kept = ref.filter_ids(ids.clone(), tok)
+    out["filter"] = {"rows": int(ids.shape[0]), "kept": kept.tolist()}
     return out
 
 

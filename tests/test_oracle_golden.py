@@ -60,3 +60,15 @@ def test_oracle_pgd_matches_reference_vector():
     gr.view(-1)[::5] = 0.0
     out = hotpath.pgd_step(img, v["eps"], v["alpha"], gr, orig)
     assert [float(x).hex() for x in out.detach().view(-1).tolist()] == v["out_hex"]
+
+
+def test_filter_ids_matches_reference_vector():
+    """filter_ids (:166-186) with a tokenizer whose round trip really fails: the oracle's per-row loop and the
+    product's single batched tokenizer call keep exactly the rows the reference keeps."""
+    from bimodalattack_b200.attack import filter_ids as product_filter_ids
+    v = _load("reference_functions.json")["filter"]
+    ids, tok = cases.filter_case()
+    want = torch.tensor(v["kept"])
+    assert 0 < want.shape[0] < v["rows"]
+    assert torch.equal(hotpath.filter_ids(ids.clone(), tok), want)
+    assert torch.equal(product_filter_ids(ids.clone(), tok), want)
