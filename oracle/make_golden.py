@@ -64,6 +64,8 @@ def function_vectors(ref) -> dict:
     ids, tok = cases.filter_case()
     kept = ref.filter_ids(ids.clone(), tok)
     out["filter"] = {"rows": int(ids.shape[0]), "kept": kept.tolist()}
+    from bimodalattack_b200 import synthetic as syn
+    out["nonascii"] = {"vocab": 1000, "ids": ref.get_nonascii_toks(syn.make_tokenizer(1000)).tolist()}
     return out
 
 

@@ -72,3 +72,11 @@ def test_filter_ids_matches_reference_vector():
     assert 0 < want.shape[0] < v["rows"]
     assert torch.equal(hotpath.filter_ids(ids.clone(), tok), want)
     assert torch.equal(product_filter_ids(ids.clone(), tok), want)
+
+
+def test_nonascii_tokens_match_reference_vector():
+    """get_nonascii_toks (reference utils.py:14-33): the not-allowed mask of allow_non_ascii=False."""
+    from bimodalattack_b200 import synthetic as syn
+    from bimodalattack_b200.utils import get_nonascii_toks
+    v = _load("reference_functions.json")["nonascii"]
+    assert get_nonascii_toks(syn.make_tokenizer(v["vocab"])).tolist() == v["ids"] and len(v["ids"]) > 0
