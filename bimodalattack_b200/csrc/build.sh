@@ -13,5 +13,5 @@ for f in pgd_step sampler scoring_ops attention_tc attention_split attention_occ
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait "$p"; done
-"$NVCC" -shared -o "$OUT" "$HERE"/_obj/{pgd_step,sampler,scoring_ops,attention_tc,attention_split,attention_occ,engine,comm,phase_a,grad_api}.o -ldl
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" "$HERE"/_obj/{pgd_step,sampler,scoring_ops,attention_tc,attention_split,attention_occ,engine,comm,phase_a,grad_api}.o -ldl
 echo "built $OUT"
